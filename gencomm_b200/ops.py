@@ -1,0 +1,241 @@
+"""Tensor-level wrappers over the C ABI: torch supplies device memory and the current stream only.
+
+Every function validates device / dtype / contiguity (the reference's error convention is Python
+exceptions) and launches asynchronously on ``torch.cuda.current_stream()``.  No
+function here synchronises with the host unless its docstring says so.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+
+FUSE_WARP_ONLY, FUSE_MAX, FUSE_ATT = 0, 1, 2
+MAX_POINTS_PER_PILLAR = 32
+MAX_AGENTS_PER_FRAME = 8
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def _chk(t, name, dtype, ndim=None):
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name} must be a torch.Tensor")
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor (gencomm_b200 has no CPU path)")
+    if t.dtype != dtype:
+        raise TypeError(f"{name} must be {dtype}, got {t.dtype}")
+    if ndim is not None and t.dim() != ndim:
+        raise ValueError(f"{name} must have {ndim} dims, got shape {tuple(t.shape)}")
+    if not t.is_contiguous():
+        raise ValueError(f"{name} must be contiguous")
+    return t
+
+
+# --------------------------------------------------------------------------------------------
+# geometry / parameter packing (host)
+# --------------------------------------------------------------------------------------------
+def grid_size(lidar_range, voxel_size):
+    """sp_voxel_preprocessor.py:41-43 / heter_encoders.py:25-28: np.round((max-min)/voxel) int64 [nx,ny,nz]."""
+    g = (np.array(lidar_range[3:6]) - np.array(lidar_range[0:3])) / np.array(voxel_size)
+    return np.round(g).astype(np.int64)
+
+
+def make_geom(lidar_range, voxel_size, max_voxels, max_points=MAX_POINTS_PER_PILLAR):
+    g = grid_size(lidar_range, voxel_size)
+    geom = _lib.VoxelGeom()
+    for j in range(3):
+        geom.range_min[j] = float(lidar_range[j])
+        geom.voxel[j] = float(voxel_size[j])
+        geom.grid[j] = int(g[j])
+    geom.max_points = int(max_points)
+    geom.max_voxels = int(max_voxels)
+    return geom
+
+
+def centre_offset(voxel_size, lidar_range):
+    """pillar_vfe.py:87-89 (python float64), rounded to fp32 when applied to fp32 tensors."""
+    return [voxel_size[j] / 2 + lidar_range[j] for j in range(3)]
+
+
+def fold_bn(bn_weight, bn_bias, bn_mean, bn_var, eps=1e-3):
+    """Eval-mode BatchNorm1d (pillar_vfe.py:25) folded to y = x*scale + shift, in fp32."""
+    scale = bn_weight.float() / torch.sqrt(bn_var.float() + eps)
+    shift = bn_bias.float() - bn_mean.float() * scale
+    return scale, shift
+
+
+def pack_pfn(weight, bn_weight, bn_bias, bn_mean, bn_var, eps=1e-3):
+    """[64,10] Linear weight + BN1d stats -> the [64,16] table of include/gencomm_b200.h."""
+    w = weight.detach().float().cpu()
+    if tuple(w.shape) != (64, 10):
+        raise ValueError("PillarVFE kernels implement num_filters=[64], 10 input features "
+                         "(use_absolute_xyz=True, with_distance=False)")
+    scale, shift = fold_bn(bn_weight.detach().cpu(), bn_bias.detach().cpu(), bn_mean.detach().cpu(),
+                           bn_var.detach().cpu(), eps)
+    t = torch.zeros(64, 16, dtype=torch.float32)
+    for j in range(3):
+        t[:, j] = (w[:, j] + w[:, 4 + j]) + w[:, 7 + j]
+        t[:, 4 + j] = w[:, j]
+        t[:, 7 + j] = -w[:, 4 + j]
+    t[:, 3] = w[:, 3]
+    t[:, 10] = scale
+    t[:, 11] = shift
+    return t.contiguous()
+
+
+# --------------------------------------------------------------------------------------------
+# (a1) voxelizer
+# --------------------------------------------------------------------------------------------
+class VoxelWorkspace:
+    """Device scratch of gc_voxelize, reusable across calls with the same capacity."""
+
+    def __init__(self, geom, n_agents, total_points, device):
+        lib = _lib.load()
+        self.geom, self.n_agents, self.total_points = geom, int(n_agents), int(total_points)
+        nbytes = lib.gc_voxelize_workspace_bytes(ctypes.byref(geom), self.n_agents, self.total_points)
+        if nbytes == 0:
+            raise ValueError("bad voxelizer workspace request")
+        self.buf = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        self.n_pillars = torch.empty(self.n_agents, dtype=torch.int32, device=device)
+
+
+def voxelize(points, point_offsets, ws, max_agent_points=0):
+    """points [sumP,4] f32, point_offsets [A+1] i32 (device) -> fills ws, returns ws.n_pillars [A] i32."""
+    lib = _lib.load()
+    _chk(points, "points", torch.float32, 2)
+    _chk(point_offsets, "point_offsets", torch.int32, 1)
+    if points.shape[1] != 4:
+        raise ValueError("points must be [P,4] (x,y,z,intensity)")
+    if point_offsets.numel() != ws.n_agents + 1 or points.shape[0] != ws.total_points:
+        raise ValueError("workspace was sized for a different batch")
+    _lib.check(lib.gc_voxelize(_ptr(points), _ptr(point_offsets), ws.n_agents, ws.total_points,
+                               int(max_agent_points), ctypes.byref(ws.geom), _ptr(ws.buf), _ptr(ws.n_pillars),
+                               _stream()), "gc_voxelize")
+    return ws.n_pillars
+
+
+def voxel_gather(points, point_offsets, ws):
+    """Reference-shaped (voxel_features [M,32,4], voxel_coords [M,4] i32, voxel_num_points [M] i32).
+
+    Synchronises once to learn sum(M) (the reference API returns exactly-sized arrays)."""
+    lib = _lib.load()
+    n_pillars = ws.n_pillars
+    offs = torch.zeros(ws.n_agents + 1, dtype=torch.int32, device=points.device)
+    offs[1:] = torch.cumsum(n_pillars, 0)
+    total = int(offs[-1].item())
+    voxels = torch.empty(total, 32, 4, dtype=torch.float32, device=points.device)
+    coords = torch.empty(total, 4, dtype=torch.int32, device=points.device)
+    npts = torch.empty(total, dtype=torch.int32, device=points.device)
+    _lib.check(lib.gc_voxel_gather(_ptr(points), _ptr(point_offsets), ws.n_agents, ws.total_points,
+                                   ctypes.byref(ws.geom), _ptr(ws.buf), _ptr(offs), total, _ptr(voxels),
+                                   _ptr(coords), _ptr(npts), _stream()), "gc_voxel_gather")
+    return voxels, coords, npts
+
+
+# --------------------------------------------------------------------------------------------
+# (a3) PillarVFE, (a4) PointPillarScatter, fused front end
+# --------------------------------------------------------------------------------------------
+def pillar_vfe(voxel_features, voxel_num_points, voxel_coords, pfn, voxel_size, centre_off):
+    lib = _lib.load()
+    _chk(voxel_features, "voxel_features", torch.float32, 3)
+    _chk(voxel_num_points, "voxel_num_points", torch.int32, 1)
+    _chk(voxel_coords, "voxel_coords", torch.int32, 2)
+    _chk(pfn, "pfn", torch.float32, 2)
+    m = voxel_features.shape[0]
+    if tuple(voxel_features.shape[1:]) != (32, 4) or tuple(voxel_coords.shape) != (m, 4) \
+            or voxel_num_points.shape[0] != m or tuple(pfn.shape) != (64, 16):
+        raise ValueError("pillar_vfe: expected voxel_features [M,32,4], coords [M,4], num_points [M], pfn [64,16]")
+    out = torch.empty(m, 64, dtype=torch.float32, device=voxel_features.device)
+    _lib.check(lib.gc_pillar_vfe(_ptr(voxel_features), _ptr(voxel_num_points), _ptr(voxel_coords), m, _ptr(pfn),
+                                 _lib.f3(voxel_size), _lib.f3(centre_off), _ptr(out), _stream()), "gc_pillar_vfe")
+    return out
+
+
+def scatter_canvas(pillar_features, voxel_coords, nx, ny, n_batch, out=None, cell_map=None):
+    lib = _lib.load()
+    _chk(pillar_features, "pillar_features", torch.float32, 2)
+    _chk(voxel_coords, "voxel_coords", torch.int32, 2)
+    m, c = pillar_features.shape
+    if tuple(voxel_coords.shape) != (m, 4):
+        raise ValueError("scatter_canvas: voxel_coords must be [M,4] (b,z,y,x)")
+    dev = pillar_features.device
+    if out is None:
+        out = torch.empty(n_batch, c, ny, nx, dtype=torch.float32, device=dev)
+    if cell_map is None:
+        cell_map = torch.empty(max(n_batch, 1) * ny * nx, dtype=torch.int32, device=dev)
+    _lib.check(lib.gc_scatter_canvas(_ptr(pillar_features), _ptr(voxel_coords), m, c, int(nx), int(ny),
+                                     int(n_batch), _ptr(cell_map), _ptr(out), _stream()), "gc_scatter_canvas")
+    return out
+
+
+def pillar_canvas(points, point_offsets, ws, pfn, centre_off, out=None):
+    """Voxelizer workspace -> BEV canvas [A,64,ny,nx] (PFN + scatter fused)."""
+    lib = _lib.load()
+    _chk(points, "points", torch.float32, 2)
+    _chk(point_offsets, "point_offsets", torch.int32, 1)
+    _chk(pfn, "pfn", torch.float32, 2)
+    g = ws.geom
+    if out is None:
+        out = torch.empty(ws.n_agents, 64, g.grid[1], g.grid[0], dtype=torch.float32, device=points.device)
+    else:
+        _chk(out, "out", torch.float32, 4)
+        if tuple(out.shape) != (ws.n_agents, 64, g.grid[1], g.grid[0]):
+            raise ValueError("pillar_canvas: bad output shape")
+    _lib.check(lib.gc_pillar_canvas(_ptr(points), _ptr(point_offsets), ws.n_agents, ws.total_points,
+                                    ctypes.byref(g), _ptr(ws.buf), _ptr(pfn), _lib.f3(centre_off), _ptr(out),
+                                    _stream()), "gc_pillar_canvas")
+    return out
+
+
+# --------------------------------------------------------------------------------------------
+# (a5)-(a9) pose normalisation, warp, fusion
+# --------------------------------------------------------------------------------------------
+def normalize_pairwise_tfm(pairwise_t_matrix, H, W, discrete_ratio, downsample_rate=1):
+    lib = _lib.load()
+    _chk(pairwise_t_matrix, "pairwise_t_matrix", torch.float64)
+    if tuple(pairwise_t_matrix.shape[-2:]) != (4, 4):
+        raise ValueError("pairwise_t_matrix must be [...,4,4]")
+    lead = tuple(pairwise_t_matrix.shape[:-2])
+    n = int(np.prod(lead)) if lead else 1
+    theta = torch.empty(*lead, 2, 3, dtype=torch.float64, device=pairwise_t_matrix.device)
+    _lib.check(lib.gc_normalize_pairwise_tfm(_ptr(pairwise_t_matrix), n, float(H), float(W), float(discrete_ratio),
+                                             float(downsample_rate), _ptr(theta), _stream()),
+               "gc_normalize_pairwise_tfm")
+    return theta
+
+
+def agent_offsets_from_record_len(record_len):
+    """record_len [B] (any int dtype, device) -> exclusive prefix [B+1] i32 on the same device, no host sync."""
+    off = torch.zeros(record_len.numel() + 1, dtype=torch.int32, device=record_len.device)
+    off[1:] = torch.cumsum(record_len.to(torch.int32), 0)
+    return off
+
+
+def warp_fuse(feat, agent_offsets, theta, mode, out=None):
+    """feat [sumN,C,H,W] f32; agent_offsets [B+1] i32; theta [B,L,L,2,3] f64 -> [B,C,H,W] (or [sumN,...])."""
+    lib = _lib.load()
+    _chk(feat, "feat", torch.float32, 4)
+    _chk(agent_offsets, "agent_offsets", torch.int32, 1)
+    _chk(theta, "theta", torch.float64, 5)
+    n_frames = agent_offsets.numel() - 1
+    total, C, H, W = feat.shape
+    B, L = theta.shape[:2]
+    if B != n_frames or theta.shape[2] != L or tuple(theta.shape[3:]) != (2, 3):
+        raise ValueError("theta must be [B,L,L,2,3] with B == len(record_len)")
+    lead = total if mode == FUSE_WARP_ONLY else n_frames
+    if out is None:
+        out = torch.empty(lead, C, H, W, dtype=torch.float32, device=feat.device)
+    else:
+        _chk(out, "out", torch.float32, 4)
+        if tuple(out.shape) != (lead, C, H, W):
+            raise ValueError("warp_fuse: bad output shape")
+    _lib.check(lib.gc_warp_fuse(_ptr(feat), _ptr(agent_offsets), n_frames, total, _ptr(theta), L, C, H, W, int(mode),
+                                _ptr(out), _stream()), "gc_warp_fuse")
+    return out

@@ -1,0 +1,112 @@
+"""Seeded synthetic OPV2V-H-shaped inputs -- numpy/torch on the host.
+
+There is no dataset on the build or GPU boxes, so every test and bench line uses these generators.
+They emit exactly the tensors ``batch['ego']`` carries in the reference
+(``intermediate_heter_fusion_dataset.py:596-755``): LiDAR points ``[P,4] f32``, pairwise poses
+``[L,L,4,4] f64``, ``record_len [B] i64``, BEV features / messages / pre-drawn sampler noise.
+"""
+import numpy as np
+import torch
+
+OPV2V_H_RANGE = [-102.4, -51.2, -3.0, 102.4, 51.2, 1.0]      # m1_att.yaml:19 -> grid 512x256x1
+SQUARE_RANGE = [-51.2, -51.2, -3.0, 51.2, 51.2, 1.0]         # BASELINE config[1] -> grid 256x256x1
+VOXEL_SIZE = [0.4, 0.4, 4.0]
+BASE_SEED = 20251017
+
+
+def _rng(frame, agent, salt=0):
+    return np.random.default_rng(BASE_SEED + 1000 * int(frame) + int(agent) + 7919 * int(salt))
+
+
+def lidar_points(frame=0, agent=0, n_points=100_000, lidar_range=OPV2V_H_RANGE, voxel=0.4,
+                 uniform=False):
+    """LiDAR-like cloud [P,4] f32 (x,y,z,intensity), pre-shuffled (pcd_utils.py:91-95 shuffles).
+
+    64 rings, elevation linspace(-25deg,+2deg), azimuth U[0,2pi), sensor 1.9 m above ground,
+    ground-hit range capped at 120 m, 15 % object returns, ~2 % outside the range box and 0.1 %
+    snapped exactly onto cell boundaries.  ``uniform=True`` gives the uniform cloud that hits the
+    max_voxels cap.
+    """
+    g = _rng(frame, agent, 1)
+    P = int(n_points)
+    xmin, ymin, zmin, xmax, ymax, zmax = lidar_range
+    if uniform:
+        x = g.uniform(xmin, xmax, P)
+        y = g.uniform(ymin, ymax, P)
+        z = g.uniform(zmin, zmax, P)
+    else:
+        ring = g.integers(0, 64, P)
+        elev = np.deg2rad(np.linspace(-25.0, 2.0, 64))[ring]
+        azim = g.uniform(0.0, 2 * np.pi, P)
+        down = elev < -1e-3
+        r = np.where(down, 1.9 / np.tan(np.where(down, -elev, 1.0)), 120.0)
+        r = np.minimum(r, 120.0) * g.uniform(0.97, 1.0, P)
+        z = np.where(down & (r < 119.0), -1.9 + g.normal(0, 0.03, P), g.uniform(-1.5, 0.8, P))
+        obj = g.random(P) < 0.15
+        r = np.where(obj, g.uniform(5.0, 100.0, P), r)
+        z = np.where(obj, g.uniform(-1.5, 0.5, P), z)
+        x = r * np.cos(azim) + g.normal(0, 0.02, P)
+        y = r * np.sin(azim) + g.normal(0, 0.02, P)
+    far = g.random(P) < 0.02                      # outside the box -> voxelizer bounds test
+    x = np.where(far, x + np.sign(x + 1e-9) * (xmax - xmin), x)
+    pts = np.stack([x, y, z, g.random(P)], axis=1).astype(np.float32)
+    snap = g.random(P) < 0.001                    # exactly on cell boundaries -> floor() edge
+    pts[snap, 0] = (np.round(pts[snap, 0] / voxel) * voxel).astype(np.float32)
+    pts[snap, 1] = (np.round(pts[snap, 1] / voxel) * voxel).astype(np.float32)
+    g.shuffle(pts, axis=0)
+    return np.ascontiguousarray(pts)
+
+
+def pose_matrix(tx, ty, yaw_deg):
+    c, s = np.cos(np.deg2rad(yaw_deg)), np.sin(np.deg2rad(yaw_deg))
+    T = np.eye(4)
+    T[0, 0], T[0, 1], T[1, 0], T[1, 1] = c, -s, s, c
+    T[0, 3], T[1, 3] = tx, ty
+    return T
+
+
+def pairwise_t_matrix(frame=0, n_agents=4, max_cav=5, spread=(60.0, 20.0)):
+    """[L,L,4,4] f64, pairwise[i,j] = solve(T_j, T_i) (transformation_utils.py:57-64)."""
+    g = _rng(frame, 0, 2)
+    Ts = [np.eye(4)]
+    for _ in range(1, n_agents):
+        Ts.append(pose_matrix(g.uniform(-spread[0], spread[0]), g.uniform(-spread[1], spread[1]),
+                              g.uniform(-180.0, 180.0)))
+    pw = np.tile(np.eye(4), (max_cav, max_cav, 1, 1))
+    for i in range(n_agents):
+        for j in range(n_agents):
+            if i != j:
+                pw[i, j] = np.linalg.solve(Ts[j], Ts[i])
+    return pw
+
+
+def bev_features(frame, n_agents, C, H, W, sparsity=0.0, salt=3):
+    g = torch.Generator().manual_seed(BASE_SEED + 1000 * int(frame) + 7919 * salt)
+    x = torch.randn(n_agents, C, H, W, generator=g)
+    if sparsity > 0:
+        keep = torch.rand(n_agents, 1, H, W, generator=g) >= sparsity
+        x = x * keep
+    return x
+
+
+def sampler_noise(frame, n_agents, C, H, W, T=3):
+    """(noise0, [T step noises]) -- injected into both oracle and kernel (App. A.6 RNG)."""
+    g = torch.Generator().manual_seed(BASE_SEED + 1000 * int(frame) + 7919 * 5)
+    n0 = torch.randn(n_agents, C, H, W, generator=g)
+    steps = [torch.randn(n_agents, C, H, W, generator=g) for _ in range(T)]
+    return n0, steps
+
+
+def pfn_weights(seed=0):
+    """PillarVFE parameters: reference default init under manual_seed, BN stats randomised so
+    BN is not an identity."""
+    g = torch.Generator().manual_seed(seed)
+    bound = 1.0 / np.sqrt(10.0)
+    w = (torch.rand(64, 10, generator=g) * 2 - 1) * bound          # nn.Linear default: U(-1/sqrt(in), 1/sqrt(in))
+    return {
+        "weight": w,
+        "bn_weight": torch.rand(64, generator=g) * 0.5 + 0.75,
+        "bn_bias": torch.randn(64, generator=g) * 0.1,
+        "bn_mean": torch.randn(64, generator=g) * 0.1,
+        "bn_var": torch.rand(64, generator=g) + 0.5,
+    }

@@ -1,0 +1,138 @@
+/*
+ * gencomm_b200 -- C ABI of the B200-native (sm_100a) GenComm per-frame hot path.
+ *
+ * The reference (jeffreychou777/GenComm, an OpenCOOD fork) is pure Python/PyTorch and has no FFI
+ * for this path; its "plugin API" is the set of Python operators listed
+ * below.  Each entry point here replaces the body of one of them and is what a ctypes binding in
+ * the reference would call.  Conventions:
+ *
+ *   - plain C: pointers + sizes, no torch types.  Unless a parameter is marked [host], every
+ *     pointer is a DEVICE pointer to contiguous memory; nothing is allocated inside;
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*), never synchronises,
+ *     and is re-entrant (all state lives in caller-provided buffers);
+ *   - return value: 0 on success, a negative GC_E* code for an argument error (nothing launched),
+ *     or a positive cudaError_t from the launch.  gc_last_error() returns a static description of
+ *     the most recent failure on the calling thread.
+ *
+ * Paths are relative to /root/reference/opencood.
+ */
+#ifndef GENCOMM_B200_H_
+#define GENCOMM_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GC_OK 0
+#define GC_EINVAL (-1)      /* bad shape / size / null pointer */
+#define GC_EUNSUPPORTED (-2) /* configuration outside what the kernels implement */
+
+#define GC_MAX_POINTS_PER_PILLAR 32 /* max_points_per_voxel of every shipped yaml */
+#define GC_PFN_OUT 64               /* pillar_vfe.num_filters = [64] */
+#define GC_MAX_AGENTS_PER_FRAME 8   /* max_cav is 5 in every shipped yaml; microbench goes to 8 */
+
+#define GC_FUSE_WARP_ONLY 0 /* warp_affine_simple / warp_feature: no reduction */
+#define GC_FUSE_MAX 1       /* MaxFusion */
+#define GC_FUSE_ATT 2       /* AttFusion (ego row of the per-pixel attention) */
+
+int gc_version(void);
+const char *gc_last_error(void);
+
+/* Voxelizer geometry: data_utils/pre_processor/sp_voxel_preprocessor.py:32-60. */
+typedef struct gcVoxelGeom {
+    float range_min[3]; /* cav_lidar_range[0:3]  x,y,z */
+    float voxel[3];     /* args.voxel_size       x,y,z */
+    int32_t grid[3];    /* round((max-min)/voxel) = nx,ny,nz (:41-43) */
+    int32_t max_points; /* max_points_per_voxel (must be 32) */
+    int32_t max_voxels; /* max_voxel_test / max_voxel_train */
+} gcVoxelGeom;
+
+/* ---------------------------------------------------------------------------------------------
+ * (a1) SpVoxelPreprocessor.preprocess -> spconv Point2VoxelCPU3d.point_to_voxel
+ *      (sp_voxel_preprocessor.py:62-85), for all agents of a batch at once.
+ *
+ * Device workspace layout is private; size it with gc_voxelize_workspace_bytes().
+ *   points        [total_points][4] f32, agents concatenated
+ *   point_offsets [n_agents+1] i32, exclusive prefix of points per agent (device)
+ *   n_pillars     [n_agents] i32 out: M_a = min(#occupied cells in first-come order, max_voxels)
+ * After the call the workspace holds, per agent, the cell->pillar map and the per-pillar list of
+ * the first 32 point indices in input order; gc_voxel_gather / gc_pillar_canvas consume it.
+ * ------------------------------------------------------------------------------------------- */
+size_t gc_voxelize_workspace_bytes(const gcVoxelGeom *geom /*[host]*/, int n_agents, int total_points);
+
+int gc_voxelize(const float *points, const int32_t *point_offsets, int n_agents, int total_points,
+                int max_agent_points /* upper bound on any one agent's point count; <=0: total_points */,
+                const gcVoxelGeom *geom /*[host]*/, void *workspace, int32_t *n_pillars, void *stream);
+
+/* Materialise the reference-shaped voxel tensors (the dict `preprocess` returns, then
+ * collate_batch_list :109-142) from the workspace:
+ *   pillar_offsets [n_agents+1] i32: exclusive prefix of n_pillars (device; caller computes it),
+ *   total_pillars = pillar_offsets[n_agents] (host copy; sizes the launch and the outputs)
+ *   voxels [sum M][32][4] f32 zero padded, coords [sum M][4] i32 (agent,z,y,x), num_points [sum M] i32
+ */
+int gc_voxel_gather(const float *points, const int32_t *point_offsets, int n_agents, int total_points,
+                    const gcVoxelGeom *geom /*[host]*/, const void *workspace,
+                    const int32_t *pillar_offsets, int total_pillars, float *voxels, int32_t *coords,
+                    int32_t *num_points, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * (a3) PillarVFE.forward + PFNLayer.forward (models/sub_modules/pillar_vfe.py:105-155, :31-53)
+ *      for use_norm=True, use_absolute_xyz=True, with_distance=False, num_filters=[64], eval BN.
+ *
+ *   pfn  [64][16] f32, packed by the host (gencomm_b200/pfn.py::pack_pfn):
+ *        [0..2] Wc = (W[k][j]+W[k][4+j])+W[k][7+j], [3] W[k][3], [4..6] W[k][0..2],
+ *        [7..9] -W[k][4..6], [10] bn scale, [11] bn shift, [12..15] 0
+ *   centre_offset[3] = voxel/2 + range_min (pillar_vfe.py:87-89), voxel[3]  -- in geom/arguments
+ *   voxels [M][32][4], num_points [M], coords [M][4] (b,z,y,x)  ->  pillar_features [M][64]
+ * ------------------------------------------------------------------------------------------- */
+int gc_pillar_vfe(const float *voxels, const int32_t *num_points, const int32_t *coords, int n_pillars,
+                  const float *pfn, const float voxel[3] /*[host]*/, const float centre_offset[3] /*[host]*/,
+                  float *pillar_features, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * (a4) PointPillarScatter.forward (models/sub_modules/point_pillar_scatter.py:19-76).
+ *      canvas[b][c][y][x] = pillar_features[m][c] for coords[m] = (b,z,y,x), zero elsewhere;
+ *      idx = z + y*nx + x (:58), nz == 1 (:17).  Written canvas-stationary: every canvas byte is
+ *      stored exactly once (no separate memset), through a dense cell->pillar map.
+ *   cell_map [n_batch][ny*nx] i32 scratch (device), fully rewritten by the call
+ *   canvas   [n_batch][C][ny][nx] f32
+ * ------------------------------------------------------------------------------------------- */
+int gc_scatter_canvas(const float *pillar_features, const int32_t *coords, int n_pillars, int C,
+                      int nx, int ny, int n_batch, int32_t *cell_map, float *canvas, void *stream);
+
+/* Fused (a1 workspace) -> (a3) -> (a4): voxel workspace straight to the BEV canvas, never
+ * materialising voxels[M,32,4] or pillar_features[M,64].  canvas [n_agents][64][ny][nx]. */
+int gc_pillar_canvas(const float *points, const int32_t *point_offsets, int n_agents, int total_points,
+                     const gcVoxelGeom *geom /*[host]*/, const void *workspace, const float *pfn,
+                     const float centre_offset[3] /*[host]*/, float *canvas, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * (a6)+(a7)+(a8)/(a9) regroup + warp_affine_simple + MaxFusion / AttFusion
+ *      (models/fuse_modules/fusion_in_one.py:48-51, :91-124, :131-151;
+ *       models/sub_modules/torch_transformation_utils.py:323-332).
+ *
+ *   feat          [sum N][C][H][W] f32 (NCHW), agents of frame b at agent_offsets[b]..[b+1]
+ *   agent_offsets [n_frames+1] i32 exclusive prefix of record_len (device)
+ *   theta         [n_frames][L][L][2][3] f64 = normalize_pairwise_tfm output (float64 on the real
+ *                 path, transformation_utils.py:40); only row [b][0][j] (ego <- agent j) is read
+ *   mode          GC_FUSE_MAX / GC_FUSE_ATT: out [n_frames][C][H][W]
+ *                 GC_FUSE_WARP_ONLY:        out [sum N][C][H][W] (total_agents must be given)
+ *   affine_grid is evaluated in float64 and only the grid is rounded to float32, exactly like
+ *   F.affine_grid(theta_f64).to(src); sampling follows ATen's grid_sampler_2d (bilinear, zeros
+ *   padding, align_corners=False).
+ * ------------------------------------------------------------------------------------------- */
+int gc_warp_fuse(const float *feat, const int32_t *agent_offsets, int n_frames, int total_agents,
+                 const double *theta, int L, int C, int H, int W, int mode, float *out, void *stream);
+
+/* (a5) normalize_pairwise_tfm (utils/transformation_utils.py:68-92):
+ *   pairwise [n][4][4] f64 -> theta [n][2][3] f64, n = B*L*L matrices. */
+int gc_normalize_pairwise_tfm(const double *pairwise, int n, double H, double W, double discrete_ratio,
+                              double downsample_rate, double *theta, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GENCOMM_B200_H_ */

@@ -1,0 +1,148 @@
+"""TEST INFRASTRUCTURE ONLY -- writes tests/golden/*.npz from the UNMODIFIED reference classes.
+
+Run in the build container (``/root/reference`` mounted):  ``python oracle/gen_golden.py``
+
+The reference ships no tests, golden vectors or fixtures for this path, so
+these fixtures are created here by importing the reference's own modules (oracle/ref_import.py)
+and executing them on CPU with seeded inputs.  They pin the oracle restatement
+(oracle/ref_ops.py, oracle/pillar_ref.c) in ``tests/test_oracle_cpu.py`` and are the committed
+ground truth for the ``-m gpu`` parity tests (``/root/reference`` does not exist on the GPU box).
+
+Voxelizer inputs come from the oracle's own spconv restatement (spconv is absent and unpinned:
+"parity unpinned"); everything downstream of the voxel tensors is produced by reference code.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from gencomm_b200 import synth  # noqa: E402
+from oracle import ref_import, ref_ops  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+SMALL_RANGE = [-12.8, -6.4, -3.0, 12.8, 6.4, 1.0]   # 64 x 32 x 1 grid at 0.4 m
+VOXEL = [0.4, 0.4, 4.0]
+
+GENCOMM_CFG = {
+    "model": {"embed_dim": 18, "in_channels": 16, "out_ch": 16, "ch": 8, "ch_mult": [1, 1],
+              "num_res_blocks": 2, "attn_resolutions": [16], "dropout": 0.0, "resamp_with_conv": True},
+    "diffusion": {"beta_schedule": "linear", "beta_start": 0.0005, "beta_end": 0.02,
+                  "num_diffusion_timesteps": 3},
+}
+
+
+def small_cloud(agent, n):
+    pts = synth.lidar_points(frame=900, agent=agent, n_points=n, lidar_range=SMALL_RANGE)
+    pts[:, :2] *= 0.12   # pull the 120 m cloud into the 25 m box (some points stay outside)
+    return np.ascontiguousarray(pts.astype(np.float32))
+
+
+def gen_pillars(ns):
+    torch.manual_seed(1)
+    clouds = [small_cloud(0, 3000), small_cloud(1, 600), small_cloud(2, 2000)]
+    vox = [ref_ops.voxelize(c, SMALL_RANGE, VOXEL, 32, 400) for c in clouds]   # cap 400 is hit
+    batch = ref_ops.collate_voxels(vox)
+    w = synth.pfn_weights(3)
+    grid = ref_ops.grid_size(SMALL_RANGE, VOXEL)
+    vfe = ns.PillarVFE({"use_norm": True, "with_distance": False, "use_absolute_xyz": True, "num_filters": [64]},
+                       num_point_features=4, voxel_size=VOXEL, point_cloud_range=SMALL_RANGE).eval()
+    with torch.no_grad():
+        vfe.pfn_layers[0].linear.weight.copy_(w["weight"])
+        vfe.pfn_layers[0].norm.weight.copy_(w["bn_weight"])
+        vfe.pfn_layers[0].norm.bias.copy_(w["bn_bias"])
+        vfe.pfn_layers[0].norm.running_mean.copy_(w["bn_mean"])
+        vfe.pfn_layers[0].norm.running_var.copy_(w["bn_var"])
+        bd = {k: v.clone() for k, v in batch.items()}
+        bd = vfe(bd)
+        sc = ns.PointPillarScatter({"num_features": 64, "grid_size": grid})
+        bd = sc(bd)
+    np.savez_compressed(
+        os.path.join(OUT, "pillars.npz"),
+        lidar_range=np.array(SMALL_RANGE), voxel_size=np.array(VOXEL), max_voxels=400,
+        points0=clouds[0], points1=clouds[1], points2=clouds[2],
+        voxel_features=batch["voxel_features"].numpy(), voxel_coords=batch["voxel_coords"].numpy(),
+        voxel_num_points=batch["voxel_num_points"].numpy(),
+        **{"pfn_" + k: v.numpy() for k, v in w.items()},
+        ref_pillar_features=bd["pillar_features"].numpy(), ref_canvas=bd["spatial_features"].numpy())
+    print("pillars.npz: M =", batch["voxel_features"].shape[0], "per agent", [v["voxel_features"].shape[0] for v in vox])
+
+
+def gen_warp(ns):
+    C, H, W = 8, 16, 24
+    record_len = torch.tensor([3, 2], dtype=torch.int64)
+    feat = synth.bev_features(901, 5, C, H, W)
+    pw = np.stack([synth.pairwise_t_matrix(901, 3, 5, spread=(6.0, 3.0)),
+                   synth.pairwise_t_matrix(902, 2, 5, spread=(6.0, 3.0))])
+    pw_t = torch.from_numpy(pw)
+    Hm, Wm = 16 * 0.8, 24 * 0.8   # metres covered by the map (heter_model_baseline.py:87-89 convention)
+    theta = ns.normalize_pairwise_tfm(pw_t.clone(), Hm, Wm, 1)
+    with torch.no_grad():
+        warped = torch.cat([ns.warp_affine_simple(x, theta[b][0, :int(record_len[b])], (H, W))
+                            for b, x in enumerate(ns.regroup(feat, record_len))])
+        mx = ns.MaxFusion()(feat, record_len, theta)
+        att = ns.AttFusion(C)(feat, record_len, theta)
+    np.savez_compressed(os.path.join(OUT, "warp_fuse.npz"), feat=feat.numpy(), record_len=record_len.numpy(),
+                        pairwise=pw, Hm=Hm, Wm=Wm, ref_theta=theta.numpy(), ref_warped=warped.numpy(),
+                        ref_max=mx.numpy(), ref_att=att.numpy())
+    print("warp_fuse.npz:", tuple(feat.shape), "theta", tuple(theta.shape))
+
+
+def gen_gencomm(ns):
+    import opencood.models.gencomm_modules.cond_diff as cd
+    torch.manual_seed(7)
+    C, H, W = 16, 16, 24
+    model = ns.GenComm(GENCOMM_CFG).eval()
+    with torch.no_grad():   # default GroupNorm affine is (1,0): randomise so it is exercised
+        for name, p in model.named_parameters():
+            if "norm" in name:
+                p.add_(0.2 * torch.randn_like(p))
+            elif name.endswith(".bias"):
+                p.add_(0.05 * torch.randn_like(p))
+    record_len = torch.tensor([2, 1], dtype=torch.int64)
+    feat = synth.bev_features(903, 3, C, H, W)
+    cond = synth.bev_features(903, 3, 2, H, W, salt=4)
+    n0, steps = synth.sampler_noise(903, 3, C, H, W, T=3)
+
+    # inject the pre-drawn noise in the reference's draw order (SURVEY.md App. A.6 RNG)
+    queue = [n0, torch.zeros(1, C, H, W), torch.zeros(1, C, H, W)]
+    step_queue = list(steps)
+    orig_randn_like, orig_noise_like = torch.randn_like, cd.noise_like
+    torch.randn_like = lambda t, *a, **k: queue.pop(0).to(t)
+    cd.noise_like = lambda shape, device, repeat=False: step_queue.pop(0)
+    try:
+        with torch.no_grad():
+            out = model(feat, cond, record_len)
+    finally:
+        torch.randn_like, cd.noise_like = orig_randn_like, orig_noise_like
+    assert not queue and not step_queue
+    with torch.no_grad():
+        x_in = torch.cat([cond, feat], dim=1)
+        t = torch.tensor([2.0, 1.0, 0.0])
+        unet_out = model.denoiser(x_in, t)
+    sd = {k: v.numpy() for k, v in model.state_dict().items()}
+    np.savez_compressed(os.path.join(OUT, "gencomm.npz"), feat=feat.numpy(), cond=cond.numpy(),
+                        record_len=record_len.numpy(), noise0=n0.numpy(),
+                        step_noises=np.stack([s.numpy() for s in steps]),
+                        ref_pred=out["pred_feature"].numpy(), unet_t=t.numpy(), ref_unet=unet_out.numpy(),
+                        **{"sd/" + k: v for k, v in sd.items()})
+    print("gencomm.npz: pred", tuple(out["pred_feature"].shape), "params",
+          sum(p.numel() for p in model.parameters()))
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    ns = ref_import.load()
+    gen_pillars(ns)
+    gen_warp(ns)
+    gen_gencomm(ns)
+    for f in sorted(os.listdir(OUT)):
+        print(f, os.path.getsize(os.path.join(OUT, f)) // 1024, "KiB")
+
+
+if __name__ == "__main__":
+    main()

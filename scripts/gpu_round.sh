@@ -1,0 +1,21 @@
+#!/bin/bash
+# One GPU-box visit: parity tests, smoke, bench, ncu launch list + full captures of the two big kernels.
+# Usage (from the repo root, under gpurun):  bash scripts/gpu_round.sh [tag]
+TAG=${1:-r01}
+OUT=gpurun_out
+mkdir -p $OUT
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > $OUT/gpu_$TAG.txt 2>&1
+echo "== pytest -m gpu" 
+timeout 900 python -m pytest tests -q -m gpu -p no:cacheprovider 2>&1 | tail -40 | tee $OUT/pytest_$TAG.log
+echo "== smoke"
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -5 | tee $OUT/smoke_$TAG.log
+echo "== bench"
+timeout 900 python bench.py --steps 20 --warmup 3 2>$OUT/bench_$TAG.err | tee $OUT/bench_$TAG.json
+tail -5 $OUT/bench_$TAG.err
+echo "== ncu launch list"
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file $OUT/launches_$TAG.csv \
+    python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $OUT/ncu_launch_$TAG.log 2>&1
+echo "== ncu full"
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"k_canvas|k_warp_fuse" -s 6 -c 4 \
+    -f -o $OUT/prof_$TAG python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $OUT/ncu_full_$TAG.log 2>&1
+ls -la $OUT

@@ -1,0 +1,54 @@
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+def pytest_collection_modifyitems(config, items):
+    if torch.cuda.is_available():
+        return
+    skip = pytest.mark.skip(reason="no CUDA device")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _build_artifacts():
+    """Oracle C library (test infrastructure) and, if stale or missing, the CUDA library."""
+    if not os.path.exists(os.path.join(ROOT, "oracle", "libgc_oracle.so")):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle")])
+    from gencomm_b200 import build
+    if os.path.exists("/usr/local/cuda/bin/nvcc"):
+        build.build()
+
+
+def load_golden(name):
+    return dict(np.load(os.path.join(GOLDEN, name), allow_pickle=False))
+
+
+@pytest.fixture(scope="session")
+def golden_pillars():
+    return load_golden("pillars.npz")
+
+
+@pytest.fixture(scope="session")
+def golden_warp():
+    return load_golden("warp_fuse.npz")
+
+
+@pytest.fixture(scope="session")
+def golden_gencomm():
+    return load_golden("gencomm.npz")

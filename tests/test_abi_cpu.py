@@ -1,0 +1,66 @@
+"""The C-ABI library loads and exports every symbol include/gencomm_b200.h declares (no compute)."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+from gencomm_b200 import _lib, ops
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "gencomm_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(gc_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_all_exported_and_bound():
+    syms = _declared_symbols()
+    assert len(syms) >= 10
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in the header but not exported"
+    assert sorted(_lib.SIGNATURES) == syms, "ctypes binding table out of sync with the header"
+    assert _lib.load().gc_version() >= 100
+
+
+def test_argument_errors_are_reported_without_a_gpu():
+    lib = _lib.load()
+    geom = ops.make_geom([-1, -1, -1, 1, 1, 1], [0.5, 0.5, 2], 100, max_points=16)   # unsupported max_points
+    rc = lib.gc_voxelize(None, None, 1, 0, 0, ctypes.byref(geom), None, None, None)
+    assert rc == -2 and b"32" in lib.gc_last_error()
+    rc = lib.gc_warp_fuse(None, None, 1, 1, None, 5, 8, 4, 4, 7, None, None)
+    assert rc == -1 and b"mode" in lib.gc_last_error()
+    with pytest.raises(RuntimeError, match="argument error"):
+        _lib.check(rc, "gc_warp_fuse")
+
+
+def test_ops_refuse_cpu_tensors():
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        ops.warp_fuse(torch.zeros(1, 1, 2, 2), torch.zeros(2, dtype=torch.int32),
+                      torch.zeros(1, 1, 1, 2, 3, dtype=torch.float64), ops.FUSE_MAX)
+
+
+def test_geometry_and_pfn_packing_host_logic():
+    g = ops.make_geom([-102.4, -51.2, -3, 102.4, 51.2, 1], [0.4, 0.4, 4], 70000)
+    assert list(g.grid) == [512, 256, 1]
+    w = torch.arange(640, dtype=torch.float32).reshape(64, 10) / 100
+    t = ops.pack_pfn(w, torch.ones(64), torch.zeros(64), torch.zeros(64), torch.ones(64) - 1e-3)
+    assert t.shape == (64, 16)
+    assert torch.equal(t[:, 0], (w[:, 0] + w[:, 4]) + w[:, 7]) and torch.equal(t[:, 7], -w[:, 4])
+    assert torch.allclose(t[:, 10], torch.ones(64)) and not t[:, 12:].any()
+
+
+def test_modules_keep_reference_state_dict_keys():
+    from gencomm_b200 import PillarVFE
+    vfe = PillarVFE({"use_norm": True, "with_distance": False, "use_absolute_xyz": True, "num_filters": [64]},
+                    4, [0.4, 0.4, 4], [-102.4, -51.2, -3, 102.4, 51.2, 1])
+    keys = set(vfe.state_dict())
+    assert {"pfn_layers.0.linear.weight", "pfn_layers.0.norm.weight", "pfn_layers.0.norm.bias",
+            "pfn_layers.0.norm.running_mean", "pfn_layers.0.norm.running_var"} <= keys
+    with pytest.raises(NotImplementedError):
+        PillarVFE({"use_norm": True, "with_distance": True, "use_absolute_xyz": True, "num_filters": [64]},
+                  4, [0.4, 0.4, 4], [-102.4, -51.2, -3, 102.4, 51.2, 1])

@@ -1,0 +1,117 @@
+"""Pins the oracle (oracle/ref_ops.py + oracle/pillar_ref.c) against the golden vectors produced by
+the unmodified reference classes (oracle/gen_golden.py).  CPU only."""
+import numpy as np
+import torch
+
+from oracle import ref_ops as R
+
+T = torch.from_numpy
+
+
+def _split_points(g):
+    return [g["points0"], g["points1"], g["points2"]]
+
+
+def test_voxelizer_restatement_is_self_consistent(golden_pillars):
+    """spconv is absent (parity unpinned): check the restatement against an independent pure-Python
+    transcription of the sequential algorithm on the golden clouds, incl. the max_voxels cap."""
+    g = golden_pillars
+    rng, vs, cap = g["lidar_range"].tolist(), g["voxel_size"].tolist(), int(g["max_voxels"])
+    grid = R.grid_size(rng, vs)
+    outs = []
+    for pts in _split_points(g):
+        out = R.voxelize(pts, rng, vs, 32, cap)
+        outs.append(out)
+        vmap, coords, vox = {}, [], []
+        for p in pts:
+            c = [int(np.floor((np.float32(p[j]) - np.float32(rng[j])) / np.float32(vs[j]))) for j in range(3)]
+            if any(c[j] < 0 or c[j] >= grid[j] for j in range(3)):
+                continue
+            key = (c[2], c[1], c[0])
+            if key not in vmap:
+                if len(coords) >= cap:
+                    continue
+                vmap[key] = len(coords)
+                coords.append(key)
+                vox.append([])
+            if len(vox[vmap[key]]) < 32:
+                vox[vmap[key]].append(p)
+        assert out["voxel_coords"].tolist() == [list(k) for k in coords]
+        assert out["voxel_num_points"].tolist() == [len(v) for v in vox]
+        for m, v in enumerate(vox):
+            assert np.array_equal(out["voxel_features"][m, :len(v)], np.stack(v))
+            assert not out["voxel_features"][m, len(v):].any()
+    batch = R.collate_voxels(outs)
+    assert np.array_equal(batch["voxel_features"].numpy(), g["voxel_features"])
+    assert np.array_equal(batch["voxel_coords"].numpy(), g["voxel_coords"])
+    assert np.array_equal(batch["voxel_num_points"].numpy(), g["voxel_num_points"])
+    assert outs[0]["voxel_features"].shape[0] == cap and outs[1]["voxel_features"].shape[0] < cap
+
+
+def _pfn(g):
+    return {k[4:]: T(v) for k, v in g.items() if k.startswith("pfn_")}
+
+
+def test_pillar_vfe_torch_order_matches_reference(golden_pillars):
+    g, w = golden_pillars, _pfn(golden_pillars)
+    out = R.pillar_vfe(T(g["voxel_features"]), T(g["voxel_num_points"]), T(g["voxel_coords"]), w["weight"],
+                       w["bn_weight"], w["bn_bias"], w["bn_mean"], w["bn_var"], g["voxel_size"].tolist(),
+                       g["lidar_range"].tolist())
+    assert torch.equal(out, T(g["ref_pillar_features"]))
+
+
+def test_pillar_vfe_kernel_order_close_to_reference(golden_pillars):
+    """The fixed evaluation order shared with the CUDA kernel is a regrouping of the same sum:
+    |delta| <= 1e-5 * max|ref| (the reference's own fp32 rounding noise is of that size)."""
+    g, w = golden_pillars, _pfn(golden_pillars)
+    sc, sh = R.fold_bn(w["bn_weight"], w["bn_bias"], w["bn_mean"], w["bn_var"])
+    out = R.pillar_vfe_kernel_order(T(g["voxel_features"]), T(g["voxel_num_points"]), T(g["voxel_coords"]),
+                                    w["weight"], sc, sh, g["voxel_size"].tolist(), g["lidar_range"].tolist())
+    ref = T(g["ref_pillar_features"])
+    assert (out - ref).abs().max().item() <= 1e-5 * ref.abs().max().item()
+
+
+def test_scatter_matches_reference_bit_exact(golden_pillars):
+    g = golden_pillars
+    grid = R.grid_size(g["lidar_range"].tolist(), g["voxel_size"].tolist())
+    canvas = R.scatter(T(g["ref_pillar_features"]), T(g["voxel_coords"]), int(grid[0]), int(grid[1]))
+    assert torch.equal(canvas, T(g["ref_canvas"]))
+
+
+def test_normalize_pairwise_tfm_bit_exact(golden_warp):
+    g = golden_warp
+    theta = R.normalize_pairwise_tfm(T(g["pairwise"]), float(g["Hm"]), float(g["Wm"]), 1)
+    assert theta.dtype == torch.float64 and torch.equal(theta, T(g["ref_theta"]))
+
+
+def test_warp_and_fusion_match_reference(golden_warp):
+    g = golden_warp
+    feat, rl, theta = T(g["feat"]), T(g["record_len"]), T(g["ref_theta"])
+    assert torch.equal(R.warp_only(feat, rl, theta), T(g["ref_warped"]))
+    assert torch.equal(R.max_fusion(feat, rl, theta), T(g["ref_max"]))
+    assert torch.equal(R.att_fusion(feat, rl, theta), T(g["ref_att"]))
+
+
+def _sd(g):
+    return {k[len("sd/denoiser."):]: T(v) for k, v in g.items() if k.startswith("sd/denoiser.")}
+
+
+def test_unet_matches_reference(golden_gencomm):
+    g = golden_gencomm
+    x = torch.cat([T(g["cond"]), T(g["feat"])], dim=1)
+    out = R.unet_forward(x, T(g["unet_t"]), _sd(g))
+    assert torch.allclose(out, T(g["ref_unet"]), rtol=0, atol=1e-6)
+
+
+def test_gencomm_schedule_matches_reference_buffers(golden_gencomm):
+    g = golden_gencomm
+    sch = R.gencomm_schedule(3)
+    for k, v in sch.items():
+        assert torch.equal(v, T(g["sd/" + k])), k
+
+
+def test_gencomm_sampler_matches_reference(golden_gencomm):
+    g = golden_gencomm
+    out = R.gencomm_sample(T(g["feat"]), T(g["cond"]), T(g["record_len"]), _sd(g), T(g["noise0"]),
+                           [T(s) for s in g["step_noises"]])
+    assert torch.allclose(out, T(g["ref_pred"]), rtol=0, atol=2e-6)
