@@ -11,4 +11,6 @@ from . import _lib, ops, synth  # noqa: F401
 from .modules import (AttFusion, MaxFusion, PFNLayer, PillarVFE, PointPillar, PointPillarScatter,  # noqa: F401
                       SpVoxelPreprocessor, normalize_pairwise_tfm, regroup, warp_affine_simple, warp_feature)
 
+from .gencomm import Config, DiffusionUNet, GenComm  # noqa: F401
+
 __version__ = "0.1.0"

@@ -43,6 +43,13 @@ SIGNATURES = {
                              c_void_p, c_void_p]),
     "gc_normalize_pairwise_tfm": (c_int, [c_void_p, c_int, c_double, c_double, c_double, c_double, c_void_p,
                                           c_void_p]),
+    "gc_gencomm_host_weight_floats": (c_size_t, [c_int]),
+    "gc_gencomm_device_weight_floats": (c_size_t, [c_int]),
+    "gc_gencomm_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
+    "gc_gencomm_sample": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                                  c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "gc_unet_forward": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                c_void_p, c_void_p, c_void_p]),
 }
 
 _lib = None

@@ -194,13 +194,22 @@ k_slot_insert(const int32_t *__restrict__ point_offsets, int n_agents, int total
     if (code >= kDropped) return;
     uint32_t *s = slots + ((size_t)a * max_voxels + (code & ~kPillarBit)) * 32;
     uint32_t v = (uint32_t)(gi - __ldg(point_offsets + a));
-    // slot values only ever decrease, so a (possibly stale) last slot below v proves v is not kept
-    if (*(volatile uint32_t *)(s + 31) < v) return;
+    // The slot array is sorted ascending at every instant and its values only ever decrease, so a slot
+    // observed below v stays below v and atomicMin(slot, v) there is a no-op: skip all of them.  The
+    // snapshot is read through L2 (ld.cg); a stale (larger) value only skips less.
+    int k0 = 0;
+    const uint4 *s4 = reinterpret_cast<const uint4 *>(s);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const uint4 u = __ldcg(s4 + q);
+        k0 += (u.x < v) + (u.y < v) + (u.z < v) + (u.w < v);
+    }
 #pragma unroll 1
-    for (int k = 0; k < 32; ++k) {
+    for (int k = k0; k < 32; ++k) {
         const uint32_t old = atomicMin(s + k, v);
         if (old == kEmpty) break;
         v = old > v ? old : v;
+        if ((k & 3) == 3 && __ldcg(s + 31) < v) break;   // 32 smaller indices already present
     }
 }
 
@@ -209,16 +218,16 @@ k_slot_insert(const int32_t *__restrict__ point_offsets, int n_agents, int total
 // Lane l owns output channels l and l+32; lane s also holds point s of the pillar.
 // ------------------------------------------------------------------------------------------------
 struct PfnLane {     // packed row of the pfn table, see include/gencomm_b200.h
-    float wc0, wc1, wc2, w3, w0, w1, w2, n4, n5, n6, scale, shift;
+    float a0, a1, a2, a3, b0, b1, b2, d0, d1, d2, shift, pad;
 };
 
 __device__ __forceinline__ PfnLane load_pfn(const float *__restrict__ pfn, int ch) {
     const float4 *r = reinterpret_cast<const float4 *>(pfn + ch * 16);
     const float4 a = __ldg(r), b = __ldg(r + 1), c = __ldg(r + 2);
     PfnLane w;
-    w.wc0 = a.x; w.wc1 = a.y; w.wc2 = a.z; w.w3 = a.w;
-    w.w0 = b.x; w.w1 = b.y; w.w2 = b.z; w.n4 = b.w;
-    w.n5 = c.x; w.n6 = c.y; w.scale = c.z; w.shift = c.w;
+    w.a0 = a.x; w.a1 = a.y; w.a2 = a.z; w.a3 = a.w;
+    w.b0 = b.x; w.b1 = b.y; w.b2 = b.z; w.d0 = b.w;
+    w.d1 = c.x; w.d2 = c.y; w.shift = c.z; w.pad = c.w;
     return w;
 }
 
@@ -229,21 +238,25 @@ __device__ __forceinline__ float tree_sum(float v) {
 }
 
 __device__ __forceinline__ float pfn_bias(const PfnLane &w, float cx, float cy, float cz, float mx, float my, float mz) {
-    float b = __fmul_rn(w.w0, cx);
-    b = __fmaf_rn(w.w1, cy, b);
-    b = __fmaf_rn(w.w2, cz, b);
-    b = __fmaf_rn(w.n4, mx, b);
-    b = __fmaf_rn(w.n5, my, b);
-    b = __fmaf_rn(w.n6, mz, b);
+    float b = __fmaf_rn(w.b0, cx, w.shift);
+    b = __fmaf_rn(w.b1, cy, b);
+    b = __fmaf_rn(w.b2, cz, b);
+    b = __fmaf_rn(w.d0, mx, b);
+    b = __fmaf_rn(w.d1, my, b);
+    b = __fmaf_rn(w.d2, mz, b);
     return b;
 }
 
-__device__ __forceinline__ float pfn_point(const PfnLane &w, float b, float xr, float yr, float zr, float pi) {
-    float acc = __fmaf_rn(w.wc0, xr, b);
-    acc = __fmaf_rn(w.wc1, yr, acc);
-    acc = __fmaf_rn(w.wc2, zr, acc);
-    acc = __fmaf_rn(w.w3, pi, acc);
-    return fmaxf(__fmaf_rn(acc, w.scale, w.shift), 0.0f);
+__device__ __forceinline__ float pfn_point(const PfnLane &w, float xr, float yr, float zr, float pi) {
+    float acc = __fmaf_rn(w.a2, zr, __fmul_rn(w.a3, pi));
+    acc = __fmaf_rn(w.a1, yr, acc);
+    return __fmaf_rn(w.a0, xr, acc);
+}
+
+__device__ __forceinline__ float pfn_finish(const PfnLane &w, float best, float b, int n) {
+    float o = fmaxf(__fadd_rn(best, b), 0.0f);
+    if (n < 32) o = fmaxf(o, w.pad);   // padded slots contribute relu(bn(0)) = max(shift, 0), pillar_vfe.py:46
+    return o;
 }
 
 // p: this lane's point (ignored when lane >= n); returns the two channel maxima of the pillar.
@@ -255,26 +268,22 @@ __device__ __forceinline__ float2 pfn_pillar(const PfnLane &wa, const PfnLane &w
     const float yr = valid ? __fsub_rn(p.y, cy) : 0.0f;
     const float zr = valid ? __fsub_rn(p.z, cz) : 0.0f;
     const float pi = valid ? p.w : 0.0f;
-    const float fn = (float)n;
-    const float mx = __fdiv_rn(tree_sum(xr), fn);
-    const float my = __fdiv_rn(tree_sum(yr), fn);
-    const float mz = __fdiv_rn(tree_sum(zr), fn);
+    const float inv_n = __frcp_rn((float)n);
+    const float mx = __fmul_rn(tree_sum(xr), inv_n);
+    const float my = __fmul_rn(tree_sum(yr), inv_n);
+    const float mz = __fmul_rn(tree_sum(zr), inv_n);
     const float ba = pfn_bias(wa, cx, cy, cz, mx, my, mz);
     const float bb = pfn_bias(wb, cx, cy, cz, mx, my, mz);
-    float best_a = 0.0f, best_b = 0.0f;
+    float best_a = -INFINITY, best_b = -INFINITY;
     for (int s = 0; s < n; ++s) {
         const float sx = __shfl_sync(0xffffffffu, xr, s);
         const float sy = __shfl_sync(0xffffffffu, yr, s);
         const float sz = __shfl_sync(0xffffffffu, zr, s);
         const float si = __shfl_sync(0xffffffffu, pi, s);
-        best_a = fmaxf(best_a, pfn_point(wa, ba, sx, sy, sz, si));
-        best_b = fmaxf(best_b, pfn_point(wb, bb, sx, sy, sz, si));
+        best_a = fmaxf(best_a, pfn_point(wa, sx, sy, sz, si));
+        best_b = fmaxf(best_b, pfn_point(wb, sx, sy, sz, si));
     }
-    if (n < 32) {   // padded slots contribute relu(bn(0)) = max(shift, 0), pillar_vfe.py:46
-        best_a = fmaxf(best_a, wa.shift);
-        best_b = fmaxf(best_b, wb.shift);
-    }
-    return make_float2(best_a, best_b);
+    return make_float2(pfn_finish(wa, best_a, ba, n), pfn_finish(wb, best_b, bb, n));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -367,7 +376,7 @@ struct FusedSrc {
 };
 
 template <class Src>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 k_canvas(Src src, int nx, int ny, int C, float *__restrict__ canvas) {
     __shared__ __align__(16) float tile[64 * kTileStride];
     __shared__ int s_code[kTileX];
@@ -419,18 +428,27 @@ k_canvas(Src src, int nx, int ny, int C, float *__restrict__ canvas) {
                 const PfnLane wa = load_pfn(fs.pfn, lane), wb = load_pfn(fs.pfn, lane + 32);
                 const int pbase = __ldg(fs.point_offsets + b);
                 const float cy = __fadd_rn(__fmul_rn((float)y, fs.vy), fs.oy);
+                // two-stage software pipeline over this warp's pillars: slot indices two ahead, point one ahead
+                auto slot_of = [&](int k) -> uint32_t {
+                    const unsigned pid = (unsigned)s_code[s_list[k]] & ~kPillarBit;
+                    return __ldg(fs.slots + ((size_t)b * fs.max_voxels + pid) * 32 + lane);
+                };
+                auto point_of = [&](uint32_t idx) -> float4 {
+                    return idx != kEmpty ? __ldg(fs.points + pbase + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
+                };
+                uint32_t idx_cur = slot_of(warp);
+                uint32_t idx_nxt = (warp + 8 < n_occ) ? slot_of(warp + 8) : kEmpty;
+                float4 p_cur = point_of(idx_cur);
                 for (int k = warp; k < n_occ; k += 8) {
+                    const float4 p_nxt = point_of(idx_nxt);
+                    const uint32_t idx_nxt2 = (k + 16 < n_occ) ? slot_of(k + 16) : kEmpty;
                     const int xc = s_list[k];
-                    const unsigned pid = (unsigned)s_code[xc] & ~kPillarBit;
-                    const uint32_t idx = __ldg(fs.slots + ((size_t)b * fs.max_voxels + pid) * 32 + lane);
-                    const bool valid = idx != kEmpty;
-                    float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (valid) p = __ldg(fs.points + pbase + idx);
-                    const int n = __popc(__ballot_sync(0xffffffffu, valid));   // slots are filled from 0
+                    const int n = __popc(__ballot_sync(0xffffffffu, idx_cur != kEmpty));   // slots fill from 0
                     const float cx = __fadd_rn(__fmul_rn((float)(x0 + xc), fs.vx), fs.ox);
-                    const float2 r = pfn_pillar(wa, wb, p, n, cx, cy, fs.cz);
+                    const float2 r = pfn_pillar(wa, wb, p_cur, n, cx, cy, fs.cz);
                     tile[lane * kTileStride + xc] = r.x;
                     tile[(lane + 32) * kTileStride + xc] = r.y;
+                    idx_cur = idx_nxt; p_cur = p_nxt; idx_nxt = idx_nxt2;
                 }
             }
         }

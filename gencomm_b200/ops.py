@@ -72,7 +72,8 @@ def fold_bn(bn_weight, bn_bias, bn_mean, bn_var, eps=1e-3):
 
 
 def pack_pfn(weight, bn_weight, bn_bias, bn_mean, bn_var, eps=1e-3):
-    """[64,10] Linear weight + BN1d stats -> the [64,16] table of include/gencomm_b200.h."""
+    """[64,10] Linear weight + BN1d stats -> the [64,16] table of include/gencomm_b200.h (fp32 host math;
+    oracle/pillar_ref.c::pack_pfn_row is the same arithmetic)."""
     w = weight.detach().float().cpu()
     if tuple(w.shape) != (64, 10):
         raise ValueError("PillarVFE kernels implement num_filters=[64], 10 input features "
@@ -81,12 +82,12 @@ def pack_pfn(weight, bn_weight, bn_bias, bn_mean, bn_var, eps=1e-3):
                            bn_var.detach().cpu(), eps)
     t = torch.zeros(64, 16, dtype=torch.float32)
     for j in range(3):
-        t[:, j] = (w[:, j] + w[:, 4 + j]) + w[:, 7 + j]
-        t[:, 4 + j] = w[:, j]
-        t[:, 7 + j] = -w[:, 4 + j]
-    t[:, 3] = w[:, 3]
-    t[:, 10] = scale
-    t[:, 11] = shift
+        t[:, j] = ((w[:, j] + w[:, 4 + j]) + w[:, 7 + j]) * scale
+        t[:, 4 + j] = w[:, j] * scale
+        t[:, 7 + j] = (-w[:, 4 + j]) * scale
+    t[:, 3] = w[:, 3] * scale
+    t[:, 10] = shift
+    t[:, 11] = torch.clamp(shift, min=0.0)
     return t.contiguous()
 
 
@@ -238,4 +239,65 @@ def warp_fuse(feat, agent_offsets, theta, mode, out=None):
             raise ValueError("warp_fuse: bad output shape")
     _lib.check(lib.gc_warp_fuse(_ptr(feat), _ptr(agent_offsets), n_frames, total, _ptr(theta), L, C, H, W, int(mode),
                                 _ptr(out), _stream()), "gc_warp_fuse")
+    return out
+
+
+# --------------------------------------------------------------------------------------------
+# (a10)/(a11) GenComm sampler + DiffusionUNet
+# --------------------------------------------------------------------------------------------
+def _host_ptr(a):
+    if not (isinstance(a, np.ndarray) and a.dtype == np.float32 and a.flags["C_CONTIGUOUS"]):
+        raise TypeError("host blobs must be C-contiguous float32 numpy arrays")
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def _check_blobs(lib, w_host, w_dev, C, T):
+    if w_host.size != lib.gc_gencomm_host_weight_floats(T) or w_dev.numel() != lib.gc_gencomm_device_weight_floats(C):
+        raise ValueError("packed denoiser weights do not match (C, T)")
+
+
+def unet_forward(cond, x, t_index, w_host, w_dev, T, workspace=None):
+    """pred = UNet(cat[cond, x], t_index) for all agents; cond [A,2,H,W], x [A,C,H,W] f32."""
+    lib = _lib.load()
+    _chk(cond, "cond", torch.float32, 4)
+    _chk(x, "x", torch.float32, 4)
+    _chk(w_dev, "w_dev", torch.float32, 1)
+    A, C, H, W = x.shape
+    if tuple(cond.shape) != (A, 2, H, W):
+        raise ValueError("cond must be [A,2,H,W]")
+    _check_blobs(lib, w_host, w_dev, C, T)
+    if workspace is None:
+        workspace = torch.empty(lib.gc_gencomm_workspace_bytes(A, C, H, W), dtype=torch.uint8, device=x.device)
+    pred = torch.empty_like(x)
+    _lib.check(lib.gc_unet_forward(_ptr(cond), _ptr(x), A, int(t_index), _host_ptr(w_host), _ptr(w_dev), C, H, W, int(T),
+                                   _ptr(workspace), _ptr(pred), _stream()), "gc_unet_forward")
+    return pred
+
+
+def gencomm_sample(feat, cond, agent_offsets, noise0, step_noise, w_host, w_dev, schedule, T, workspace=None, out=None):
+    """GenComm eval sampler; feat [sumN,C,H,W], cond [sumN,2,H,W], noise0 like feat, step_noise [>=T-1,sumN,C,H,W]."""
+    lib = _lib.load()
+    _chk(feat, "feat", torch.float32, 4)
+    _chk(cond, "cond", torch.float32, 4)
+    _chk(agent_offsets, "agent_offsets", torch.int32, 1)
+    _chk(noise0, "noise0", torch.float32, 4)
+    _chk(w_dev, "w_dev", torch.float32, 1)
+    A, C, H, W = feat.shape
+    if tuple(cond.shape) != (A, 2, H, W) or noise0.shape != feat.shape:
+        raise ValueError("gencomm_sample: cond must be [A,2,H,W] and noise0 like feat")
+    if T > 1:
+        _chk(step_noise, "step_noise", torch.float32, 5)
+        if step_noise.shape[0] < T - 1 or tuple(step_noise.shape[1:]) != (A, C, H, W):
+            raise ValueError("gencomm_sample: step_noise must be [>=T-1, A, C, H, W]")
+    _check_blobs(lib, w_host, w_dev, C, T)
+    if schedule.shape != (T, 5):
+        raise ValueError("schedule must be [T,5]")
+    if workspace is None:
+        workspace = torch.empty(lib.gc_gencomm_workspace_bytes(A, C, H, W), dtype=torch.uint8, device=feat.device)
+    if out is None:
+        out = torch.empty_like(feat)
+    _lib.check(lib.gc_gencomm_sample(_ptr(feat), _ptr(cond), _ptr(agent_offsets), agent_offsets.numel() - 1, A,
+                                     _ptr(noise0), _ptr(step_noise) if T > 1 else None, _host_ptr(w_host), _ptr(w_dev),
+                                     _host_ptr(schedule), C, H, W, int(T), _ptr(workspace), _ptr(out), _stream()),
+               "gc_gencomm_sample")
     return out

@@ -82,9 +82,10 @@ int gc_voxel_gather(const float *points, const int32_t *point_offsets, int n_age
  * (a3) PillarVFE.forward + PFNLayer.forward (models/sub_modules/pillar_vfe.py:105-155, :31-53)
  *      for use_norm=True, use_absolute_xyz=True, with_distance=False, num_filters=[64], eval BN.
  *
- *   pfn  [64][16] f32, packed by the host (gencomm_b200/pfn.py::pack_pfn):
- *        [0..2] Wc = (W[k][j]+W[k][4+j])+W[k][7+j], [3] W[k][3], [4..6] W[k][0..2],
- *        [7..9] -W[k][4..6], [10] bn scale, [11] bn shift, [12..15] 0
+ *   pfn  [64][16] f32 per output channel k, packed by the host (gencomm_b200/ops.py::pack_pfn) with the
+ *        eval BatchNorm (scale, shift) folded in:
+ *        [0..2] A = ((W[k][j]+W[k][4+j])+W[k][7+j])*scale, [3] W[k][3]*scale, [4..6] W[k][0..2]*scale,
+ *        [7..9] (-W[k][4..6])*scale, [10] shift, [11] max(shift,0), [12..15] 0
  *   centre_offset[3] = voxel/2 + range_min (pillar_vfe.py:87-89), voxel[3]  -- in geom/arguments
  *   voxels [M][32][4], num_points [M], coords [M][4] (b,z,y,x)  ->  pillar_features [M][64]
  * ------------------------------------------------------------------------------------------- */
@@ -131,6 +132,43 @@ int gc_warp_fuse(const float *feat, const int32_t *agent_offsets, int n_frames, 
  *   pairwise [n][4][4] f64 -> theta [n][2][3] f64, n = B*L*L matrices. */
 int gc_normalize_pairwise_tfm(const double *pairwise, int n, double H, double W, double discrete_ratio,
                               double downsample_rate, double *theta, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * (a10)+(a11) GenComm.forward (eval branch) + DiffusionUNet.forward
+ *      (models/gencomm_modules/cond_diff.py:331-383, :262-329; models/gencomm_modules/unet.py:307-344)
+ *      for ch=8, ch_mult=[1,1], num_res_blocks=2, resamp_with_conv=True (no attention block is ever
+ *      instantiated by the shipped configs).  x0-parameterised ancestral sampling, T steps:
+ *        x_T = sqrt(ac_T) * ego(frame of agent) + sqrt(1-ac_T) * noise0            (:333-337, :372)
+ *        t = T-1..1: x0 = UNet(cat[cond, x_t], t); x_{t-1} = c1_t x0 + c2_t x_t + sigma_t noise_t  (:272-279, :310)
+ *        t = 0:      pred = UNet(cat[cond, x_0'], 0)                                  (:292-294, :313)
+ *      Noise is an INPUT (the reference draws it with torch.randn; bit-parity with that stream is
+ *      not a goal): noise0 [sumN][C][H][W]; step_noise [T-1][sumN][C][H][W] for
+ *      t = T-1, ..., 1.
+ *
+ *   feat  [sumN][C][H][W] f32, cond [sumN][2][H][W] f32 (the 2-channel messages), pred like feat
+ *   agent_offsets [n_frames+1] i32 (device), exclusive prefix of record_len
+ *   w_host [host]  gc_gencomm_host_weight_floats(T) floats, packed by gencomm_b200/gencomm.py::pack_unet:
+ *          T x 26 conv records (execution order; [tap][cin16][cout8] weights, bias incl. the
+ *          timestep-embedding projection of that step, GroupNorm affine, nin_shortcut), then
+ *          conv_in.bias[8], norm_out.weight[8], norm_out.bias[8]
+ *   w_dev  [device] gc_gencomm_device_weight_floats(C) floats: conv_in [C+2][9][8], conv_out [C][9][8], conv_out.bias [C]
+ *   schedule_host [host] [T][5]: sqrt_alphas_cumprod, sqrt_one_minus_alphas_cumprod,
+ *          posterior_mean_coef1, posterior_mean_coef2, exp(0.5*posterior_log_variance_clipped)
+ *   workspace: gc_gencomm_workspace_bytes(sumN, C, H, W) bytes (device)
+ * ------------------------------------------------------------------------------------------- */
+size_t gc_gencomm_host_weight_floats(int T);
+size_t gc_gencomm_device_weight_floats(int C);
+size_t gc_gencomm_workspace_bytes(int total_agents, int C, int H, int W);
+
+int gc_gencomm_sample(const float *feat, const float *cond, const int32_t *agent_offsets, int n_frames,
+                      int total_agents, const float *noise0, const float *step_noise,
+                      const float *w_host /*[host]*/, const float *w_dev, const float *schedule_host /*[host]*/,
+                      int C, int H, int W, int T, void *workspace, float *pred, void *stream);
+
+/* One denoiser evaluation pred = UNet(cat[cond, x], t_index) for all agents (diagnostics / tests). */
+int gc_unet_forward(const float *cond, const float *x, int total_agents, int t_index,
+                    const float *w_host /*[host]*/, const float *w_dev, int C, int H, int W, int T,
+                    void *workspace, float *pred, void *stream);
 
 #ifdef __cplusplus
 }

@@ -91,24 +91,26 @@ int gc_ref_voxelize(const float *points, int n_points, const float *range6, cons
 
 /* ---------------------------------------------------------------------------------------------
  * PillarVFE, fixed evaluation order ("kernel order").  32 slots per pillar, n valid points.
- * The reference computes, per slot s and output channel k (pillar_vfe.py:118-149, :39):
+ * The reference computes, per slot s and output channel k (pillar_vfe.py:118-149, :39, :42-46):
  *     lin = W0 x + W1 y + W2 z + W3 i + W4 (x-mx) + W5 (y-my) + W6 (z-mz) + W7 (x-cx) + W8 (y-cy) + W9 (z-cz)
+ *     out = max_s relu(lin * scale + shift)            (eval BatchNorm folded: scale, shift)
  * with (mx,my,mz) the pillar mean and (cx,cy,cz) the pillar centre.  With r = p - centre (exact in
  * fp32 by Sterbenz whenever |p| >= voxel) and m' = mean(r) = m - centre this is algebraically
- *     lin = (W0+W4+W7) xr + (W1+W5+W8) yr + (W2+W6+W9) zr + W3 i
- *           + [W0 cx + W1 cy + W2 cz - W4 m'x - W5 m'y - W6 m'z]          (per-pillar bias)
- * which needs 4 instead of 10 FMAs per (point, channel) and has smaller cancellation error than
- * the literal form.  Evaluation order (every rounding listed; the CUDA kernel is identical):
+ *     lin*scale + shift = [A0 xr + A1 yr + A2 zr + A3 i] + [shift + B0 cx + B1 cy + B2 cz + D0 m'x + D1 m'y + D2 m'z]
+ *     A_j = ((W_j + W_{4+j}) + W_{7+j}) * scale (j<3),  A_3 = W_3 * scale,  B_j = W_j * scale,  D_j = (-W_{4+j}) * scale
+ * i.e. 4 instead of 10 FMAs per (point, channel), a per-pillar bias, and -- because rounding is
+ * monotone -- the bias can be added after the max over the points.  The 12 constants per channel are
+ * computed once on the host in fp32 (gencomm_b200.ops.pack_pfn; pack_pfn_row() below is the same
+ * arithmetic).  Evaluation order (every rounding listed; the CUDA kernel is identical):
  *   centre_j  = (float)c_j * voxel_j + offset_j          (round after mul, round after add; :123-132)
  *   r_j[s]    = p_j[s] - centre_j   for s < n, 0 for padded slots
  *   sum_j     = xor-butterfly tree over the 32 slots: v[s] += v[s^16]; ^8; ^4; ^2; ^1
- *   m'_j      = sum_j / (float)n
- *   Wc_kj     = (W[k][j] + W[k][4+j]) + W[k][7+j]         (j = 0..2, fp32)
- *   b_k       = W[k][0]*cx; b = fmaf(W[k][1],cy,b); b = fmaf(W[k][2],cz,b);
- *               b = fmaf(-W[k][4],m'x,b); b = fmaf(-W[k][5],m'y,b); b = fmaf(-W[k][6],m'z,b)
- *   lin_k[s]  = fmaf(W[k][3], i, fmaf(Wc_k2, zr, fmaf(Wc_k1, yr, fmaf(Wc_k0, xr, b_k))))
- *   y         = max(fmaf(lin, scale_k, shift_k), 0)        (BN eval folded: :25,:42; relu :45)
- *   out_k     = max over s < n of y, and with max(shift_k, 0) when n < 32   (padded slots, :46)
+ *   m'_j      = sum_j * (1.0f / (float)n)
+ *   b_k       = fmaf(B0,cx,shift); b = fmaf(B1,cy,b); b = fmaf(B2,cz,b);
+ *               b = fmaf(D0,m'x,b); b = fmaf(D1,m'y,b); b = fmaf(D2,m'z,b)
+ *   acc_k[s]  = fmaf(A0, xr, fmaf(A1, yr, fmaf(A2, zr, A3 * i)))
+ *   out_k     = max(max_{s<n} acc_k[s] + b_k, 0), and max with max(shift_k, 0) when n < 32
+ *               (padded slots contribute relu(bn(0)), :46)
  * coords are (b,z,y,x) rows of 4 int32.
  * ------------------------------------------------------------------------------------------- */
 static float tree_sum32(const float *v) {
@@ -125,11 +127,31 @@ static float tree_sum32(const float *v) {
     return t[0];
 }
 
+/* row layout shared with include/gencomm_b200.h: [0..3] A, [4..6] B, [7..9] D, [10] shift, [11] max(shift,0) */
+static void pack_pfn_row(const float *w /* [10] */, float scale, float shift, float *row /* [12] */) {
+    for (int j = 0; j < 3; ++j) {
+        volatile float t = w[j] + w[4 + j];
+        t = t + w[7 + j];
+        volatile float a = t * scale;
+        volatile float b = w[j] * scale;
+        volatile float d = (-w[4 + j]) * scale;
+        row[j] = a;
+        row[4 + j] = b;
+        row[7 + j] = d;
+    }
+    volatile float a3 = w[3] * scale;
+    row[3] = a3;
+    row[10] = shift;
+    row[11] = shift > 0.0f ? shift : 0.0f;
+}
+
 void gc_ref_pillar_vfe(const float *voxels /* [M][32][4] */, const int32_t *num_points,
                        const int32_t *coords4 /* [M][4] b,z,y,x */, int M,
                        const float *W /* [64][10] */, const float *scale, const float *shift,
                        const float *vsize3, const float *offset3 /* x,y,z centre offsets */,
                        float *out /* [M][64] */) {
+    float tab[64][12];
+    for (int k = 0; k < 64; ++k) pack_pfn_row(W + k * 10, scale[k], shift[k], tab[k]);
     for (int m = 0; m < M; ++m) {
         const float *vx = voxels + (size_t)m * 32 * 4;
         const int n = num_points[m];
@@ -146,34 +168,31 @@ void gc_ref_pillar_vfe(const float *voxels /* [M][32][4] */, const int32_t *num_
                 volatile float d = vx[s * 4 + j] - centre[j];
                 r[j][s] = (s < n) ? d : 0.0f;
             }
+        volatile float inv_n = 1.0f / (float)n;
         for (int j = 0; j < 3; ++j) {
-            volatile float q = tree_sum32(r[j]) / (float)n;
+            volatile float q = tree_sum32(r[j]) * inv_n;
             mp[j] = q;
         }
         for (int k = 0; k < 64; ++k) {
-            const float *w = W + k * 10;
-            volatile float wc0 = w[0] + w[4]; wc0 = wc0 + w[7];
-            volatile float wc1 = w[1] + w[5]; wc1 = wc1 + w[8];
-            volatile float wc2 = w[2] + w[6]; wc2 = wc2 + w[9];
-            volatile float b0 = w[0] * centre[0];
-            float b = b0;
-            b = fmaf(w[1], centre[1], b);
-            b = fmaf(w[2], centre[2], b);
-            b = fmaf(-w[4], mp[0], b);
-            b = fmaf(-w[5], mp[1], b);
-            b = fmaf(-w[6], mp[2], b);
-            float best = 0.0f; /* relu output is >= 0 */
+            const float *t = tab[k];
+            float b = fmaf(t[4], centre[0], t[10]);
+            b = fmaf(t[5], centre[1], b);
+            b = fmaf(t[6], centre[2], b);
+            b = fmaf(t[7], mp[0], b);
+            b = fmaf(t[8], mp[1], b);
+            b = fmaf(t[9], mp[2], b);
+            float best = -INFINITY;
             for (int s = 0; s < n && s < 32; ++s) {
-                float acc = fmaf(wc0, r[0][s], b);
-                acc = fmaf(wc1, r[1][s], acc);
-                acc = fmaf(wc2, r[2][s], acc);
-                acc = fmaf(w[3], vx[s * 4 + 3], acc);
-                float y = fmaf(acc, scale[k], shift[k]);
-                y = y > 0.0f ? y : 0.0f;
-                if (y > best) best = y;
+                volatile float a3 = t[3] * vx[s * 4 + 3];
+                float acc = fmaf(t[2], r[2][s], a3);
+                acc = fmaf(t[1], r[1][s], acc);
+                acc = fmaf(t[0], r[0][s], acc);
+                if (acc > best) best = acc;
             }
-            if (n < 32 && shift[k] > best) best = shift[k];
-            out[(size_t)m * 64 + k] = best;
+            volatile float y = best + b;
+            float o = y > 0.0f ? y : 0.0f;
+            if (n < 32 && t[11] > o) o = t[11];
+            out[(size_t)m * 64 + k] = o;
         }
     }
 }

@@ -48,10 +48,12 @@ def test_geometry_and_pfn_packing_host_logic():
     g = ops.make_geom([-102.4, -51.2, -3, 102.4, 51.2, 1], [0.4, 0.4, 4], 70000)
     assert list(g.grid) == [512, 256, 1]
     w = torch.arange(640, dtype=torch.float32).reshape(64, 10) / 100
-    t = ops.pack_pfn(w, torch.ones(64), torch.zeros(64), torch.zeros(64), torch.ones(64) - 1e-3)
+    gamma, beta, mean, var = torch.full((64,), 2.0), torch.full((64,), -0.5), torch.full((64,), 0.25), torch.ones(64)
+    t = ops.pack_pfn(w, gamma, beta, mean, var, eps=0.0)     # scale = 2, shift = -0.5 - 0.25*2 = -1
     assert t.shape == (64, 16)
-    assert torch.equal(t[:, 0], (w[:, 0] + w[:, 4]) + w[:, 7]) and torch.equal(t[:, 7], -w[:, 4])
-    assert torch.allclose(t[:, 10], torch.ones(64)) and not t[:, 12:].any()
+    assert torch.equal(t[:, 0], ((w[:, 0] + w[:, 4]) + w[:, 7]) * 2) and torch.equal(t[:, 7], -w[:, 4] * 2)
+    assert torch.equal(t[:, 3], w[:, 3] * 2) and torch.equal(t[:, 5], w[:, 1] * 2)
+    assert torch.equal(t[:, 10], torch.full((64,), -1.0)) and not t[:, 11:].any()
 
 
 def test_modules_keep_reference_state_dict_keys():
