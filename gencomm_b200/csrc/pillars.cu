@@ -181,19 +181,22 @@ k_pillar_assign(const int32_t *__restrict__ point_offsets, const int32_t *__rest
 //    slot and carries max(slot, v) on, so the multiset {slots} U {carried} is invariant and the final
 //    slot contents are the 32 smallest indices in ascending order, whatever the interleaving.
 // ------------------------------------------------------------------------------------------------
+// grid = (n_agents, chunks): blockIdx.x (fastest-scheduled) is the agent, blockIdx.y the 256-point chunk, so
+// the machine sweeps every agent's points in index order.  Late (large-index) points of a crowded cell then
+// find 32 smaller indices already in place and leave without a single atomic.
 __global__ void __launch_bounds__(256)
-k_slot_insert(const int32_t *__restrict__ point_offsets, int n_agents, int total_points,
-              const int32_t *__restrict__ point_cell, const uint32_t *__restrict__ cell_code, int ncell,
-              int max_voxels, uint32_t *__restrict__ slots) {
-    const int gi = blockIdx.x * blockDim.x + threadIdx.x;
-    if (gi >= total_points) return;
-    const int c = __ldg(point_cell + gi);
+k_slot_insert(const int32_t *__restrict__ point_offsets, const int32_t *__restrict__ point_cell,
+              const uint32_t *__restrict__ cell_code, int ncell, int max_voxels, uint32_t *__restrict__ slots) {
+    const int a = blockIdx.x;
+    const int base = __ldg(point_offsets + a);
+    const int i = blockIdx.y * blockDim.x + threadIdx.x;
+    if (i >= __ldg(point_offsets + a + 1) - base) return;
+    const int c = __ldg(point_cell + base + i);
     if (c < 0) return;
-    const int a = find_segment(point_offsets, n_agents, gi);
     const uint32_t code = __ldg(cell_code + (size_t)a * ncell + c);
     if (code >= kDropped) return;
     uint32_t *s = slots + ((size_t)a * max_voxels + (code & ~kPillarBit)) * 32;
-    uint32_t v = (uint32_t)(gi - __ldg(point_offsets + a));
+    uint32_t v = (uint32_t)i;
     // The slot array is sorted ascending at every instant and its values only ever decrease, so a slot
     // observed below v stays below v and atomicMin(slot, v) there is a no-op: skip all of them.  The
     // snapshot is read through L2 (ld.cg); a stale (larger) value only skips less.
@@ -547,8 +550,10 @@ extern "C" int gc_voxelize(const float *points, const int32_t *point_offsets, in
                                                          n_pillars);
     GC_LAUNCH_CHECK("k_pillar_assign");
     if (total_points > 0) {
-        k_slot_insert<<<(total_points + 255) / 256, 256, 0, st>>>(point_offsets, n_agents, total_points, w.point_cell,
-                                                                 w.cell_code, g.ncell, g.max_voxels, w.slots);
+        const int chunks = (max_agent_points + 255) / 256;
+        GC_REQUIRE(chunks <= 65535, GC_EUNSUPPORTED, "gc_voxelize: more than 16.7M points per agent");
+        k_slot_insert<<<dim3(n_agents, chunks), 256, 0, st>>>(point_offsets, w.point_cell, w.cell_code, g.ncell,
+                                                            g.max_voxels, w.slots);
         GC_LAUNCH_CHECK("k_slot_insert");
     }
     return GC_OK;

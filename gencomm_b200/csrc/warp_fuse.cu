@@ -18,69 +18,15 @@
 // F.affine_grid(theta_f64).to(src) does; computing them in float32 moves results by up to 5e-5.
 // Unnormalisation, floor, the four weights and the tap accumulation order follow ATen's
 // grid_sampler_2d CUDA kernel (align_corners=False, padding zeros).
-#include "common.cuh"
+#include <stdlib.h>
+
+#include "warp_common.cuh"
 
 namespace gc {
 
-constexpr int kMaxN = GC_MAX_AGENTS_PER_FRAME;
-
-// ATen linspace(-1,1,n) * (n-1)/n, evaluated in float64 (AffineGridGenerator.cpp: linspace_from_neg_one).
-__host__ __device__ __forceinline__ double base_coord(int i, int n) {
-    if (n <= 1) return 0.0;
-    const double step = 2.0 / (double)(n - 1);
-    const double v = (i < n / 2) ? (-1.0 + step * (double)i) : (1.0 - step * (double)(n - 1 - i));
-    return v * (double)(n - 1) / (double)n;
-}
-
-struct Tap {
-    float w_nw, w_ne, w_sw, w_se;
-    int off;          // y0 * W + x0 (may be out of range; guarded by the valid bits)
-    unsigned valid;   // bit0 nw, bit1 ne, bit2 sw, bit3 se; taps with zero weight are dropped
-};
-
-// theta: 6 doubles (row-major 2x3).  (xs, ys): float64 base grid coordinates of the output pixel.
-__device__ __forceinline__ Tap make_tap(const double *__restrict__ th, double xs, double ys, int H, int W) {
-    // bmm of [xs, ys, 1] with theta^T (float64), then .to(float32)
-    const float gx = (float)(xs * th[0] + ys * th[1] + th[2]);
-    const float gy = (float)(xs * th[3] + ys * th[4] + th[5]);
-    // grid_sampler_unnormalize, align_corners=False: ((coord + 1) * size - 1) / 2
-    const float ix = __fmaf_rn(gx + 1.0f, (float)W, -1.0f) * 0.5f;
-    const float iy = __fmaf_rn(gy + 1.0f, (float)H, -1.0f) * 0.5f;
-    const float fx = floorf(ix), fy = floorf(iy);
-    Tap t;
-    // nw = (ix_se - ix)(iy_se - iy), ne = (ix - ix_sw)(iy_sw - iy), sw = (ix_ne - ix)(iy - iy_ne), se = (ix - ix_nw)(iy - iy_nw)
-    const float ex = (fx + 1.0f) - ix, wx = ix - fx;
-    const float sy = (fy + 1.0f) - iy, ny_ = iy - fy;
-    t.w_nw = ex * sy;
-    t.w_ne = wx * sy;
-    t.w_sw = ex * ny_;
-    t.w_se = wx * ny_;
-    // clamp before the int conversion so absurd coordinates stay defined; they are out of range anyway
-    const int x0 = (int)fminf(fmaxf(fx, -2.0f), (float)W);
-    const int y0 = (int)fminf(fmaxf(fy, -2.0f), (float)H);
-    const bool xin0 = x0 >= 0 && x0 < W, xin1 = x0 + 1 >= 0 && x0 + 1 < W;
-    const bool yin0 = y0 >= 0 && y0 < H, yin1 = y0 + 1 >= 0 && y0 + 1 < H;
-    // a tap whose weight is exactly 0 contributes +-0 and can be skipped (features are finite)
-    t.valid = ((xin0 && yin0 && t.w_nw != 0.0f) ? 1u : 0u) | ((xin1 && yin0 && t.w_ne != 0.0f) ? 2u : 0u) |
-              ((xin0 && yin1 && t.w_sw != 0.0f) ? 4u : 0u) | ((xin1 && yin1 && t.w_se != 0.0f) ? 8u : 0u);
-    t.off = y0 * W + x0;
-    if (!(ix == ix) || !(iy == iy)) t.valid = 0;   // NaN transform
-    return t;
-}
-
-// ATen order: out = 0; out += nw_val*nw; += ne; += sw; += se   (each a fused multiply-add under nvcc)
-__device__ __forceinline__ float sample(const float *__restrict__ plane, const Tap &t, int W) {
-    const float *p = plane + t.off;
-    const float a = (t.valid & 1u) ? __ldg(p) : 0.0f;
-    const float b = (t.valid & 2u) ? __ldg(p + 1) : 0.0f;
-    const float c = (t.valid & 4u) ? __ldg(p + W) : 0.0f;
-    const float d = (t.valid & 8u) ? __ldg(p + W + 1) : 0.0f;
-    float acc = a * t.w_nw;
-    acc = __fmaf_rn(b, t.w_ne, acc);
-    acc = __fmaf_rn(c, t.w_sw, acc);
-    acc = __fmaf_rn(d, t.w_se, acc);
-    return acc;
-}
+// warp_fuse_tma.cu: 0 = launched, 1 = not eligible (use the gather kernels below), otherwise an error code
+int warp_fuse_tma(const float *feat, const int32_t *agent_offsets, int n_frames, int total_agents,
+                  const double *theta, int L, int C, int H, int W, int mode, int nmax, float *out, cudaStream_t st);
 
 // ------------------------------------------------------------------------------------------------
 // Generic fused kernel: grid (ceil(W/32), ceil(H/8), n_frames), block 32x8, one pixel per thread.
@@ -245,16 +191,24 @@ extern "C" int gc_warp_fuse(const float *feat, const int32_t *agent_offsets, int
     const unsigned gx = (W + 31) / 32, gy = (H + 7) / 8;
     GC_REQUIRE(gy <= 65535 && n_frames <= 65535 && total_agents <= 65535, GC_EUNSUPPORTED,
                "gc_warp_fuse: grid too large");
+    // compile-time agent bound: every frame has >= 1 agent and at most L
+    int nmax = total_agents - (n_frames - 1);
+    if (nmax > L) nmax = L;
+    if (mode != GC_FUSE_WARP_ONLY)
+        GC_REQUIRE(nmax >= 1 && nmax <= kMaxN, GC_EUNSUPPORTED,
+                   "gc_warp_fuse: up to %d agents per frame supported (bound %d)", kMaxN, nmax);
+    // fast path: TMA-staged tiles (warp_fuse_tma.cu); GC_WARP_FUSE_GATHER=1 forces the gather kernels
+    const char *env = getenv("GC_WARP_FUSE_GATHER");
+    const bool force_gather = env && env[0] == '1';
+    if (!force_gather) {
+        const int rc = warp_fuse_tma(feat, agent_offsets, n_frames, total_agents, theta, L, C, H, W, mode, nmax, out, st);
+        if (rc != 1) return rc;
+    }
     if (mode == GC_FUSE_WARP_ONLY) {
         k_warp_only<<<dim3(gx, gy, total_agents), block, 0, st>>>(feat, agent_offsets, n_frames, theta, L, C, H, W, out);
         GC_LAUNCH_CHECK("k_warp_only");
         return GC_OK;
     }
-    // compile-time agent bound: every frame has >= 1 agent and at most L
-    int nmax = total_agents - (n_frames - 1);
-    if (nmax > L) nmax = L;
-    GC_REQUIRE(nmax >= 1 && nmax <= kMaxN, GC_EUNSUPPORTED,
-               "gc_warp_fuse: up to %d agents per frame supported (bound %d)", kMaxN, nmax);
     const float sqrt_c = (float)sqrt((double)C);   // np.sqrt(dim) cast to the tensor dtype
     const dim3 grid(gx, gy, n_frames);
     int rc = (mode == GC_FUSE_MAX)

@@ -14,6 +14,14 @@ DEV = "cuda"
 TOL = 1e-5
 
 
+@pytest.fixture(params=["tma", "gather"], autouse=True)
+def fuse_path(request, monkeypatch):
+    """Every test runs through both implementations of gc_warp_fuse: the TMA-staged fast path
+    (csrc/warp_fuse_tma.cu; used when W % 4 == 0 and <= 5 agents per frame) and the gather kernels."""
+    monkeypatch.setenv("GC_WARP_FUSE_GATHER", "1" if request.param == "gather" else "0")
+    return request.param
+
+
 def rel_err(out, ref):
     return (out - ref).abs().max().item() / max(ref.abs().max().item(), 1e-30)
 
@@ -50,7 +58,7 @@ def _frames(seed, record_len, C, H, W, L=5, sparsity=0.0):
 
 @pytest.mark.parametrize("record_len,C,H,W,L", [
     ([4], 64, 64, 64, 5), ([5, 3, 1], 32, 32, 64, 5), ([2, 2], 128, 64, 128, 5), ([3], 16, 20, 50, 5),
-    ([8], 24, 33, 31, 8), ([1], 8, 16, 16, 5)])
+    ([8], 24, 33, 31, 8), ([1], 8, 16, 16, 5), ([3, 4], 8, 100, 72, 5), ([2], 4, 40, 260, 5)])
 def test_fusion_matches_oracle(record_len, C, H, W, L):
     feat, rl, theta = _frames(10 + C, record_len, C, H, W, L, sparsity=0.3)
     fd, rd, td = feat.to(DEV), rl.to(DEV), theta.to(DEV)
@@ -96,3 +104,19 @@ def test_far_away_agent_contributes_zeros():
     out = G.warp_feature(feat.to(DEV), rl.to(DEV), theta.to(DEV)).cpu()
     assert not out[1].any() and torch.equal(out[0], feat[0])
     assert rel_err(G.AttFusion(C)(feat.to(DEV), rl.to(DEV), theta.to(DEV)).cpu(), R.att_fusion(feat, rl, theta)) <= TOL
+
+
+def test_non_isometric_affine_overflows_the_box_and_still_matches():
+    """A zooming affine map makes the source footprint of a 32x32 tile larger than the 48x48 TMA box:
+    the kernel must detect it per tile and sample that agent from global memory."""
+    C, H, W = 6, 96, 128
+    feat = synth.bev_features(9, 3, C, H, W)
+    theta = torch.zeros(1, 5, 5, 2, 3, dtype=torch.float64)
+    theta[..., 0, 0] = 1.0; theta[..., 1, 1] = 1.0
+    theta[0, 0, 1] = torch.tensor([[2.5, 0.3, 0.1], [-0.2, 1.9, -0.05]])     # zoom out x2.5 / x1.9
+    theta[0, 0, 2] = torch.tensor([[0.2, 0.0, 0.4], [0.0, 0.25, -0.3]])      # zoom in x5 / x4
+    rl = torch.tensor([3])
+    fd, rd, td = feat.to(DEV), rl.to(DEV), theta.to(DEV)
+    assert rel_err(G.warp_feature(fd, rd, td).cpu(), R.warp_only(feat, rl, theta)) <= TOL
+    assert rel_err(G.MaxFusion()(fd, rd, td).cpu(), R.max_fusion(feat, rl, theta)) <= TOL
+    assert rel_err(G.AttFusion(C)(fd, rd, td).cpu(), R.att_fusion(feat, rl, theta)) <= TOL
