@@ -7,7 +7,7 @@
 //
 //   * a CTA owns a 32x32 output tile of one frame (1024 threads, one pixel each, one warp per tile row);
 //   * the source footprint of that tile under agent j's affine map is a rotated square that always fits a
-//     48x48 box; ONE cp.async.bulk.tensor (TMA) per (agent, channel) copies that box of the NCHW plane into
+//     52x48 box; ONE cp.async.bulk.tensor (TMA) per (agent, channel) copies that box of the NCHW plane into
 //     shared memory.  The box origin may be negative / beyond the plane: TMA zero-fills out-of-bounds
 //     elements, which is exactly grid_sample's padding_mode='zeros';
 //   * boxes flow through a ring of shared-memory stages guarded by full/empty mbarriers (thread 0 is the TMA
@@ -26,8 +26,12 @@
 namespace gc {
 
 constexpr int kTile = 32;
-constexpr int kBox = 48;                         // 31*sqrt(2) + 3 = 46.9 -> 48 (inner dim multiple of 4 floats)
-constexpr int kBoxBytes = kBox * kBox * 4;       // 9216, a multiple of 128
+// Footprint of a 32x32 tile under an isometry: 31*sqrt(2) + 3 = 46.9 -> 47 pixels per side.  TMA needs the
+// box start 16-byte aligned in global memory, so the x origin is floored to a multiple of 4 floats (up to 3
+// extra columns): 52 x 48.
+constexpr int kBoxW = 52, kBoxH = 48;
+constexpr int kBoxFloats = kBoxW * kBoxH;
+constexpr int kBoxBytes = kBoxFloats * 4;        // 9984, a multiple of 128
 constexpr int kTmaMaxN = 5;                      // register budget of a 1024-thread CTA (64 regs/thread)
 constexpr int kMaxStages = 4;
 
@@ -98,7 +102,9 @@ __global__ void __launch_bounds__(1024, 1)
 k_warp_fuse_tma(const __grid_constant__ CUtensorMap tmap, const float *__restrict__ feat,
                 const int32_t *__restrict__ agent_offsets, int n_frames, const double *__restrict__ theta, int L,
                 int C, int H, int W, float sqrt_c, int stages, int stage_agents, float *__restrict__ out) {
-    extern __shared__ __align__(128) uint8_t smem[];
+    extern __shared__ uint8_t smem_raw[];
+    // TMA destinations must be 128-byte aligned; the dynamic segment follows the static variables below
+    float *const ring = reinterpret_cast<float *>(smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u));
     __shared__ uint64_t full_bar[kMaxStages], empty_bar[kMaxStages];
     __shared__ int s_bx[NMAX], s_by[NMAX], s_path[NMAX], s_slot[NMAX];
     __shared__ int s_ntma;
@@ -142,9 +148,10 @@ k_warp_fuse_tma(const __grid_constant__ CUtensorMap tmap, const float *__restric
                 minx = min(minx, t.x0); maxx = max(maxx, t.x0);
                 miny = min(miny, t.y0); maxy = max(maxy, t.y0);
             }
-            bx = minx; by = miny;
+            bx = minx & ~3;   // floor to a multiple of 4 (two's complement): 16-byte aligned box start
+            by = miny;
             if (maxx + 1 < 0 || minx >= W || maxy + 1 < 0 || miny >= H) path = kPathZero;          // nothing in view
-            else if (maxx - minx + 2 <= kBox && maxy - miny + 2 <= kBox) path = kPathTma;
+            else if (maxx - bx + 2 <= kBoxW && maxy - miny + 2 <= kBoxH) path = kPathTma;
             else path = kPathGather;
         }
         s_bx[lane] = bx; s_by[lane] = by; s_path[lane] = path;
@@ -165,7 +172,7 @@ k_warp_fuse_tma(const __grid_constant__ CUtensorMap tmap, const float *__restric
             const TapS t = make_tap_xy(th_base + j * 6, xs, ys, H, W);
             tap[j].w_nw = t.w_nw; tap[j].w_ne = t.w_ne; tap[j].w_sw = t.w_sw; tap[j].w_se = t.w_se;
             if (s_path[j] == kPathTma) {
-                tap[j].off = s_slot[j] * (kBox * kBox) + (t.y0 - s_by[j]) * kBox + (t.x0 - s_bx[j]);
+                tap[j].off = s_slot[j] * kBoxFloats + (t.y0 - s_by[j]) * kBoxW + (t.x0 - s_bx[j]);
             } else {
                 const bool xin0 = t.x0 >= 0 && t.x0 < W, xin1 = t.x0 + 1 >= 0 && t.x0 + 1 < W;
                 const bool yin0 = t.y0 >= 0 && t.y0 < H, yin1 = t.y0 + 1 >= 0 && t.y0 + 1 < H;
@@ -179,20 +186,23 @@ k_warp_fuse_tma(const __grid_constant__ CUtensorMap tmap, const float *__restric
     const size_t plane = (size_t)H * W;
     const int passes = MODE == GC_FUSE_ATT ? 2 : 1;
     const int total = C * passes;
-    const size_t stage_floats = (size_t)stage_agents * kBox * kBox;
+    const size_t stage_floats = (size_t)stage_agents * kBoxFloats;
 
-    auto issue = [&](int it) {   // thread 0 only
-        const int s = it % stages, c = it % C;
-        if (it >= stages) mbar_wait(&empty_bar[s], ((it / stages) - 1) & 1);
-        mbar_expect_tx(&full_bar[s], (uint32_t)n_tma * kBoxBytes);
-        float *dst = reinterpret_cast<float *>(smem) + (size_t)s * stage_floats;
-        for (int j = 0; j < n; ++j) {
-            if (s_path[j] == kPathTma)
-                tma_load_box(dst + s_slot[j] * (kBox * kBox), &tmap, s_bx[j], s_by[j], (a0 + j) * C + c, &full_bar[s]);
-        }
-    };
+    // producer (thread 0 only): arm the stage's full barrier and launch one box copy per TMA agent
+#define GC_ISSUE(IT)                                                                                          \
+    do {                                                                                                      \
+        const int it_ = (IT), s_ = it_ % stages, c_ = it_ % C;                                                \
+        if (it_ >= stages) mbar_wait(&empty_bar[s_], ((it_ / stages) - 1) & 1);                               \
+        mbar_expect_tx(&full_bar[s_], (uint32_t)n_tma * kBoxBytes);                                           \
+        float *dst_ = ring + (size_t)s_ * stage_floats;                                                       \
+        for (int j_ = 0; j_ < n; ++j_) {                                                                      \
+            if (s_path[j_] == kPathTma)                                                                       \
+                tma_load_box(dst_ + s_slot[j_] * kBoxFloats, &tmap, s_bx[j_], s_by[j_], (a0 + j_) * C + c_, \
+                             &full_bar[s_]);                                                                  \
+        }                                                                                                     \
+    } while (0)
     if (threadIdx.x == 0 && n_tma > 0) {
-        for (int it = 0; it < stages - 1 && it < total; ++it) issue(it);
+        for (int it = 0; it < stages - 1 && it < total; ++it) GC_ISSUE(it);
     }
 
     const float *src = feat + (size_t)a0 * C * plane;
@@ -205,10 +215,10 @@ k_warp_fuse_tma(const __grid_constant__ CUtensorMap tmap, const float *__restric
     for (int it = 0; it < total; ++it) {
         const int s = it % stages, c = it % C;
         if (n_tma > 0) {
-            if (threadIdx.x == 0 && it + stages - 1 < total) issue(it + stages - 1);
+            if (threadIdx.x == 0 && it + stages - 1 < total) GC_ISSUE(it + stages - 1);
             mbar_wait(&full_bar[s], (it / stages) & 1);
         }
-        const float *box = reinterpret_cast<const float *>(smem) + (size_t)s * stage_floats;
+        const float *box = ring + (size_t)s * stage_floats;
         float v[NMAX];
 #pragma unroll
         for (int j = 0; j < NMAX; ++j) {
@@ -219,8 +229,8 @@ k_warp_fuse_tma(const __grid_constant__ CUtensorMap tmap, const float *__restric
                     const float *p = box + tap[j].off;
                     float acc = p[0] * tap[j].w_nw;
                     acc = __fmaf_rn(p[1], tap[j].w_ne, acc);
-                    acc = __fmaf_rn(p[kBox], tap[j].w_sw, acc);
-                    acc = __fmaf_rn(p[kBox + 1], tap[j].w_se, acc);
+                    acc = __fmaf_rn(p[kBoxW], tap[j].w_sw, acc);
+                    acc = __fmaf_rn(p[kBoxW + 1], tap[j].w_se, acc);
                     v[j] = acc;
                 } else if (path == kPathGather && active) {
                     Tap g;
@@ -309,7 +319,7 @@ int warp_fuse_tma(const float *feat, const int32_t *agent_offsets, int n_frames,
     CUtensorMap map;
     const cuuint64_t gdim[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)total_agents * C};
     const cuuint64_t gstride[2] = {(cuuint64_t)W * 4, (cuuint64_t)H * W * 4};
-    const cuuint32_t box[3] = {kBox, kBox, 1};
+    const cuuint32_t box[3] = {kBoxW, kBoxH, 1};
     const cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = encode(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(feat), gdim, gstride, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -317,10 +327,10 @@ int warp_fuse_tma(const float *feat, const int32_t *agent_offsets, int n_frames,
     if (r != CUDA_SUCCESS) return 1;
 
     const int stage_agents = mode == GC_FUSE_WARP_ONLY ? 1 : nmax;
-    int stages = (int)((226 * 1024) / ((size_t)stage_agents * kBoxBytes));
+    int stages = (int)((225 * 1024) / ((size_t)stage_agents * kBoxBytes));
     stages = stages > kMaxStages ? kMaxStages : stages;
     if (stages < 2) return 1;
-    const size_t smem = (size_t)stages * stage_agents * kBoxBytes;
+    const size_t smem = (size_t)stages * stage_agents * kBoxBytes + 128;   // + manual 128-B alignment slack
     const dim3 grid((W + kTile - 1) / kTile, (H + kTile - 1) / kTile, mode == GC_FUSE_WARP_ONLY ? total_agents : n_frames);
     if (grid.y > 65535 || grid.z > 65535) return 1;
     const float sqrt_c = (float)sqrt((double)C);
