@@ -1,0 +1,78 @@
+"""Frame sharding across the GPUs of one box.
+
+Collaborative frames are independent units (the reference processes them one by one,
+tools/inference.py:131-227), so the path shards with NO data-path collective: global frame f runs on
+rank ``f % world``.  The only exchange is an end-of-run ``all_gather`` of small per-frame summaries
+(top-K responses of the fused map as a detection proxy until decode/NMS exists, plus per-stage
+timings), a few KB per rank: latency-bound, NVLink bandwidth is irrelevant.
+
+Works with any ``torch.distributed`` backend (NCCL on the GPU box, gloo in the CPU tests).
+"""
+import torch
+import torch.distributed as dist
+
+TOPK = 16
+
+
+def frames_for_rank(n_frames, rank, world):
+    """Global frame indices owned by `rank` (round-robin, like a DistributedSampler without padding)."""
+    return list(range(int(rank), int(n_frames), int(world)))
+
+
+def frame_summary(fused, k=TOPK):
+    """fused [C,H,W] -> (values [k] f32, flat pixel indices [k] i64) of the per-pixel channel maximum."""
+    resp = fused.amax(dim=0).flatten()
+    v, i = torch.topk(resp, min(k, resp.numel()))
+    if v.numel() < k:
+        v = torch.cat([v, v.new_full((k - v.numel(),), float("-inf"))])
+        i = torch.cat([i, i.new_full((k - i.numel(),), -1)])
+    return v.float(), i.long()
+
+
+def gather_summaries(local, n_frames, device, k=TOPK, n_timings=0):
+    """All-gather per-frame summaries.
+
+    local: {global_frame_idx: (values [k], indices [k], timings [n_timings])} for this rank's frames.
+    Returns (values [n_frames,k], indices [n_frames,k], timings [n_frames,n_timings], owner [n_frames]) on every
+    rank, rows ordered by global frame index.  Ranks may own different numbers of frames (ragged): rows are
+    padded to the per-rank maximum and a count is exchanged with them.
+    """
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    per_rank = (int(n_frames) + world - 1) // world
+    width = 1 + k + k + n_timings                      # frame id, values, indices (as f64), timings
+    buf = torch.full((per_rank, width), -1.0, dtype=torch.float64, device=device)
+    for row, f in enumerate(sorted(local)):
+        v, i, t = local[f]
+        buf[row, 0] = float(f)
+        buf[row, 1:1 + k] = v.to(device=device, dtype=torch.float64)
+        buf[row, 1 + k:1 + 2 * k] = i.to(device=device, dtype=torch.float64)
+        if n_timings:
+            buf[row, 1 + 2 * k:] = torch.as_tensor(t, dtype=torch.float64, device=device)
+    if world > 1:
+        parts = [torch.empty_like(buf) for _ in range(world)]
+        dist.all_gather(parts, buf)
+    else:
+        parts = [buf]
+    values = torch.full((n_frames, k), float("nan"), dtype=torch.float32)
+    indices = torch.full((n_frames, k), -1, dtype=torch.int64)
+    timings = torch.zeros((n_frames, n_timings), dtype=torch.float64)
+    owner = torch.full((n_frames,), -1, dtype=torch.int64)
+    for r, p in enumerate(parts):
+        p = p.cpu()
+        for row in p:
+            f = int(row[0])
+            if f < 0:
+                continue
+            if owner[f] != -1:
+                raise RuntimeError(f"frame {f} reported by ranks {int(owner[f])} and {r}")
+            owner[f] = r
+            values[f] = row[1:1 + k].float()
+            indices[f] = row[1 + k:1 + 2 * k].long()
+            timings[f] = row[1 + 2 * k:]
+    if (owner < 0).any():
+        raise RuntimeError(f"frames {torch.nonzero(owner < 0).flatten().tolist()} were not processed by any rank")
+    expect = torch.arange(n_frames) % world
+    if not torch.equal(owner, expect):
+        raise RuntimeError("frame ownership does not follow frame_idx % world")
+    return values, indices, timings, owner

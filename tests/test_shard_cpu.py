@@ -1,0 +1,72 @@
+"""N>1 path on CPU: world_size-2 gloo processes shard frames by frame_idx % world and all-gather
+per-frame summaries.  No kernel runs here (the hot path has no CPU implementation):
+the per-frame "fused maps" are seeded random tensors, identical to what a single process computes,
+so the gathered result must equal the single-process result row for row."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from gencomm_b200 import shard
+
+N_FRAMES, C, H, W = 7, 4, 6, 10      # odd frame count -> ragged ownership (rank 0: 4 frames, rank 1: 3)
+
+
+def fake_fused(frame):
+    g = torch.Generator().manual_seed(1234 + frame)
+    return torch.randn(C, H, W, generator=g)
+
+
+def single_process():
+    local = {f: shard.frame_summary(fake_fused(f)) + ([float(f), 2.0 * f],) for f in range(N_FRAMES)}
+    return shard.gather_summaries(local, N_FRAMES, torch.device("cpu"), n_timings=2)
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        mine = shard.frames_for_rank(N_FRAMES, rank, world)
+        local = {f: shard.frame_summary(fake_fused(f)) + ([float(f), 2.0 * f],) for f in mine}
+        v, i, t, owner = shard.gather_summaries(local, N_FRAMES, torch.device("cpu"), n_timings=2)
+        out[rank] = (v, i, t, owner, mine)
+    finally:
+        dist.destroy_process_group()
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def test_frames_for_rank_partition():
+    for world in (1, 2, 3, 8):
+        seen = sorted(f for r in range(world) for f in shard.frames_for_rank(11, r, world))
+        assert seen == list(range(11))
+    assert shard.frames_for_rank(7, 1, 2) == [1, 3, 5]
+
+
+def test_world2_gloo_gather_matches_single_process():
+    ref = single_process()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    assert sorted(out.keys()) == [0, 1]
+    assert out[0][4] == [0, 2, 4, 6] and out[1][4] == [1, 3, 5]
+    for rank in (0, 1):
+        v, i, t, owner, _ = out[rank]
+        assert torch.equal(v, ref[0]) and torch.equal(i, ref[1]) and torch.equal(t, ref[2])
+        assert owner.tolist() == [f % 2 for f in range(N_FRAMES)]
+
+
+def test_missing_frame_is_reported():
+    local = {f: shard.frame_summary(fake_fused(f)) + ([0.0, 0.0],) for f in range(N_FRAMES - 1)}
+    try:
+        shard.gather_summaries(local, N_FRAMES, torch.device("cpu"), n_timings=2)
+    except RuntimeError as e:
+        assert "not processed" in str(e)
+    else:
+        raise AssertionError("missing frame went unnoticed")
