@@ -24,9 +24,9 @@
 
 namespace gc {
 
-// warp_fuse_tma.cu: 0 = launched, 1 = not eligible (use the gather kernels below), otherwise an error code
-int warp_fuse_tma(const float *feat, const int32_t *agent_offsets, int n_frames, int total_agents,
-                  const double *theta, int L, int C, int H, int W, int mode, int nmax, float *out, cudaStream_t st);
+// warp_fuse_tile.cu: 0 = launched, 1 = not eligible (use the gather kernels below), otherwise an error code
+int warp_fuse_tile(const float *feat, const int32_t *agent_offsets, int n_frames, int total_agents,
+                   const double *theta, int L, int C, int H, int W, int mode, int nmax, float *out, cudaStream_t st);
 
 // ------------------------------------------------------------------------------------------------
 // Generic fused kernel: grid (ceil(W/32), ceil(H/8), n_frames), block 32x8, one pixel per thread.
@@ -197,11 +197,11 @@ extern "C" int gc_warp_fuse(const float *feat, const int32_t *agent_offsets, int
     if (mode != GC_FUSE_WARP_ONLY)
         GC_REQUIRE(nmax >= 1 && nmax <= kMaxN, GC_EUNSUPPORTED,
                    "gc_warp_fuse: up to %d agents per frame supported (bound %d)", kMaxN, nmax);
-    // fast path: TMA-staged tiles (warp_fuse_tma.cu); GC_WARP_FUSE_GATHER=1 forces the gather kernels
+    // fast path: TMA-staged tiles (warp_fuse_tile.cu); GC_WARP_FUSE_GATHER=1 forces the gather kernels
     const char *env = getenv("GC_WARP_FUSE_GATHER");
     const bool force_gather = env && env[0] == '1';
     if (!force_gather) {
-        const int rc = warp_fuse_tma(feat, agent_offsets, n_frames, total_agents, theta, L, C, H, W, mode, nmax, out, st);
+        const int rc = warp_fuse_tile(feat, agent_offsets, n_frames, total_agents, theta, L, C, H, W, mode, nmax, out, st);
         if (rc != 1) return rc;
     }
     if (mode == GC_FUSE_WARP_ONLY) {
