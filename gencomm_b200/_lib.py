@@ -39,7 +39,7 @@ SIGNATURES = {
                                   c_void_p]),
     "gc_pillar_canvas": (c_int, [c_void_p, c_void_p, c_int, c_int, _GEOM_P, c_void_p, c_void_p, _F3, c_void_p,
                                  c_void_p]),
-    "gc_warp_fuse": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int,
+    "gc_warp_fuse": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int,
                              c_void_p, c_void_p]),
     "gc_normalize_pairwise_tfm": (c_int, [c_void_p, c_int, c_double, c_double, c_double, c_double, c_void_p,
                                           c_void_p]),
@@ -47,9 +47,9 @@ SIGNATURES = {
     "gc_gencomm_device_weight_floats": (c_size_t, [c_int]),
     "gc_gencomm_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "gc_gencomm_sample": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
-                                  c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+                                  c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "gc_unet_forward": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
-                                c_void_p, c_void_p, c_void_p]),
+                                c_int, c_void_p, c_void_p, c_void_p]),
 }
 
 _lib = None

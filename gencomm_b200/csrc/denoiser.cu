@@ -22,6 +22,7 @@
 // boundary tensors; the sampler arithmetic (q_posterior + noise) is fused into conv_out's
 // epilogue, q_sample is one elementwise kernel.  28 launches per step, 0 host syncs.
 #include "common.cuh"
+#include "denoiser_tc.cuh"
 
 namespace gc {
 
@@ -213,8 +214,6 @@ k_conv_c8(const float *__restrict__ in_a, const float *__restrict__ in_b, const 
 // conv_in: cat[cond(2), x_t(C)] (NCHW) -> 8 channels (NHWC8), 3x3 pad 1.  unet.py:315
 // weights: device [C+2][9][8] (cin, tap, cout).
 // ------------------------------------------------------------------------------------------------
-struct Bias8 { float b[8]; };
-
 __global__ void __launch_bounds__(256)
 k_conv_in(const float *__restrict__ cond, const float *__restrict__ x, const float *__restrict__ w, Bias8 bias,
           int C, int H, int W, float *__restrict__ out, float *__restrict__ stats_out) {
@@ -283,8 +282,6 @@ k_conv_in(const float *__restrict__ cond, const float *__restrict__ x, const flo
 //   mode 1 (t  > 0):  x_t <- (c1*x0 + c2*x_t) + sigma*noise        (in place, x_{t-1})
 // weights: device [C][9][8] (cout, tap, cin), bias device [C].  grid.z = agent * (C/64) + split.
 // ------------------------------------------------------------------------------------------------
-struct Affine8 { float gamma[8], beta[8]; };
-
 __global__ void __launch_bounds__(256)
 k_conv_out(const float *__restrict__ in, const float *__restrict__ st_in, int tiles_in,
            const float *__restrict__ w, const float *__restrict__ bias, Affine8 aff, int C, int H, int W, int mode,
@@ -445,12 +442,18 @@ struct HostTail {     // trailing part of the host weight blob, after T * kC8Lay
 // One DiffusionUNet evaluation; the result goes through k_conv_out's epilogue.
 static int unet_eval(cudaStream_t st, int A, int C, int H, int W, const float *cond, UnetWorkspace &ws,
                      const C8Params *prm, const HostTail &tail, const float *w_in, const float *w_out,
-                     const float *b_out, int mode, float c1, float c2, float sigma, const float *noise, float *pred) {
+                     const float *b_out, int mode, float c1, float c2, float sigma, const float *noise, float *pred,
+                     int precision) {
     Act *p = ws.p, *q = ws.q;
     Bias8 bi;
     for (int i = 0; i < 8; ++i) bi.b[i] = tail.conv_in_bias[i];
     const dim3 gridP((W + kTW - 1) / kTW, (H + kTH - 1) / kTH, A);
-    k_conv_in<<<gridP, 256, 0, st>>>(cond, ws.x, w_in, bi, C, H, W, p[0].data, p[0].stats);         // hs[0]
+    if ((precision & GC_PREC_TC_CONV_IN) && conv_in_tc_eligible(C, H, W)) {                        // hs[0], tcgen05
+        p[0].tiles = conv_in_tc_tiles(H, W);
+        if (int rc = conv_in_tc(st, A, cond, ws.x, w_in, bi, C, H, W, p[0].data, p[0].stats)) return rc;
+    } else {
+        k_conv_in<<<gridP, 256, 0, st>>>(cond, ws.x, w_in, bi, C, H, W, p[0].data, p[0].stats);     // hs[0]
+    }
     resblock8(st, A, p[0], p[1], p[2], prm + 0);                                                   // down.0.block.0 -> hs[1]
     resblock8(st, A, p[2], p[3], p[4], prm + 2);                                                   // down.0.block.1 -> hs[2]
     launch_c8<8, false, kDown, kNone>(st, A, p[4], nullptr, nullptr, nullptr, q[0], prm[4]);       // downsample -> hs[3]
@@ -467,10 +470,16 @@ static int unet_eval(cudaStream_t st, int A, int C, int H, int W, const float *c
     resblock16(st, A, p[9], p[0], p[10], p[11], prm + 24);                                         // up.0.block.2  (pops hs[0])
     Affine8 aff;
     for (int i = 0; i < 8; ++i) { aff.gamma[i] = tail.norm_out_gamma[i]; aff.beta[i] = tail.norm_out_beta[i]; }
-    const int splits = (C + 63) / 64;
-    const dim3 gridO(gridP.x, gridP.y, A * splits);
-    k_conv_out<<<gridO, 256, 0, st>>>(p[11].data, p[11].stats, p[11].tiles, w_out, b_out, aff, C, H, W, mode, c1, c2,
-                                      sigma, noise, ws.x, pred);
+    if ((precision & GC_PREC_TC_CONV_OUT) && conv_out_tc_eligible(C, H, W)) {
+        if (int rc = conv_out_tc(st, A, p[11].data, p[11].stats, p[11].tiles, w_out, b_out, aff, C, H, W, mode, c1, c2,
+                                 sigma, noise, ws.x, pred, (precision & GC_PREC_TC_MATERIALIZE) ? 1 : 0))
+            return rc;
+    } else {
+        const int splits = (C + 63) / 64;
+        const dim3 gridO(gridP.x, gridP.y, A * splits);
+        k_conv_out<<<gridO, 256, 0, st>>>(p[11].data, p[11].stats, p[11].tiles, w_out, b_out, aff, C, H, W, mode, c1, c2,
+                                          sigma, noise, ws.x, pred);
+    }
     GC_LAUNCH_CHECK("unet_eval");
     return GC_OK;
 }
@@ -502,8 +511,8 @@ static int check_unet_args(int A, int C, int H, int W, int T) {
 
 // One denoiser evaluation x0 = UNet(cat[cond, x], t) for tests/diagnostics: writes pred [A][C][H][W].
 extern "C" int gc_unet_forward(const float *cond, const float *x, int total_agents, int t_index, const float *w_host,
-                               const float *w_dev, int C, int H, int W, int T, void *workspace, float *pred,
-                               void *stream) {
+                               const float *w_dev, int C, int H, int W, int T, int precision, void *workspace,
+                               float *pred, void *stream) {
     if (int rc = check_unet_args(total_agents, C, H, W, T)) return rc;
     GC_REQUIRE(cond && x && w_host && w_dev && workspace && pred, GC_EINVAL, "gc_unet_forward: null pointer");
     GC_REQUIRE(t_index >= 0 && t_index < T, GC_EINVAL, "gc_unet_forward: bad timestep");
@@ -513,13 +522,14 @@ extern "C" int gc_unet_forward(const float *cond, const float *x, int total_agen
     const C8Params *prm = reinterpret_cast<const C8Params *>(w_host) + (size_t)t_index * kC8Layers;
     const HostTail &tail = *reinterpret_cast<const HostTail *>(reinterpret_cast<const C8Params *>(w_host) + (size_t)T * kC8Layers);
     const float *w_in = w_dev, *w_out = w_dev + (size_t)(C + 2) * 72, *b_out = w_out + (size_t)C * 72;
-    return unet_eval(st, total_agents, C, H, W, cond, ws, prm, tail, w_in, w_out, b_out, 0, 0.f, 0.f, 0.f, nullptr, pred);
+    return unet_eval(st, total_agents, C, H, W, cond, ws, prm, tail, w_in, w_out, b_out, 0, 0.f, 0.f, 0.f, nullptr, pred,
+                     precision);
 }
 
 extern "C" int gc_gencomm_sample(const float *feat, const float *cond, const int32_t *agent_offsets, int n_frames,
                                  int total_agents, const float *noise0, const float *step_noise,
                                  const float *w_host, const float *w_dev, const float *schedule_host, int C, int H,
-                                 int W, int T, void *workspace, float *pred, void *stream) {
+                                 int W, int T, int precision, void *workspace, float *pred, void *stream) {
     if (int rc = check_unet_args(total_agents, C, H, W, T)) return rc;
     GC_REQUIRE(feat && cond && agent_offsets && noise0 && w_host && w_dev && schedule_host && workspace && pred,
                GC_EINVAL, "gc_gencomm_sample: null pointer");
@@ -542,7 +552,7 @@ extern "C" int gc_gencomm_sample(const float *feat, const float *cond, const int
         const float *s = schedule_host + (size_t)t * 5;
         const float *nz = t > 0 ? step_noise + (size_t)(T - 1 - t) * total_agents * per_agent : nullptr;
         int rc = unet_eval(st, total_agents, C, H, W, cond, ws, prm, tail, w_in, w_out, b_out, t > 0 ? 1 : 0, s[2], s[3],
-                           s[4], nz, pred);
+                           s[4], nz, pred, precision);
         if (rc) return rc;
     }
     return GC_OK;

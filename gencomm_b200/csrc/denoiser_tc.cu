@@ -1,0 +1,469 @@
+// tcgen05 (5th-gen tensor core) implicit-GEMM kernels for the two GEMM-shaped layers of the GenComm
+// denoiser: conv_in ((C+2) -> 8, K = 9(C+2)) and norm_out+swish+conv_out (8 -> C, K = 72), which carry
+// 63 % of the denoiser FLOPs.  bf16 operands, fp32 accumulation in TMEM.
+//
+// Reference semantics: models/gencomm_modules/unet.py:315 (conv_in), :341-343 (norm_out, swish,
+// conv_out); the sampler update fused into conv_out's epilogue is cond_diff.py:272-279, :310-313.
+//
+// Implicit GEMM without im2col.  D[M = 128 pixels of one image row, N] += A[M, K] * B[K, N].
+// A is the activation row in "NHWC8 bf16" form in shared memory: pixel p = 16 bytes = 8 channels, which
+// is exactly one row of a K-major no-swizzle UMMA core matrix (8 rows x 16 bytes, rows 16 bytes apart).
+// With SBO = 128 B the 16 row-groups of an M = 128 operand are 128 consecutive pixels, so the A operand
+// of tap (ky, kx) is simply the staged row y+ky-1 starting at pixel x0+kx-1: a descriptor whose start
+// address is shifted by kx * 16 bytes.  The two K core matrices of one K = 16 MMA are
+//   * conv_in : two 8-channel groups at the same tap        (LBO = distance between channel-group planes)
+//   * conv_out: taps kx and kx+1 of the same row            (LBO = 16 B: the next pixel; the fourth
+//               "tap" kx = 3 of each row has zero weights, K = 3 * 32 = 96)
+// so the staged rows are read in place by the tensor core for all nine taps.
+//
+// One elected thread issues tcgen05.mma; completion is tracked with tcgen05.commit -> mbarrier; the
+// epilogue reads TMEM with tcgen05.ld.32x32b (lane = pixel, so per-channel global stores are coalesced).
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+#include "denoiser_tc.cuh"
+
+namespace gc {
+namespace tc {
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// K-major, SWIZZLE_NONE shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, version 1)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = (uint64_t)((saddr >> 4) & 0x3FFFu);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+    d |= 1ull << 46;
+    return d;
+}
+// kind::f16 instruction descriptor: D = f32, A = B = bf16, both K-major, dense
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t"
+        "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+template <int COLS>
+__device__ __forceinline__ void tmem_alloc(uint32_t *slot) {   // one full warp
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "n"(COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_free(uint32_t base) {     // the same warp
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(base), "n"(COLS) : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
+    uint32_t r[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);   // .x = lo (low 16 bits), .y = hi
+    return *reinterpret_cast<const uint32_t *>(&h);
+}
+__device__ __forceinline__ uint4 pack8(const float (&v)[8]) {
+    return make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+}
+__device__ __forceinline__ float swish(float v) { return __fdividef(v, 1.0f + __expf(-v)); }
+
+// GroupNorm(4 groups of 2 channels) coefficients of one 8-channel NHWC8 tensor from per-tile partial sums
+// (same arithmetic as gn_coeff<8> in denoiser.cu: fixed order, float64).
+__device__ __forceinline__ void gn_coeff8(int c, int agent, const float *__restrict__ st, int tiles, int hw, float gamma,
+                                          float beta, float *ga, float *gb) {
+    st += (size_t)agent * tiles * 8;
+    const int p = c >> 1;
+    double s = 0.0, ss = 0.0;
+    for (int t = 0; t < tiles; ++t) { s += st[t * 8 + 2 * p]; ss += st[t * 8 + 2 * p + 1]; }
+    const double cnt = (double)hw * 2.0;
+    const double mean = s / cnt;
+    double var = ss / cnt - mean * mean;
+    var = var < 0.0 ? 0.0 : var;
+    const double rstd = 1.0 / sqrt(var + 1e-6);
+    *ga = (float)((double)gamma * rstd);
+    *gb = (float)((double)beta - mean * (double)gamma * rstd);
+}
+
+// ------------------------------------------------------------------------------------------------
+// norm_out + swish + conv_out on tensor cores.  grid = (W/128, H, A * C/NT), 128 threads.
+//   in  [A][H][W][8] f32 (NHWC8) + GroupNorm partial sums;  w [C][9][8] f32 (cout, tap, cin); bias [C]
+//   mode 0: pred = x0;  mode 1: x <- (c1*x0 + c2*x) + sigma*noise   (NCHW f32)
+// ------------------------------------------------------------------------------------------------
+constexpr int kOutRowPx = 132;   // staged pixels per row: x0-1 .. x0+130 (taps kx = 0..3 of pixel 127 reach 130)
+
+template <int NT>
+__global__ void __launch_bounds__(128)
+k_conv_out_tc(const float *__restrict__ in, const float *__restrict__ st_in, int tiles_in, const float *__restrict__ w,
+              const float *__restrict__ bias, Affine8 aff, int C, int H, int W, int mode, float c1, float c2, float sigma,
+              const float *__restrict__ noise, float *__restrict__ x, float *__restrict__ pred, int materialize) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    // [B: 12 k-chunks][NT rows][16 B]  |  [A rows: 3][132 px][16 B]  |  [A materialised: 12][128][16 B] (debug mode)
+    uint4 *b_s = reinterpret_cast<uint4 *>(smem);
+    uint4 *a_rows = b_s + 12 * NT;
+    uint4 *a_mat = a_rows + 3 * kOutRowPx;
+    __shared__ float s_ga[8], s_gb[8], s_bias[NT];
+    __shared__ __align__(8) uint64_t s_bar;
+    __shared__ uint32_t s_tmem;
+
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int splits = C / NT;
+    const int agent = blockIdx.z / splits, co0 = (blockIdx.z % splits) * NT;
+    const int x0 = blockIdx.x * 128, y = blockIdx.y;
+
+    if (warp == 0) tmem_alloc<NT>(&s_tmem);
+    if (tid == 32) { mbar_init(smem_u32(&s_bar), 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    if (tid >= 64 && tid < 72) {
+        const int c = tid - 64;
+        gn_coeff8(c, agent, st_in, tiles_in, H * W, aff.gamma[c], aff.beta[c], &s_ga[c], &s_gb[c]);
+    }
+    for (int i = tid; i < NT; i += 128) s_bias[i] = __ldg(bias + co0 + i);
+    // ---- B operand: weights -> bf16, K-major core matrices; k-chunk kc = ky*4 + kx, kx == 3 is zero ----
+    for (int i = tid; i < 12 * NT; i += 128) {
+        const int n = i % NT, kc = i / NT, ky = kc >> 2, kx = kc & 3;
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (kx < 3) {
+            const float4 *src = reinterpret_cast<const float4 *>(w + ((size_t)(co0 + n) * 9 + ky * 3 + kx) * 8);
+            const float4 lo = __ldg(src), hi = __ldg(src + 1);
+            v = make_uint4(pack_bf16(lo.x, lo.y), pack_bf16(lo.z, lo.w), pack_bf16(hi.x, hi.y), pack_bf16(hi.z, hi.w));
+        }
+        b_s[kc * NT + n] = v;
+    }
+    __syncthreads();
+    // ---- A rows: GroupNorm + swish -> bf16; zero outside the image (padding applies AFTER the activation) ----
+    for (int i = tid; i < 3 * kOutRowPx; i += 128) {
+        const int r = i / kOutRowPx, px = i % kOutRowPx;
+        const int gy = y - 1 + r, gx = x0 - 1 + px;
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (px < 130 && gy >= 0 && gy < H && gx >= 0 && gx < W) {
+            const float4 *src = reinterpret_cast<const float4 *>(in + (((size_t)agent * H + gy) * W + gx) * 8);
+            const float4 lo = __ldg(src), hi = __ldg(src + 1);
+            float f[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+#pragma unroll
+            for (int c = 0; c < 8; ++c) f[c] = swish(fmaf(f[c], s_ga[c], s_gb[c]));
+            v = pack8(f);
+        }
+        a_rows[i] = v;
+    }
+    if (materialize) {   // debug/validation variant: explicit im2col blocks, no overlapping operand windows
+        __syncthreads();
+        for (int kc = 0; kc < 12; ++kc) a_mat[kc * 128 + tid] = a_rows[(kc >> 2) * kOutRowPx + tid + (kc & 3)];
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = s_tmem;
+
+    if (tid == 0) {
+        constexpr uint32_t idesc = make_idesc(128, NT);
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {   // K = 16 slices: row ky = j/2, taps kx = 2*(j%2), 2*(j%2)+1
+            const uint64_t adesc = materialize
+                ? make_desc(smem_u32(a_mat + (2 * j) * 128), 2048u, 128u)
+                : make_desc(smem_u32(a_rows + (j >> 1) * kOutRowPx + (j & 1) * 2), 16u, 128u);
+            const uint64_t bdesc = make_desc(smem_u32(b_s + (2 * j) * NT), (uint32_t)NT * 16u, 128u);
+            mma_bf16(tmem, adesc, bdesc, idesc, j > 0 ? 1u : 0u);
+        }
+        mma_commit(smem_u32(&s_bar));
+    }
+    mbar_wait(smem_u32(&s_bar), 0u);
+    tc_fence_after();
+
+    // ---- epilogue: lane = pixel; 16 channels per TMEM load; per-channel stores are 128 B per warp ----
+    const size_t plane = (size_t)H * W;
+    size_t idx = ((size_t)agent * C + co0) * plane + (size_t)y * W + x0 + tid;
+    const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
+#pragma unroll 1
+    for (int c0 = 0; c0 < NT; c0 += 16) {
+        float v[16];
+        tmem_ld16(taddr + (uint32_t)c0, v);
+        if (mode == 0) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) pred[idx + (size_t)i * plane] = v[i] + s_bias[c0 + i];
+        } else {
+            float xv[16], nz[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) { xv[i] = x[idx + (size_t)i * plane]; nz[i] = __ldg(noise + idx + (size_t)i * plane); }
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const float mean = __fadd_rn(__fmul_rn(c1, v[i] + s_bias[c0 + i]), __fmul_rn(c2, xv[i]));
+                x[idx + (size_t)i * plane] = __fadd_rn(mean, __fmul_rn(sigma, nz[i]));
+            }
+        }
+        idx += 16 * plane;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_free<NT>(tmem);
+}
+
+// ------------------------------------------------------------------------------------------------
+// conv_in on tensor cores: cat[cond(2), x_t(C)] (NCHW f32) -> 8 channels (NHWC8 f32) + GroupNorm partial sums.
+// grid = (W/128, ceil(H/4), A), 128 threads.  K is walked in chunks of 16 input channels (two 8-channel
+// groups; GEMM channel order = x_0..x_{C-1}, cond_0, cond_1, zero padding), double buffered: while the
+// tensor core consumes chunk q (9 taps x 4 rows = 36 MMAs of 128 x 16 x 16) the threads stage chunk q+1.
+// M = 128 needs N % 16 == 0: the B descriptor uses SBO = 0, so output columns 8..15 alias 0..7 and are ignored.
+//   w [C+2][9][8] f32 (cin in the reference's cat order, tap, cout)
+// ------------------------------------------------------------------------------------------------
+constexpr int kInRows = 4;                 // output rows per CTA
+constexpr int kInStaged = kInRows + 2;     // staged input rows
+constexpr int kInRowPx = 130;              // x0-1 .. x0+128
+constexpr int kInGroupU4 = kInStaged * kInRowPx;   // uint4 per channel group per buffer
+
+__global__ void __launch_bounds__(128)
+k_conv_in_tc(const float *__restrict__ cond, const float *__restrict__ x, const float *__restrict__ w, Bias8 bias, int C,
+             int H, int W, float *__restrict__ out, float *__restrict__ stats_out) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    // [A: 2 buffers][2 groups][6 rows][130 px][16 B]  |  [B: chunks][9 taps][2 groups][8 cout][16 B]
+    uint4 *a_s = reinterpret_cast<uint4 *>(smem);
+    uint4 *b_s = a_s + 2 * 2 * kInGroupU4;
+    __shared__ __align__(8) uint64_t s_empty[2], s_done;
+    __shared__ uint32_t s_tmem;
+    __shared__ float s_part[4][8];
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int agent = blockIdx.z, x0 = blockIdx.x * 128, y0 = blockIdx.y * kInRows;
+    const int groups = C / 8 + 1, chunks = (groups + 1) / 2;
+    const size_t plane = (size_t)H * W;
+
+    if (warp == 0) tmem_alloc<64>(&s_tmem);
+    if (tid == 32) {
+        mbar_init(smem_u32(&s_empty[0]), 1); mbar_init(smem_u32(&s_empty[1]), 1); mbar_init(smem_u32(&s_done), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // ---- B operand for every chunk: [q][tap][gsel][n] = 8 consecutive GEMM channels of output n ----
+    for (int i = tid; i < chunks * 9 * 2 * 8; i += 128) {
+        const int n = i & 7, gsel = (i >> 3) & 1, tap = (i >> 4) % 9, q = (i >> 4) / 9;
+        const int g = 2 * q + gsel;
+        float f[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const int kc = 8 * g + c;                       // GEMM channel
+            const int cin = kc < C ? kc + 2 : kc - C;       // reference channel (cond first)
+            f[c] = kc < C + 2 ? __ldg(w + ((size_t)cin * 9 + tap) * 8 + n) : 0.0f;
+        }
+        b_s[i] = pack8(f);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = s_tmem;
+    const uint32_t a_base = smem_u32(a_s), b_base = smem_u32(b_s);
+    constexpr uint32_t idesc = make_idesc(128, 16);
+    constexpr uint32_t kGroupBytes = kInGroupU4 * 16u, kBufBytes = 2u * kGroupBytes;
+
+    for (int q = 0; q < chunks; ++q) {
+        const int b = q & 1;
+        if (q >= 2) mbar_wait(smem_u32(&s_empty[b]), (uint32_t)((q >> 1) - 1) & 1u);   // MMAs of chunk q-2 retired
+        uint4 *buf = a_s + b * 2 * kInGroupU4;
+        // ---- stage chunk q: thread = pixel column, all 6 rows, both channel groups ----
+        for (int px = tid; px < kInRowPx; px += 128) {
+            const int gx = x0 - 1 + px;
+            const bool xin = gx >= 0 && gx < W;
+#pragma unroll
+            for (int gsel = 0; gsel < 2; ++gsel) {
+                const int g = 2 * q + gsel;
+#pragma unroll
+                for (int r = 0; r < kInStaged; ++r) {
+                    const int gy = y0 - 1 + r;
+                    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+                    if (xin && gy >= 0 && gy < H && g < groups) {
+                        const size_t pix = (size_t)gy * W + gx;
+                        float f[8];
+                        if (g < C / 8) {
+                            const float *src = x + ((size_t)agent * C + 8 * g) * plane + pix;
+#pragma unroll
+                            for (int c = 0; c < 8; ++c) f[c] = __ldg(src + (size_t)c * plane);
+                        } else {
+                            const float *src = cond + (size_t)agent * 2 * plane + pix;
+                            f[0] = __ldg(src); f[1] = __ldg(src + plane);
+#pragma unroll
+                            for (int c = 2; c < 8; ++c) f[c] = 0.0f;
+                        }
+                        v = pack8(f);
+                    }
+                    buf[(gsel * kInStaged + r) * kInRowPx + px] = v;
+                }
+            }
+        }
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+            const uint32_t a_buf = a_base + (uint32_t)b * kBufBytes;
+#pragma unroll 1
+            for (int tap = 0; tap < 9; ++tap) {
+                const int ky = tap / 3, kx = tap % 3;
+                const uint64_t bdesc = make_desc(b_base + (uint32_t)((q * 9 + tap) * 2) * 128u, 128u, 0u);
+#pragma unroll
+                for (int r = 0; r < kInRows; ++r) {
+                    const uint64_t adesc = make_desc(a_buf + (uint32_t)((r + ky) * kInRowPx + kx) * 16u, kGroupBytes, 128u);
+                    mma_bf16(tmem + (uint32_t)(r * 16), adesc, bdesc, idesc, (q > 0 || tap > 0) ? 1u : 0u);
+                }
+            }
+            mma_commit(smem_u32(&s_empty[b]));
+            if (q == chunks - 1) mma_commit(smem_u32(&s_done));
+        }
+    }
+    mbar_wait(smem_u32(&s_done), 0u);
+    tc_fence_after();
+
+    // ---- epilogue: thread = pixel; bias, NHWC8 store, GroupNorm partial sums of the tile ----
+    const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
+    float q8[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) q8[i] = 0.0f;
+#pragma unroll
+    for (int r = 0; r < kInRows; ++r) {
+        float v[8];
+        tmem_ld8(taddr + (uint32_t)(r * 16), v);
+        const int yy = y0 + r;
+        if (yy < H) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] += bias.b[i];
+            float4 *dst = reinterpret_cast<float4 *>(out + (((size_t)agent * H + yy) * W + x0 + tid) * 8);
+            dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+            dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+#pragma unroll
+            for (int p = 0; p < 4; ++p) {
+                q8[2 * p] += v[2 * p] + v[2 * p + 1];
+                q8[2 * p + 1] += v[2 * p] * v[2 * p] + v[2 * p + 1] * v[2 * p + 1];
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) q8[i] += __shfl_xor_sync(0xffffffffu, q8[i], m);
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s_part[warp][i] = q8[i];
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (tid < 8) {
+        const float t = (s_part[0][tid] + s_part[1][tid]) + (s_part[2][tid] + s_part[3][tid]);
+        const int tiles = gridDim.x * gridDim.y, tile = blockIdx.y * gridDim.x + blockIdx.x;
+        stats_out[((size_t)agent * tiles + tile) * 8 + tid] = t;
+    }
+    if (warp == 0) tmem_free<64>(tmem);
+}
+
+}  // namespace tc
+
+// ------------------------------------------------------------------------------------------------
+// host launchers (called from denoiser.cu)
+// ------------------------------------------------------------------------------------------------
+bool conv_in_tc_eligible(int C, int H, int W) {
+    (void)H;
+    if (W % 128 != 0 || C % 8 != 0 || C < 8) return false;
+    const int chunks = (C / 8 + 1 + 1) / 2;
+    const size_t smem = (size_t)2 * 2 * tc::kInGroupU4 * 16 + (size_t)chunks * 9 * 2 * 128;
+    return smem <= 200 * 1024;
+}
+
+int conv_in_tc_tiles(int H, int W) { return (W / 128) * ((H + tc::kInRows - 1) / tc::kInRows); }
+
+int conv_in_tc(cudaStream_t st, int A, const float *cond, const float *x, const float *w, const Bias8 &bias, int C, int H,
+               int W, float *out, float *stats_out) {
+    const int chunks = (C / 8 + 1 + 1) / 2;
+    const size_t smem = (size_t)2 * 2 * tc::kInGroupU4 * 16 + (size_t)chunks * 9 * 2 * 128;
+    static size_t configured = 0;
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(tc::k_conv_in_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { (void)cudaGetLastError(); set_error("k_conv_in_tc: cudaFuncSetAttribute failed (%d)", (int)e); return (int)e; }
+        configured = smem;
+    }
+    const dim3 grid(W / 128, (H + tc::kInRows - 1) / tc::kInRows, A);
+    tc::k_conv_in_tc<<<grid, 128, smem, st>>>(cond, x, w, bias, C, H, W, out, stats_out);
+    GC_LAUNCH_CHECK("k_conv_in_tc");
+    return GC_OK;
+}
+
+static int pick_nt(int C) {
+    if (C % 256 == 0) return 256;
+    if (C % 128 == 0) return 128;
+    if (C % 64 == 0) return 64;
+    return 0;
+}
+
+bool conv_out_tc_eligible(int C, int H, int W) {
+    (void)H;
+    return W % 128 == 0 && pick_nt(C) != 0;
+}
+
+template <int NT>
+static int launch_out(cudaStream_t st, int A, const float *in, const float *st_in, int tiles_in, const float *w,
+                      const float *bias, const Affine8 &aff, int C, int H, int W, int mode, float c1, float c2, float sigma,
+                      const float *noise, float *x, float *pred, int materialize) {
+    const size_t smem = (size_t)12 * NT * 16 + (size_t)3 * tc::kOutRowPx * 16 + (size_t)12 * 128 * 16;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(tc::k_conv_out_tc<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { (void)cudaGetLastError(); set_error("k_conv_out_tc: cudaFuncSetAttribute failed (%d)", (int)e); return (int)e; }
+        configured = true;
+    }
+    const dim3 grid(W / 128, H, A * (C / NT));
+    tc::k_conv_out_tc<NT><<<grid, 128, smem, st>>>(in, st_in, tiles_in, w, bias, aff, C, H, W, mode, c1, c2, sigma, noise, x,
+                                                   pred, materialize);
+    GC_LAUNCH_CHECK("k_conv_out_tc");
+    return GC_OK;
+}
+
+int conv_out_tc(cudaStream_t st, int A, const float *in, const float *st_in, int tiles_in, const float *w, const float *bias,
+                const Affine8 &aff, int C, int H, int W, int mode, float c1, float c2, float sigma, const float *noise,
+                float *x, float *pred, int materialize) {
+    switch (pick_nt(C)) {
+        case 256: return launch_out<256>(st, A, in, st_in, tiles_in, w, bias, aff, C, H, W, mode, c1, c2, sigma, noise, x, pred, materialize);
+        case 128: return launch_out<128>(st, A, in, st_in, tiles_in, w, bias, aff, C, H, W, mode, c1, c2, sigma, noise, x, pred, materialize);
+        case 64: return launch_out<64>(st, A, in, st_in, tiles_in, w, bias, aff, C, H, W, mode, c1, c2, sigma, noise, x, pred, materialize);
+        default: break;
+    }
+    set_error("conv_out_tc: unsupported channel count %d", C);
+    return GC_EUNSUPPORTED;
+}
+
+}  // namespace gc

@@ -178,7 +178,7 @@ static int launch_fuse(int nmax, dim3 grid, dim3 block, cudaStream_t st, const f
 using namespace gc;
 
 extern "C" int gc_warp_fuse(const float *feat, const int32_t *agent_offsets, int n_frames, int total_agents,
-                            const double *theta, int L, int C, int H, int W, int mode, float *out, void *stream) {
+                            int max_agents_per_frame, const double *theta, int L, int C, int H, int W, int mode, float *out, void *stream) {
     GC_REQUIRE(n_frames >= 0 && total_agents >= 0 && L > 0 && C > 0 && H > 0 && W > 0, GC_EINVAL,
                "gc_warp_fuse: bad sizes");
     GC_REQUIRE(mode == GC_FUSE_WARP_ONLY || mode == GC_FUSE_MAX || mode == GC_FUSE_ATT, GC_EINVAL,
@@ -194,6 +194,7 @@ extern "C" int gc_warp_fuse(const float *feat, const int32_t *agent_offsets, int
     // compile-time agent bound: every frame has >= 1 agent and at most L
     int nmax = total_agents - (n_frames - 1);
     if (nmax > L) nmax = L;
+    if (max_agents_per_frame > 0 && max_agents_per_frame < nmax) nmax = max_agents_per_frame;   // caller's bound
     if (mode != GC_FUSE_WARP_ONLY)
         GC_REQUIRE(nmax >= 1 && nmax <= kMaxN, GC_EUNSUPPORTED,
                    "gc_warp_fuse: up to %d agents per frame supported (bound %d)", kMaxN, nmax);

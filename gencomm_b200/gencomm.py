@@ -192,6 +192,7 @@ class DiffusionUNet(nn.Module):
         self.norm_out = _gn(8)
         self.conv_out = nn.Conv2d(8, m.out_ch, 3, 1, 1)
         self._packed = None
+        self.precision = ops.PREC_BF16_TC   # see GenComm.precision
 
     def packed(self, T, device):
         """(host blob, device blob) for T steps, rebuilt when any parameter changes."""
@@ -208,7 +209,7 @@ class DiffusionUNet(nn.Module):
         T = max(tv + 1, 3)
         host, dev = self.packed(T, x.device)
         cond, xt = x[:, :2].contiguous(), x[:, 2:].contiguous()
-        return ops.unet_forward(cond, xt, tv, host, dev, T)
+        return ops.unet_forward(cond, xt, tv, host, dev, T, precision=self.precision)
 
 
 class GenComm(nn.Module):
@@ -216,6 +217,10 @@ class GenComm(nn.Module):
 
     Extension: ``forward(..., noise=(noise0, [step noises]))`` injects pre-drawn Gaussian noise (parity tests);
     by default it is drawn on the device with ``torch.randn`` in the reference's order.
+
+    ``precision``: ``'bf16'`` (default) runs conv_in / conv_out as bf16 tcgen05 implicit GEMMs with fp32
+    accumulation where the shape allows (W % 128 == 0, C % 64 == 0) and everything else in fp32;
+    ``'fp32'`` keeps every layer in fp32 (parity path, <= 1e-4 of the reference).
     """
 
     def __init__(self, model_cfg):
@@ -229,6 +234,16 @@ class GenComm(nn.Module):
         for k, v in buf.items():
             self.register_buffer(k, v)
         self._ws = None
+
+    @property
+    def precision(self):
+        return 'fp32' if self.denoiser.precision == ops.PREC_F32 else 'bf16'
+
+    @precision.setter
+    def precision(self, value):
+        if isinstance(value, str):
+            value = {'fp32': ops.PREC_F32, 'bf16': ops.PREC_BF16_TC}[value]
+        self.denoiser.precision = int(value)
 
     def forward(self, spatial_features, conditions, record_len=None, noise=None):
         if self.training:
@@ -254,7 +269,7 @@ class GenComm(nn.Module):
         if self._ws is None or self._ws.numel() < ws_bytes or self._ws.device != dev:
             self._ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         pred = ops.gencomm_sample(x, conditions.contiguous(), off, n0.contiguous(), steps.contiguous(), host, wdev,
-                                  self._table, T, self._ws)
+                                  self._table, T, self._ws, precision=self.denoiser.precision)
         out = {'pred_feature': pred}
         if t1n is not None:   # visualisation-only samples of the first frame's ego (cond_diff.py:368-371)
             ego = x[:1]

@@ -271,10 +271,18 @@ def warp_affine_simple(src, M, dsize, mode='bilinear', padding_mode='zeros', ali
     return ops.warp_fuse(src.contiguous(), off, theta, ops.FUSE_WARP_ONLY)
 
 
+def _max_agents(record_len):
+    """Host-side bound on the agents per frame when record_len lives on the host (no device read-back)."""
+    if isinstance(record_len, torch.Tensor):
+        return int(record_len.max()) if record_len.device.type == "cpu" and record_len.numel() else 0
+    rl = np.asarray(record_len)
+    return int(rl.max()) if rl.size else 0
+
+
 def _fuse(x, record_len, affine_matrix, mode):
     off = _as_offsets(record_len, x.device)
     theta = affine_matrix if affine_matrix.dtype == torch.float64 else affine_matrix.double()
-    return ops.warp_fuse(x.contiguous(), off, theta.contiguous(), mode)
+    return ops.warp_fuse(x.contiguous(), off, theta.contiguous(), mode, max_agents=_max_agents(record_len))
 
 
 def warp_feature(x, record_len, affine_matrix):

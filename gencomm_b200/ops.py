@@ -12,6 +12,8 @@ import torch
 from . import _lib
 
 FUSE_WARP_ONLY, FUSE_MAX, FUSE_ATT = 0, 1, 2
+# denoiser arithmetic (include/gencomm_b200.h GC_PREC_*)
+PREC_F32, PREC_TC_CONV_IN, PREC_TC_CONV_OUT, PREC_BF16_TC, PREC_TC_MATERIALIZE = 0, 1, 2, 3, 4
 MAX_POINTS_PER_PILLAR = 32
 MAX_AGENTS_PER_FRAME = 8
 
@@ -219,8 +221,10 @@ def agent_offsets_from_record_len(record_len):
     return off
 
 
-def warp_fuse(feat, agent_offsets, theta, mode, out=None):
-    """feat [sumN,C,H,W] f32; agent_offsets [B+1] i32; theta [B,L,L,2,3] f64 -> [B,C,H,W] (or [sumN,...])."""
+def warp_fuse(feat, agent_offsets, theta, mode, out=None, max_agents=0):
+    """feat [sumN,C,H,W] f32; agent_offsets [B+1] i32; theta [B,L,L,2,3] f64 -> [B,C,H,W] (or [sumN,...]).
+    max_agents: host-side upper bound on the agents of any one frame (0 = unknown), lets the library pick the
+    kernel specialisation without reading record_len back from the device."""
     lib = _lib.load()
     _chk(feat, "feat", torch.float32, 4)
     _chk(agent_offsets, "agent_offsets", torch.int32, 1)
@@ -237,7 +241,7 @@ def warp_fuse(feat, agent_offsets, theta, mode, out=None):
         _chk(out, "out", torch.float32, 4)
         if tuple(out.shape) != (lead, C, H, W):
             raise ValueError("warp_fuse: bad output shape")
-    _lib.check(lib.gc_warp_fuse(_ptr(feat), _ptr(agent_offsets), n_frames, total, _ptr(theta), L, C, H, W, int(mode),
+    _lib.check(lib.gc_warp_fuse(_ptr(feat), _ptr(agent_offsets), n_frames, total, int(max_agents), _ptr(theta), L, C, H, W, int(mode),
                                 _ptr(out), _stream()), "gc_warp_fuse")
     return out
 
@@ -256,7 +260,7 @@ def _check_blobs(lib, w_host, w_dev, C, T):
         raise ValueError("packed denoiser weights do not match (C, T)")
 
 
-def unet_forward(cond, x, t_index, w_host, w_dev, T, workspace=None):
+def unet_forward(cond, x, t_index, w_host, w_dev, T, workspace=None, precision=0):
     """pred = UNet(cat[cond, x], t_index) for all agents; cond [A,2,H,W], x [A,C,H,W] f32."""
     lib = _lib.load()
     _chk(cond, "cond", torch.float32, 4)
@@ -270,11 +274,12 @@ def unet_forward(cond, x, t_index, w_host, w_dev, T, workspace=None):
         workspace = torch.empty(lib.gc_gencomm_workspace_bytes(A, C, H, W), dtype=torch.uint8, device=x.device)
     pred = torch.empty_like(x)
     _lib.check(lib.gc_unet_forward(_ptr(cond), _ptr(x), A, int(t_index), _host_ptr(w_host), _ptr(w_dev), C, H, W, int(T),
-                                   _ptr(workspace), _ptr(pred), _stream()), "gc_unet_forward")
+                                   int(precision), _ptr(workspace), _ptr(pred), _stream()), "gc_unet_forward")
     return pred
 
 
-def gencomm_sample(feat, cond, agent_offsets, noise0, step_noise, w_host, w_dev, schedule, T, workspace=None, out=None):
+def gencomm_sample(feat, cond, agent_offsets, noise0, step_noise, w_host, w_dev, schedule, T, workspace=None, out=None,
+                   precision=0):
     """GenComm eval sampler; feat [sumN,C,H,W], cond [sumN,2,H,W], noise0 like feat, step_noise [>=T-1,sumN,C,H,W]."""
     lib = _lib.load()
     _chk(feat, "feat", torch.float32, 4)
@@ -298,6 +303,7 @@ def gencomm_sample(feat, cond, agent_offsets, noise0, step_noise, w_host, w_dev,
         out = torch.empty_like(feat)
     _lib.check(lib.gc_gencomm_sample(_ptr(feat), _ptr(cond), _ptr(agent_offsets), agent_offsets.numel() - 1, A,
                                      _ptr(noise0), _ptr(step_noise) if T > 1 else None, _host_ptr(w_host), _ptr(w_dev),
-                                     _host_ptr(schedule), C, H, W, int(T), _ptr(workspace), _ptr(out), _stream()),
+                                     _host_ptr(schedule), C, H, W, int(T), int(precision), _ptr(workspace), _ptr(out),
+                                     _stream()),
                "gc_gencomm_sample")
     return out

@@ -80,7 +80,7 @@ class FramePipeline:
         theta = ops.normalize_pairwise_tfm(pairwise, self.Hm, self.Wm, 1.0)
         if events:
             events[0].record()
-        ops.warp_fuse(feat, self.agent_offsets, theta, self.mode, out=self.fused)
+        ops.warp_fuse(feat, self.agent_offsets, theta, self.mode, out=self.fused, max_agents=self.N)
         if events:
             events[1].record()
         return self.fused

@@ -38,6 +38,15 @@ extern "C" {
 #define GC_FUSE_MAX 1       /* MaxFusion */
 #define GC_FUSE_ATT 2       /* AttFusion (ego row of the per-pixel attention) */
 
+/* Denoiser arithmetic (bit mask).  0 = every layer in fp32 on CUDA cores (parity path, <= 1e-4 of the
+ * fp32 reference).  The TC bits run the GEMM-shaped layers as bf16 tcgen05 implicit GEMMs with fp32
+ * accumulation in TMEM where the shape is eligible (W % 128 == 0, C % 64 == 0), fp32 otherwise. */
+#define GC_PREC_F32 0
+#define GC_PREC_TC_CONV_IN 1   /* conv_in  ((C+2) -> 8, K = 9(C+2)) */
+#define GC_PREC_TC_CONV_OUT 2  /* norm_out + swish + conv_out (8 -> C, K = 72) */
+#define GC_PREC_BF16_TC 3      /* both */
+#define GC_PREC_TC_MATERIALIZE 4 /* validation: explicit im2col operand instead of overlapping windows */
+
 int gc_version(void);
 const char *gc_last_error(void);
 
@@ -126,6 +135,7 @@ int gc_pillar_canvas(const float *points, const int32_t *point_offsets, int n_ag
  *   padding, align_corners=False).
  * ------------------------------------------------------------------------------------------- */
 int gc_warp_fuse(const float *feat, const int32_t *agent_offsets, int n_frames, int total_agents,
+                 int max_agents_per_frame /* host-side upper bound on any record_len entry; <= 0: unknown (L is used) */,
                  const double *theta, int L, int C, int H, int W, int mode, float *out, void *stream);
 
 /* (a5) normalize_pairwise_tfm (utils/transformation_utils.py:68-92):
@@ -163,12 +173,13 @@ size_t gc_gencomm_workspace_bytes(int total_agents, int C, int H, int W);
 int gc_gencomm_sample(const float *feat, const float *cond, const int32_t *agent_offsets, int n_frames,
                       int total_agents, const float *noise0, const float *step_noise,
                       const float *w_host /*[host]*/, const float *w_dev, const float *schedule_host /*[host]*/,
-                      int C, int H, int W, int T, void *workspace, float *pred, void *stream);
+                      int C, int H, int W, int T, int precision /* GC_PREC_* */, void *workspace, float *pred,
+                      void *stream);
 
 /* One denoiser evaluation pred = UNet(cat[cond, x], t_index) for all agents (diagnostics / tests). */
 int gc_unet_forward(const float *cond, const float *x, int total_agents, int t_index,
                     const float *w_host /*[host]*/, const float *w_dev, int C, int H, int W, int T,
-                    void *workspace, float *pred, void *stream);
+                    int precision /* GC_PREC_* */, void *workspace, float *pred, void *stream);
 
 #ifdef __cplusplus
 }

@@ -61,10 +61,10 @@ def main():
             lead = F * N if mode == ops.FUSE_WARP_ONLY else F
             out = torch.empty(lead, C, H, W, device="cuda")
             os.environ["GC_WARP_FUSE_GATHER"] = "0"
-            t_tile = timeit(lambda: ops.warp_fuse(feat, off, theta, mode, out=out))
+            t_tile = timeit(lambda: ops.warp_fuse(feat, off, theta, mode, out=out, max_agents=N))
             res_tile = out.clone()
             os.environ["GC_WARP_FUSE_GATHER"] = "1"
-            t_gather = timeit(lambda: ops.warp_fuse(feat, off, theta, mode, out=out), iters=3, warm=1)
+            t_gather = timeit(lambda: ops.warp_fuse(feat, off, theta, mode, out=out, max_agents=N), iters=3, warm=1)
             diff = (res_tile - out).abs().max().item()
             os.environ["GC_WARP_FUSE_GATHER"] = "0"
             nbytes = 4 * F * N * C * H * W + 4 * lead * C * H * W

@@ -32,7 +32,7 @@ def test_argument_errors_are_reported_without_a_gpu():
     geom = ops.make_geom([-1, -1, -1, 1, 1, 1], [0.5, 0.5, 2], 100, max_points=16)   # unsupported max_points
     rc = lib.gc_voxelize(None, None, 1, 0, 0, ctypes.byref(geom), None, None, None)
     assert rc == -2 and b"32" in lib.gc_last_error()
-    rc = lib.gc_warp_fuse(None, None, 1, 1, None, 5, 8, 4, 4, 7, None, None)
+    rc = lib.gc_warp_fuse(None, None, 1, 1, 0, None, 5, 8, 4, 4, 7, None, None)
     assert rc == -1 and b"mode" in lib.gc_last_error()
     with pytest.raises(RuntimeError, match="argument error"):
         _lib.check(rc, "gc_warp_fuse")
