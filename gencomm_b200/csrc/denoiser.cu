@@ -47,8 +47,9 @@ __device__ __forceinline__ float swish(float v) { return __fdividef(v, 1.0f + __
 // stats: [A][tiles][8] = per channel pair p: (sum, sum of squares) at [2p], [2p+1].
 template <int CIN>
 __device__ __forceinline__ void gn_coeff(int c, int agent, const float *__restrict__ st_a,
-                                         const float *__restrict__ st_b, int tiles, int hw, float gamma,
-                                         float beta, float *ga, float *gb) {
+                                         const float *__restrict__ st_b, int tiles_a, int tiles_b, int hw,
+                                         float gamma, float beta, float *ga, float *gb) {
+    const int tiles = c < 8 ? tiles_a : tiles_b;   // the two tensors may come from kernels with different tilings
     const float *st = (c < 8 ? st_a : st_b) + (size_t)agent * tiles * 8;
     const int cc = c & 7;
     double s = 0.0, ss = 0.0;
@@ -107,7 +108,7 @@ __device__ __forceinline__ void write_tile_stats(const float (&v)[8], float *__r
 template <int CIN, bool PRE_GN, int GEOM, int RES>
 __global__ void __launch_bounds__(256)
 k_conv_c8(const float *__restrict__ in_a, const float *__restrict__ in_b, const float *__restrict__ st_a,
-          const float *__restrict__ st_b, int tiles_in, const float *__restrict__ res_a,
+          const float *__restrict__ st_b, int tiles_in, int tiles_in_b, const float *__restrict__ res_a,
           const float *__restrict__ res_b, float *__restrict__ out, float *__restrict__ stats_out, int H, int W,
           const __grid_constant__ C8Params prm) {
     constexpr int Q = CIN / 4;
@@ -122,7 +123,7 @@ k_conv_c8(const float *__restrict__ in_a, const float *__restrict__ in_b, const 
     const int Win = GEOM == kDown ? W * 2 : (GEOM == kUp ? W / 2 : W);
 
     if (PRE_GN) {
-        if (tid < CIN) gn_coeff<CIN>(tid, agent, st_a, st_b, tiles_in, Hin * Win, prm.gamma[tid], prm.beta[tid],
+        if (tid < CIN) gn_coeff<CIN>(tid, agent, st_a, st_b, tiles_in, tiles_in_b, Hin * Win, prm.gamma[tid], prm.beta[tid],
                                      &s_ga[tid], &s_gb[tid]);
         __syncthreads();
     }
@@ -297,7 +298,7 @@ k_conv_out(const float *__restrict__ in, const float *__restrict__ st_in, int ti
     const int x0 = blockIdx.x * kTW, y0 = blockIdx.y * kTH;
     const int nco = min(64, C - co0);
 
-    if (tid < 8) gn_coeff<8>(tid, agent, st_in, st_in, tiles_in, H * W, aff.gamma[tid], aff.beta[tid], &s_ga[tid], &s_gb[tid]);
+    if (tid < 8) gn_coeff<8>(tid, agent, st_in, st_in, tiles_in, tiles_in, H * W, aff.gamma[tid], aff.beta[tid], &s_ga[tid], &s_gb[tid]);
     for (int i = tid; i < nco * 72; i += 256) (&w_s[0][0])[i] = __ldg(w + (size_t)co0 * 72 + i);
     if (tid < nco) b_s[tid] = __ldg(bias + co0 + tid);
     __syncthreads();
@@ -419,7 +420,8 @@ static void launch_c8(cudaStream_t st, int A, const Act &ia, const Act *ib, cons
                       const C8Params &prm) {
     const dim3 grid((o.W + kTW - 1) / kTW, (o.H + kTH - 1) / kTH, A);
     k_conv_c8<CIN, PRE_GN, GEOM, RES><<<grid, 256, 0, st>>>(
-        ia.data, ib ? ib->data : ia.data, ia.stats, ib ? ib->stats : ia.stats, ia.tiles, ra ? ra->data : nullptr,
+        ia.data, ib ? ib->data : ia.data, ia.stats, ib ? ib->stats : ia.stats, ia.tiles, ib ? ib->tiles : ia.tiles,
+        ra ? ra->data : nullptr,
         rb ? rb->data : nullptr, o.data, o.stats, o.H, o.W, prm);
 }
 

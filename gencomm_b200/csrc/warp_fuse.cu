@@ -27,6 +27,9 @@ namespace gc {
 // warp_fuse_tile.cu: 0 = launched, 1 = not eligible (use the gather kernels below), otherwise an error code
 int warp_fuse_tile(const float *feat, const int32_t *agent_offsets, int n_frames, int total_agents,
                    const double *theta, int L, int C, int H, int W, int mode, int nmax, float *out, cudaStream_t st);
+// warp_fuse_persist.cu (persistent CTAs, producer runs ahead across tiles): same contract
+int warp_fuse_persist(const float *feat, const int32_t *agent_offsets, int n_frames, int total_agents,
+                      const double *theta, int L, int C, int H, int W, int mode, int nmax, float *out, cudaStream_t st);
 
 // ------------------------------------------------------------------------------------------------
 // Generic fused kernel: grid (ceil(W/32), ceil(H/8), n_frames), block 32x8, one pixel per thread.
@@ -202,7 +205,10 @@ extern "C" int gc_warp_fuse(const float *feat, const int32_t *agent_offsets, int
     const char *env = getenv("GC_WARP_FUSE_GATHER");
     const bool force_gather = env && env[0] == '1';
     if (!force_gather) {
-        const int rc = warp_fuse_tile(feat, agent_offsets, n_frames, total_agents, theta, L, C, H, W, mode, nmax, out, st);
+        const char *impl = getenv("GC_FUSE_IMPL");   // "tile": the round-1b per-tile kernel (kept for A/B measurements)
+        const int rc = (impl && impl[0] == 't')
+            ? warp_fuse_tile(feat, agent_offsets, n_frames, total_agents, theta, L, C, H, W, mode, nmax, out, st)
+            : warp_fuse_persist(feat, agent_offsets, n_frames, total_agents, theta, L, C, H, W, mode, nmax, out, st);
         if (rc != 1) return rc;
     }
     if (mode == GC_FUSE_WARP_ONLY) {
