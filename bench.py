@@ -46,19 +46,76 @@ def load_peaks():
 # clocks sampling during the timed region
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
+    """Samples SM clock, power and clock-event reasons of one GPU while the timed region runs: NVML in a background
+    thread (every 2 ms), `nvidia-smi -lms` as the fallback when NVML is unavailable."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
-        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        import threading
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self.power = []
+        self._stop = threading.Event()
+        self.thread = self.p = self.f = None
         try:
-            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                       "-lms", "100", "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
-        except OSError:
-            self.p = None
+            import pynvml
+            pynvml.nvmlInit()
+            # CUDA_VISIBLE_DEVICES may remap indices: resolve through the PCI bus id of the current device
+            bus = torch.cuda.get_device_properties(gpu_index).pci_bus_id if hasattr(
+                torch.cuda.get_device_properties(gpu_index), "pci_bus_id") else None
+            h = None
+            if bus is not None:
+                for i in range(pynvml.nvmlDeviceGetCount()):
+                    hi = pynvml.nvmlDeviceGetHandleByIndex(i)
+                    if pynvml.nvmlDeviceGetPciInfo(hi).bus == bus:
+                        h = hi
+                        break
+            if h is None:
+                h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            names = {pynvml.nvmlClocksEventReasonHwSlowdown: "hw_slowdown",
+                     pynvml.nvmlClocksEventReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                     pynvml.nvmlClocksEventReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                     pynvml.nvmlClocksEventReasonSwPowerCap: "sw_power_cap"}
+
+            def run():
+                while not self._stop.is_set():
+                    try:
+                        self.samples.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                        self.power.append(pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0)
+                        mask = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+                        for bit, n in names.items():
+                            if mask & bit:
+                                self.reasons.add(n)
+                    except Exception:
+                        pass
+                    time.sleep(0.002)
+
+            self.thread = threading.Thread(target=run, daemon=True)
+            self.thread.start()
+            self.how = "nvml"
+        except Exception:
+            self.how = "nvidia-smi"
+            self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+            try:
+                self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                           "-lms", "20", "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
+            except OSError:
+                self.p = None
+
+    def mark(self):
+        """Start of the timed region: drop what was sampled during warm-up."""
+        self._mark = len(self.samples)
 
     def stop(self):
+        if self.thread is not None:
+            self._stop.set()
+            self.thread.join(timeout=2)
+            sm = self.samples[getattr(self, "_mark", 0):] or self.samples
+            return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.max_mhz,
+                    "power_w_max": max(self.power) if self.power else None, "samples": len(sm),
+                    "reasons": sorted(self.reasons), "how": self.how}
         if self.p is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -83,7 +140,7 @@ class ClockSampler:
                 if v.strip().lower().startswith("active"):
                     reasons.add(n)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "reasons": sorted(reasons), "how": self.how}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -133,6 +190,46 @@ def run_reference(args):
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0}))
+
+
+# ------------------------------------------------------------------------------------------------
+# secondary measurement (BASELINE.json configs[2] shape): GenComm 3-step conditional-diffusion sampler
+# ------------------------------------------------------------------------------------------------
+def gencomm_sampler_extra(dev, frames=8, agents=4, C=128, H=64, W=128, iters=10):
+    """GenComm eval sampler (cond_diff.py:331-383) on F frames x 4 agents of OPV2V-H feature shape, device resident,
+    CUDA events.  Reported next to the headline; not part of `value`."""
+    import gencomm_b200 as G
+    from gencomm_b200 import synth
+    torch.manual_seed(0)
+    m = G.GenComm({"model": {"embed_dim": C + 2, "in_channels": C, "out_ch": C, "ch": 8, "ch_mult": [1, 1],
+                             "num_res_blocks": 2, "attn_resolutions": [16], "dropout": 0.0, "resamp_with_conv": True},
+                   "diffusion": {"beta_schedule": "linear", "beta_start": 0.0005, "beta_end": 0.02,
+                                 "num_diffusion_timesteps": 3}}).to(dev).eval()
+    A = frames * agents
+    feat = synth.bev_features(40, A, C, H, W).to(dev)
+    cond = synth.bev_features(40, A, 2, H, W, salt=4).to(dev)
+    n0, steps = synth.sampler_noise(40, A, C, H, W, T=3)
+    noise = (n0.to(dev), torch.stack(steps).to(dev))
+    rl = torch.full((frames,), agents, dtype=torch.int64)
+    out = {"workload": f"configs[2]-shaped: GenComm sampler, {frames} frames x {agents} agents, C={C}, {H}x{W}, T=3",
+           "launches_per_call": 1 + 3 * 28}
+    for name in ("bf16", "fp32"):
+        m.precision = name
+        for _ in range(3):
+            m(feat, cond, rl, noise=noise)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(iters):
+            m(feat, cond, rl, noise=noise)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / iters
+        out[name] = {"ms_per_call": ms, "frames_per_s": frames / (ms * 1e-3),
+                     "tflops": frames * agents * 3 * 486.8e6 / (ms * 1e-3) / 1e12}   # 486.8 MFLOP per agent-step (SURVEY A.7)
+    out["precision_note"] = ("bf16: conv_in/conv_out as tcgen05 implicit GEMMs (bf16 operands, fp32 TMEM accumulation), "
+                             "GroupNorm/middle layers/posterior fp32; fp32: all CUDA-core fp32")
+    return out
 
 
 # ------------------------------------------------------------------------------------------------
@@ -186,19 +283,20 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # ---------------- device-resident timing ----------------
+    sampler = ClockSampler(local) if rank == 0 else None   # covers both timed regions (device-resident and e2e)
     for w in range(Wm):
         pipe.step(dev_pts[w % n_sets], dev_pw[w % n_sets])
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(K)]
     t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    sampler = ClockSampler(local) if rank == 0 else None
     barrier()
+    if sampler:
+        sampler.mark()
     t_start.record()
     for k in range(K):
         pipe.step(dev_pts[k % n_sets], dev_pw[k % n_sets], ev_canvas=ev[k][0:2], ev_fuse=ev[k][2:4])
     t_end.record()
     barrier()
     elapsed_ms = t_start.elapsed_time(t_end)
-    clocks = sampler.stop() if sampler else None
     canvas_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in ev]))
     fuse_ms = float(np.mean([e[2].elapsed_time(e[3]) for e in ev]))
     checksum = float(pipe.fused.double().sum().item())
@@ -245,10 +343,18 @@ def run_ours(args):
     e_end.record(s_out)
     barrier()
     e2e_ms = e_start.elapsed_time(e_end)
+    clocks = sampler.stop() if sampler else None
     pipe.fused = own_fused
     h2d = host_pts[0].numel() * 4 + host_pw[0].numel() * 8
     d2h = h_out[0].numel() * 4
     e2e_check = float(h_out[(K - 1) % slots].double().sum().item())
+
+    sampler_extra = None
+    if rank == 0 and world == 1 and not args.no_extras:
+        try:
+            sampler_extra = gencomm_sampler_extra(dev)
+        except Exception as exc:   # secondary measurement must never take the headline down
+            sampler_extra = {"error": repr(exc)}
 
     # ---------------- max over ranks, gather of checksums + timings ----------------
     times = torch.tensor([elapsed_ms, e2e_ms], dtype=torch.float64, device=dev)
@@ -295,6 +401,7 @@ def run_ours(args):
                          "algorithmic_bytes_per_launch": kernels[dom]["bytes"], "ms_per_launch": kernels[dom]["ms"]},
             "kernels": kernels,
             "cpu_baseline": cpu_baseline,
+            "gencomm_sampler": sampler_extra,
             "checksum": checksum,
         }
         if gathered is not None:
@@ -307,11 +414,12 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--frames-per-step", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the secondary GenComm sampler measurement")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

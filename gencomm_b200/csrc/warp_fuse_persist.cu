@@ -40,6 +40,7 @@ namespace persist {
 
 constexpr int kTileMaxN = 5;
 constexpr int kMaxStages = 8;
+constexpr int kGeomSlots = 4;   // tiles of geometry the geometry warp may run ahead
 constexpr int kDynSmemBytes = 224 * 1024;
 
 constexpr int isqrt_ceil(int v) {
@@ -54,7 +55,7 @@ struct Cfg {
     static constexpr int P = TW * TH;                  // pixels per tile
     static constexpr int CHS = G * KC;                 // channel planes per pipeline stage
     static constexpr int kConsumers = P * G;
-    static constexpr int kThreads = kConsumers + 32;   // + producer warp
+    static constexpr int kThreads = kConsumers + 64;   // + producer warp + geometry warp
     // x0 = floor(ix) spans at most ceil(diagonal) + 1 values over the tile, + 1 for the x0+1 tap
     static constexpr int EXT = isqrt_ceil((TW - 1) * (TW - 1) + (TH - 1) * (TH - 1)) + 2;
     static constexpr int BW = (EXT + 3 + 3) & ~3;      // + up to 3 columns: box x origin floored to 16 bytes
@@ -427,7 +428,7 @@ k_fuse_persist(const __grid_constant__ CUtensorMap tmap_box, const __grid_consta
                const double *__restrict__ theta, int L, int C, int H, int W, float sqrt_c, LaunchPlan plan,
                float *__restrict__ out) {
     constexpr int NMAX = kTileMaxN;
-    constexpr int TW = C_::TW, TH = C_::TH, G = C_::G, P = C_::P, CHS = C_::CHS;
+    constexpr int TW = C_::TW, TH = C_::TH, P = C_::P, CHS = C_::CHS;
     constexpr int BW = C_::BW, BOXF = C_::BOXF, kConsumers = C_::kConsumers;
 
     extern __shared__ uint8_t smem_raw[];
@@ -438,42 +439,64 @@ k_fuse_persist(const __grid_constant__ CUtensorMap tmap_box, const __grid_consta
     const uint32_t park_addr = ring_addr + (uint32_t)plan.stages * slot_bytes;
     float *const scratch = reinterpret_cast<float *>(base + (size_t)plan.stages * slot_bytes + (size_t)plan.park_slots * C * P * 4);
     __shared__ __align__(8) uint64_t full_bar[kMaxStages], empty_bar[kMaxStages];
-    __shared__ int s_geom[2][NMAX][3];
-    __shared__ int s_slow[2];
+    __shared__ __align__(8) uint64_t gfull_bar[kGeomSlots], gempty_bar[kGeomSlots];
+    __shared__ int s_geom[kGeomSlots][NMAX][3];
+    __shared__ int s_slow[kGeomSlots];
 
     const int tid = threadIdx.x, lane = tid & 31;
     const bool is_consumer = tid < kConsumers;
     const uint32_t full_addr = smem_u32(full_bar), empty_addr = smem_u32(empty_bar);
+    const uint32_t gfull_addr = smem_u32(gfull_bar), gempty_addr = smem_u32(gempty_bar);
     const int chunks = (C + CHS - 1) / CHS;
     const size_t plane = (size_t)H * W;
     const int tiles_per_frame = plan.tiles_x * plan.tiles_y;
 
     if (tid == 0) {
         for (int s = 0; s < kMaxStages; ++s) { mbar_init(full_addr + 8u * s, 1); mbar_init(empty_addr + 8u * s, kConsumers / 32); }
+        for (int s = 0; s < kGeomSlots; ++s) { mbar_init(gfull_addr + 8u * s, 1); mbar_init(gempty_addr + 8u * s, kConsumers / 32 + 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
 
-    // ---- producer warp: runs ahead of the consumers through the ring, across tile boundaries --------------
-    if (!is_consumer) {
-        int s = 0;
+    // ---- geometry warp: box origins / paths of the tiles ahead, published through a small ring so that neither the
+    // producer nor the consumers have the float64 corner evaluation (and the per-tile identity check) on their path
+    if (tid >= kConsumers + 32) {
+        int slot = 0;
         uint32_t parity = 1;   // first lap: the slots are free
         for (int t = blockIdx.x; t < plan.n_tiles; t += gridDim.x) {
             const int b = t / tiles_per_frame, r = t - b * tiles_per_frame;
             const int w0 = (r % plan.tiles_x) * TW, h0 = (r / plan.tiles_x) * TH;
             const int a0 = __ldg(agent_offsets + b);
             const int n = min(min(__ldg(agent_offsets + b + 1) - a0, plan.n_bound), L);
-            const Geom g = tile_geom<C_>(lane, n, theta + (size_t)b * L * L * 6, w0, h0, H, W);
-            const bool slow = __any_sync(0xffffffffu, g.path == kPathGather) || n < 1;
-            if (slow) continue;   // consumers gather this tile from global memory
+            const Geom gm = tile_geom<C_>(lane, n, theta + (size_t)b * L * L * 6, w0, h0, H, W);
+            const bool slow = __any_sync(0xffffffffu, gm.path == kPathGather) || n < 1;
+            mbar_wait(gempty_addr + 8u * slot, parity);
+            if (lane < NMAX) { s_geom[slot][lane][0] = gm.bx; s_geom[slot][lane][1] = gm.by; s_geom[slot][lane][2] = gm.path; }
+            if (lane == 0) s_slow[slot] = slow ? 1 : 0;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(gfull_addr + 8u * slot);
+            if (++slot == kGeomSlots) { slot = 0; parity ^= 1u; }
+        }
+        return;
+    }
+
+    // ---- producer: one thread keeps the ring full, across tile boundaries -------------------------------------
+    if (!is_consumer) {
+        if (lane != 0) return;
+        int s = 0, slot = 0;
+        uint32_t parity = 1, gparity = 0;   // ring slots start free; geometry slots start empty
+        for (int t = blockIdx.x; t < plan.n_tiles; t += gridDim.x) {
+            const int b = t / tiles_per_frame;
+            const int a0 = __ldg(agent_offsets + b);
+            const int n = min(min(__ldg(agent_offsets + b + 1) - a0, plan.n_bound), L);
+            mbar_wait(gfull_addr + 8u * slot, gparity);
+            const bool slow = s_slow[slot] != 0;
             int bx[NMAX], by[NMAX], path[NMAX];
 #pragma unroll
-            for (int j = 0; j < NMAX; ++j) {
-                bx[j] = __shfl_sync(0xffffffffu, g.bx, j);
-                by[j] = __shfl_sync(0xffffffffu, g.by, j);
-                path[j] = __shfl_sync(0xffffffffu, g.path, j);
-            }
-            if (lane != 0) continue;
+            for (int j = 0; j < NMAX; ++j) { bx[j] = s_geom[slot][j][0]; by[j] = s_geom[slot][j][1]; path[j] = s_geom[slot][j][2]; }
+            mbar_arrive(gempty_addr + 8u * slot);
+            if (++slot == kGeomSlots) { slot = 0; gparity ^= 1u; }
+            if (slow) continue;   // consumers gather this tile from global memory
             const int n_id = path[0] == kPathIdent ? 1 : 0;
             const int parked = n - n_id;
             const bool park_mode = MODE == GC_FUSE_ATT && parked <= plan.park_slots;
@@ -503,10 +526,11 @@ k_fuse_persist(const __grid_constant__ CUtensorMap tmap_box, const __grid_consta
     x.ring_addr = ring_addr; x.slot_bytes = slot_bytes; x.park_addr = park_addr;
     x.full_addr = full_addr; x.empty_addr = empty_addr;
     x.stages = plan.stages; x.chunks = chunks; x.C = C;
-    x.lane = lane; x.g = g; x.p = p; x.sqrt_c = sqrt_c; x.scratch = scratch; x.plane = plane;
+    x.lane = lane; x.g = g; x.p = p; x.sqrt_c = sqrt_c; x.plane = plane;
     x.s = 0; x.parity = 0;
 
-    int it_tile = 0;
+    int slot = 0, it_tile = 0;
+    uint32_t gparity = 0;
     for (int t = blockIdx.x; t < plan.n_tiles; t += gridDim.x, it_tile ^= 1) {
         const int b = t / tiles_per_frame, r = t - b * tiles_per_frame;
         const int w0 = (r % plan.tiles_x) * TW, h0 = (r / plan.tiles_x) * TH;
@@ -515,45 +539,52 @@ k_fuse_persist(const __grid_constant__ CUtensorMap tmap_box, const __grid_consta
         const int a0 = __ldg(agent_offsets + b);
         const int n = min(min(__ldg(agent_offsets + b + 1) - a0, plan.n_bound), L);
         const double *th_base = theta + (size_t)b * L * L * 6;   // row [b][0][j]
-
-        if (tid < 32) {   // consumer warp 0 publishes the boxes of this tile
-            const Geom gm = tile_geom<C_>(lane, n, th_base, w0, h0, H, W);
-            const bool slow = __any_sync(0xffffffffu, gm.path == kPathGather) || n < 1;
-            if (lane < NMAX) { s_geom[it_tile][lane][0] = gm.bx; s_geom[it_tile][lane][1] = gm.by; s_geom[it_tile][lane][2] = gm.path; }
-            if (lane == 0) s_slow[it_tile] = slow ? 1 : 0;
-        }
-        consumer_sync<kConsumers>();
-
         const size_t pix = (size_t)(active ? h : 0) * W + (active ? w : 0);
         x.active = active;
         x.src_pix = feat + (size_t)a0 * C * plane + pix;
         // this thread's first channel is g; consecutive channels of the thread are G planes apart
         x.dst = out + ((size_t)(MODE == GC_FUSE_WARP_ONLY ? a0 : b) * C + g) * plane + pix;
+        x.scratch = scratch + it_tile * C_::kScratch;   // double buffered: a warp may run one tile ahead of another
 
-        if (s_slow[it_tile]) {
-            if (n >= 1) gather_tile<MODE, C_>(x, n, th_base, w, h, H, W);
-            continue;
-        }
-        // ---- own taps for every agent; fold the geometry into one shared-memory byte offset per agent ----
+        // own taps for every agent (independent of the tile geometry, overlaps the wait below)
         const double xs = base_coord(min(w, W - 1), W), ys = base_coord(min(h, H - 1), H);
         float wt[NMAX][4];
-        uint32_t ta[NMAX];
-        const bool id0 = s_geom[it_tile][0][2] == kPathIdent;
+        int tx0[NMAX], ty0[NMAX];
 #pragma unroll
         for (int j = 0; j < NMAX; ++j) {
             wt[j][0] = wt[j][1] = wt[j][2] = wt[j][3] = 0.0f;
+            tx0[j] = ty0[j] = 0;
+            if (j < n) {
+                const TapS tp = make_tap_xy(th_base + j * 6, xs, ys, H, W);
+                wt[j][0] = tp.w_nw; wt[j][1] = tp.w_ne; wt[j][2] = tp.w_sw; wt[j][3] = tp.w_se;
+                tx0[j] = tp.x0; ty0[j] = tp.y0;
+            }
+        }
+        // geometry of this tile from the geometry warp
+        mbar_wait(gfull_addr + 8u * slot, gparity);
+        const bool slow = s_slow[slot] != 0;
+        const bool id0 = s_geom[slot][0][2] == kPathIdent;
+        uint32_t ta[NMAX];
+#pragma unroll
+        for (int j = 0; j < NMAX; ++j) {
             ta[j] = (uint32_t)(j * CHS * BOXF) * 4u;
             if (j < n) {
                 if (j == 0 && id0) {
                     ta[j] += (uint32_t)(g * P + p) * 4u;
                 } else {
-                    const TapS tp = make_tap_xy(th_base + j * 6, xs, ys, H, W);
-                    wt[j][0] = tp.w_nw; wt[j][1] = tp.w_ne; wt[j][2] = tp.w_sw; wt[j][3] = tp.w_se;
                     // inactive threads of a partial tile may fall outside the box: keep their address inside it
-                    const int dx = active ? tp.x0 - s_geom[it_tile][j][0] : 0, dy = active ? tp.y0 - s_geom[it_tile][j][1] : 0;
+                    const int dx = active ? tx0[j] - s_geom[slot][j][0] : 0, dy = active ? ty0[j] - s_geom[slot][j][1] : 0;
                     ta[j] += (uint32_t)(g * BOXF + dy * BW + dx) * 4u;
                 }
             }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(gempty_addr + 8u * slot);
+        if (++slot == kGeomSlots) { slot = 0; gparity ^= 1u; }
+
+        if (slow) {
+            if (n >= 1) gather_tile<MODE, C_>(x, n, th_base, w, h, H, W);
+            continue;
         }
         const int parked = n - (id0 ? 1 : 0);
         x.park_mode = MODE == GC_FUSE_ATT && parked <= plan.park_slots;
@@ -624,7 +655,7 @@ static int launch(cudaStream_t st, const float *feat, const int32_t *off, int n_
     plan.n_bound = n_bound;
     plan.slot_floats = n_bound * C_::CHS * C_::BOXF;
     const long long cap = (kDynSmemBytes - 128) / 4;   // floats
-    const long long scratch = MODE == GC_FUSE_ATT ? C_::kScratch : 0;
+    const long long scratch = MODE == GC_FUSE_ATT ? 2 * C_::kScratch : 0;   // double buffered by tile parity
     plan.park_slots = 0;
     if (MODE == GC_FUSE_ATT) {
         // park the sampled vectors of all agents but the ego (normally the identity map) when that leaves at least
