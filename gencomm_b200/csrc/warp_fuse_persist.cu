@@ -61,9 +61,10 @@ struct Cfg {
     static constexpr int BW = (EXT + 3 + 3) & ~3;      // + up to 3 columns: box x origin floored to 16 bytes
     static constexpr int BH = EXT;
     static constexpr int BOXF = BW * BH;
+    static constexpr int kAgentFloats = (CHS * BOXF + 31) & ~31;   // per-agent region of a stage slot (128-byte aligned)
     static constexpr int kScratch = kTileMaxN * P * G;   // AttFusion score reduction [G][N][P]
     static_assert(P % 32 == 0 && TW % 4 == 0, "tile rows must be 16-byte multiples, groups warp aligned");
-    static_assert((CHS * BOXF * 4) % 128 == 0 && (CHS * P * 4) % 128 == 0, "TMA destinations are 128-byte aligned");
+    static_assert(kConsumers % 32 == 0, "whole consumer warps");
     static_assert(kThreads <= 1024, "block too large");
 };
 
@@ -510,7 +511,7 @@ k_fuse_persist(const __grid_constant__ CUtensorMap tmap_box, const __grid_consta
 #pragma unroll
                 for (int j = 0; j < NMAX; ++j) {
                     if (j < n)
-                        tma_load_box(dst + (uint32_t)(j * CHS * BOXF) * 4u, path[j] == kPathIdent ? &tmap_id : &tmap_box,
+                        tma_load_box(dst + (uint32_t)(j * C_::kAgentFloats) * 4u, path[j] == kPathIdent ? &tmap_id : &tmap_box,
                                      bx[j], by[j], (a0 + j) * C + chunk * CHS, full_addr + 8u * s);
                 }
                 if (++s == plan.stages) { s = 0; parity ^= 1u; }
@@ -567,7 +568,7 @@ k_fuse_persist(const __grid_constant__ CUtensorMap tmap_box, const __grid_consta
         uint32_t ta[NMAX];
 #pragma unroll
         for (int j = 0; j < NMAX; ++j) {
-            ta[j] = (uint32_t)(j * CHS * BOXF) * 4u;
+            ta[j] = (uint32_t)(j * C_::kAgentFloats) * 4u;
             if (j < n) {
                 if (j == 0 && id0) {
                     ta[j] += (uint32_t)(g * P + p) * 4u;
@@ -653,7 +654,7 @@ static int launch(cudaStream_t st, const float *feat, const int32_t *off, int n_
     if (n_tiles >= (1ll << 30)) return 1;
     plan.n_tiles = (int)n_tiles;
     plan.n_bound = n_bound;
-    plan.slot_floats = n_bound * C_::CHS * C_::BOXF;
+    plan.slot_floats = n_bound * C_::kAgentFloats;
     const long long cap = (kDynSmemBytes - 128) / 4;   // floats
     const long long scratch = MODE == GC_FUSE_ATT ? 2 * C_::kScratch : 0;   // double buffered by tile parity
     plan.park_slots = 0;
@@ -701,25 +702,27 @@ int warp_fuse_persist(const float *feat, const int32_t *agent_offsets, int n_fra
     if ((W & 3) != 0 || ((uintptr_t)feat & 15) != 0) return 1;
     if (nmax > kTileMaxN || nmax < 1) return 1;
     if ((long long)total_agents * C >= (1ll << 31)) return 1;
-    using CfgA = Cfg<16, 8, 4, 1>;   // 4 channel planes per stage, 512 consumers
-    using CfgB = Cfg<16, 8, 4, 2>;   // 8 channel planes per stage
-    using CfgC = Cfg<16, 8, 2, 2>;   // 4 channel planes per stage, 256 consumers, 2 channels per thread and stage
-    int variant = 0;
+    // variant table (GC_FUSE_CFG=<k> overrides the default of a mode; measured on B200 in profiles/)
+    int variant = -1;
     if (const char *e = getenv("GC_FUSE_CFG")) variant = atoi(e);
-#define GC_LAUNCH(MODE, CFG) launch<MODE, CFG>(st, feat, agent_offsets, n_frames, total_agents, theta, L, C, H, W, nmax, out)
-    if (mode == GC_FUSE_WARP_ONLY) {
-        if (variant == 1) return GC_LAUNCH(GC_FUSE_WARP_ONLY, CfgA);
-        if (variant == 2) return GC_LAUNCH(GC_FUSE_WARP_ONLY, CfgC);
-        return GC_LAUNCH(GC_FUSE_WARP_ONLY, CfgB);
+#define GC_LAUNCH(MODE, ...) launch<MODE, Cfg<__VA_ARGS__>>(st, feat, agent_offsets, n_frames, total_agents, theta, L, C, H, W, nmax, out)
+#define GC_VARIANTS(MODE, DEFAULT)                                                  \
+    switch (variant < 0 ? DEFAULT : variant) {                                      \
+        case 0: return GC_LAUNCH(MODE, 16, 8, 4, 1);                                \
+        case 1: return GC_LAUNCH(MODE, 16, 8, 4, 2);                                \
+        case 2: return GC_LAUNCH(MODE, 16, 8, 2, 2);                                \
+        case 3: return GC_LAUNCH(MODE, 16, 8, 2, 4);                                \
+        case 4: return GC_LAUNCH(MODE, 16, 16, 1, 2);                               \
+        case 5: return GC_LAUNCH(MODE, 16, 16, 1, 4);                               \
+        case 6: return GC_LAUNCH(MODE, 32, 16, 1, 2);                               \
+        case 7: return GC_LAUNCH(MODE, 16, 8, 1, 4);                                \
+        default: return GC_LAUNCH(MODE, 16, 8, 2, 2);                               \
     }
-    if (mode == GC_FUSE_MAX) {
-        if (variant == 1) return GC_LAUNCH(GC_FUSE_MAX, CfgA);
-        if (variant == 2) return GC_LAUNCH(GC_FUSE_MAX, CfgC);
-        return GC_LAUNCH(GC_FUSE_MAX, CfgB);
-    }
-    if (variant == 1) return GC_LAUNCH(GC_FUSE_ATT, CfgB);
-    if (variant == 2) return GC_LAUNCH(GC_FUSE_ATT, CfgC);
-    return GC_LAUNCH(GC_FUSE_ATT, CfgA);
+    // defaults from the B200 sweep profiles/r01g_bench_fuse_cfg*.txt: 16x16 tiles, one thread per pixel
+    if (mode == GC_FUSE_WARP_ONLY) { GC_VARIANTS(GC_FUSE_WARP_ONLY, 4) }
+    if (mode == GC_FUSE_MAX) { GC_VARIANTS(GC_FUSE_MAX, 5) }
+    GC_VARIANTS(GC_FUSE_ATT, 5)
+#undef GC_VARIANTS
 #undef GC_LAUNCH
 }
 
