@@ -293,54 +293,6 @@ __device__ __forceinline__ float2 pfn_pillar(const PfnLane &wa, const PfnLane &w
     return make_float2(pfn_finish(wa, best_a, ba, n), pfn_finish(wb, best_b, bb, n));
 }
 
-// Two pillars per warp: half-warp h = lane >> 4 evaluates one pillar; lane hl = lane & 15 holds its points hl (pa) and
-// hl + 16 (pb) and owns output channels hl, hl+16, hl+32, hl+48.  Bit-identical to pfn_pillar: the first level of the
-// 32-lane xor tree (v[l] + v[l^16]) becomes pa + pb inside the lane, the remaining levels stay inside the half-warp,
-// and every channel sees the same FMA chain per point.  n: valid points of THIS half-warp's pillar (0 = no pillar).
-__device__ __forceinline__ void pfn_pillar_half(const PfnLane (&w)[4], float4 pa, float4 pb, int n, float cx, float cy,
-                                                float cz, float (&out)[4]) {
-    const int lane = threadIdx.x & 31, hl = lane & 15, hbase = lane & 16;
-    const bool va = hl < n, vb = hl + 16 < n;
-    const float xa = va ? __fsub_rn(pa.x, cx) : 0.0f, ya = va ? __fsub_rn(pa.y, cy) : 0.0f;
-    const float za = va ? __fsub_rn(pa.z, cz) : 0.0f, ia = va ? pa.w : 0.0f;
-    const float xb = vb ? __fsub_rn(pb.x, cx) : 0.0f, yb = vb ? __fsub_rn(pb.y, cy) : 0.0f;
-    const float zb = vb ? __fsub_rn(pb.z, cz) : 0.0f, ib = vb ? pb.w : 0.0f;
-    float sx = __fadd_rn(xa, xb), sy = __fadd_rn(ya, yb), sz = __fadd_rn(za, zb);
-#pragma unroll
-    for (int m = 8; m >= 1; m >>= 1) {
-        sx = __fadd_rn(sx, __shfl_xor_sync(0xffffffffu, sx, m));
-        sy = __fadd_rn(sy, __shfl_xor_sync(0xffffffffu, sy, m));
-        sz = __fadd_rn(sz, __shfl_xor_sync(0xffffffffu, sz, m));
-    }
-    const float inv_n = __frcp_rn((float)n);
-    const float mx = __fmul_rn(sx, inv_n), my = __fmul_rn(sy, inv_n), mz = __fmul_rn(sz, inv_n);
-    float bias[4], best[4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) { bias[q] = pfn_bias(w[q], cx, cy, cz, mx, my, mz); best[q] = -INFINITY; }
-    // the two pillars of the warp may hold different point counts: run to the larger one, masked
-    const int n_other = __shfl_xor_sync(0xffffffffu, n, 16);
-    const int n_max = max(n, n_other);
-    const int n_lo = min(n_max, 16);
-    for (int s = 0; s < n_lo; ++s) {
-        const float px = __shfl_sync(0xffffffffu, xa, hbase | s), py = __shfl_sync(0xffffffffu, ya, hbase | s);
-        const float pz = __shfl_sync(0xffffffffu, za, hbase | s), pi = __shfl_sync(0xffffffffu, ia, hbase | s);
-        if (s < n) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) best[q] = fmaxf(best[q], pfn_point(w[q], px, py, pz, pi));
-        }
-    }
-    for (int s = 16; s < n_max; ++s) {
-        const float px = __shfl_sync(0xffffffffu, xb, hbase | (s - 16)), py = __shfl_sync(0xffffffffu, yb, hbase | (s - 16));
-        const float pz = __shfl_sync(0xffffffffu, zb, hbase | (s - 16)), pi = __shfl_sync(0xffffffffu, ib, hbase | (s - 16));
-        if (s < n) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) best[q] = fmaxf(best[q], pfn_point(w[q], px, py, pz, pi));
-        }
-    }
-#pragma unroll
-    for (int q = 0; q < 4; ++q) out[q] = pfn_finish(w[q], best[q], bias[q], n);
-}
-
 // ------------------------------------------------------------------------------------------------
 // Standalone PillarVFE on reference-shaped voxel tensors: one warp per pillar.
 // ------------------------------------------------------------------------------------------------
@@ -431,7 +383,7 @@ struct FusedSrc {
 };
 
 template <class Src>
-__global__ void __launch_bounds__(256, Src::kFused ? 3 : 4)
+__global__ void __launch_bounds__(256, 4)
 k_canvas(Src src, int nx, int ny, int C, float *__restrict__ canvas) {
     __shared__ __align__(16) float tile[64 * kTileStride];
     __shared__ int s_code[kTileX];
@@ -479,49 +431,31 @@ k_canvas(Src src, int nx, int ny, int C, float *__restrict__ canvas) {
             }
         } else {
             const Src &fs = src;
-            if (2 * warp < n_occ) {   // warp-uniform; skips the weight loads for empty tiles
-                // two pillars per warp (one per half-warp), 4 channels per lane: see pfn_pillar_half
-                const int hl = lane & 15, half = lane >> 4;
-                PfnLane w4[4];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) w4[q] = load_pfn(fs.pfn, hl + 16 * q);
+            if (warp < n_occ) {   // warp-uniform; skips the weight loads for empty tiles
+                const PfnLane wa = load_pfn(fs.pfn, lane), wb = load_pfn(fs.pfn, lane + 32);
                 const int pbase = __ldg(fs.point_offsets + b);
                 const float cy = __fadd_rn(__fmul_rn((float)y, fs.vy), fs.oy);
-                // two-stage software pipeline over this half-warp's pillars: slot indices two ahead, points one ahead
-                auto slots_of = [&](int k, uint32_t &ia, uint32_t &ib) {
-                    ia = ib = kEmpty;
-                    if (k < n_occ) {
-                        const unsigned pid = (unsigned)s_code[s_list[k]] & ~kPillarBit;
-                        const uint32_t *row = fs.slots + ((size_t)b * fs.max_voxels + pid) * 32;
-                        ia = __ldg(row + hl); ib = __ldg(row + hl + 16);
-                    }
+                // two-stage software pipeline over this warp's pillars: slot indices two ahead, point one ahead
+                auto slot_of = [&](int k) -> uint32_t {
+                    const unsigned pid = (unsigned)s_code[s_list[k]] & ~kPillarBit;
+                    return __ldg(fs.slots + ((size_t)b * fs.max_voxels + pid) * 32 + lane);
                 };
                 auto point_of = [&](uint32_t idx) -> float4 {
                     return idx != kEmpty ? __ldg(fs.points + pbase + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
                 };
-                const int k0 = 2 * warp + half;
-                uint32_t ia_cur, ib_cur, ia_nxt, ib_nxt;
-                slots_of(k0, ia_cur, ib_cur);
-                slots_of(k0 + 16, ia_nxt, ib_nxt);
-                float4 pa_cur = point_of(ia_cur), pb_cur = point_of(ib_cur);
-                for (int kw = 2 * warp; kw < n_occ; kw += 16) {   // warp-uniform loop; k = this half-warp's pillar
-                    const int k = kw + half;
-                    const float4 pa_nxt = point_of(ia_nxt), pb_nxt = point_of(ib_nxt);
-                    uint32_t ia_nxt2, ib_nxt2;
-                    slots_of(k + 32, ia_nxt2, ib_nxt2);
-                    // slots fill from 0: the count is the number of occupied slots of this half-warp's row
-                    const unsigned bal_a = __ballot_sync(0xffffffffu, ia_cur != kEmpty);
-                    const unsigned bal_b = __ballot_sync(0xffffffffu, ib_cur != kEmpty);
-                    const int n = __popc((bal_a >> (16 * half)) & 0xFFFFu) + __popc((bal_b >> (16 * half)) & 0xFFFFu);
-                    const int xc = k < n_occ ? s_list[k] : 0;
+                uint32_t idx_cur = slot_of(warp);
+                uint32_t idx_nxt = (warp + 8 < n_occ) ? slot_of(warp + 8) : kEmpty;
+                float4 p_cur = point_of(idx_cur);
+                for (int k = warp; k < n_occ; k += 8) {
+                    const float4 p_nxt = point_of(idx_nxt);
+                    const uint32_t idx_nxt2 = (k + 16 < n_occ) ? slot_of(k + 16) : kEmpty;
+                    const int xc = s_list[k];
+                    const int n = __popc(__ballot_sync(0xffffffffu, idx_cur != kEmpty));   // slots fill from 0
                     const float cx = __fadd_rn(__fmul_rn((float)(x0 + xc), fs.vx), fs.ox);
-                    float r[4];
-                    pfn_pillar_half(w4, pa_cur, pb_cur, n, cx, cy, fs.cz, r);
-                    if (k < n_occ) {
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) tile[(hl + 16 * q) * kTileStride + xc] = r[q];
-                    }
-                    ia_cur = ia_nxt; ib_cur = ib_nxt; pa_cur = pa_nxt; pb_cur = pb_nxt; ia_nxt = ia_nxt2; ib_nxt = ib_nxt2;
+                    const float2 r = pfn_pillar(wa, wb, p_cur, n, cx, cy, fs.cz);
+                    tile[lane * kTileStride + xc] = r.x;
+                    tile[(lane + 32) * kTileStride + xc] = r.y;
+                    idx_cur = idx_nxt; p_cur = p_nxt; idx_nxt = idx_nxt2;
                 }
             }
         }
