@@ -63,6 +63,8 @@ struct Cfg {
     static constexpr int BOXF = BW * BH;
     static constexpr int kAgentFloats = (CHS * BOXF + 31) & ~31;   // per-agent region of a stage slot (128-byte aligned)
     static constexpr int kScratch = kTileMaxN * P * G;   // AttFusion score reduction [G][N][P]
+    // tensor-memory park: one thread per pixel owning 4 consecutive channels per stage, lanes = pixel % 128
+    static constexpr bool kTmemOK = G == 1 && KC == 4 && P % 128 == 0;
     static_assert(P % 32 == 0 && TW % 4 == 0, "tile rows must be 16-byte multiples, groups warp aligned");
     static_assert(kConsumers % 32 == 0, "whole consumer warps");
     static_assert(kThreads <= 1024, "block too large");
@@ -110,6 +112,39 @@ template <int OFF>
 __device__ __forceinline__ void sts(uint32_t addr, float v) {
     asm volatile("st.shared.f32 [%0+%1], %2;" ::"r"(addr), "n"(OFF), "f"(v) : "memory");
 }
+// ---- tensor memory as a 256 KB per-SM scratchpad (AttFusion park): lane = pixel % 128, column = (agent, channel) ----
+__device__ __forceinline__ void tmem_alloc_all(uint32_t *slot) {   // one full warp; all 512 columns (1 CTA per SM)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_free_all(uint32_t base) {     // the same warp
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(base) : "memory");
+}
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, float a, float b, float c, float d) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(__float_as_uint(a)),
+                 "r"(__float_as_uint(b)), "r"(__float_as_uint(c)), "r"(__float_as_uint(d)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
+    uint32_t r[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 template <int... Is, class F>
 __device__ __forceinline__ void static_for_impl(std::integer_sequence<int, Is...>, F &&f) {
     (f(std::integral_constant<int, Is>{}), ...);
@@ -195,6 +230,8 @@ struct Ctx {
     uint32_t ring_addr, slot_bytes, park_addr, full_addr, empty_addr;
     int stages, chunks, C;
     bool park_mode, active;
+    bool park_tmem;        // the park lives in tensor memory (G == 1, KC == 4 configurations)
+    uint32_t tmem_park;    // TMEM address of (this thread's lane, column of park slot 0 / channel 0 of its pixel set)
     int lane, g, p;
     float sqrt_c;
     float *scratch;
@@ -210,15 +247,20 @@ struct Ctx {
 template <int N, class C_>
 __device__ __forceinline__ void att_softmax(const Ctx &x, float (&score)[N]) {
     constexpr int G = C_::G, P = C_::P;
+    if (G > 1) {
 #pragma unroll
-    for (int j = 0; j < N; ++j) x.scratch[(x.g * N + j) * P + x.p] = score[j];
-    consumer_sync<C_::kConsumers>();
+        for (int j = 0; j < N; ++j) x.scratch[(x.g * N + j) * P + x.p] = score[j];
+        consumer_sync<C_::kConsumers>();
+    }
     float mx = -INFINITY;
 #pragma unroll
     for (int j = 0; j < N; ++j) {
-        float t = 0.0f;
+        float t = score[j];   // G == 1: the thread already holds the full dot product
+        if (G > 1) {
+            t = 0.0f;
 #pragma unroll
-        for (int gg = 0; gg < G; ++gg) t += x.scratch[(gg * N + j) * P + x.p];
+            for (int gg = 0; gg < G; ++gg) t += x.scratch[(gg * N + j) * P + x.p];
+        }
         score[j] = __fdiv_rn(t, x.sqrt_c);
         mx = fmaxf(mx, score[j]);
     }
@@ -235,6 +277,7 @@ __device__ __forceinline__ void att_softmax(const Ctx &x, float (&score)[N]) {
 template <int MODE, int N, bool IDENT0, class C_>
 __device__ __forceinline__ void fast_loop(Ctx &x, const float (&wt)[kTileMaxN][4], const uint32_t (&ta)[kTileMaxN]) {
     constexpr int G = C_::G, KC = C_::KC, P = C_::P, CHS = C_::CHS, BW = C_::BW, BOXF = C_::BOXF;
+    constexpr bool kTmemOK = C_::kTmemOK;
     const int total = x.chunks * ((MODE == GC_FUSE_ATT && !x.park_mode) ? 2 : 1);
     const size_t dst_step = (size_t)G * x.plane;
     const uint32_t slot_stride = (uint32_t)x.C * P * 4u;
@@ -284,7 +327,14 @@ __device__ __forceinline__ void fast_loop(Ctx &x, const float (&wt)[kTileMaxN][4
                 } else if (!second) {   // scores s_j += <w_0, w_j>; park the sampled vectors
 #pragma unroll
                     for (int j = 0; j < N; ++j) score[j] = __fmaf_rn(v[0], v[j], score[j]);
-                    if (x.park_mode) {
+                    if (kTmemOK && x.park_tmem) {
+                        // tensor-memory park: 4 columns per channel = the (up to 4) parked agents of this pixel
+                        if (x.park_mode) {
+                            constexpr int o = IDENT0 ? 1 : 0;   // first parked agent
+                            tmem_st4(x.tmem_park + (uint32_t)((c0 + G * kc) * 4), v[o < N ? o : 0], v[o + 1 < N ? o + 1 : 0],
+                                     v[o + 2 < N ? o + 2 : 0], v[o + 3 < N ? o + 3 : 0]);
+                        }
+                    } else if (x.park_mode) {
                         static_for<N>([&](auto j_) {
                             constexpr int j = decltype(j_)::value;
                             if (!(j == 0 && IDENT0)) sts<kc * G * P * 4>(pk[j], v[j]);
@@ -310,6 +360,35 @@ __device__ __forceinline__ void fast_loop(Ctx &x, const float (&wt)[kTileMaxN][4
     }
     x.s = s; x.parity = parity;
 
+    if constexpr (kTmemOK && MODE == GC_FUSE_ATT) {
+        if (x.park_tmem && x.park_mode) {
+            // out = sum_j a_j w_j from the vectors parked in tensor memory: one 16-column load = 4 channels x 4 agents
+            constexpr int o = IDENT0 ? 1 : 0;
+            tmem_wait_st();
+            const float *sp = x.src_pix;
+            for (int c = 0; c < x.C; c += 4) {   // C % 4 == 0 in this mode
+                float pv[16], ego[4];
+                tmem_ld16(x.tmem_park + (uint32_t)(c * 4), pv);
+                if (IDENT0) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) ego[i] = x.active ? __ldg(sp + (size_t)i * x.plane) : 0.0f;
+                }
+                tmem_wait_ld();
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    float acc = 0.0f;
+#pragma unroll
+                    for (int j = 0; j < N; ++j) {
+                        const float v = (j == 0 && IDENT0) ? ego[i] : pv[i * 4 + (j - o < 0 ? 0 : j - o)];
+                        acc = __fmaf_rn(score[j], v, acc);
+                    }
+                    if (x.active) dst[(size_t)i * x.plane] = acc;
+                }
+                dst += 4 * x.plane; sp += 4 * x.plane;
+            }
+            return;
+        }
+    }
     if (MODE == GC_FUSE_ATT && x.park_mode) {
         // out = sum_j a_j w_j from the parked vectors; the identity ego is re-read from global memory (L2 hits)
         uint32_t pkb = x.park_addr + (uint32_t)(x.g * P + x.p) * 4u;
@@ -419,6 +498,7 @@ struct LaunchPlan {
     int tiles_x, tiles_y, n_tiles;
     int stages, slot_floats, park_slots;   // park_slots: agents whose sampled vectors fit the park (ATT), 0 = two passes
     int n_bound;
+    int park_tmem;   // 1: the AttFusion park lives in tensor memory (no shared memory taken from the ring)
 };
 
 // MODE: GC_FUSE_WARP_ONLY, GC_FUSE_MAX, GC_FUSE_ATT; grid = min(n_tiles, #SM) persistent CTAs
@@ -438,11 +518,13 @@ k_fuse_persist(const __grid_constant__ CUtensorMap tmap_box, const __grid_consta
     const uint32_t ring_addr = smem_u32(base);
     const uint32_t slot_bytes = (uint32_t)plan.slot_floats * 4u;
     const uint32_t park_addr = ring_addr + (uint32_t)plan.stages * slot_bytes;
-    float *const scratch = reinterpret_cast<float *>(base + (size_t)plan.stages * slot_bytes + (size_t)plan.park_slots * C * P * 4);
+    float *const scratch = reinterpret_cast<float *>(base + (size_t)plan.stages * slot_bytes +
+                                                     (plan.park_tmem ? 0 : (size_t)plan.park_slots * C * P * 4));
     __shared__ __align__(8) uint64_t full_bar[kMaxStages], empty_bar[kMaxStages];
     __shared__ __align__(8) uint64_t gfull_bar[kGeomSlots], gempty_bar[kGeomSlots];
     __shared__ int s_geom[kGeomSlots][NMAX][3];
     __shared__ int s_slow[kGeomSlots];
+    __shared__ uint32_t s_tmem;
 
     const int tid = threadIdx.x, lane = tid & 31;
     const bool is_consumer = tid < kConsumers;
@@ -457,7 +539,10 @@ k_fuse_persist(const __grid_constant__ CUtensorMap tmap_box, const __grid_consta
         for (int s = 0; s < kGeomSlots; ++s) { mbar_init(gfull_addr + 8u * s, 1); mbar_init(gempty_addr + 8u * s, kConsumers / 32 + 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    if (MODE == GC_FUSE_ATT && plan.park_tmem && tid < 32) tmem_alloc_all(&s_tmem);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
     // ---- geometry warp: box origins / paths of the tiles ahead, published through a small ring so that neither the
     // producer nor the consumers have the float64 corner evaluation (and the per-tile identity check) on their path
@@ -529,6 +614,9 @@ k_fuse_persist(const __grid_constant__ CUtensorMap tmap_box, const __grid_consta
     x.stages = plan.stages; x.chunks = chunks; x.C = C;
     x.lane = lane; x.g = g; x.p = p; x.sqrt_c = sqrt_c; x.plane = plane;
     x.s = 0; x.parity = 0;
+    x.park_tmem = MODE == GC_FUSE_ATT && plan.park_tmem != 0;
+    // lane quadrant of this warp = (tid / 32) % 4 = (p / 32) % 4 because P % 128 == 0; pixel set p / 128 owns its own columns
+    x.tmem_park = x.park_tmem ? s_tmem + ((uint32_t)(((tid >> 5) & 3) * 32) << 16) + (uint32_t)((p / 128) * C * 4) : 0u;
 
     int slot = 0, it_tile = 0;
     uint32_t gparity = 0;
@@ -601,6 +689,11 @@ k_fuse_persist(const __grid_constant__ CUtensorMap tmap_box, const __grid_consta
         }
 #undef GC_FAST
     }
+    if (MODE == GC_FUSE_ATT && plan.park_tmem) {   // every consumer is done with tensor memory
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        consumer_sync<kConsumers>();
+        if (tid < 32) tmem_free_all(s_tmem);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -658,13 +751,18 @@ static int launch(cudaStream_t st, const float *feat, const int32_t *off, int n_
     const long long cap = (kDynSmemBytes - 128) / 4;   // floats
     const long long scratch = MODE == GC_FUSE_ATT ? 2 * C_::kScratch : 0;   // double buffered by tile parity
     plan.park_slots = 0;
-    if (MODE == GC_FUSE_ATT) {
+    plan.park_tmem = 0;
+    if (MODE == GC_FUSE_ATT && C_::kTmemOK && C % 4 == 0 && n_bound > 1 &&
+        (long long)(C_::P / 128) * C * 4 <= 512 && !getenv("GC_FUSE_NO_TMEM")) {   // 4 columns per (pixel set, channel)
+        plan.park_tmem = 1;               // 512 columns x 128 lanes x 32 bit of tensor memory hold the park
+        plan.park_slots = n_bound - 1;
+    } else if (MODE == GC_FUSE_ATT) {
         // park the sampled vectors of all agents but the ego (normally the identity map) when that leaves at least
         // two ring stages; otherwise (and for tiles whose ego is not the identity) AttFusion takes two passes
         const long long park = (long long)(n_bound - 1) * C * C_::P;
         if (cap - scratch - park >= 2ll * plan.slot_floats) plan.park_slots = n_bound - 1;
     }
-    const long long ring = cap - scratch - (long long)plan.park_slots * C * C_::P;
+    const long long ring = cap - scratch - (plan.park_tmem ? 0 : (long long)plan.park_slots * C * C_::P);
     long long stages = ring / plan.slot_floats;
     if (stages < 2) return 1;
     plan.stages = (int)(stages > kMaxStages ? kMaxStages : stages);
