@@ -267,14 +267,18 @@ __device__ __forceinline__ float pfn_finish(const PfnLane &w, float best, float 
 }
 
 // p: this lane's point (ignored when lane >= n); returns the two channel maxima of the pillar.
+// stage: 32 float4 of shared memory private to the calling warp.  The decorated points are exchanged through it
+// (one broadcast LDS.128 per point instead of four shuffles); arithmetic and order are unchanged.
 __device__ __forceinline__ float2 pfn_pillar(const PfnLane &wa, const PfnLane &wb, float4 p, int n, float cx,
-                                             float cy, float cz) {
+                                             float cy, float cz, float4 *__restrict__ stage) {
     const int lane = threadIdx.x & 31;
     const bool valid = lane < n;
     const float xr = valid ? __fsub_rn(p.x, cx) : 0.0f;
     const float yr = valid ? __fsub_rn(p.y, cy) : 0.0f;
     const float zr = valid ? __fsub_rn(p.z, cz) : 0.0f;
     const float pi = valid ? p.w : 0.0f;
+    __syncwarp();                                   // every lane is done reading the previous pillar's points
+    stage[lane] = make_float4(xr, yr, zr, pi);
     const float inv_n = __frcp_rn((float)n);
     const float mx = __fmul_rn(tree_sum(xr), inv_n);
     const float my = __fmul_rn(tree_sum(yr), inv_n);
@@ -282,13 +286,12 @@ __device__ __forceinline__ float2 pfn_pillar(const PfnLane &wa, const PfnLane &w
     const float ba = pfn_bias(wa, cx, cy, cz, mx, my, mz);
     const float bb = pfn_bias(wb, cx, cy, cz, mx, my, mz);
     float best_a = -INFINITY, best_b = -INFINITY;
+    __syncwarp();                                   // staged points visible to the whole warp
+#pragma unroll 4
     for (int s = 0; s < n; ++s) {
-        const float sx = __shfl_sync(0xffffffffu, xr, s);
-        const float sy = __shfl_sync(0xffffffffu, yr, s);
-        const float sz = __shfl_sync(0xffffffffu, zr, s);
-        const float si = __shfl_sync(0xffffffffu, pi, s);
-        best_a = fmaxf(best_a, pfn_point(wa, sx, sy, sz, si));
-        best_b = fmaxf(best_b, pfn_point(wb, sx, sy, sz, si));
+        const float4 q = stage[s];
+        best_a = fmaxf(best_a, pfn_point(wa, q.x, q.y, q.z, q.w));
+        best_b = fmaxf(best_b, pfn_point(wb, q.x, q.y, q.z, q.w));
     }
     return make_float2(pfn_finish(wa, best_a, ba, n), pfn_finish(wb, best_b, bb, n));
 }
@@ -310,8 +313,9 @@ k_pillar_vfe(const float4 *__restrict__ voxels, const int32_t *__restrict__ num_
     const float cx = __fadd_rn(__fmul_rn((float)c.w, vx), ox);
     const float cy = __fadd_rn(__fmul_rn((float)c.z, vy), oy);
     const float cz = __fadd_rn(__fmul_rn((float)c.y, vz), oz);
+    __shared__ float4 s_stage[8][32];
     const float4 p = __ldg(voxels + (size_t)m * 32 + lane);
-    const float2 r = pfn_pillar(wa, wb, p, n, cx, cy, cz);
+    const float2 r = pfn_pillar(wa, wb, p, n, cx, cy, cz, s_stage[threadIdx.x >> 5]);
     out[(size_t)m * 64 + lane] = r.x;
     out[(size_t)m * 64 + lane + 32] = r.y;
 }
@@ -389,6 +393,7 @@ k_canvas(Src src, int nx, int ny, int C, float *__restrict__ canvas) {
     __shared__ int s_code[kTileX];
     __shared__ int s_list[kTileX];
     __shared__ unsigned s_mask[4];
+    __shared__ float4 s_stage[8][32];   // per-warp point exchange of pfn_pillar
 
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const int x0 = blockIdx.x * kTileX, y = blockIdx.y, b = blockIdx.z;
@@ -416,10 +421,18 @@ k_canvas(Src src, int nx, int ny, int C, float *__restrict__ canvas) {
     __syncthreads();
 
     const bool vec_ok = (nx & 3) == 0;
-    const unsigned my_mask = lane < 8 ? m0 : lane < 16 ? m1 : lane < 24 ? m2 : m3;
-    const unsigned nib = (my_mask >> ((lane & 7) * 4)) & 0xFu;   // occupancy of cells 4*lane .. 4*lane+3
+    const size_t plane = (size_t)ny * nx;
 
     for (int c0 = 0; c0 < C; c0 += 64) {
+        // the tile starts as zeros (empty cells); the load phase overwrites the occupied columns, so the store
+        // phase is a plain shared -> global copy (no per-quad occupancy selects)
+        {
+            float4 *t4 = reinterpret_cast<float4 *>(tile);
+            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int i = t; i < 64 * kTileStride / 4; i += 256) t4[i] = z;
+        }
+        __syncthreads();
         // ---- load phase: one warp per occupied cell -------------------------------------------
         if constexpr (!Src::kFused) {
             const Src &fs = src;
@@ -452,7 +465,7 @@ k_canvas(Src src, int nx, int ny, int C, float *__restrict__ canvas) {
                     const int xc = s_list[k];
                     const int n = __popc(__ballot_sync(0xffffffffu, idx_cur != kEmpty));   // slots fill from 0
                     const float cx = __fadd_rn(__fmul_rn((float)(x0 + xc), fs.vx), fs.ox);
-                    const float2 r = pfn_pillar(wa, wb, p_cur, n, cx, cy, fs.cz);
+                    const float2 r = pfn_pillar(wa, wb, p_cur, n, cx, cy, fs.cz, s_stage[warp]);
                     tile[lane * kTileStride + xc] = r.x;
                     tile[(lane + 32) * kTileStride + xc] = r.y;
                     idx_cur = idx_nxt; p_cur = p_nxt; idx_nxt = idx_nxt2;
@@ -461,27 +474,26 @@ k_canvas(Src src, int nx, int ny, int C, float *__restrict__ canvas) {
         }
         __syncthreads();
         // ---- store phase: every canvas byte of the tile exactly once ---------------------------
-#pragma unroll
-        for (int it = 0; it < 8; ++it) {
-            const int ch = it * 8 + warp;
-            if (c0 + ch >= C) continue;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (nib) {
-                const float4 tv = *reinterpret_cast<const float4 *>(&tile[ch * kTileStride + 4 * lane]);
-                v.x = (nib & 1u) ? tv.x : 0.f;
-                v.y = (nib & 2u) ? tv.y : 0.f;
-                v.z = (nib & 4u) ? tv.z : 0.f;
-                v.w = (nib & 8u) ? tv.w : 0.f;
-            }
+        {
             const int x = x0 + 4 * lane;
-            float *dst = canvas + (((size_t)b * C + c0 + ch) * ny + y) * nx + x;
+            float *dst = canvas + ((size_t)b * C + c0 + warp) * plane + (size_t)y * nx + x;
+            const float4 *src4 = reinterpret_cast<const float4 *>(tile + warp * kTileStride) + lane;
             if (vec_ok && x + 3 < nx) {
-                *reinterpret_cast<float4 *>(dst) = v;
+#pragma unroll
+                for (int it = 0; it < 8; ++it) {
+                    if (c0 + it * 8 + warp < C) *reinterpret_cast<float4 *>(dst + (size_t)it * 8 * plane) = src4[it * 8 * (kTileStride / 4)];
+                }
             } else {
-                if (x < nx) dst[0] = v.x;
-                if (x + 1 < nx) dst[1] = v.y;
-                if (x + 2 < nx) dst[2] = v.z;
-                if (x + 3 < nx) dst[3] = v.w;
+#pragma unroll
+                for (int it = 0; it < 8; ++it) {
+                    if (c0 + it * 8 + warp >= C) continue;
+                    const float4 v = src4[it * 8 * (kTileStride / 4)];
+                    float *d = dst + (size_t)it * 8 * plane;
+                    if (x < nx) d[0] = v.x;
+                    if (x + 1 < nx) d[1] = v.y;
+                    if (x + 2 < nx) d[2] = v.z;
+                    if (x + 3 < nx) d[3] = v.w;
+                }
             }
         }
         __syncthreads();
