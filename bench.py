@@ -213,7 +213,7 @@ def gencomm_sampler_extra(dev, frames=8, agents=4, C=128, H=64, W=128, iters=10)
     rl = torch.full((frames,), agents, dtype=torch.int64)
     out = {"workload": f"configs[2]-shaped: GenComm sampler, {frames} frames x {agents} agents, C={C}, {H}x{W}, T=3",
            "launches_per_call": 1 + 3 * 28}
-    for name in ("bf16", "fp32"):
+    for name in ("tc", "bf16", "fp32"):
         m.precision = name
         for _ in range(3):
             m(feat, cond, rl, noise=noise)
@@ -227,8 +227,9 @@ def gencomm_sampler_extra(dev, frames=8, agents=4, C=128, H=64, W=128, iters=10)
         ms = e0.elapsed_time(e1) / iters
         out[name] = {"ms_per_call": ms, "frames_per_s": frames / (ms * 1e-3),
                      "tflops": frames * agents * 3 * 486.8e6 / (ms * 1e-3) / 1e12}   # 486.8 MFLOP per agent-step
-    out["precision_note"] = ("bf16: conv_in/conv_out as tcgen05 implicit GEMMs (bf16 operands, fp32 TMEM accumulation), "
-                             "GroupNorm/middle layers/posterior fp32; fp32: all CUDA-core fp32")
+    out["precision_note"] = ("tc: conv_in/conv_out as bf16 tcgen05 implicit GEMMs + full-resolution width-8 middle layers as tf32 "
+                             "tcgen05 implicit GEMMs (fp32 TMEM accumulation; GroupNorm statistics, half-resolution layers and "
+                             "posterior arithmetic fp32); bf16: conv_in/conv_out only; fp32: all CUDA-core fp32")
     return out
 
 

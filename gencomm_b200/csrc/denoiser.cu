@@ -29,18 +29,6 @@ namespace gc {
 constexpr int kTH = 8, kTW = 32;   // output tile per CTA (256 threads, one pixel each)
 constexpr int kC8Layers = 26;      // 3x3 convs with 8 outputs per UNet evaluation, execution order
 
-struct C8Params {                  // passed by value as a __grid_constant__ kernel parameter
-    float w[9][16][8];             // [tap][cin][cout]
-    float bias[8];                 // conv bias (+ temb projection for conv1 of a ResnetBlock, per step)
-    float gamma[16], beta[16];     // GroupNorm affine of the (concatenated) input
-    float nin_w[16][8];            // 1x1 nin_shortcut [cin][cout]
-    float nin_b[8];
-};
-static_assert(sizeof(C8Params) == 1328 * 4, "C8Params layout is part of the packed weight format");
-
-enum Geom { kSame = 0, kDown = 1, kUp = 2 };
-enum Res { kNone = 0, kIdent = 1, kNin = 2 };
-
 __device__ __forceinline__ float swish(float v) { return __fdividef(v, 1.0f + __expf(-v)); }
 
 // GroupNorm(4 groups) scale/offset of channel c of a CIN-channel input made of one or two NHWC8 tensors.
@@ -386,6 +374,7 @@ struct Act {          // NHWC8 activation + per-tile statistics
 
 struct UnetWorkspace {
     float *x;                 // [A][C][H][W] current x_t (NCHW)
+    void *tc_packed;          // bf16 B operands of conv_in / conv_out (denoiser_tc.cu)
     Act p[12], q[15];
     size_t bytes;
 };
@@ -402,6 +391,7 @@ static UnetWorkspace carve_unet(void *base, int A, int C, int H, int W) {
         return (float *)p;
     };
     ws.x = take((size_t)A * C * H * W * 4);
+    ws.tc_packed = take(conv_tc_packed_bytes(C));
     auto mk = [&](int h, int w) {
         Act a;
         a.H = h; a.W = w; a.tiles = tiles_of(h, w);
@@ -415,9 +405,21 @@ static UnetWorkspace carve_unet(void *base, int A, int C, int H, int W) {
     return ws;
 }
 
+static int g_precision = 0;   // set by unet_eval for the launch helpers below (host-side, per call)
+
 template <int CIN, bool PRE_GN, int GEOM, int RES>
 static void launch_c8(cudaStream_t st, int A, const Act &ia, const Act *ib, const Act *ra, const Act *rb, Act &o,
                       const C8Params &prm) {
+    if ((g_precision & GC_PREC_TC_MIDDLE) && conv_c8_tc_eligible(GEOM, o.H, o.W)) {   // tf32 tensor cores
+        int tiles = 0;
+        if (conv_c8_tc(st, A, CIN, PRE_GN, GEOM, RES, ia.data, ib ? ib->data : ia.data, ia.stats, ib ? ib->stats : ia.stats,
+                       ia.tiles, ib ? ib->tiles : ia.tiles, ra ? ra->data : nullptr, rb ? rb->data : nullptr, o.data, o.stats,
+                       o.H, o.W, prm, &tiles) == GC_OK) {
+            o.tiles = tiles;
+            return;
+        }
+    }
+    o.tiles = tiles_of(o.H, o.W);
     const dim3 grid((o.W + kTW - 1) / kTW, (o.H + kTH - 1) / kTH, A);
     k_conv_c8<CIN, PRE_GN, GEOM, RES><<<grid, 256, 0, st>>>(
         ia.data, ib ? ib->data : ia.data, ia.stats, ib ? ib->stats : ia.stats, ia.tiles, ib ? ib->tiles : ia.tiles,
@@ -447,12 +449,13 @@ static int unet_eval(cudaStream_t st, int A, int C, int H, int W, const float *c
                      const float *b_out, int mode, float c1, float c2, float sigma, const float *noise, float *pred,
                      int precision) {
     Act *p = ws.p, *q = ws.q;
+    g_precision = precision;
     Bias8 bi;
     for (int i = 0; i < 8; ++i) bi.b[i] = tail.conv_in_bias[i];
     const dim3 gridP((W + kTW - 1) / kTW, (H + kTH - 1) / kTH, A);
     if ((precision & GC_PREC_TC_CONV_IN) && conv_in_tc_eligible(C, H, W)) {                        // hs[0], tcgen05
         p[0].tiles = conv_in_tc_tiles(H, W);
-        if (int rc = conv_in_tc(st, A, cond, ws.x, w_in, bi, C, H, W, p[0].data, p[0].stats)) return rc;
+        if (int rc = conv_in_tc(st, A, cond, ws.x, ws.tc_packed, bi, C, H, W, p[0].data, p[0].stats)) return rc;
     } else {
         k_conv_in<<<gridP, 256, 0, st>>>(cond, ws.x, w_in, bi, C, H, W, p[0].data, p[0].stats);     // hs[0]
     }
@@ -473,7 +476,7 @@ static int unet_eval(cudaStream_t st, int A, int C, int H, int W, const float *c
     Affine8 aff;
     for (int i = 0; i < 8; ++i) { aff.gamma[i] = tail.norm_out_gamma[i]; aff.beta[i] = tail.norm_out_beta[i]; }
     if ((precision & GC_PREC_TC_CONV_OUT) && conv_out_tc_eligible(C, H, W)) {
-        if (int rc = conv_out_tc(st, A, p[11].data, p[11].stats, p[11].tiles, w_out, b_out, aff, C, H, W, mode, c1, c2,
+        if (int rc = conv_out_tc(st, A, p[11].data, p[11].stats, p[11].tiles, ws.tc_packed, b_out, aff, C, H, W, mode, c1, c2,
                                  sigma, noise, ws.x, pred, (precision & GC_PREC_TC_MATERIALIZE) ? 1 : 0))
             return rc;
     } else {
@@ -524,6 +527,8 @@ extern "C" int gc_unet_forward(const float *cond, const float *x, int total_agen
     const C8Params *prm = reinterpret_cast<const C8Params *>(w_host) + (size_t)t_index * kC8Layers;
     const HostTail &tail = *reinterpret_cast<const HostTail *>(reinterpret_cast<const C8Params *>(w_host) + (size_t)T * kC8Layers);
     const float *w_in = w_dev, *w_out = w_dev + (size_t)(C + 2) * 72, *b_out = w_out + (size_t)C * 72;
+    if (precision & GC_PREC_BF16_TC)
+        if (int rc = conv_tc_pack_weights(st, w_in, w_out, C, ws.tc_packed)) return rc;
     return unet_eval(st, total_agents, C, H, W, cond, ws, prm, tail, w_in, w_out, b_out, 0, 0.f, 0.f, 0.f, nullptr, pred,
                      precision);
 }
@@ -544,6 +549,8 @@ extern "C" int gc_gencomm_sample(const float *feat, const float *cond, const int
     const float *w_in = w_dev, *w_out = w_dev + (size_t)(C + 2) * 72, *b_out = w_out + (size_t)C * 72;
     // schedule_host: [T][5] = sqrt_alphas_cumprod, sqrt_one_minus_alphas_cumprod, posterior_mean_coef1,
     //                         posterior_mean_coef2, exp(0.5 * posterior_log_variance_clipped)
+    if (precision & GC_PREC_BF16_TC)
+        if (int rc = conv_tc_pack_weights(st, w_in, w_out, C, ws.tc_packed)) return rc;
     const float *sT = schedule_host + (size_t)(T - 1) * 5;
     int gx = (int)((per_agent / 4 + 255) / 256);
     gx = gx > 1024 ? 1024 : gx;

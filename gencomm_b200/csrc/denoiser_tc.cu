@@ -126,6 +126,40 @@ __device__ __forceinline__ void gn_coeff8(int c, int agent, const float *__restr
 }
 
 // ------------------------------------------------------------------------------------------------
+// One-time (per call) repack of the fp32 conv weights into the bf16 UMMA B-operand byte layouts, so that every CTA
+// copies its B operand with coalesced 16-byte loads instead of converting scattered fp32 weights itself.
+//   conv_out: [12 k-chunks (ky*4+kx, kx == 3 zero)][C rows][8 bf16]          from w [C][9][8] (cout, tap, cin)
+//   conv_in : [chunks][9 taps][2 groups][8 cout][8 bf16]                     from w [C+2][9][8] (cin, tap, cout)
+// ------------------------------------------------------------------------------------------------
+__global__ void k_pack_conv_out_w(const float *__restrict__ w, int C, uint4 *__restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 12 * C) return;
+    const int n = i % C, kc = i / C, ky = kc >> 2, kx = kc & 3;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (kx < 3) {
+        const float4 *src = reinterpret_cast<const float4 *>(w + ((size_t)n * 9 + ky * 3 + kx) * 8);
+        const float4 lo = __ldg(src), hi = __ldg(src + 1);
+        v = make_uint4(pack_bf16(lo.x, lo.y), pack_bf16(lo.z, lo.w), pack_bf16(hi.x, hi.y), pack_bf16(hi.z, hi.w));
+    }
+    out[i] = v;
+}
+
+__global__ void k_pack_conv_in_w(const float *__restrict__ w, int C, int chunks, uint4 *__restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= chunks * 9 * 2 * 8) return;
+    const int n = i & 7, gsel = (i >> 3) & 1, tap = (i >> 4) % 9, q = (i >> 4) / 9;
+    const int g = 2 * q + gsel;
+    float f[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const int kc = 8 * g + c;                       // GEMM channel: x_0..x_{C-1}, cond_0, cond_1, zeros
+        const int cin = kc < C ? kc + 2 : kc - C;       // reference channel (cond first)
+        f[c] = kc < C + 2 ? __ldg(w + ((size_t)cin * 9 + tap) * 8 + n) : 0.0f;
+    }
+    out[i] = pack8(f);
+}
+
+// ------------------------------------------------------------------------------------------------
 // norm_out + swish + conv_out on tensor cores.  grid = (W/128, H, A * C/NT), 128 threads.
 //   in  [A][H][W][8] f32 (NHWC8) + GroupNorm partial sums;  w [C][9][8] f32 (cout, tap, cin); bias [C]
 //   mode 0: pred = x0;  mode 1: x <- (c1*x0 + c2*x) + sigma*noise   (NCHW f32)
@@ -134,7 +168,7 @@ constexpr int kOutRowPx = 132;   // staged pixels per row: x0-1 .. x0+130 (taps 
 
 template <int NT>
 __global__ void __launch_bounds__(128)
-k_conv_out_tc(const float *__restrict__ in, const float *__restrict__ st_in, int tiles_in, const float *__restrict__ w,
+k_conv_out_tc(const float *__restrict__ in, const float *__restrict__ st_in, int tiles_in, const uint4 *__restrict__ wp,
               const float *__restrict__ bias, Affine8 aff, int C, int H, int W, int mode, float c1, float c2, float sigma,
               const float *__restrict__ noise, float *__restrict__ x, float *__restrict__ pred, int materialize) {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -158,16 +192,10 @@ k_conv_out_tc(const float *__restrict__ in, const float *__restrict__ st_in, int
         gn_coeff8(c, agent, st_in, tiles_in, H * W, aff.gamma[c], aff.beta[c], &s_ga[c], &s_gb[c]);
     }
     for (int i = tid; i < NT; i += 128) s_bias[i] = __ldg(bias + co0 + i);
-    // ---- B operand: weights -> bf16, K-major core matrices; k-chunk kc = ky*4 + kx, kx == 3 is zero ----
+    // ---- B operand: pre-packed bf16 K-major core matrices [kc][C][16 B]; this CTA's NT rows of every k-chunk ----
     for (int i = tid; i < 12 * NT; i += 128) {
-        const int n = i % NT, kc = i / NT, ky = kc >> 2, kx = kc & 3;
-        uint4 v = make_uint4(0u, 0u, 0u, 0u);
-        if (kx < 3) {
-            const float4 *src = reinterpret_cast<const float4 *>(w + ((size_t)(co0 + n) * 9 + ky * 3 + kx) * 8);
-            const float4 lo = __ldg(src), hi = __ldg(src + 1);
-            v = make_uint4(pack_bf16(lo.x, lo.y), pack_bf16(lo.z, lo.w), pack_bf16(hi.x, hi.y), pack_bf16(hi.z, hi.w));
-        }
-        b_s[kc * NT + n] = v;
+        const int n = i % NT, kc = i / NT;
+        b_s[i] = __ldg(wp + (size_t)kc * C + co0 + n);
     }
     __syncthreads();
     // ---- A rows: GroupNorm + swish -> bf16; zero outside the image (padding applies AFTER the activation) ----
@@ -252,7 +280,7 @@ constexpr int kInRowPx = 130;              // x0-1 .. x0+128
 constexpr int kInGroupU4 = kInStaged * kInRowPx;   // uint4 per channel group per buffer
 
 __global__ void __launch_bounds__(128)
-k_conv_in_tc(const float *__restrict__ cond, const float *__restrict__ x, const float *__restrict__ w, Bias8 bias, int C,
+k_conv_in_tc(const float *__restrict__ cond, const float *__restrict__ x, const uint4 *__restrict__ wp, Bias8 bias, int C,
              int H, int W, float *__restrict__ out, float *__restrict__ stats_out) {
     extern __shared__ __align__(128) uint8_t smem[];
     // [A: 2 buffers][2 groups][6 rows][130 px][16 B]  |  [B: chunks][9 taps][2 groups][8 cout][16 B]
@@ -272,19 +300,8 @@ k_conv_in_tc(const float *__restrict__ cond, const float *__restrict__ x, const 
         mbar_init(smem_u32(&s_empty[0]), 1); mbar_init(smem_u32(&s_empty[1]), 1); mbar_init(smem_u32(&s_done), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    // ---- B operand for every chunk: [q][tap][gsel][n] = 8 consecutive GEMM channels of output n ----
-    for (int i = tid; i < chunks * 9 * 2 * 8; i += 128) {
-        const int n = i & 7, gsel = (i >> 3) & 1, tap = (i >> 4) % 9, q = (i >> 4) / 9;
-        const int g = 2 * q + gsel;
-        float f[8];
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            const int kc = 8 * g + c;                       // GEMM channel
-            const int cin = kc < C ? kc + 2 : kc - C;       // reference channel (cond first)
-            f[c] = kc < C + 2 ? __ldg(w + ((size_t)cin * 9 + tap) * 8 + n) : 0.0f;
-        }
-        b_s[i] = pack8(f);
-    }
+    // ---- B operand for every chunk: pre-packed [q][tap][gsel][n][8 bf16] ----
+    for (int i = tid; i < chunks * 9 * 2 * 8; i += 128) b_s[i] = __ldg(wp + i);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -297,34 +314,39 @@ k_conv_in_tc(const float *__restrict__ cond, const float *__restrict__ x, const 
         const int b = q & 1;
         if (q >= 2) mbar_wait(smem_u32(&s_empty[b]), (uint32_t)((q >> 1) - 1) & 1u);   // MMAs of chunk q-2 retired
         uint4 *buf = a_s + b * 2 * kInGroupU4;
-        // ---- stage chunk q: thread = pixel column, all 6 rows, both channel groups ----
+        // ---- stage chunk q: thread = pixel column; per channel group all 6 rows x 8 channels are loaded first
+        // (48 independent loads in flight per thread), then packed to bf16 and stored ----
         for (int px = tid; px < kInRowPx; px += 128) {
             const int gx = x0 - 1 + px;
             const bool xin = gx >= 0 && gx < W;
 #pragma unroll
             for (int gsel = 0; gsel < 2; ++gsel) {
                 const int g = 2 * q + gsel;
+                float f[kInStaged][8];
+                if (xin && g < C / 8) {
+                    const float *src = x + ((size_t)agent * C + 8 * g) * plane + gx;
 #pragma unroll
-                for (int r = 0; r < kInStaged; ++r) {
-                    const int gy = y0 - 1 + r;
-                    uint4 v = make_uint4(0u, 0u, 0u, 0u);
-                    if (xin && gy >= 0 && gy < H && g < groups) {
-                        const size_t pix = (size_t)gy * W + gx;
-                        float f[8];
-                        if (g < C / 8) {
-                            const float *src = x + ((size_t)agent * C + 8 * g) * plane + pix;
+                    for (int r = 0; r < kInStaged; ++r) {
+                        const int gy = y0 - 1 + r;
+                        const bool yin = gy >= 0 && gy < H;
+                        const float *sr = src + (size_t)(yin ? gy : 0) * W;
 #pragma unroll
-                            for (int c = 0; c < 8; ++c) f[c] = __ldg(src + (size_t)c * plane);
-                        } else {
-                            const float *src = cond + (size_t)agent * 2 * plane + pix;
-                            f[0] = __ldg(src); f[1] = __ldg(src + plane);
-#pragma unroll
-                            for (int c = 2; c < 8; ++c) f[c] = 0.0f;
-                        }
-                        v = pack8(f);
+                        for (int c = 0; c < 8; ++c) f[r][c] = yin ? __ldg(sr + (size_t)c * plane) : 0.0f;
                     }
-                    buf[(gsel * kInStaged + r) * kInRowPx + px] = v;
+                } else {
+#pragma unroll
+                    for (int r = 0; r < kInStaged; ++r) {
+                        const int gy = y0 - 1 + r;
+                        const bool ok = xin && g == C / 8 && gy >= 0 && gy < H;
+                        const float *sr = cond + (size_t)agent * 2 * plane + (size_t)(ok ? gy : 0) * W + (ok ? gx : 0);
+                        f[r][0] = ok ? __ldg(sr) : 0.0f;
+                        f[r][1] = ok ? __ldg(sr + plane) : 0.0f;
+#pragma unroll
+                        for (int c = 2; c < 8; ++c) f[r][c] = 0.0f;
+                    }
                 }
+#pragma unroll
+                for (int r = 0; r < kInStaged; ++r) buf[(gsel * kInStaged + r) * kInRowPx + px] = pack8(f[r]);
             }
         }
         fence_async_smem();
@@ -392,6 +414,214 @@ k_conv_in_tc(const float *__restrict__ cond, const float *__restrict__ x, const 
     if (warp == 0) tmem_free<64>(tmem);
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Width-8 middle layers on tensor cores: 3x3 conv, CIN (8 or 16) -> 8 channels on NHWC8 fp32 tensors, tf32 operands
+// (fp32 storage, no conversion pass), fp32 accumulation in TMEM.  unet.py:117-138 (ResnetBlock), :40-56 (Upsample).
+// grid = (W/128, ceil(H/4), A), 128 threads; H, W are the OUTPUT dims (kUp: the input is H/2 x W/2).
+//
+// For 32-bit operands a K-major core matrix is 8 rows x 4 elements, so the 8 channels of a pixel are staged as two
+// 16-byte halves in two planes [half][row][pixel]; one K = 8 MMA reads the two halves of one channel group
+// (LBO = plane stride) at the tap's shifted start address.  GroupNorm + swish are applied while staging (padding is
+// zero AFTER the activation); bias / timestep embedding, the residual or the 1x1 nin_shortcut and the GroupNorm
+// partial sums of the output are the epilogue.  N = 16 with SBO = 0 on B (columns 8..15 alias 0..7, ignored).
+// ------------------------------------------------------------------------------------------------
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+constexpr int kMidRows = 4, kMidStaged = kMidRows + 2, kMidRowPx = 130;
+constexpr int kMidPlaneU4 = kMidStaged * kMidRowPx;   // uint4 (16-byte pixel halves) per plane
+
+template <int CIN, bool PRE_GN, int GEOM, int RES>
+__global__ void __launch_bounds__(128)
+k_conv_c8_tc(const float *__restrict__ in_a, const float *__restrict__ in_b, const float *__restrict__ st_a,
+             const float *__restrict__ st_b, int tiles_a, int tiles_b, const float *__restrict__ res_a,
+             const float *__restrict__ res_b, float *__restrict__ out, float *__restrict__ stats_out, int H, int W,
+             const __grid_constant__ C8Params prm) {
+    constexpr int CG = CIN / 8;                       // channel groups of 8
+    extern __shared__ __align__(128) uint8_t smem[];
+    // [A: CG groups x 2 halves planes][6 rows][130 px][16 B]  |  [B: 9 taps][CG][2 halves][8 cout][16 B]
+    float4 *a_s = reinterpret_cast<float4 *>(smem);
+    float4 *b_s = a_s + CG * 2 * kMidPlaneU4;
+    __shared__ __align__(8) uint64_t s_done;
+    __shared__ uint32_t s_tmem;
+    __shared__ float s_ga[16], s_gb[16], s_part[4][8];
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int agent = blockIdx.z, x0 = blockIdx.x * 128, y0 = blockIdx.y * kMidRows;
+    const int Hin = GEOM == kUp ? H / 2 : H, Win = GEOM == kUp ? W / 2 : W;
+
+    if (warp == 0) tmem_alloc<kMidRows * 16 <= 32 ? 32 : 64>(&s_tmem);
+    if (tid == 32) { mbar_init(smem_u32(&s_done), 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    if (PRE_GN && tid >= 64 && tid < 64 + CIN) {
+        // GroupNorm(4 groups) coefficients from per-tile partial sums (same fixed-order float64 combination as
+        // gn_coeff<CIN> in denoiser.cu): CIN == 8: one channel pair per group; CIN == 16: two pairs of one tensor
+        const int c = tid - 64, cc = c & 7;
+        const int tiles = c < 8 ? tiles_a : tiles_b;
+        const float *st = (c < 8 ? st_a : st_b) + (size_t)agent * tiles * 8;
+        double sum = 0.0, ssq = 0.0;
+        if (CIN == 8) {
+            const int pr = cc >> 1;
+            for (int t = 0; t < tiles; ++t) { sum += st[t * 8 + 2 * pr]; ssq += st[t * 8 + 2 * pr + 1]; }
+        } else {
+            const int pr = (cc >> 2) * 2;
+            for (int t = 0; t < tiles; ++t) {
+                sum += (double)st[t * 8 + 2 * pr] + (double)st[t * 8 + 2 * pr + 2];
+                ssq += (double)st[t * 8 + 2 * pr + 1] + (double)st[t * 8 + 2 * pr + 3];
+            }
+        }
+        const double cnt = (double)Hin * Win * (CIN == 8 ? 2.0 : 4.0);
+        const double mean = sum / cnt;
+        double var = ssq / cnt - mean * mean;
+        var = var < 0.0 ? 0.0 : var;
+        const double rstd = 1.0 / sqrt(var + 1e-6);
+        s_ga[c] = (float)((double)prm.gamma[c] * rstd);
+        s_gb[c] = (float)((double)prm.beta[c] - mean * (double)prm.gamma[c] * rstd);
+    }
+    // ---- B operand: [tap][cg][half][n] = w[tap][cg*8 + half*4 .. +3][n] ----
+    for (int i = tid; i < 9 * CG * 2 * 8; i += 128) {
+        const int n = i & 7, half = (i >> 3) & 1, cg = (i >> 4) % CG, tap = (i >> 4) / CG;
+        const int c = cg * 8 + half * 4;
+        b_s[i] = make_float4(prm.w[tap][c][n], prm.w[tap][c + 1][n], prm.w[tap][c + 2][n], prm.w[tap][c + 3][n]);
+    }
+    __syncthreads();
+    // ---- A operand: thread = pixel column, 6 rows; all loads of a channel group first, then activation + store ----
+    for (int px = tid; px < kMidRowPx; px += 128) {
+        const int gx = x0 - 1 + px;
+        const bool xin = gx >= 0 && gx < W;
+        const int ix = GEOM == kUp ? gx >> 1 : gx;      // nearest x2 upsample (unet.py:52-53)
+#pragma unroll
+        for (int cg = 0; cg < CG; ++cg) {
+            const float *src = (cg == 0 ? in_a : in_b) + (size_t)agent * Hin * Win * 8;
+            float4 v[kMidStaged][2];
+#pragma unroll
+            for (int r = 0; r < kMidStaged; ++r) {
+                const int gy = y0 - 1 + r;
+                const bool ok = xin && gy >= 0 && gy < H;
+                const int iy = GEOM == kUp ? gy >> 1 : gy;
+                const float4 *q = reinterpret_cast<const float4 *>(src + ((size_t)(ok ? iy : 0) * Win + (ok ? ix : 0)) * 8);
+                v[r][0] = ok ? __ldg(q) : make_float4(0.f, 0.f, 0.f, 0.f);
+                v[r][1] = ok ? __ldg(q + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int r = 0; r < kMidStaged; ++r) {
+                const int gy = y0 - 1 + r;
+                const bool ok = xin && gy >= 0 && gy < H;
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    float4 u = v[r][half];
+                    if (PRE_GN && ok) {
+                        const int c = cg * 8 + half * 4;
+                        u.x = swish(fmaf(u.x, s_ga[c + 0], s_gb[c + 0]));
+                        u.y = swish(fmaf(u.y, s_ga[c + 1], s_gb[c + 1]));
+                        u.z = swish(fmaf(u.z, s_ga[c + 2], s_gb[c + 2]));
+                        u.w = swish(fmaf(u.w, s_ga[c + 3], s_gb[c + 3]));
+                    }
+                    a_s[((cg * 2 + half) * kMidStaged + r) * kMidRowPx + px] = u;
+                }
+            }
+        }
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = s_tmem;
+    if (tid == 0) {
+        constexpr uint32_t idesc = make_idesc_tf32(128, 16);
+        constexpr uint32_t kPlaneBytes = kMidPlaneU4 * 16u;
+        const uint32_t a_base = smem_u32(a_s), b_base = smem_u32(b_s);
+#pragma unroll 1
+        for (int tap = 0; tap < 9; ++tap) {
+            const int ky = tap / 3, kx = tap % 3;
+#pragma unroll
+            for (int cg = 0; cg < CG; ++cg) {
+                const uint64_t bdesc = make_desc(b_base + (uint32_t)((tap * CG + cg) * 2) * 128u, 128u, 0u);
+#pragma unroll
+                for (int r = 0; r < kMidRows; ++r) {
+                    const uint64_t adesc = make_desc(a_base + (uint32_t)(cg * 2) * kPlaneBytes + (uint32_t)((r + ky) * kMidRowPx + kx) * 16u,
+                                                     kPlaneBytes, 128u);
+                    mma_tf32(tmem + (uint32_t)(r * 16), adesc, bdesc, idesc, (tap > 0 || cg > 0) ? 1u : 0u);
+                }
+            }
+        }
+        mma_commit(smem_u32(&s_done));
+    }
+    mbar_wait(smem_u32(&s_done), 0u);
+    tc_fence_after();
+
+    // ---- epilogue: thread = pixel ----
+    const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
+    float q8[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) q8[i] = 0.0f;
+#pragma unroll
+    for (int r = 0; r < kMidRows; ++r) {
+        float acc[8];
+        tmem_ld8(taddr + (uint32_t)(r * 16), acc);
+        const int yy = y0 + r;
+        if (yy < H) {
+            const size_t pix = ((size_t)agent * H + yy) * W + x0 + tid;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[i] += prm.bias[i];
+            if (RES != kNone) {
+                const float4 a0 = __ldg(reinterpret_cast<const float4 *>(res_a + pix * 8));
+                const float4 a1 = __ldg(reinterpret_cast<const float4 *>(res_a + pix * 8 + 4));
+                if (RES == kIdent) {
+                    acc[0] += a0.x; acc[1] += a0.y; acc[2] += a0.z; acc[3] += a0.w;
+                    acc[4] += a1.x; acc[5] += a1.y; acc[6] += a1.z; acc[7] += a1.w;
+                } else {
+                    const float4 b0 = __ldg(reinterpret_cast<const float4 *>(res_b + pix * 8));
+                    const float4 b1 = __ldg(reinterpret_cast<const float4 *>(res_b + pix * 8 + 4));
+                    const float xr[16] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w,
+                                          b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+                    for (int o = 0; o < 8; ++o) {
+                        float sh = prm.nin_b[o];
+#pragma unroll
+                        for (int ci = 0; ci < 16; ++ci) sh = fmaf(xr[ci], prm.nin_w[ci][o], sh);
+                        acc[o] += sh;
+                    }
+                }
+            }
+            float4 *dst = reinterpret_cast<float4 *>(out + pix * 8);
+            dst[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+            dst[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+#pragma unroll
+            for (int pr = 0; pr < 4; ++pr) {
+                q8[2 * pr] += acc[2 * pr] + acc[2 * pr + 1];
+                q8[2 * pr + 1] += acc[2 * pr] * acc[2 * pr] + acc[2 * pr + 1] * acc[2 * pr + 1];
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) q8[i] += __shfl_xor_sync(0xffffffffu, q8[i], m);
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s_part[warp][i] = q8[i];
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (tid < 8) {
+        const float t = (s_part[0][tid] + s_part[1][tid]) + (s_part[2][tid] + s_part[3][tid]);
+        const int tiles = gridDim.x * gridDim.y, tile = blockIdx.y * gridDim.x + blockIdx.x;
+        stats_out[((size_t)agent * tiles + tile) * 8 + tid] = t;
+    }
+    if (warp == 0) tmem_free<kMidRows * 16 <= 32 ? 32 : 64>(tmem);
+}
+
 }  // namespace tc
 
 // ------------------------------------------------------------------------------------------------
@@ -407,8 +637,24 @@ bool conv_in_tc_eligible(int C, int H, int W) {
 
 int conv_in_tc_tiles(int H, int W) { return (W / 128) * ((H + tc::kInRows - 1) / tc::kInRows); }
 
-int conv_in_tc(cudaStream_t st, int A, const float *cond, const float *x, const float *w, const Bias8 &bias, int C, int H,
+size_t conv_tc_packed_bytes(int C) {   // conv_in B operand, then conv_out B operand
+    const size_t chunks = (size_t)(C / 8 + 1 + 1) / 2;
+    return align_up(chunks * 9 * 2 * 8 * 16, 256) + (size_t)12 * C * 16;
+}
+
+int conv_tc_pack_weights(cudaStream_t st, const float *w_in, const float *w_out, int C, void *packed) {
+    const int chunks = (C / 8 + 1 + 1) / 2;
+    uint4 *pin = reinterpret_cast<uint4 *>(packed);
+    uint4 *pout = reinterpret_cast<uint4 *>(reinterpret_cast<char *>(packed) + align_up((size_t)chunks * 9 * 2 * 8 * 16, 256));
+    tc::k_pack_conv_in_w<<<(chunks * 9 * 2 * 8 + 127) / 128, 128, 0, st>>>(w_in, C, chunks, pin);
+    tc::k_pack_conv_out_w<<<(12 * C + 127) / 128, 128, 0, st>>>(w_out, C, pout);
+    GC_LAUNCH_CHECK("conv_tc_pack_weights");
+    return GC_OK;
+}
+
+int conv_in_tc(cudaStream_t st, int A, const float *cond, const float *x, const void *packed, const Bias8 &bias, int C, int H,
                int W, float *out, float *stats_out) {
+    const uint4 *w = reinterpret_cast<const uint4 *>(packed);
     const int chunks = (C / 8 + 1 + 1) / 2;
     const size_t smem = (size_t)2 * 2 * tc::kInGroupU4 * 16 + (size_t)chunks * 9 * 2 * 128;
     static size_t configured = 0;
@@ -436,7 +682,7 @@ bool conv_out_tc_eligible(int C, int H, int W) {
 }
 
 template <int NT>
-static int launch_out(cudaStream_t st, int A, const float *in, const float *st_in, int tiles_in, const float *w,
+static int launch_out(cudaStream_t st, int A, const float *in, const float *st_in, int tiles_in, const uint4 *w,
                       const float *bias, const Affine8 &aff, int C, int H, int W, int mode, float c1, float c2, float sigma,
                       const float *noise, float *x, float *pred, int materialize) {
     const size_t smem = (size_t)12 * NT * 16 + (size_t)3 * tc::kOutRowPx * 16 + (size_t)12 * 128 * 16;
@@ -453,9 +699,11 @@ static int launch_out(cudaStream_t st, int A, const float *in, const float *st_i
     return GC_OK;
 }
 
-int conv_out_tc(cudaStream_t st, int A, const float *in, const float *st_in, int tiles_in, const float *w, const float *bias,
+int conv_out_tc(cudaStream_t st, int A, const float *in, const float *st_in, int tiles_in, const void *packed, const float *bias,
                 const Affine8 &aff, int C, int H, int W, int mode, float c1, float c2, float sigma, const float *noise,
                 float *x, float *pred, int materialize) {
+    const int chunks = (C / 8 + 1 + 1) / 2;
+    const uint4 *w = reinterpret_cast<const uint4 *>(reinterpret_cast<const char *>(packed) + align_up((size_t)chunks * 9 * 2 * 8 * 16, 256));
     switch (pick_nt(C)) {
         case 256: return launch_out<256>(st, A, in, st_in, tiles_in, w, bias, aff, C, H, W, mode, c1, c2, sigma, noise, x, pred, materialize);
         case 128: return launch_out<128>(st, A, in, st_in, tiles_in, w, bias, aff, C, H, W, mode, c1, c2, sigma, noise, x, pred, materialize);
@@ -463,6 +711,48 @@ int conv_out_tc(cudaStream_t st, int A, const float *in, const float *st_in, int
         default: break;
     }
     set_error("conv_out_tc: unsupported channel count %d", C);
+    return GC_EUNSUPPORTED;
+}
+
+bool conv_c8_tc_eligible(int geom, int H, int W) {
+    (void)H;
+    return W % 128 == 0 && (geom == kSame || geom == kUp) && (geom != kUp || (H % 2 == 0));
+}
+
+template <int CIN, bool PRE_GN, int GEOM, int RES>
+static int launch_c8_tc(cudaStream_t st, int A, const float *in_a, const float *in_b, const float *st_a, const float *st_b,
+                        int tiles_a, int tiles_b, const float *res_a, const float *res_b, float *out, float *stats_out, int H,
+                        int W, const C8Params &prm) {
+    constexpr int CG = CIN / 8;
+    const size_t smem = (size_t)CG * 2 * tc::kMidPlaneU4 * 16 + (size_t)9 * CG * 2 * 128;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(tc::k_conv_c8_tc<CIN, PRE_GN, GEOM, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { (void)cudaGetLastError(); set_error("k_conv_c8_tc: cudaFuncSetAttribute failed (%d)", (int)e); return (int)e; }
+        configured = true;
+    }
+    const dim3 grid(W / 128, (H + tc::kMidRows - 1) / tc::kMidRows, A);
+    tc::k_conv_c8_tc<CIN, PRE_GN, GEOM, RES><<<grid, 128, smem, st>>>(in_a, in_b, st_a, st_b, tiles_a, tiles_b, res_a, res_b, out,
+                                                                      stats_out, H, W, prm);
+    GC_LAUNCH_CHECK("k_conv_c8_tc");
+    return GC_OK;
+}
+
+int conv_c8_tc(cudaStream_t st, int A, int cin, bool pre_gn, int geom, int res, const float *in_a, const float *in_b,
+               const float *st_a, const float *st_b, int tiles_a, int tiles_b, const float *res_a, const float *res_b,
+               float *out, float *stats_out, int H, int W, const C8Params &prm, int *tiles_out) {
+    *tiles_out = (W / 128) * ((H + tc::kMidRows - 1) / tc::kMidRows);
+#define GC_C8(CIN, PRE, GEOM, RES)                                                                                   \
+    if (cin == CIN && pre_gn == PRE && geom == GEOM && res == RES)                                                   \
+        return launch_c8_tc<CIN, PRE, GEOM, RES>(st, A, in_a, in_b, st_a, st_b, tiles_a, tiles_b, res_a, res_b, out, \
+                                                 stats_out, H, W, prm);
+    GC_C8(8, true, kSame, kNone)
+    GC_C8(8, true, kSame, kIdent)
+    GC_C8(8, true, kSame, kNin)
+    GC_C8(16, true, kSame, kNone)
+    GC_C8(8, false, kUp, kNone)
+#undef GC_C8
+    set_error("conv_c8_tc: unsupported layer variant (cin %d, geom %d, res %d)", cin, geom, res);
     return GC_EUNSUPPORTED;
 }
 

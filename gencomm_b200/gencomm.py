@@ -192,7 +192,7 @@ class DiffusionUNet(nn.Module):
         self.norm_out = _gn(8)
         self.conv_out = nn.Conv2d(8, m.out_ch, 3, 1, 1)
         self._packed = None
-        self.precision = ops.PREC_BF16_TC   # see GenComm.precision
+        self.precision = ops.PREC_TC_ALL   # see GenComm.precision
 
     def packed(self, T, device):
         """(host blob, device blob) for T steps, rebuilt when any parameter changes."""
@@ -218,8 +218,9 @@ class GenComm(nn.Module):
     Extension: ``forward(..., noise=(noise0, [step noises]))`` injects pre-drawn Gaussian noise (parity tests);
     by default it is drawn on the device with ``torch.randn`` in the reference's order.
 
-    ``precision``: ``'bf16'`` (default) runs conv_in / conv_out as bf16 tcgen05 implicit GEMMs with fp32
+    ``precision``: ``'bf16'`` runs conv_in / conv_out as bf16 tcgen05 implicit GEMMs with fp32
     accumulation where the shape allows (W % 128 == 0, C % 64 == 0) and everything else in fp32;
+    ``'tc'`` additionally runs the full-resolution width-8 middle layers as tf32 tcgen05 implicit GEMMs;
     ``'fp32'`` keeps every layer in fp32 (parity path, <= 1e-4 of the reference).
     """
 
@@ -237,12 +238,12 @@ class GenComm(nn.Module):
 
     @property
     def precision(self):
-        return 'fp32' if self.denoiser.precision == ops.PREC_F32 else 'bf16'
+        return {ops.PREC_F32: 'fp32', ops.PREC_BF16_TC: 'bf16', ops.PREC_TC_ALL: 'tc'}.get(self.denoiser.precision, 'custom')
 
     @precision.setter
     def precision(self, value):
         if isinstance(value, str):
-            value = {'fp32': ops.PREC_F32, 'bf16': ops.PREC_BF16_TC}[value]
+            value = {'fp32': ops.PREC_F32, 'bf16': ops.PREC_BF16_TC, 'tc': ops.PREC_TC_ALL}[value]
         self.denoiser.precision = int(value)
 
     def forward(self, spatial_features, conditions, record_len=None, noise=None):

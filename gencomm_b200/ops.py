@@ -14,6 +14,7 @@ from . import _lib
 FUSE_WARP_ONLY, FUSE_MAX, FUSE_ATT = 0, 1, 2
 # denoiser arithmetic (include/gencomm_b200.h GC_PREC_*)
 PREC_F32, PREC_TC_CONV_IN, PREC_TC_CONV_OUT, PREC_BF16_TC, PREC_TC_MATERIALIZE = 0, 1, 2, 3, 4
+PREC_TC_MIDDLE, PREC_TC_ALL = 8, 11
 MAX_POINTS_PER_PILLAR = 32
 MAX_AGENTS_PER_FRAME = 8
 

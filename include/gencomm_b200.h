@@ -46,6 +46,8 @@ extern "C" {
 #define GC_PREC_TC_CONV_OUT 2  /* norm_out + swish + conv_out (8 -> C, K = 72) */
 #define GC_PREC_BF16_TC 3      /* both */
 #define GC_PREC_TC_MATERIALIZE 4 /* validation: explicit im2col operand instead of overlapping windows */
+#define GC_PREC_TC_MIDDLE 8    /* full-resolution width-8 middle layers as tf32 tcgen05 implicit GEMMs */
+#define GC_PREC_TC_ALL 11      /* conv_in/conv_out bf16 + middle layers tf32 */
 
 int gc_version(void);
 const char *gc_last_error(void);

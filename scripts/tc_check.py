@@ -69,7 +69,7 @@ def main():
     ref_u = m.denoiser(x, t)
     ref_s = m(feat, cond, rl, noise=noise)["pred_feature"]
     torch.cuda.synchronize()
-    names = {1: "conv_in tc", 2: "conv_out tc", 2 | 4: "conv_out tc (materialized A)", 3: "both tc", 3 | 4: "both tc (materialized A)"}
+    names = {1: "conv_in tc", 2: "conv_out tc", 2 | 4: "conv_out tc (materialized A)", 3: "both tc", 8: "middle tf32 tc", 11: "all tc"}
     for prec, name in names.items():
         m.denoiser.precision = prec
         u = m.denoiser(x, t)
@@ -79,7 +79,11 @@ def main():
     s = m(feat, cond, rl, noise=noise)["pred_feature"]
     torch.cuda.synchronize()
     print(f"sampler bf16-tc vs fp32: max-rel {rel(s, ref_s)[0]:.3e} mean-rel {rel(s, ref_s)[1]:.3e}", flush=True)
-    for prec, name in ((0, "fp32"), (3, "bf16 tc")):
+    m.denoiser.precision = ops.PREC_TC_ALL
+    s = m(feat, cond, rl, noise=noise)["pred_feature"]
+    torch.cuda.synchronize()
+    print(f"sampler all-tc vs fp32: max-rel {rel(s, ref_s)[0]:.3e} mean-rel {rel(s, ref_s)[1]:.3e}", flush=True)
+    for prec, name in ((0, "fp32"), (3, "bf16 tc"), (11, "all tc")):
         m.denoiser.precision = prec
         ms = timeit(lambda: m(feat, cond, rl, noise=noise))
         print(f"sampler {name:8s} A={A} C={C} {H}x{W}: {ms:.3f} ms / call ({ms / A:.3f} ms per agent)", flush=True)

@@ -119,10 +119,18 @@ def test_sampler_bf16_tensor_core_path(C, H, W, record_len):
     m.precision = ops.PREC_BF16_TC | ops.PREC_TC_MATERIALIZE
     out2 = m(*args, noise=noise)["pred_feature"]
     assert torch.equal(out, out2)
+    # 'tc': additionally the full-resolution width-8 middle layers as tf32 tcgen05 implicit GEMMs; same tolerance
+    m.precision = "tc"
+    out3 = m(*args, noise=noise)["pred_feature"]
+    emax3 = rel_err(out3.cpu(), ref)
+    emean3 = ((out3.cpu() - ref).abs().mean() / ref.abs().mean()).item()
+    print(f"gencomm all-tc  C={C} {H}x{W} N={record_len}: max-rel {emax3:.2e} mean-rel {emean3:.2e}")
+    assert emax3 <= TOL_BF16_MAX and emean3 <= TOL_BF16_MEAN
+    assert not torch.equal(out3, out), "tf32 middle layers not taken"
     # a single denoiser evaluation per layer selection
     x = torch.cat([cond, feat], dim=1)
     r = R.unet_forward(x, torch.full((A,), 1.0), sd)
-    for prec in (ops.PREC_TC_CONV_IN, ops.PREC_TC_CONV_OUT, ops.PREC_BF16_TC):
+    for prec in (ops.PREC_TC_CONV_IN, ops.PREC_TC_CONV_OUT, ops.PREC_BF16_TC, ops.PREC_TC_MIDDLE, ops.PREC_TC_ALL):
         m.precision = prec
         o = m.denoiser(x.to(DEV), torch.full((A,), 1, device=DEV))
         assert rel_err(o.cpu(), r) <= TOL_BF16_MAX, prec
