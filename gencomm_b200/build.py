@@ -33,12 +33,30 @@ def _stale():
 def build(force=False, verbose=False):
     if not force and not _stale():
         return LIB
-    cmd = [NVCC] + FLAGS + ["-o", LIB] + sources()
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    log = res.stdout + res.stderr
+    from concurrent.futures import ThreadPoolExecutor
+    objdir = os.path.join(HERE, "build")
+    os.makedirs(objdir, exist_ok=True)
+    cflags = [f for f in FLAGS if f != "-shared"]
+
+    def compile_one(src):
+        obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
+        cmd = [NVCC] + cflags + ["-c", "-o", obj, src]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        return obj, " ".join(cmd) + "\n" + res.stdout + res.stderr, res.returncode
+
+    # every translation unit is independent (no relocatable device code): compile them in parallel, then link
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as pool:
+        results = list(pool.map(compile_one, sources()))
+    log = "".join(r[1] for r in results)
+    rc = max(r[2] for r in results)
+    if rc == 0:
+        cmd = [NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + [r[0] for r in results]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        log += " ".join(cmd) + "\n" + res.stdout + res.stderr
+        rc = res.returncode
     with open(os.path.join(HERE, "build.log"), "w") as f:
-        f.write(" ".join(cmd) + "\n" + log)
-    if res.returncode != 0:
+        f.write(log)
+    if rc != 0:
         sys.stderr.write(log)
         raise RuntimeError("nvcc failed building libgencomm_b200.so")
     if verbose:

@@ -38,7 +38,7 @@
 namespace gc {
 namespace persist {
 
-constexpr int kTileMaxN = 5;
+constexpr int kTileMaxN = 8;
 constexpr int kMaxStages = 8;
 constexpr int kGeomSlots = 4;   // tiles of geometry the geometry warp may run ahead
 constexpr int kDynSmemBytes = 224 * 1024;
@@ -684,7 +684,7 @@ k_fuse_persist(const __grid_constant__ CUtensorMap tmap_box, const __grid_consta
         else fast_loop<MODE, N, false, C_>(x, wt, ta);                                \
         break;
         switch (n) {
-            GC_FAST(1) GC_FAST(2) GC_FAST(3) GC_FAST(4) GC_FAST(5)
+            GC_FAST(1) GC_FAST(2) GC_FAST(3) GC_FAST(4) GC_FAST(5) GC_FAST(6) GC_FAST(7) GC_FAST(8)
             default: break;
         }
 #undef GC_FAST
@@ -752,7 +752,7 @@ static int launch(cudaStream_t st, const float *feat, const int32_t *off, int n_
     const long long scratch = MODE == GC_FUSE_ATT ? 2 * C_::kScratch : 0;   // double buffered by tile parity
     plan.park_slots = 0;
     plan.park_tmem = 0;
-    if (MODE == GC_FUSE_ATT && C_::kTmemOK && C % 4 == 0 && n_bound > 1 &&
+    if (MODE == GC_FUSE_ATT && C_::kTmemOK && C % 4 == 0 && n_bound > 1 && n_bound <= 5 &&
         (long long)(C_::P / 128) * C * 4 <= 512 && !getenv("GC_FUSE_NO_TMEM")) {   // 4 columns per (pixel set, channel)
         plan.park_tmem = 1;               // 512 columns x 128 lanes x 32 bit of tensor memory hold the park
         plan.park_slots = n_bound - 1;
@@ -806,20 +806,17 @@ int warp_fuse_persist(const float *feat, const int32_t *agent_offsets, int n_fra
 #define GC_LAUNCH(MODE, ...) launch<MODE, Cfg<__VA_ARGS__>>(st, feat, agent_offsets, n_frames, total_agents, theta, L, C, H, W, nmax, out)
 #define GC_VARIANTS(MODE, DEFAULT)                                                  \
     switch (variant < 0 ? DEFAULT : variant) {                                      \
-        case 0: return GC_LAUNCH(MODE, 16, 8, 4, 1);                                \
-        case 1: return GC_LAUNCH(MODE, 16, 8, 4, 2);                                \
         case 2: return GC_LAUNCH(MODE, 16, 8, 2, 2);                                \
-        case 3: return GC_LAUNCH(MODE, 16, 8, 2, 4);                                \
         case 4: return GC_LAUNCH(MODE, 16, 16, 1, 2);                               \
         case 5: return GC_LAUNCH(MODE, 16, 16, 1, 4);                               \
-        case 6: return GC_LAUNCH(MODE, 32, 16, 1, 2);                               \
-        case 7: return GC_LAUNCH(MODE, 16, 8, 1, 4);                                \
-        default: return GC_LAUNCH(MODE, 16, 8, 2, 2);                               \
+        default: return GC_LAUNCH(MODE, 16, 16, 1, 2);                              \
     }
-    // defaults from the B200 sweep profiles/r01g_bench_fuse_cfg*.txt: 16x16 tiles, one thread per pixel
-    if (mode == GC_FUSE_WARP_ONLY) { GC_VARIANTS(GC_FUSE_WARP_ONLY, 4) }
-    if (mode == GC_FUSE_MAX) { GC_VARIANTS(GC_FUSE_MAX, 5) }
-    GC_VARIANTS(GC_FUSE_ATT, 5)
+    // defaults from the B200 sweep profiles/r01g_bench_fuse_cfg*.txt: 16x16 tiles, one thread per pixel; 4 channels per
+    // thread and stage while the slot (n_bound boxes) leaves >= 3 stages, 2 channels for frames with more than 5 agents
+    const int dflt = nmax > 5 ? 4 : 5;
+    if (mode == GC_FUSE_WARP_ONLY) { GC_VARIANTS(GC_FUSE_WARP_ONLY, (nmax > 5 ? 4 : 4)) }
+    if (mode == GC_FUSE_MAX) { GC_VARIANTS(GC_FUSE_MAX, dflt) }
+    GC_VARIANTS(GC_FUSE_ATT, dflt)
 #undef GC_VARIANTS
 #undef GC_LAUNCH
 }

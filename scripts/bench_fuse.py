@@ -50,7 +50,8 @@ def main():
         if os.path.exists(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")) else 6650.0
     shapes = [(4, 64, 256, 256), (4, 128, 64, 128), (5, 256, 64, 128)]
     if not args.quick:
-        shapes += [(2, 64, 256, 256), (4, 64, 256, 512), (4, 128, 256, 256), (4, 256, 256, 256), (5, 64, 512, 512)]
+        shapes += [(2, 64, 256, 256), (8, 64, 256, 256), (4, 64, 256, 512), (4, 128, 256, 256), (4, 256, 256, 256), (5, 64, 512, 512),
+                   (8, 128, 128, 256), (8, 256, 512, 512)]
     modes = list(MODES) if args.mode == "all" else [args.mode]
     print(f"{'mode':5s} {'N':>2s} {'C':>4s} {'H':>4s} {'W':>4s} {'F':>3s} {'tile ms':>9s} {'GB/s':>8s} {'frac':>6s} {'gather ms':>10s} {'maxdiff':>9s}")
     for N, C, H, W in shapes:

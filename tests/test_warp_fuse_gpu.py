@@ -14,11 +14,21 @@ DEV = "cuda"
 TOL = 1e-5
 
 
-@pytest.fixture(params=["tma", "gather"], autouse=True)
+@pytest.fixture(params=["persist", "persist16x8", "tile", "gather"], autouse=True)
 def fuse_path(request, monkeypatch):
-    """Every test runs through both implementations of gc_warp_fuse: the TMA-staged fast path
-    (csrc/warp_fuse_tma.cu; used when W % 4 == 0 and <= 5 agents per frame) and the gather kernels."""
+    """Every test runs through every implementation of gc_warp_fuse: the persistent TMA-staged default
+    (csrc/warp_fuse_persist.cu: 16x16 tiles, AttFusion park in tensor memory where it fits; also its 16x8 / 2-group
+    configuration with the shared-memory park), the round-1b per-tile kernel (csrc/warp_fuse_tile.cu) and the gather
+    kernels (csrc/warp_fuse.cu).  Shapes the TMA paths do not take (W % 4 != 0) fall through to the gather kernels."""
     monkeypatch.setenv("GC_WARP_FUSE_GATHER", "1" if request.param == "gather" else "0")
+    if request.param == "tile":
+        monkeypatch.setenv("GC_FUSE_IMPL", "tile")
+    else:
+        monkeypatch.delenv("GC_FUSE_IMPL", raising=False)
+    if request.param == "persist16x8":
+        monkeypatch.setenv("GC_FUSE_CFG", "2")
+    else:
+        monkeypatch.delenv("GC_FUSE_CFG", raising=False)
     return request.param
 
 
@@ -58,7 +68,8 @@ def _frames(seed, record_len, C, H, W, L=5, sparsity=0.0):
 
 @pytest.mark.parametrize("record_len,C,H,W,L", [
     ([4], 64, 64, 64, 5), ([5, 3, 1], 32, 32, 64, 5), ([2, 2], 128, 64, 128, 5), ([3], 16, 20, 50, 5),
-    ([8], 24, 33, 31, 8), ([1], 8, 16, 16, 5), ([3, 4], 8, 100, 72, 5), ([2], 4, 40, 260, 5)])
+    ([8], 24, 33, 31, 8), ([1], 8, 16, 16, 5), ([3, 4], 8, 100, 72, 5), ([2], 4, 40, 260, 5),
+    ([8, 6], 16, 48, 64, 8), ([7], 64, 32, 128, 8), ([4, 3], 64, 48, 80, 5), ([5], 12, 40, 36, 5)])
 def test_fusion_matches_oracle(record_len, C, H, W, L):
     feat, rl, theta = _frames(10 + C, record_len, C, H, W, L, sparsity=0.3)
     fd, rd, td = feat.to(DEV), rl.to(DEV), theta.to(DEV)
