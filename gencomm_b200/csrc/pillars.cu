@@ -22,6 +22,11 @@
 // All of it is HBM-bound integer/byte work + ~1 kFLOP per pillar; no tensor cores.
 #include "common.cuh"
 
+#include <cuda.h>
+#include <cudaTypedefs.h>
+#include <stdlib.h>
+#include <string.h>
+
 namespace gc {
 
 // ------------------------------------------------------------------------------------------------
@@ -500,6 +505,410 @@ k_canvas(Src src, int nx, int ny, int C, float *__restrict__ canvas) {
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// 4b. persistent canvas writer for the fused front end (round-1q; the default for nx % 4 == 0).
+//
+//     What ncu said about k_canvas<FusedSrc> (profiles/r01l): issue slots 57 % busy, stalls = the three
+//     CTA barriers per tile (zero -> PFN -> store) + the serial tail of the most crowded warp; ~220 warp
+//     instructions per pillar.  This version removes the block-wide barriers and halves the instructions:
+//       * one persistent CTA of 8 PFN warps + 1 store warp; two 64 x 128 tiles in shared memory.
+//       * PFN warps never synchronise with each other: warp w owns the cells {4(w+8i)+j} of every tile, takes
+//         them from a register-resident list (one 16-byte code load per lane and tile, prefetched a tile ahead)
+//         and runs a pillar pipeline that crosses tile boundaries (slot row two pillars ahead, points one ahead).
+//         A warp only waits when it is a whole tile ahead of the store warp (mbarrier full/empty pair per tile).
+//       * the store warp ships a finished tile with 64 row-wise bulk copies shared -> global
+//         (cp.async.bulk, 512 B per channel row, every canvas byte written exactly once), waits for the
+//         shared-memory reads only, re-zeroes the tile if a pillar was written into it and hands it back.
+//       * the PFN arithmetic is unchanged (bit-exact against oracle/pillar_ref.c) but issued as packed
+//         fp32 pairs (FFMA2/FMUL2/FADD2, sm_100): two points per instruction, the pillar's points staged
+//         component-wise so one LDS.128 yields two aligned register pairs; padded lanes duplicate point 0
+//         (max unchanged), so the loop has no tail; the xor-tree of the mean skips the levels whose
+//         partners are all padded zeros (x + 0 is exact).
+// ------------------------------------------------------------------------------------------------
+constexpr int kCvTileFloats = 64 * kTileX;   // four 128B-swizzled TMA boxes of [64 channels][32 cells]
+
+constexpr int kCvLists = 8;   // cell-list ring depth (>= NB + 1: lists are built ahead of the tiles)
+
+template <int W, int NB>
+struct CvSmem {
+    float tile[NB][kCvTileFloats];   // must stay first: every box is 1024-byte aligned
+    float stage[W][4][32];           // x, y, z, intensity rows of the pillar being evaluated
+    uint2 list[kCvLists][kTileX];    // (slot row, x | y << 16) of the occupied cells of a tile
+    int list_n[kCvLists];            // number of entries
+    int list_pbase[kCvLists];        // first point of the tile's agent
+    int list_take[kCvLists];         // next entry to hand out (atomic)
+    float inv_n[36];                 // 1 / n, correctly rounded
+    unsigned long long full[NB], empty[NB], ready[kCvLists];
+    int dirty[NB];
+};
+
+__device__ __forceinline__ uint32_t cv_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cv_mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void cv_mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void cv_mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "CV_WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra CV_DONE_%=;\n\t"
+        "bra CV_WAIT_%=;\n\t"
+        "CV_DONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ bool cv_mbar_test(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void cv_fence_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void cv_tma_store_box(const CUtensorMap *map, uint32_t src, int x, int y, int plane) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];"
+                 ::"l"(reinterpret_cast<uint64_t>(map)), "r"(x), "r"(y), "r"(plane), "r"(src) : "memory");
+}
+__device__ __forceinline__ void cv_bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cv_bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+
+struct PfnPacked {
+    float a0a, a1a, a2a, a3a;    // channel `lane`      (FFMA2 takes a scalar multiplier for both halves)
+    float a0b, a1b, a2b, a3b;    // channel `lane + 32`
+    float2 b0, b1, b2, d0, d1, d2, shift;   // (channel lane, channel lane + 32)
+};
+
+__device__ __forceinline__ PfnPacked pack_pfn(const PfnLane &wa, const PfnLane &wb) {
+    PfnPacked w;
+    w.a0a = wa.a0; w.a1a = wa.a1; w.a2a = wa.a2; w.a3a = wa.a3;
+    w.a0b = wb.a0; w.a1b = wb.a1; w.a2b = wb.a2; w.a3b = wb.a3;
+    w.b0 = make_float2(wa.b0, wb.b0); w.b1 = make_float2(wa.b1, wb.b1); w.b2 = make_float2(wa.b2, wb.b2);
+    w.d0 = make_float2(wa.d0, wb.d0); w.d1 = make_float2(wa.d1, wb.d1); w.d2 = make_float2(wa.d2, wb.d2);
+    w.shift = make_float2(wa.shift, wb.shift);
+    return w;
+}
+
+__device__ __forceinline__ float2 dup2(float v) { return make_float2(v, v); }
+
+// Same roundings, same order as pfn_pillar().  p = this lane's point for lane < n, a copy of point 0 otherwise.
+__device__ __forceinline__ float2 pfn_pillar_packed(const PfnPacked &w, float4 p, int n, float inv_n, float cx,
+                                                    float cy, float cz, float *__restrict__ stage, int lane) {
+    const float xr = __fsub_rn(p.x, cx), yr = __fsub_rn(p.y, cy), zr = __fsub_rn(p.z, cz);
+    __syncwarp();                                   // the previous pillar's stage reads are done
+    stage[lane] = xr;
+    stage[32 + lane] = yr;
+    stage[64 + lane] = zr;
+    stage[96 + lane] = p.w;
+    const bool valid = lane < n;
+    float sx = valid ? xr : 0.0f, sy = valid ? yr : 0.0f, sz = valid ? zr : 0.0f;
+    // xor-butterfly over the 32 slots; a level whose partner lanes are all padded zeros adds exact zeros to the
+    // lanes that reach lane 0, so it is skipped (n is warp-uniform)
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) {
+        if (n > m) {
+            sx = __fadd_rn(sx, __shfl_xor_sync(0xffffffffu, sx, m));
+            sy = __fadd_rn(sy, __shfl_xor_sync(0xffffffffu, sy, m));
+            sz = __fadd_rn(sz, __shfl_xor_sync(0xffffffffu, sz, m));
+        }
+    }
+    if (n <= 16) {   // a shortened butterfly only covers the lanes below the first executed level
+        sx = __shfl_sync(0xffffffffu, sx, 0);
+        sy = __shfl_sync(0xffffffffu, sy, 0);
+        sz = __shfl_sync(0xffffffffu, sz, 0);
+    }
+    float2 bias = __ffma2_rn(w.b0, dup2(cx), w.shift);
+    bias = __ffma2_rn(w.b1, dup2(cy), bias);
+    bias = __ffma2_rn(w.b2, dup2(cz), bias);
+    bias = __ffma2_rn(w.d0, dup2(__fmul_rn(sx, inv_n)), bias);
+    bias = __ffma2_rn(w.d1, dup2(__fmul_rn(sy, inv_n)), bias);
+    bias = __ffma2_rn(w.d2, dup2(__fmul_rn(sz, inv_n)), bias);
+    float best_a = -INFINITY, best_b = -INFINITY;
+    __syncwarp();                                   // staged points visible to the whole warp
+    const float4 *s4 = reinterpret_cast<const float4 *>(stage);
+    for (int q = 0; q * 4 < n; ++q) {
+        const float4 X = s4[q], Y = s4[8 + q], Z = s4[16 + q], I = s4[24 + q];
+        float2 u, v;
+        u = __fmul2_rn(dup2(w.a3a), make_float2(I.x, I.y));
+        v = __fmul2_rn(dup2(w.a3a), make_float2(I.z, I.w));
+        u = __ffma2_rn(dup2(w.a2a), make_float2(Z.x, Z.y), u);
+        v = __ffma2_rn(dup2(w.a2a), make_float2(Z.z, Z.w), v);
+        u = __ffma2_rn(dup2(w.a1a), make_float2(Y.x, Y.y), u);
+        v = __ffma2_rn(dup2(w.a1a), make_float2(Y.z, Y.w), v);
+        u = __ffma2_rn(dup2(w.a0a), make_float2(X.x, X.y), u);
+        v = __ffma2_rn(dup2(w.a0a), make_float2(X.z, X.w), v);
+        best_a = fmaxf(fmaxf(best_a, u.x), u.y);
+        best_a = fmaxf(fmaxf(best_a, v.x), v.y);
+        u = __fmul2_rn(dup2(w.a3b), make_float2(I.x, I.y));
+        v = __fmul2_rn(dup2(w.a3b), make_float2(I.z, I.w));
+        u = __ffma2_rn(dup2(w.a2b), make_float2(Z.x, Z.y), u);
+        v = __ffma2_rn(dup2(w.a2b), make_float2(Z.z, Z.w), v);
+        u = __ffma2_rn(dup2(w.a1b), make_float2(Y.x, Y.y), u);
+        v = __ffma2_rn(dup2(w.a1b), make_float2(Y.z, Y.w), v);
+        u = __ffma2_rn(dup2(w.a0b), make_float2(X.x, X.y), u);
+        v = __ffma2_rn(dup2(w.a0b), make_float2(X.z, X.w), v);
+        best_b = fmaxf(fmaxf(best_b, u.x), u.y);
+        best_b = fmaxf(fmaxf(best_b, v.x), v.y);
+    }
+    const float2 o = __fadd2_rn(make_float2(best_a, best_b), bias);
+    // relu, and for n < 32 the padded slots' relu(bn(0)) = max(shift, 0):  max(max(o,0), max(shift,0)) = max3(o, 0, shift)
+    float oa = fmaxf(o.x, 0.0f), ob = fmaxf(o.y, 0.0f);
+    if (n < 32) { oa = fmaxf(oa, w.shift.x); ob = fmaxf(ob, w.shift.y); }
+    return make_float2(oa, ob);
+}
+
+// tile sequence of one CTA: T_i = blockIdx.x + i * gridDim.x, walked incrementally (no divisions per tile);
+// the step gridDim.x is decomposed into (sb, sy, stx) once on the host
+struct CvStep { int sb, sy, stx; };
+struct CvTile {
+    int b, y, tx;
+    __device__ __forceinline__ void init(int T, int ny, int tiles_x) {
+        tx = T % tiles_x; const int r = T / tiles_x; y = r % ny; b = r / ny;
+    }
+    __device__ __forceinline__ void advance(const CvStep &s, int ny, int tiles_x) {
+        tx += s.stx;
+        if (tx >= tiles_x) { tx -= tiles_x; ++y; }
+        y += s.sy;
+        if (y >= ny) { y -= ny; ++b; }
+        b += s.sb;
+    }
+};
+
+struct CvEnt { int i; int xy; int pbase; };        // i < 0: end of stream
+struct CvSlot { CvEnt e; uint32_t idx; float4 p; };   // one pillar in flight
+
+template <int W, int NB, int MINB>
+__global__ void __launch_bounds__((W + 1) * 32, MINB)
+k_canvas_persist(const __grid_constant__ CUtensorMap tmap, const FusedSrc src, const int nx, const int ny,
+                 const int n_agents, const CvStep step) {
+    using Smem = CvSmem<W, NB>;
+    constexpr int kThreads = (W + 1) * 32;
+    static_assert(kCvLists > NB && (kCvLists & (kCvLists - 1)) == 0, "list ring");
+    extern __shared__ __align__(1024) unsigned char cv_smem_raw[];   // 1024-byte alignment: swizzled TMA boxes
+    Smem &sm = *reinterpret_cast<Smem *>(cv_smem_raw);
+    if ((cv_smem_u32(cv_smem_raw) & 1023u) != 0u) __trap();
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int tiles_x = (nx + kTileX - 1) / kTileX;
+    const int total_tiles = n_agents * ny * tiles_x;
+    const int n_my = (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // >= 1 (grid <= tiles)
+
+    {
+        float4 *t4 = reinterpret_cast<float4 *>(&sm.tile[0][0]);
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = t; i < NB * kCvTileFloats / 4; i += kThreads) t4[i] = z;
+    }
+    if (t < 36) sm.inv_n[t] = __frcp_rn((float)t);
+    if (t == 0) {
+        for (int s = 0; s < NB; ++s) {
+            cv_mbar_init(cv_smem_u32(&sm.full[s]), W);
+            cv_mbar_init(cv_smem_u32(&sm.empty[s]), 1);
+            sm.dirty[s] = 0;
+        }
+        for (int s = 0; s < kCvLists; ++s) cv_mbar_init(cv_smem_u32(&sm.ready[s]), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const uint32_t full0 = cv_smem_u32(&sm.full[0]), empty0 = cv_smem_u32(&sm.empty[0]);
+    const uint32_t ready0 = cv_smem_u32(&sm.ready[0]), take0 = cv_smem_u32(&sm.list_take[0]);
+
+    if (warp == W) {
+        // ------------------------------ control warp ----------------------------------------------
+        // builds the occupied-cell list of every tile kCvLists tiles ahead, ships finished tiles
+        CvTile lt;           // tile whose list is built next
+        lt.init(blockIdx.x, ny, tiles_x);
+        int lt_i = 0, lt_b = -1, lt_pbase = 0;
+        auto load_codes = [&](const CvTile &q) -> int4 {
+            const int x = q.tx * kTileX + 4 * lane;
+            if (x >= nx) return make_int4(-1, -1, -1, -1);
+            return __ldg(reinterpret_cast<const int4 *>(src.cell_code + ((size_t)q.b * ny + q.y) * nx + x));
+        };
+        int4 codes = load_codes(lt);
+        // L2 warm-up for the PFN warps' two dependent gathers (slot row -> points), which are otherwise DRAM-latency
+        // bound: the first 8 point indices of this lane's (<= 4) occupied cells are loaded when the list is built
+        // (that also pulls the slot rows into L2) and the points they name are prefetched one tile later.
+        uint4 pf[8];
+        int pf_pbase = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) pf[k] = make_uint4(kEmpty, kEmpty, kEmpty, kEmpty);
+        auto prefetch_point = [&](uint32_t idx) {
+            if (idx != kEmpty) asm volatile("prefetch.global.L2 [%0];" ::"l"(src.points + pf_pbase + idx));
+        };
+        auto build_list = [&]() {   // list of tile lt_i into ring slot lt_i % kCvLists; then lt advances
+            const int slot = lt_i & (kCvLists - 1);
+            const int4 c = codes;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                prefetch_point(pf[k].x); prefetch_point(pf[k].y); prefetch_point(pf[k].z); prefetch_point(pf[k].w);
+            }
+            if (lt.b != lt_b) { lt_b = lt.b; lt_pbase = __ldg(src.point_offsets + lt.b); }
+            pf_pbase = lt_pbase;
+            const uint32_t row0 = (uint32_t)lt.b * (uint32_t)src.max_voxels;
+            const int xy0 = (lt.tx * kTileX + 4 * lane) | (lt.y << 16);
+            const bool o0 = FusedSrc::occupied(c.x), o1 = FusedSrc::occupied(c.y);
+            const bool o2 = FusedSrc::occupied(c.z), o3 = FusedSrc::occupied(c.w);
+            const int mine = (int)o0 + (int)o1 + (int)o2 + (int)o3;
+            int incl = mine;   // inclusive prefix over the lanes
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += v;
+            }
+            int pos = incl - mine;
+            uint2 *l = &sm.list[slot][0];
+            const uint4 none = make_uint4(kEmpty, kEmpty, kEmpty, kEmpty);
+            auto put = [&](bool occ, int code, int j) {
+                const uint32_t row = row0 + ((unsigned)code & ~kPillarBit);
+                if (occ) l[pos++] = make_uint2(row, xy0 + j);
+                const uint4 *r4 = reinterpret_cast<const uint4 *>(src.slots + (size_t)row * 32);
+                pf[2 * j] = occ ? __ldg(r4) : none;
+                pf[2 * j + 1] = occ ? __ldg(r4 + 1) : none;
+            };
+            put(o0, c.x, 0);
+            put(o1, c.y, 1);
+            put(o2, c.z, 2);
+            put(o3, c.w, 3);
+            if (lane == 31) { sm.list_n[slot] = incl; sm.list_pbase[slot] = lt_pbase; sm.list_take[slot] = 0; }
+            __syncwarp();
+            if (lane == 0) cv_mbar_arrive(ready0 + 8u * slot);
+            ++lt_i;
+            if (lt_i < n_my) { lt.advance(step, ny, tiles_x); codes = load_codes(lt); }
+        };
+        for (int k = 0; k < kCvLists && lt_i < n_my; ++k) build_list();
+
+        CvTile it;
+        it.init(blockIdx.x, ny, tiles_x);
+        int buf = 0;
+        uint32_t parity = 0;
+#pragma unroll 1
+        for (int i = 0; i < n_my; ++i) {
+            cv_mbar_wait(full0 + 8u * buf, parity);   // every PFN warp is done with tile i and with list i
+            cv_fence_async();
+            if (lane == 0) {   // four [32 cells][64 channels] boxes; the part of a box beyond nx is clipped by the TMA unit
+                const int x0 = it.tx * kTileX;
+                const uint32_t s_box = cv_smem_u32(&sm.tile[buf][0]);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (x0 + 32 * k < nx) cv_tma_store_box(&tmap, s_box + 8192u * k, x0 + 32 * k, it.y, it.b * 64);
+                cv_bulk_commit();
+            }
+            if (lt_i < n_my) build_list();            // reuses the ring slot of list i; overlaps the bulk reads
+            if (lane == 0) cv_bulk_wait_read();
+            __syncwarp();
+            if (sm.dirty[buf]) {   // warp-uniform
+                float4 *t4 = reinterpret_cast<float4 *>(&sm.tile[buf][0]);
+                const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 6
+                for (int k = lane; k < kCvTileFloats / 4; k += 32) t4[k] = z;
+                __syncwarp();
+                if (lane == 0) sm.dirty[buf] = 0;
+            }
+            __syncwarp();
+            if (lane == 0) cv_mbar_arrive(empty0 + 8u * buf);
+            it.advance(step, ny, tiles_x);
+            if (++buf == NB) { buf = 0; parity ^= 1u; }
+        }
+        return;
+    }
+
+    // ---------------------------------- PFN warps -------------------------------------------------
+    const PfnPacked w = pack_pfn(load_pfn(src.pfn, lane), load_pfn(src.pfn, lane + 32));
+    float *const stage = &sm.stage[warp][0][0];
+    float *const tile_lane = &sm.tile[0][lane * 32];   // row `lane` of box 0 (row lane + 32 is 1024 floats on)
+
+    // Generator: takes the next unclaimed occupied cell of the CTA's tile stream (dynamic distribution over the
+    // PFN warps, one shared-memory atomic per pillar) and issues the load of its slot row.
+    int g_i = -1, g_n = 0, g_pbase = 0;   // list being consumed (g_n = 0: exhausted); g_i == n_my: end of stream
+    // Never blocks: when the next list is not built yet (the control warp builds list i + kCvLists only after every
+    // PFN warp has handed in tile i) it yields a bubble {i = first tile that may still get cells of this warp,
+    // xy = -1}, so the evaluation stage can hand in the tiles below it and the control warp can go on.
+    auto next = [&](CvSlot &s) {
+        s.idx = kEmpty;
+#pragma unroll 1
+        while (true) {
+            if (g_n > 0) {
+                const int slot = g_i & (kCvLists - 1);
+                int k = 0;
+                if (lane == 0)   // plain atom.shared (nvcc's warp-aggregation prologue is pure overhead for one lane)
+                    asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(k) : "r"(take0 + 4u * slot) : "memory");
+                k = __shfl_sync(0xffffffffu, k, 0);
+                if (k < g_n) {
+                    const uint2 v = sm.list[slot][k];
+                    s.e = CvEnt{g_i, (int)v.y, g_pbase};
+                    s.idx = __ldg(src.slots + (size_t)v.x * 32 + lane);
+                    return;
+                }
+                g_n = 0;
+            }
+            if (g_i >= n_my - 1) { g_i = n_my; s.e = CvEnt{-1, -1, 0}; return; }
+            const int slot = (g_i + 1) & (kCvLists - 1);
+            if (!cv_mbar_test(ready0 + 8u * slot, (uint32_t)((g_i + 1) / kCvLists) & 1u)) {
+                s.e = CvEnt{g_i + 1, -1, 0};
+                return;
+            }
+            ++g_i;
+            g_n = sm.list_n[slot];
+            g_pbase = sm.list_pbase[slot];
+        }
+    };
+    auto load_point = [&](CvSlot &s) {
+        const uint32_t first = __shfl_sync(0xffffffffu, s.idx, 0);
+        if (first != kEmpty)   // false only at the end of the stream (a pillar has >= 1 point)
+            s.p = __ldg(src.points + s.e.pbase + (s.idx != kEmpty ? s.idx : first));   // padded lanes: copy of point 0
+    };
+
+    int cur_i = 0, cur_buf = 0;   // tile this warp is writing into
+    uint32_t cur_par = 1;         // parity to wait for on empty[cur_buf] (fresh barrier: phase "1" is complete)
+    bool wrote = false;
+    auto finish_tiles_until = [&](int target) {   // hand tiles cur_i .. target-1 to the control warp
+#pragma unroll 1
+        while (cur_i < target) {
+            if (wrote && lane == 0) sm.dirty[cur_buf] = 1;
+            wrote = false;
+            cv_fence_async();
+            __syncwarp();
+            if (lane == 0) cv_mbar_arrive(full0 + 8u * cur_buf);
+            ++cur_i;
+            if (++cur_buf == NB) { cur_buf = 0; cur_par ^= 1u; }
+            if (cur_i < n_my) cv_mbar_wait(empty0 + 8u * cur_buf, cur_par);
+        }
+    };
+    // one pipeline step: s0 is evaluated, s1 gets its points, s2 becomes the pillar after s1
+    auto pipe = [&](CvSlot &s0, CvSlot &s1, CvSlot &s2) {
+        load_point(s1);
+        next(s2);
+        if (cur_i < s0.e.i) finish_tiles_until(s0.e.i);
+        if (s0.e.xy < 0) return;   // bubble
+        const int n = __popc(__ballot_sync(0xffffffffu, s0.idx != kEmpty));   // slots fill from 0
+        const int x = s0.e.xy & 0xFFFF, y = s0.e.xy >> 16;
+        const float cx = __fadd_rn(__fmul_rn((float)x, src.vx), src.ox);
+        const float cy = __fadd_rn(__fmul_rn((float)y, src.vy), src.oy);
+        const float2 r = pfn_pillar_packed(w, s0.p, n, sm.inv_n[n], cx, cy, src.cz, stage, lane);
+        // cell xc of the tile = box xc / 32, 16-byte chunk (xc % 32) / 4 XOR (row & 7)  (CU_TENSOR_MAP_SWIZZLE_128B)
+        const int xc = x & (kTileX - 1);
+        float *tl = tile_lane + cur_buf * kCvTileFloats + (xc >> 5) * 2048 + ((((xc >> 2) ^ lane) & 7) << 2) + (xc & 3);
+        tl[0] = r.x;
+        tl[1024] = r.y;
+        wrote = true;
+    };
+
+    CvSlot A, B, C;
+    A.p = B.p = C.p = make_float4(0.f, 0.f, 0.f, 0.f);
+    next(A);
+    next(B);
+    load_point(A);
+#pragma unroll 1
+    while (true) {
+        if (A.e.i < 0) break;
+        pipe(A, B, C);
+        if (B.e.i < 0) break;
+        pipe(B, C, A);
+        if (C.e.i < 0) break;
+        pipe(C, A, B);
+    }
+    finish_tiles_until(n_my);
+}
+
 // dense cell -> pillar-row map for the standalone scatter
 __global__ void __launch_bounds__(256)
 k_build_cell_map(const int4 *__restrict__ coords, int n_pillars, int nx, int ny, int n_batch,
@@ -510,6 +919,61 @@ k_build_cell_map(const int4 *__restrict__ coords, int n_pillars, int nx, int ny,
     const long long idx = (long long)c.y + (long long)c.z * nx + c.w;
     if (c.x < 0 || c.x >= n_batch || idx < 0 || idx >= (long long)nx * ny) return;
     cell_map[(size_t)c.x * nx * ny + idx] = m;
+}
+
+static PFN_cuTensorMapEncodeTiled_v12000 cv_get_encode() {
+    static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+        (void)cudaGetLastError();
+    }
+    return fn;
+}
+
+// canvas [A*64][ny][nx] f32 as a 3-D tensor; box = 32 cells x 1 row x 64 channel planes, 128-byte swizzle in shared memory
+static bool cv_encode_map(CUtensorMap *map, float *canvas, int nx, int ny, long long planes) {
+    PFN_cuTensorMapEncodeTiled_v12000 encode = cv_get_encode();
+    if (!encode) return false;
+    const cuuint64_t gdim[3] = {(cuuint64_t)nx, (cuuint64_t)ny, (cuuint64_t)planes};
+    const cuuint64_t gstride[2] = {(cuuint64_t)nx * 4, (cuuint64_t)ny * nx * 4};
+    const cuuint32_t box[3] = {32, 1, 64};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    return encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, canvas, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int W, int NB, int MINB>
+static int launch_canvas_persist(const FusedSrc &src, const GeomDev &g, int n_agents, long long tiles, float *canvas,
+                                 cudaStream_t st) {
+    using Smem = CvSmem<W, NB>;
+    constexpr size_t kSmemBytes = sizeof(Smem);
+    static int sms = 0, per_sm = 0;
+    if (sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaFuncSetAttribute(k_canvas_persist<W, NB, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_canvas_persist<W, NB, MINB>, (W + 1) * 32, kSmemBytes);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (per_sm < 1) per_sm = 1;
+    }
+    CUtensorMap map;
+    if (!cv_encode_map(&map, canvas, g.grid[0], g.grid[1], (long long)n_agents * 64)) return -1;   // caller falls back
+    const int grid = (int)(tiles < (long long)sms * per_sm ? tiles : (long long)sms * per_sm);
+    const int tiles_x = (g.grid[0] + kTileX - 1) / kTileX;
+    CvStep step;
+    step.stx = grid % tiles_x;
+    step.sy = (grid / tiles_x) % g.grid[1];
+    step.sb = (grid / tiles_x) / g.grid[1];
+    k_canvas_persist<W, NB, MINB><<<grid, (W + 1) * 32, kSmemBytes, st>>>(map, src, g.grid[0], g.grid[1], n_agents, step);
+    GC_LAUNCH_CHECK("k_canvas_persist");
+    return GC_OK;
 }
 
 static int make_geom(const gcVoxelGeom *geom, GeomDev *g) {
@@ -649,6 +1113,31 @@ extern "C" int gc_pillar_canvas(const float *points, const int32_t *point_offset
     src.ox = centre_offset[0];
     src.oy = centre_offset[1];
     src.cz = 0.0f * g.voxel[2] + centre_offset[2];
+    const char *impl = getenv("GC_CANVAS_IMPL");   // "tile": the round-1a per-tile kernel (kept for A/B measurements)
+    const bool use_tile = (impl && strcmp(impl, "tile") == 0) || (g.grid[0] & 3) != 0;
+    if (!use_tile) {
+        const long long tiles = (long long)n_agents * g.grid[1] * ((g.grid[0] + kTileX - 1) / kTileX);
+        GC_REQUIRE(tiles < (1ll << 31) && (long long)n_agents * g.max_voxels < (1ll << 32) && g.grid[0] <= 65535 &&
+                       g.grid[1] <= 32767,
+                   GC_EUNSUPPORTED, "gc_pillar_canvas: grid / agent count too large for the persistent writer");
+        static int cfg = -1;
+        if (cfg < 0) {
+            const char *e = getenv("GC_CANVAS_CFG");   // A/B of the CTA shape; see DESIGN.md section 3
+            cfg = e ? atoi(e) : 0;
+        }
+        int rc;
+        cudaStream_t st = (cudaStream_t)stream;
+        switch (cfg) {
+            case 1: rc = launch_canvas_persist<10, 2, 2>(src, g, n_agents, tiles, canvas, st); break;
+            case 2: rc = launch_canvas_persist<10, 3, 2>(src, g, n_agents, tiles, canvas, st); break;
+            case 3: rc = launch_canvas_persist<8, 3, 2>(src, g, n_agents, tiles, canvas, st); break;
+            case 4: rc = launch_canvas_persist<6, 2, 3>(src, g, n_agents, tiles, canvas, st); break;
+            case 5: rc = launch_canvas_persist<15, 4, 1>(src, g, n_agents, tiles, canvas, st); break;
+            case 6: rc = launch_canvas_persist<8, 2, 3>(src, g, n_agents, tiles, canvas, st); break;
+            default: rc = launch_canvas_persist<10, 3, 2>(src, g, n_agents, tiles, canvas, st); break;
+        }
+        if (rc != -1) return rc;   // -1: no cuTensorMapEncodeTiled in this driver -> per-tile kernel
+    }
     k_canvas<FusedSrc><<<dim3((g.grid[0] + kTileX - 1) / kTileX, g.grid[1], n_agents), 256, 0,
                          (cudaStream_t)stream>>>(src, g.grid[0], g.grid[1], GC_PFN_OUT, canvas);
     GC_LAUNCH_CHECK("k_canvas<FusedSrc>");
