@@ -370,8 +370,8 @@ def run_ours(args):
     if rank == 0:
         frames = world * F * K
         kernels = {
-            "k_canvas<FusedSrc> (PFN+scatter)": {"ms": canvas_ms, "bytes": pipe.scatter_bytes()},
-            "k_warp_fuse<ATT> (warp+regroup+AttFusion)": {"ms": fuse_ms, "bytes": pipe.fuse_bytes()},
+            "k_canvas_persist (PFN+scatter)": {"ms": canvas_ms, "bytes": pipe.scatter_bytes()},
+            "k_fuse_persist<ATT> (warp+regroup+AttFusion)": {"ms": fuse_ms, "bytes": pipe.fuse_bytes()},
         }
         for v in kernels.values():
             v["gbs"] = v["bytes"] / (v["ms"] * 1e-3) / 1e9

@@ -527,17 +527,18 @@ k_canvas(Src src, int nx, int ny, int C, float *__restrict__ canvas) {
 // ------------------------------------------------------------------------------------------------
 constexpr int kCvTileFloats = 64 * kTileX;   // four 128B-swizzled TMA boxes of [64 channels][32 cells]
 
-constexpr int kCvLists = 8;   // cell-list ring depth (>= NB + 1: lists are built ahead of the tiles)
 
-template <int W, int NB>
+template <int W, int NB, bool PAIR>
 struct CvSmem {
+    static constexpr int kCvLists = NB >= 4 ? 8 : 4;   // cell-list ring depth (> NB: lists are built ahead of the tiles)
     float tile[NB][kCvTileFloats];   // must stay first: every box is 1024-byte aligned
-    float stage[W][4][32];           // x, y, z, intensity rows of the pillar being evaluated
+    float stage[W][PAIR ? 2 : 1][4][32];   // x, y, z, intensity rows of the pillar(s) being evaluated
     uint2 list[kCvLists][kTileX];    // (slot row, x | y << 16) of the occupied cells of a tile
     int list_n[kCvLists];            // number of entries
     int list_pbase[kCvLists];        // first point of the tile's agent
     int list_take[kCvLists];         // next entry to hand out (atomic)
     float inv_n[36];                 // 1 / n, correctly rounded
+    float4 pfn_bd[16][7];            // PAIR: (B0,B1,B2,D0,D1,D2,shift) x channels hl + 16 j of half-lane hl
     unsigned long long full[NB], empty[NB], ready[kCvLists];
     int dirty[NB];
 };
@@ -573,6 +574,7 @@ __device__ __forceinline__ void cv_tma_store_box(const CUtensorMap *map, uint32_
 }
 __device__ __forceinline__ void cv_bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cv_bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void cv_bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 
 struct PfnPacked {
     float a0a, a1a, a2a, a3a;    // channel `lane`      (FFMA2 takes a scalar multiplier for both halves)
@@ -603,20 +605,13 @@ __device__ __forceinline__ float2 pfn_pillar_packed(const PfnPacked &w, float4 p
     stage[96 + lane] = p.w;
     const bool valid = lane < n;
     float sx = valid ? xr : 0.0f, sy = valid ? yr : 0.0f, sz = valid ? zr : 0.0f;
-    // xor-butterfly over the 32 slots; a level whose partner lanes are all padded zeros adds exact zeros to the
-    // lanes that reach lane 0, so it is skipped (n is warp-uniform)
+    // xor-butterfly over the 32 slots, the oracle's order (skipping the all-zero upper levels of small pillars was
+    // measured: the uniform branches + the final broadcast cost more instructions than the levels they save)
 #pragma unroll
     for (int m = 16; m >= 1; m >>= 1) {
-        if (n > m) {
-            sx = __fadd_rn(sx, __shfl_xor_sync(0xffffffffu, sx, m));
-            sy = __fadd_rn(sy, __shfl_xor_sync(0xffffffffu, sy, m));
-            sz = __fadd_rn(sz, __shfl_xor_sync(0xffffffffu, sz, m));
-        }
-    }
-    if (n <= 16) {   // a shortened butterfly only covers the lanes below the first executed level
-        sx = __shfl_sync(0xffffffffu, sx, 0);
-        sy = __shfl_sync(0xffffffffu, sy, 0);
-        sz = __shfl_sync(0xffffffffu, sz, 0);
+        sx = __fadd_rn(sx, __shfl_xor_sync(0xffffffffu, sx, m));
+        sy = __fadd_rn(sy, __shfl_xor_sync(0xffffffffu, sy, m));
+        sz = __fadd_rn(sz, __shfl_xor_sync(0xffffffffu, sz, m));
     }
     float2 bias = __ffma2_rn(w.b0, dup2(cx), w.shift);
     bias = __ffma2_rn(w.b1, dup2(cy), bias);
@@ -678,11 +673,12 @@ struct CvTile {
 struct CvEnt { int i; int xy; int pbase; };        // i < 0: end of stream
 struct CvSlot { CvEnt e; uint32_t idx; float4 p; };   // one pillar in flight
 
-template <int W, int NB, int MINB>
+template <int W, int NB, int MINB, bool PAIR, bool PIPE>
 __global__ void __launch_bounds__((W + 1) * 32, MINB)
 k_canvas_persist(const __grid_constant__ CUtensorMap tmap, const FusedSrc src, const int nx, const int ny,
                  const int n_agents, const CvStep step) {
-    using Smem = CvSmem<W, NB>;
+    using Smem = CvSmem<W, NB, PAIR>;
+    constexpr int kCvLists = Smem::kCvLists;
     constexpr int kThreads = (W + 1) * 32;
     static_assert(kCvLists > NB && (kCvLists & (kCvLists - 1)) == 0, "list ring");
     extern __shared__ __align__(1024) unsigned char cv_smem_raw[];   // 1024-byte alignment: swizzled TMA boxes
@@ -699,6 +695,17 @@ k_canvas_persist(const __grid_constant__ CUtensorMap tmap, const FusedSrc src, c
         for (int i = t; i < NB * kCvTileFloats / 4; i += kThreads) t4[i] = z;
     }
     if (t < 36) sm.inv_n[t] = __frcp_rn((float)t);
+    if (PAIR && t < 16) {
+        const PfnLane q0 = load_pfn(src.pfn, t), q1 = load_pfn(src.pfn, t + 16), q2 = load_pfn(src.pfn, t + 32),
+                      q3 = load_pfn(src.pfn, t + 48);
+        sm.pfn_bd[t][0] = make_float4(q0.b0, q1.b0, q2.b0, q3.b0);
+        sm.pfn_bd[t][1] = make_float4(q0.b1, q1.b1, q2.b1, q3.b1);
+        sm.pfn_bd[t][2] = make_float4(q0.b2, q1.b2, q2.b2, q3.b2);
+        sm.pfn_bd[t][3] = make_float4(q0.d0, q1.d0, q2.d0, q3.d0);
+        sm.pfn_bd[t][4] = make_float4(q0.d1, q1.d1, q2.d1, q3.d1);
+        sm.pfn_bd[t][5] = make_float4(q0.d2, q1.d2, q2.d2, q3.d2);
+        sm.pfn_bd[t][6] = make_float4(q0.shift, q1.shift, q2.shift, q3.shift);
+    }
     if (t == 0) {
         for (int s = 0; s < NB; ++s) {
             cv_mbar_init(cv_smem_u32(&sm.full[s]), W);
@@ -724,25 +731,13 @@ k_canvas_persist(const __grid_constant__ CUtensorMap tmap, const FusedSrc src, c
             return __ldg(reinterpret_cast<const int4 *>(src.cell_code + ((size_t)q.b * ny + q.y) * nx + x));
         };
         int4 codes = load_codes(lt);
-        // L2 warm-up for the PFN warps' two dependent gathers (slot row -> points), which are otherwise DRAM-latency
-        // bound: the first 8 point indices of this lane's (<= 4) occupied cells are loaded when the list is built
-        // (that also pulls the slot rows into L2) and the points they name are prefetched one tile later.
-        uint4 pf[8];
-        int pf_pbase = 0;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) pf[k] = make_uint4(kEmpty, kEmpty, kEmpty, kEmpty);
-        auto prefetch_point = [&](uint32_t idx) {
-            if (idx != kEmpty) asm volatile("prefetch.global.L2 [%0];" ::"l"(src.points + pf_pbase + idx));
-        };
+        // L2 warm-up: the slot rows of a tile's pillars are prefetched when its list is built (a few tiles before
+        // the PFN warps gather them).  Loading the point indices here as well, to prefetch the points too, was
+        // measured and dropped: the loads put a DRAM latency into this warp's per-tile chain.
         auto build_list = [&]() {   // list of tile lt_i into ring slot lt_i % kCvLists; then lt advances
             const int slot = lt_i & (kCvLists - 1);
             const int4 c = codes;
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                prefetch_point(pf[k].x); prefetch_point(pf[k].y); prefetch_point(pf[k].z); prefetch_point(pf[k].w);
-            }
             if (lt.b != lt_b) { lt_b = lt.b; lt_pbase = __ldg(src.point_offsets + lt.b); }
-            pf_pbase = lt_pbase;
             const uint32_t row0 = (uint32_t)lt.b * (uint32_t)src.max_voxels;
             const int xy0 = (lt.tx * kTileX + 4 * lane) | (lt.y << 16);
             const bool o0 = FusedSrc::occupied(c.x), o1 = FusedSrc::occupied(c.y);
@@ -756,13 +751,12 @@ k_canvas_persist(const __grid_constant__ CUtensorMap tmap, const FusedSrc src, c
             }
             int pos = incl - mine;
             uint2 *l = &sm.list[slot][0];
-            const uint4 none = make_uint4(kEmpty, kEmpty, kEmpty, kEmpty);
             auto put = [&](bool occ, int code, int j) {
-                const uint32_t row = row0 + ((unsigned)code & ~kPillarBit);
-                if (occ) l[pos++] = make_uint2(row, xy0 + j);
-                const uint4 *r4 = reinterpret_cast<const uint4 *>(src.slots + (size_t)row * 32);
-                pf[2 * j] = occ ? __ldg(r4) : none;
-                pf[2 * j + 1] = occ ? __ldg(r4 + 1) : none;
+                if (occ) {
+                    const uint32_t row = row0 + ((unsigned)code & ~kPillarBit);
+                    l[pos++] = make_uint2(row, xy0 + j);
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(src.slots + (size_t)row * 32));
+                }
             };
             put(o0, c.x, 0);
             put(o1, c.y, 1);
@@ -780,6 +774,19 @@ k_canvas_persist(const __grid_constant__ CUtensorMap tmap, const FusedSrc src, c
         it.init(blockIdx.x, ny, tiles_x);
         int buf = 0;
         uint32_t parity = 0;
+        auto release = [&](int rb) {   // buffer rb has been read by its TMA store: zero it if needed, hand it back
+            if (sm.dirty[rb]) {   // warp-uniform
+                float4 *t4 = reinterpret_cast<float4 *>(&sm.tile[rb][0]);
+                const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 8
+                for (int k = lane; k < kCvTileFloats / 4; k += 32) t4[k] = z;
+                __syncwarp();
+                if (lane == 0) sm.dirty[rb] = 0;
+            }
+            __syncwarp();
+            if (lane == 0) cv_mbar_arrive(empty0 + 8u * rb);
+        };
+        int prev = -1;
 #pragma unroll 1
         for (int i = 0; i < n_my; ++i) {
             cv_mbar_wait(full0 + 8u * buf, parity);   // every PFN warp is done with tile i and with list i
@@ -793,27 +800,216 @@ k_canvas_persist(const __grid_constant__ CUtensorMap tmap, const FusedSrc src, c
                 cv_bulk_commit();
             }
             if (lt_i < n_my) build_list();            // reuses the ring slot of list i; overlaps the bulk reads
-            if (lane == 0) cv_bulk_wait_read();
-            __syncwarp();
-            if (sm.dirty[buf]) {   // warp-uniform
-                float4 *t4 = reinterpret_cast<float4 *>(&sm.tile[buf][0]);
-                const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 6
-                for (int k = lane; k < kCvTileFloats / 4; k += 32) t4[k] = z;
+            // the shared-memory reads of tile i overlap the next iteration: only tile i - 1 is reclaimed here
+            if (PIPE) {
+                if (prev >= 0) {
+                    if (lane == 0) cv_bulk_wait_read1();
+                    __syncwarp();
+                    release(prev);
+                }
+                prev = buf;
+            } else {
+                if (lane == 0) cv_bulk_wait_read();
                 __syncwarp();
-                if (lane == 0) sm.dirty[buf] = 0;
+                release(buf);
             }
-            __syncwarp();
-            if (lane == 0) cv_mbar_arrive(empty0 + 8u * buf);
             it.advance(step, ny, tiles_x);
             if (++buf == NB) { buf = 0; parity ^= 1u; }
         }
+        if (lane == 0) cv_bulk_wait_read();   // shared memory must outlive the last reads
+        __syncwarp();
         return;
     }
 
     // ---------------------------------- PFN warps -------------------------------------------------
+    if constexpr (PAIR) {
+        // Two pillars per warp: half-warp h = lane / 16 evaluates list entry k + h; lane hl = lane % 16 owns the
+        // output channels hl + 16 j (j < 4) and holds points hl and hl + 16 of its pillar.  The per-pillar
+        // bookkeeping (claim, loads, centre, mean, barriers) is issued once for both pillars, which is what bounds
+        // the single-pillar variant (ncu r01q: ~280 warp instructions per pillar, 46 of them PFN arithmetic).
+        const int half = lane >> 4, hl = lane & 15;
+        float a0[4], a1[4], a2[4], a3[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const PfnLane q = load_pfn(src.pfn, hl + 16 * j);
+            a0[j] = q.a0; a1[j] = q.a1; a2[j] = q.a2; a3[j] = q.a3;
+        }
+        const float4 *const bd = &sm.pfn_bd[hl][0];   // the bias constants stay in shared memory (28 registers otherwise)
+        float *const stage = &sm.stage[warp][half][0][0];
+        // row hl of box 0; rows hl + 16 j are 512 j floats on and share the swizzle phase (16 j % 8 == 0)
+        float *const tile_lane = &sm.tile[0][hl * 32];
+
+        struct Slot { int i, xy, pbase; uint32_t idx0, idx1; float4 p0, p1; };   // xy per half (-1: no pillar)
+        int g_i = -1, g_n = 0, g_pbase = 0;
+        auto next = [&](Slot &s) {
+            s.idx0 = s.idx1 = kEmpty;
+            s.xy = -1;
+#pragma unroll 1
+            while (true) {
+                if (g_n > 0) {
+                    const int slot = g_i & (kCvLists - 1);
+                    int k = 0;
+                    if (lane == 0)
+                        asm volatile("atom.shared.add.u32 %0, [%1], 2;" : "=r"(k) : "r"(take0 + 4u * slot) : "memory");
+                    k = __shfl_sync(0xffffffffu, k, 0);
+                    if (k < g_n) {
+                        s.i = g_i;
+                        s.pbase = g_pbase;
+                        if (k + half < g_n) {
+                            const uint2 v = sm.list[slot][k + half];
+                            s.xy = (int)v.y;
+                            const uint32_t *row = src.slots + (size_t)v.x * 32 + hl;
+                            s.idx0 = __ldg(row);
+                            s.idx1 = __ldg(row + 16);
+                        }
+                        return;
+                    }
+                    g_n = 0;
+                }
+                if (g_i >= n_my - 1) { g_i = n_my; s.i = -1; return; }
+                const int slot = (g_i + 1) & (kCvLists - 1);
+                if (!cv_mbar_test(ready0 + 8u * slot, (uint32_t)((g_i + 1) / kCvLists) & 1u)) { s.i = g_i + 1; return; }
+                ++g_i;
+                g_n = sm.list_n[slot];
+                g_pbase = sm.list_pbase[slot];
+            }
+        };
+        auto load_points = [&](Slot &s) {
+            const uint32_t first = __shfl_sync(0xffffffffu, s.idx0, 0, 16);
+            const bool more = __any_sync(0xffffffffu, s.idx1 != kEmpty);   // a pillar of the pair has > 16 points
+            if (first != kEmpty) {   // per half; padded lanes take a copy of point 0 of their pillar
+                s.p0 = __ldg(src.points + s.pbase + (s.idx0 != kEmpty ? s.idx0 : first));
+                if (more) s.p1 = __ldg(src.points + s.pbase + (s.idx1 != kEmpty ? s.idx1 : first));
+            }
+        };
+        int cur_i = 0, cur_buf = 0;
+        uint32_t cur_par = 1;
+        bool wrote = false;
+        auto finish_tiles_until = [&](int target) {
+#pragma unroll 1
+            while (cur_i < target) {
+                if (wrote) {
+                    if (lane == 0) sm.dirty[cur_buf] = 1;
+                    cv_fence_async();
+                    wrote = false;
+                }
+                __syncwarp();
+                if (lane == 0) cv_mbar_arrive(full0 + 8u * cur_buf);
+                ++cur_i;
+                if (++cur_buf == NB) { cur_buf = 0; cur_par ^= 1u; }
+                if (cur_i < n_my) cv_mbar_wait(empty0 + 8u * cur_buf, cur_par);
+            }
+        };
+        auto pipe = [&](Slot &s0, Slot &s1, Slot &s2) {
+            load_points(s1);
+            next(s2);
+            if (cur_i < s0.i) finish_tiles_until(s0.i);
+            const unsigned bal0 = __ballot_sync(0xffffffffu, s0.idx0 != kEmpty);
+            const unsigned bal1 = __ballot_sync(0xffffffffu, s0.idx1 != kEmpty);
+            if (bal0 == 0u) return;   // bubble
+            const int n_lo = __popc(bal0 & 0xFFFFu) + __popc(bal1 & 0xFFFFu);
+            const int n_hi = __popc(bal0 >> 16) + __popc(bal1 >> 16);
+            const int n = half ? n_hi : n_lo;          // slots fill from 0
+            const int nmax = max(n_lo, n_hi);          // warp-uniform
+            const int x = s0.xy & 0xFFFF, y = s0.xy >> 16;
+            const float cx = __fadd_rn(__fmul_rn((float)x, src.vx), src.ox);
+            const float cy = __fadd_rn(__fmul_rn((float)y, src.vy), src.oy);
+            const float cz = src.cz;
+            const float xr0 = __fsub_rn(s0.p0.x, cx), yr0 = __fsub_rn(s0.p0.y, cy), zr0 = __fsub_rn(s0.p0.z, cz);
+            const bool v0 = hl < n;
+            float sx = v0 ? xr0 : 0.0f, sy = v0 ? yr0 : 0.0f, sz = v0 ? zr0 : 0.0f;
+            __syncwarp();
+            stage[hl] = xr0;
+            stage[32 + hl] = yr0;
+            stage[64 + hl] = zr0;
+            stage[96 + hl] = s0.p0.w;
+            if (bal1 != 0u) {   // warp-uniform: some pillar of the pair has more than 16 points
+                const float xr1 = __fsub_rn(s0.p1.x, cx), yr1 = __fsub_rn(s0.p1.y, cy), zr1 = __fsub_rn(s0.p1.z, cz);
+                stage[16 + hl] = xr1;
+                stage[48 + hl] = yr1;
+                stage[80 + hl] = zr1;
+                stage[112 + hl] = s0.p1.w;
+                // xor-butterfly of the oracle: level 16 pairs slot s with s + 16 = this lane's two points
+                const bool v1 = hl + 16 < n;
+                sx = __fadd_rn(sx, v1 ? xr1 : 0.0f);
+                sy = __fadd_rn(sy, v1 ? yr1 : 0.0f);
+                sz = __fadd_rn(sz, v1 ? zr1 : 0.0f);
+            }
+#pragma unroll
+            for (int m = 8; m >= 1; m >>= 1) {
+                sx = __fadd_rn(sx, __shfl_xor_sync(0xffffffffu, sx, m));
+                sy = __fadd_rn(sy, __shfl_xor_sync(0xffffffffu, sy, m));
+                sz = __fadd_rn(sz, __shfl_xor_sync(0xffffffffu, sz, m));
+            }
+            const float inv_n = sm.inv_n[n];
+            const float mx = __fmul_rn(sx, inv_n), my = __fmul_rn(sy, inv_n), mz = __fmul_rn(sz, inv_n);
+            float2 bias[2];
+            const float4 sh = bd[6];
+            {
+                const float4 B0 = bd[0], B1 = bd[1], B2 = bd[2], D0 = bd[3], D1 = bd[4], D2 = bd[5];
+                float2 lo = __ffma2_rn(make_float2(B0.x, B0.y), dup2(cx), make_float2(sh.x, sh.y));
+                float2 hi = __ffma2_rn(make_float2(B0.z, B0.w), dup2(cx), make_float2(sh.z, sh.w));
+                lo = __ffma2_rn(make_float2(B1.x, B1.y), dup2(cy), lo); hi = __ffma2_rn(make_float2(B1.z, B1.w), dup2(cy), hi);
+                lo = __ffma2_rn(make_float2(B2.x, B2.y), dup2(cz), lo); hi = __ffma2_rn(make_float2(B2.z, B2.w), dup2(cz), hi);
+                lo = __ffma2_rn(make_float2(D0.x, D0.y), dup2(mx), lo); hi = __ffma2_rn(make_float2(D0.z, D0.w), dup2(mx), hi);
+                lo = __ffma2_rn(make_float2(D1.x, D1.y), dup2(my), lo); hi = __ffma2_rn(make_float2(D1.z, D1.w), dup2(my), hi);
+                bias[0] = __ffma2_rn(make_float2(D2.x, D2.y), dup2(mz), lo);
+                bias[1] = __ffma2_rn(make_float2(D2.z, D2.w), dup2(mz), hi);
+            }
+            float best[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+            __syncwarp();
+            const float4 *s4 = reinterpret_cast<const float4 *>(stage);
+#pragma unroll 1
+            for (int q = 0; q * 4 < nmax; ++q) {
+                const float4 X = s4[q], Y = s4[8 + q], Z = s4[16 + q], I = s4[24 + q];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float2 u = __fmul2_rn(dup2(a3[j]), make_float2(I.x, I.y));
+                    float2 v = __fmul2_rn(dup2(a3[j]), make_float2(I.z, I.w));
+                    u = __ffma2_rn(dup2(a2[j]), make_float2(Z.x, Z.y), u);
+                    v = __ffma2_rn(dup2(a2[j]), make_float2(Z.z, Z.w), v);
+                    u = __ffma2_rn(dup2(a1[j]), make_float2(Y.x, Y.y), u);
+                    v = __ffma2_rn(dup2(a1[j]), make_float2(Y.z, Y.w), v);
+                    u = __ffma2_rn(dup2(a0[j]), make_float2(X.x, X.y), u);
+                    v = __ffma2_rn(dup2(a0[j]), make_float2(X.z, X.w), v);
+                    best[j] = fmaxf(fmaxf(best[j], u.x), u.y);
+                    best[j] = fmaxf(fmaxf(best[j], v.x), v.y);
+                }
+            }
+            if (s0.xy >= 0) {
+                const int xc = x & (kTileX - 1);
+                float *tl = tile_lane + cur_buf * kCvTileFloats + (xc >> 5) * 2048 + ((((xc >> 2) ^ hl) & 7) << 2) + (xc & 3);
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const float2 o = __fadd2_rn(make_float2(best[2 * j], best[2 * j + 1]), bias[j]);
+                    float oa = fmaxf(o.x, 0.0f), ob = fmaxf(o.y, 0.0f);
+                    if (n < 32) { oa = fmaxf(oa, j ? sh.z : sh.x); ob = fmaxf(ob, j ? sh.w : sh.y); }
+                    tl[(2 * j) * 512] = oa;
+                    tl[(2 * j + 1) * 512] = ob;
+                }
+            }
+            wrote = true;
+        };
+        Slot A, B, C;
+        A.p0 = A.p1 = B.p0 = B.p1 = C.p0 = C.p1 = make_float4(0.f, 0.f, 0.f, 0.f);
+        A.pbase = B.pbase = C.pbase = 0;
+        next(A);
+        next(B);
+        load_points(A);
+#pragma unroll 1
+        while (true) {
+            if (A.i < 0) break;
+            pipe(A, B, C);
+            if (B.i < 0) break;
+            pipe(B, C, A);
+            if (C.i < 0) break;
+            pipe(C, A, B);
+        }
+        finish_tiles_until(n_my);
+        return;
+    }
     const PfnPacked w = pack_pfn(load_pfn(src.pfn, lane), load_pfn(src.pfn, lane + 32));
-    float *const stage = &sm.stage[warp][0][0];
+    float *const stage = &sm.stage[warp][0][0][0];
     float *const tile_lane = &sm.tile[0][lane * 32];   // row `lane` of box 0 (row lane + 32 is 1024 floats on)
 
     // Generator: takes the next unclaimed occupied cell of the CTA's tile stream (dynamic distribution over the
@@ -863,9 +1059,11 @@ k_canvas_persist(const __grid_constant__ CUtensorMap tmap, const FusedSrc src, c
     auto finish_tiles_until = [&](int target) {   // hand tiles cur_i .. target-1 to the control warp
 #pragma unroll 1
         while (cur_i < target) {
-            if (wrote && lane == 0) sm.dirty[cur_buf] = 1;
-            wrote = false;
-            cv_fence_async();
+            if (wrote) {
+                if (lane == 0) sm.dirty[cur_buf] = 1;
+                cv_fence_async();
+                wrote = false;
+            }
             __syncwarp();
             if (lane == 0) cv_mbar_arrive(full0 + 8u * cur_buf);
             ++cur_i;
@@ -949,17 +1147,17 @@ static bool cv_encode_map(CUtensorMap *map, float *canvas, int nx, int ny, long 
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int W, int NB, int MINB>
+template <int W, int NB, int MINB, bool PAIR, bool PIPE>
 static int launch_canvas_persist(const FusedSrc &src, const GeomDev &g, int n_agents, long long tiles, float *canvas,
                                  cudaStream_t st) {
-    using Smem = CvSmem<W, NB>;
+    using Smem = CvSmem<W, NB, PAIR>;
     constexpr size_t kSmemBytes = sizeof(Smem);
     static int sms = 0, per_sm = 0;
     if (sms == 0) {
         int dev = 0;
         cudaGetDevice(&dev);
-        cudaFuncSetAttribute(k_canvas_persist<W, NB, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_canvas_persist<W, NB, MINB>, (W + 1) * 32, kSmemBytes);
+        cudaFuncSetAttribute(k_canvas_persist<W, NB, MINB, PAIR, PIPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_canvas_persist<W, NB, MINB, PAIR, PIPE>, (W + 1) * 32, kSmemBytes);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         if (per_sm < 1) per_sm = 1;
     }
@@ -971,7 +1169,7 @@ static int launch_canvas_persist(const FusedSrc &src, const GeomDev &g, int n_ag
     step.stx = grid % tiles_x;
     step.sy = (grid / tiles_x) % g.grid[1];
     step.sb = (grid / tiles_x) / g.grid[1];
-    k_canvas_persist<W, NB, MINB><<<grid, (W + 1) * 32, kSmemBytes, st>>>(map, src, g.grid[0], g.grid[1], n_agents, step);
+    k_canvas_persist<W, NB, MINB, PAIR, PIPE><<<grid, (W + 1) * 32, kSmemBytes, st>>>(map, src, g.grid[0], g.grid[1], n_agents, step);
     GC_LAUNCH_CHECK("k_canvas_persist");
     return GC_OK;
 }
@@ -1113,8 +1311,16 @@ extern "C" int gc_pillar_canvas(const float *points, const int32_t *point_offset
     src.ox = centre_offset[0];
     src.oy = centre_offset[1];
     src.cz = 0.0f * g.voxel[2] + centre_offset[2];
-    const char *impl = getenv("GC_CANVAS_IMPL");   // "tile": the round-1a per-tile kernel (kept for A/B measurements)
-    const bool use_tile = (impl && strcmp(impl, "tile") == 0) || (g.grid[0] & 3) != 0;
+    // Two writers, same results (bit-exact, tests run both).  The persistent writer wins when the canvas is densely
+    // occupied (B200, 8x4 agents x 100k points: 256x256 grid, 27 % of the cells occupied: 0.204 vs 0.249 ms) and loses
+    // when it is sparse (512x256 grid, 16 %: 0.49 vs 0.40 ms -- too few pillars per tile to hide its per-tile
+    // hand-over latency), so the default is chosen from the mean number of points per cell; GC_CANVAS_IMPL=tile|persist
+    // overrides.
+    const char *impl = getenv("GC_CANVAS_IMPL");
+    const bool dense = (double)total_points >= 1.0 * (double)n_agents * (double)g.ncell;
+    bool use_tile = impl ? strcmp(impl, "tile") == 0 : !dense;
+    if (impl && strcmp(impl, "persist") == 0) use_tile = false;
+    if ((g.grid[0] & 3) != 0) use_tile = true;
     if (!use_tile) {
         const long long tiles = (long long)n_agents * g.grid[1] * ((g.grid[0] + kTileX - 1) / kTileX);
         GC_REQUIRE(tiles < (1ll << 31) && (long long)n_agents * g.max_voxels < (1ll << 32) && g.grid[0] <= 65535 &&
@@ -1128,13 +1334,11 @@ extern "C" int gc_pillar_canvas(const float *points, const int32_t *point_offset
         int rc;
         cudaStream_t st = (cudaStream_t)stream;
         switch (cfg) {
-            case 1: rc = launch_canvas_persist<10, 2, 2>(src, g, n_agents, tiles, canvas, st); break;
-            case 2: rc = launch_canvas_persist<10, 3, 2>(src, g, n_agents, tiles, canvas, st); break;
-            case 3: rc = launch_canvas_persist<8, 3, 2>(src, g, n_agents, tiles, canvas, st); break;
-            case 4: rc = launch_canvas_persist<6, 2, 3>(src, g, n_agents, tiles, canvas, st); break;
-            case 5: rc = launch_canvas_persist<15, 4, 1>(src, g, n_agents, tiles, canvas, st); break;
-            case 6: rc = launch_canvas_persist<8, 2, 3>(src, g, n_agents, tiles, canvas, st); break;
-            default: rc = launch_canvas_persist<10, 3, 2>(src, g, n_agents, tiles, canvas, st); break;
+            case 1: rc = launch_canvas_persist<15, 6, 1, true, false>(src, g, n_agents, tiles, canvas, st); break;
+            case 2: rc = launch_canvas_persist<15, 6, 1, true, true>(src, g, n_agents, tiles, canvas, st); break;
+            case 3: rc = launch_canvas_persist<9, 3, 2, true, true>(src, g, n_agents, tiles, canvas, st); break;
+            case 4: rc = launch_canvas_persist<10, 3, 2, false, false>(src, g, n_agents, tiles, canvas, st); break;
+            default: rc = launch_canvas_persist<9, 3, 2, true, false>(src, g, n_agents, tiles, canvas, st); break;
         }
         if (rc != -1) return rc;   // -1: no cuTensorMapEncodeTiled in this driver -> per-tile kernel
     }

@@ -16,7 +16,7 @@ echo "== ncu launch list"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file $OUT/launches_$TAG.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-extras > $OUT/ncu_launch_$TAG.log 2>&1
 echo "== ncu full"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"k_canvas|k_fuse_tile|k_slot_insert" -s 9 -c 3 \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"k_canvas_persist|k_fuse_persist|k_slot_insert" -s 6 -c 3 \
     -f -o $OUT/prof_$TAG python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-extras > $OUT/ncu_full_$TAG.log 2>&1
 ls -la $OUT
 echo "== fuse microbench"

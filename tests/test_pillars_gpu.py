@@ -119,10 +119,13 @@ def test_scatter_odd_shapes(C, nx, ny):
     assert not out[1].any()
 
 
+@pytest.mark.parametrize("writer", ["tile", "persist"])
 @pytest.mark.parametrize("rng,uniform", [(synth.OPV2V_H_RANGE, False), (synth.SQUARE_RANGE, False),
                                          (synth.OPV2V_H_RANGE, True)])
-def test_fused_front_end_full_size(rng, uniform):
-    """points -> canvas in one pipeline == oracle voxelize -> kernel-order PFN -> scatter, bit-exact."""
+def test_fused_front_end_full_size(rng, uniform, writer, monkeypatch):
+    """points -> canvas in one pipeline == oracle voxelize -> kernel-order PFN -> scatter, bit-exact, through both
+    canvas writers (per-tile kernel and persistent TMA-store writer)."""
+    monkeypatch.setenv("GC_CANVAS_IMPL", writer)
     vs, cap = synth.VOXEL_SIZE, 70000
     clouds = [synth.lidar_points(2, a, 100_000, lidar_range=rng, uniform=uniform) for a in range(4)]
     clouds[2] = clouds[2][:777]   # ragged
@@ -158,3 +161,43 @@ def test_fused_front_end_full_size(rng, uniform):
     # size-independent property: occupied canvas cells == voxel coordinates
     occ = (canvas != 0).any(1).nonzero()
     assert occ.shape[0] <= batch["voxel_coords"].shape[0]
+
+
+@pytest.mark.parametrize("writer", ["tile", "persist"])
+@pytest.mark.parametrize("nx,ny", [(20, 10), (132, 3), (256, 1), (516, 7)])
+def test_canvas_writers_small_and_ragged_grids(nx, ny, writer, monkeypatch):
+    """Partial tiles (nx not a multiple of 128), single rows, empty agents, crowded cells (> 32 points), one agent:
+    both canvas writers against the oracle, bit-exact."""
+    monkeypatch.setenv("GC_CANVAS_IMPL", writer)
+    vs = [0.4, 0.4, 4.0]
+    rng = [0.0, 0.0, -3.0, 0.4 * nx, 0.4 * ny, 1.0]
+    g = np.random.default_rng(nx * 1000 + ny)
+    def cloud(n):
+        return np.c_[g.uniform(-1, 0.4 * nx + 1, n), g.uniform(-1, 0.4 * ny + 1, n), g.uniform(-3, 1, n),
+                     g.random(n)].astype(np.float32)
+    crowded = cloud(400); crowded[:300, 0] = 0.4 * (nx - 1) + 0.2; crowded[:300, 1] = 0.2   # 300 points in the last cell of row 0
+    clouds = [cloud(3000), np.zeros((0, 4), np.float32), crowded, cloud(1), cloud(5000)]
+    for sub in (clouds, clouds[:1]):
+        cap = 2000
+        w = synth.pfn_weights(3)
+        enc = PointPillar({"lidar_range": rng, "voxel_size": vs, "max_voxels": cap,
+                           "pillar_vfe": {"use_norm": True, "with_distance": False, "use_absolute_xyz": True,
+                                          "num_filters": [64]},
+                           "point_pillar_scatter": {"num_features": 64}})
+        layer = enc.pillar_vfe.pfn_layers[0]
+        with torch.no_grad():
+            layer.linear.weight.copy_(w["weight"]); layer.norm.weight.copy_(w["bn_weight"])
+            layer.norm.bias.copy_(w["bn_bias"]); layer.norm.running_mean.copy_(w["bn_mean"])
+            layer.norm.running_var.copy_(w["bn_var"])
+        enc = enc.to(DEV).eval()
+        sizes = [c.shape[0] for c in sub]
+        pts = T(np.concatenate(sub)).to(DEV)
+        off = torch.tensor(np.concatenate([[0], np.cumsum(sizes)]), dtype=torch.int32, device=DEV)
+        canvas = enc({"inputs_m1": {"points": pts, "point_offsets": off, "max_agent_points": max(sizes)}}, "m1").cpu()
+        batch = _oracle_batch(sub, rng, vs, cap)
+        sc, sh = R.fold_bn(w["bn_weight"], w["bn_bias"], w["bn_mean"], w["bn_var"])
+        feats = R.pillar_vfe_kernel_order(batch["voxel_features"], batch["voxel_num_points"], batch["voxel_coords"],
+                                          w["weight"], sc, sh, vs, rng)
+        ref = R.scatter(feats, batch["voxel_coords"], nx, ny, len(sub))
+        assert canvas.shape == ref.shape
+        assert torch.equal(canvas, ref)
