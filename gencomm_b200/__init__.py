@@ -12,5 +12,6 @@ from .modules import (AttFusion, MaxFusion, PFNLayer, PillarVFE, PointPillar, Po
                       SpVoxelPreprocessor, normalize_pairwise_tfm, regroup, warp_affine_simple, warp_feature)
 
 from .gencomm import Config, DiffusionUNet, GenComm  # noqa: F401
+from .message_extractor import BEVDeformableExtractor, MessageExtractorv2  # noqa: F401
 
 __version__ = "0.1.0"

@@ -1,0 +1,486 @@
+// MessageExtractorv2 for sm_100a: the module that turns an agent's BEV feature into the
+// 2-channel message GenComm's sampler is conditioned on.
+//
+// Replaces (paths relative to /root/reference/opencood):
+//   models/gencomm_modules/message_extractor_v2.py:70-120  (BEVDeformableExtractor / MessageExtractorv2)
+//     offset1 = Conv2d(C -> 18, 3x3)            :74,  :97
+//     dcn1    = torchvision DeformConv2d(C -> 64, 3x3, padding 1)   :78, :101   (deformable im2col + GEMM)
+//     attn    = AvgPool -> 1x1 (64 -> 32) -> ReLU -> 1x1 (32 -> 64) -> Sigmoid   :88-94, :108
+//     fuse    = 1x1 (64 -> 64) -> ReLU -> 1x1 (64 -> 2)                            :82-86, :111
+//
+// Both 3x3 convolutions are real dense contractions (K = 9 C = 1152 at C = 128): they run as ONE tcgen05 implicit-GEMM
+// kernel template, k_me_conv<NOUT, DEFORM>:
+//   * CTA = 128 consecutive pixels (M = 128) of one agent, 256 threads.  Thread (pixel m, channel half h) builds its part
+//     of the A operand: per tap the four bilinear corners + weights are evaluated once (torchvision's
+//     bilinear_interpolate, zero outside the image; the plain convolution is the same code with zero offsets and one
+//     corner), then 32 channels are sampled, rounded to bf16 and stored as 16-byte rows of K-major no-swizzle core
+//     matrices -- the deformable im2col never exists in global memory.
+//   * K is walked in stages of one tap x 64 channels (four K = 16 MMAs), double buffered: the gather of stage s+1
+//     overlaps the MMAs of stage s; stage reuse is guarded by tcgen05.commit -> mbarrier.
+//   * B operand: the weights, pre-packed once to bf16 core-matrix order (gc_me_pack_weights), 8 KB per stage from L2.
+//   * D: fp32 accumulators in TMEM (NOUT columns), epilogue tcgen05.ld.32x32b (lane = pixel -> coalesced NCHW stores),
+//     bias, and -- for the deformable layer -- the per-tile channel sums the average pool needs (deterministic order).
+// The tail (global average pool -> squeeze/excite -> two 1x1 convolutions) is 1 % of the FLOPs: CUDA-core fp32 kernels,
+// the excitation folded into the first 1x1's weights per agent.
+//
+// Arithmetic: bf16 operands, fp32 accumulation for the two 3x3 layers; everything else fp32.  Tolerance vs the fp32
+// reference is written in tests/test_message_extractor_gpu.py.
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace gc {
+namespace me {
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// K-major, SWIZZLE_NONE shared-memory matrix descriptor (the same encoding denoiser_tc.cu validated on the B200)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = (uint64_t)((saddr >> 4) & 0x3FFFu);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+    d |= 1ull << 46;
+    return d;
+}
+// kind::f16 instruction descriptor: D = f32, A = B = bf16, both K-major, dense
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "ME_WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra ME_DONE_%=;\n\t"
+        "bra ME_WAIT_%=;\n\t"
+        "ME_DONE_%=:\n\t"
+        "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+template <int COLS>
+__device__ __forceinline__ void tmem_alloc(uint32_t *slot) {   // one full warp
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "n"(COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_free(uint32_t base) {     // the same warp
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(base), "n"(COLS) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);   // .x = lo (low 16 bits), .y = hi
+    return *reinterpret_cast<const uint32_t *>(&h);
+}
+
+constexpr int kPix = 128;            // pixels per CTA = M
+constexpr int kStageCh = 64;         // input channels per stage (four K = 16 MMAs)
+constexpr int kThreads = 256;
+constexpr int kABytes = kStageCh * kPix * 2;   // 16 KB: [8 channel groups][128 pixels][8 bf16]
+
+// ------------------------------------------------------------------------------------------------
+// weights [NOUT_real][C][3][3] f32 -> bf16 B operand, per stage (tap, 64-channel chunk):
+//   [k8 = 8 channel groups][n8 = NOUT/8][8 rows n][8 bf16 k]     (rows >= NOUT_real are zero)
+// ------------------------------------------------------------------------------------------------
+//   split: every stage is followed by its residual plane  lo = bf16(w - float(bf16(w)))  (the "bf16x3" offset layer)
+__device__ __forceinline__ float bf16_residual(float v) { return v - __bfloat162float(__float2bfloat16_rn(v)); }
+
+__global__ void k_me_pack(const float *__restrict__ w, int n_real, int NOUT, int C, int split, uint4 *__restrict__ out) {
+    const int chunks = C / kStageCh;
+    const int per_stage = 8 * NOUT;            // uint4 (8 k values of one row n) per stage and plane
+    const int total = 9 * chunks * per_stage;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int n = i % NOUT;                // i = ((stage * 8 + k8) * (NOUT/8) + n8) * 8 + (n % 8)  with n = n8 * 8 + n % 8
+    const int k8 = (i / NOUT) % 8;
+    const int stage = i / per_stage;
+    const int tap = stage / chunks, chunk = stage % chunks;
+    uint32_t p[4], q[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        float v[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const int c = chunk * kStageCh + k8 * 8 + 2 * j + e;
+            v[e] = n < n_real ? w[((size_t)n * C + c) * 9 + tap] : 0.0f;
+        }
+        p[j] = pack_bf16(v[0], v[1]);
+        q[j] = pack_bf16(bf16_residual(v[0]), bf16_residual(v[1]));
+    }
+    const int within = i - stage * per_stage;
+    if (split) {
+        out[(size_t)stage * 2 * per_stage + within] = make_uint4(p[0], p[1], p[2], p[3]);
+        out[(size_t)stage * 2 * per_stage + per_stage + within] = make_uint4(q[0], q[1], q[2], q[3]);
+    } else {
+        out[i] = make_uint4(p[0], p[1], p[2], p[3]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// 3x3 (deformable) convolution as a tcgen05 implicit GEMM.  grid = (H*W/128, n_agents), 256 threads.
+//   x [A][C][H][W] f32; offset [A][18][H][W] f32 (DEFORM; channel 2k = dy, 2k+1 = dx of tap k); wp: k_me_pack output
+//   out [A][n_store][H][W] f32 (+ bias);  tile_sums [A][tiles*4][NOUT] (DEFORM): channel sums over 32-pixel groups
+// ------------------------------------------------------------------------------------------------
+template <int NOUT, bool DEFORM>
+__global__ void __launch_bounds__(kThreads)
+k_me_conv(const float *__restrict__ x, const float *__restrict__ offset, const uint4 *__restrict__ wp,
+          const float *__restrict__ bias, int C, int H, int W, int n_store, float *__restrict__ out,
+          float *__restrict__ tile_sums) {
+    // The plain (offset) layer runs as "bf16x3": A and B are split into a bf16 value and a bf16 residual and three MMAs
+    // (hi*hi + lo*hi + hi*lo) rebuild ~16 mantissa bits, because its output positions the deformable layer's taps:
+    // a bf16-only offset (rel. error 4e-3) moves a tap by 0.02 px at 5 px, which on high-frequency features costs
+    // more accuracy than the deformable layer's own bf16 rounding.
+    constexpr bool SPLIT = !DEFORM;
+    constexpr int kPlanes = SPLIT ? 2 : 1;
+    constexpr int kBBytes = kStageCh * NOUT * 2 * kPlanes;
+    constexpr int kAStage = kABytes * kPlanes;
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t *a_s = smem;                      // [2][kPlanes][kABytes]
+    uint8_t *b_s = smem + 2 * kAStage;        // [2][kPlanes][kStageCh * NOUT * 2]
+    __shared__ __align__(8) uint64_t s_empty[2], s_done;
+    __shared__ uint32_t s_tmem;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int m = tid & (kPix - 1), half = tid >> 7;
+    const int agent = blockIdx.y, tile = blockIdx.x;
+    const int HW = H * W;
+    const int pix = tile * kPix + m;
+    const int py = pix / W, px = pix - py * W;
+    const int chunks = C / kStageCh, stages = 9 * chunks;
+
+    if (warp == 0) tmem_alloc<NOUT>(&s_tmem);
+    if (tid == 32) {
+        mbar_init(smem_u32(&s_empty[0]), 1); mbar_init(smem_u32(&s_empty[1]), 1); mbar_init(smem_u32(&s_done), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = s_tmem;
+    const uint32_t a_base = smem_u32(a_s), b_base = smem_u32(b_s);
+    constexpr uint32_t idesc = make_idesc(128, NOUT);
+
+    const float *xa = x + (size_t)agent * C * HW;
+    int o1 = 0, o2 = 0, o3 = 0, o4 = 0;
+    float w1 = 0.f, w2 = 0.f, w3 = 0.f, w4 = 0.f;
+
+    for (int s = 0; s < stages; ++s) {
+        const int b = s & 1;
+        const int tap = s / chunks, chunk = s - tap * chunks;
+        if (chunk == 0) {
+            // sampling position of this pixel for the tap (torchvision deformable_im2col / bilinear_interpolate)
+            const int ky = tap / 3, kx = tap - 3 * ky;
+            if (DEFORM) {
+                const float *op = offset + ((size_t)agent * 18 + 2 * tap) * HW + pix;
+                const float hh_ = (float)(py - 1 + ky) + __ldg(op);
+                const float ww_ = (float)(px - 1 + kx) + __ldg(op + HW);
+                const bool inside = hh_ > -1.0f && hh_ < (float)H && ww_ > -1.0f && ww_ < (float)W;
+                const float hf = floorf(hh_), wf = floorf(ww_);
+                const int hl = (int)hf, wl = (int)wf, hh = hl + 1, wh = wl + 1;
+                const float lh = hh_ - hf, lw = ww_ - wf, uh = 1.0f - lh, uw = 1.0f - lw;
+                const bool t_ok = inside && hl >= 0, b_ok = inside && hh <= H - 1;
+                const bool l_ok = wl >= 0, r_ok = wh <= W - 1;
+                const int hlc = min(max(hl, 0), H - 1), hhc = min(max(hh, 0), H - 1);
+                const int wlc = min(max(wl, 0), W - 1), whc = min(max(wh, 0), W - 1);
+                o1 = hlc * W + wlc; o2 = hlc * W + whc; o3 = hhc * W + wlc; o4 = hhc * W + whc;
+                w1 = (t_ok && l_ok) ? uh * uw : 0.0f;
+                w2 = (t_ok && r_ok) ? uh * lw : 0.0f;
+                w3 = (b_ok && l_ok) ? lh * uw : 0.0f;
+                w4 = (b_ok && r_ok) ? lh * lw : 0.0f;
+            } else {
+                const int yy = py - 1 + ky, xx = px - 1 + kx;
+                const bool ok = yy >= 0 && yy < H && xx >= 0 && xx < W;
+                o1 = ok ? yy * W + xx : 0;
+                w1 = ok ? 1.0f : 0.0f;
+            }
+        }
+        if (s >= 2) mbar_wait(smem_u32(&s_empty[b]), (uint32_t)((s >> 1) - 1) & 1u);   // MMAs of stage s-2 retired
+        // ---- B stage: kBBytes contiguous bytes of the packed weights ----
+        {
+            const uint4 *src = wp + (size_t)s * (kBBytes / 16);
+            uint4 *dst = reinterpret_cast<uint4 *>(b_s + b * kBBytes);
+            for (int i = tid; i < kBBytes / 16; i += kThreads) dst[i] = __ldg(src + i);
+        }
+        // ---- A stage: this thread's pixel x 32 channels (4 groups of 8) ----
+        {
+            const float *xc = xa + (size_t)(chunk * kStageCh + half * 32) * HW;
+            uint4 *dst = reinterpret_cast<uint4 *>(a_s + b * kAStage) + (half * 4) * kPix + m;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                float v[8];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const float *p = xc + (size_t)(g * 8 + c) * HW;
+                    if (DEFORM) {
+                        // torchvision: val = hh*hw*v1 + hh*lw*v2 + lh*hw*v3 + lh*lw*v4 (left to right)
+                        float t = w1 * __ldg(p + o1);
+                        t += w2 * __ldg(p + o2);
+                        t += w3 * __ldg(p + o3);
+                        t += w4 * __ldg(p + o4);
+                        v[c] = t;
+                    } else {
+                        v[c] = w1 * __ldg(p + o1);
+                    }
+                }
+                dst[g * kPix] = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]),
+                                           pack_bf16(v[6], v[7]));
+                if (SPLIT) {
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) v[c] = bf16_residual(v[c]);
+                    dst[kABytes / 16 + g * kPix] = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]),
+                                                              pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+                }
+            }
+        }
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+            const uint32_t a_buf = a_base + (uint32_t)b * kAStage, b_buf = b_base + (uint32_t)b * kBBytes;
+            constexpr uint32_t kBPlane = kStageCh * NOUT * 2;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {   // K = 16: channel groups 2j and 2j+1
+                const uint32_t a_off = (uint32_t)(2 * j) * (kPix * 16u), b_off = (uint32_t)(2 * j) * (NOUT * 16u);
+                const uint64_t a_hi = make_desc(a_buf + a_off, kPix * 16u, 128u);
+                const uint64_t b_hi = make_desc(b_buf + b_off, NOUT * 16u, 128u);
+                mma_bf16(tmem, a_hi, b_hi, idesc, (s > 0 || j > 0) ? 1u : 0u);
+                if (SPLIT) {
+                    const uint64_t a_lo = make_desc(a_buf + kABytes + a_off, kPix * 16u, 128u);
+                    const uint64_t b_lo = make_desc(b_buf + kBPlane + b_off, NOUT * 16u, 128u);
+                    mma_bf16(tmem, a_lo, b_hi, idesc, 1u);
+                    mma_bf16(tmem, a_hi, b_lo, idesc, 1u);
+                }
+            }
+            mma_commit(smem_u32(&s_empty[b]));
+            if (s == stages - 1) mma_commit(smem_u32(&s_done));
+        }
+    }
+    mbar_wait(smem_u32(&s_done), 0u);
+    tc_fence_after();
+
+    // ---- epilogue: warp w reads TMEM lanes 32 (w % 4) .. +31 (= pixels) and columns (w / 4) * NOUT/2 .. ----
+    {
+        const int q = warp & 3, ch0 = (warp >> 2) * (NOUT / 2);
+        const int p_out = tile * kPix + q * 32 + lane;
+        const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)ch0;
+#pragma unroll
+        for (int c16 = 0; c16 < NOUT / 2; c16 += 16) {
+            float v[16];
+            tmem_ld16(taddr + (uint32_t)c16, v);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const int ch = ch0 + c16 + i;
+                if (ch < n_store) {
+                    const float r = v[i] + __ldg(bias + ch);
+                    out[((size_t)agent * n_store + ch) * HW + p_out] = r;
+                    if (DEFORM) {
+                        float t = r;
+#pragma unroll
+                        for (int d = 16; d >= 1; d >>= 1) t += __shfl_xor_sync(0xffffffffu, t, d);
+                        if (lane == 0) tile_sums[((size_t)agent * gridDim.x * 4 + tile * 4 + q) * NOUT + ch] = t;
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_free<NOUT>(tmem);
+}
+
+// ------------------------------------------------------------------------------------------------
+// tail parameters (device blob, floats), see include/gencomm_b200.h
+// ------------------------------------------------------------------------------------------------
+constexpr int kOffBias = 0;                      // offset1.bias [18]
+constexpr int kDcnBias = 32;                     // dcn1.bias [64]
+constexpr int kAttn1W = kDcnBias + 64;           // attn.1.weight [32][64]
+constexpr int kAttn1B = kAttn1W + 32 * 64;       // attn.1.bias [32]
+constexpr int kAttn2W = kAttn1B + 32;            // attn.3.weight [64][32]
+constexpr int kAttn2B = kAttn2W + 64 * 32;       // attn.3.bias [64]
+constexpr int kFuse1W = kAttn2B + 64;            // fuse.0.weight [64][64]
+constexpr int kFuse1B = kFuse1W + 64 * 64;       // fuse.0.bias [64]
+constexpr int kFuse2W = kFuse1B + 64;            // fuse.2.weight [2][64]
+constexpr int kFuse2B = kFuse2W + 2 * 64;        // fuse.2.bias [2]
+constexpr int kTailFloats = kFuse2B + 2 + 6;     // padded to a multiple of 8
+
+// global average pool (fixed summation order) + squeeze/excite.  grid = n_agents, 64 threads.
+__global__ void __launch_bounds__(64)
+k_me_attn(const float *__restrict__ tile_sums, int groups, int HW, const float *__restrict__ prm, float *__restrict__ attn) {
+    __shared__ float s_mean[64], s_hid[32];
+    const int a = blockIdx.x, c = threadIdx.x;
+    const float *ts = tile_sums + (size_t)a * groups * 64;
+    float s = 0.0f;
+    for (int g = 0; g < groups; ++g) s += ts[(size_t)g * 64 + c];
+    s_mean[c] = s / (float)HW;
+    __syncthreads();
+    if (c < 32) {
+        float h = prm[kAttn1B + c];
+        for (int k = 0; k < 64; ++k) h = fmaf(prm[kAttn1W + c * 64 + k], s_mean[k], h);
+        s_hid[c] = fmaxf(h, 0.0f);
+    }
+    __syncthreads();
+    float z = prm[kAttn2B + c];
+    for (int k = 0; k < 32; ++k) z = fmaf(prm[kAttn2W + c * 32 + k], s_hid[k], z);
+    attn[a * 64 + c] = 1.0f / (1.0f + expf(-z));
+}
+
+// enhanced = b1 * attn; out = fuse.2(relu(fuse.0(enhanced))).  grid = (H*W/128, n_agents), 128 threads (thread = pixel).
+// The excitation is folded into fuse.0's weights per agent: W'[o][c] = W[o][c] * attn[c].
+__global__ void __launch_bounds__(128)
+k_me_tail(const float *__restrict__ b1, const float *__restrict__ attn, const float *__restrict__ prm, int HW,
+          float *__restrict__ out) {
+    __shared__ __align__(16) float s_w[64][64];   // [c][o]
+    __shared__ float s_b[64], s_w2[2][64];
+    const int a = blockIdx.y, tid = threadIdx.x;
+    for (int i = tid; i < 64 * 64; i += 128) {
+        const int o = i >> 6, c = i & 63;
+        s_w[c][o] = prm[kFuse1W + i] * attn[a * 64 + c];
+    }
+    if (tid < 64) { s_b[tid] = prm[kFuse1B + tid]; s_w2[0][tid] = prm[kFuse2W + tid]; s_w2[1][tid] = prm[kFuse2W + 64 + tid]; }
+    __syncthreads();
+    const int p = blockIdx.x * 128 + tid;
+    if (p >= HW) return;
+    float acc[64];
+#pragma unroll
+    for (int o = 0; o < 64; ++o) acc[o] = 0.0f;
+    const float *src = b1 + (size_t)a * 64 * HW + p;
+#pragma unroll 2
+    for (int c = 0; c < 64; ++c) {
+        const float v = __ldg(src + (size_t)c * HW);
+        const float4 *wr = reinterpret_cast<const float4 *>(&s_w[c][0]);
+#pragma unroll
+        for (int o4 = 0; o4 < 16; ++o4) {
+            const float4 w = wr[o4];
+            acc[4 * o4 + 0] = fmaf(w.x, v, acc[4 * o4 + 0]);
+            acc[4 * o4 + 1] = fmaf(w.y, v, acc[4 * o4 + 1]);
+            acc[4 * o4 + 2] = fmaf(w.z, v, acc[4 * o4 + 2]);
+            acc[4 * o4 + 3] = fmaf(w.w, v, acc[4 * o4 + 3]);
+        }
+    }
+    float r0 = prm[kFuse2B], r1 = prm[kFuse2B + 1];
+#pragma unroll
+    for (int o = 0; o < 64; ++o) {
+        const float h = fmaxf(acc[o] + s_b[o], 0.0f);
+        r0 = fmaf(s_w2[0][o], h, r0);
+        r1 = fmaf(s_w2[1][o], h, r1);
+    }
+    out[((size_t)a * 2 + 0) * HW + p] = r0;
+    out[((size_t)a * 2 + 1) * HW + p] = r1;
+}
+
+struct Workspace {
+    float *offset;      // [A][18][HW]
+    float *b1;          // [A][64][HW]
+    float *tile_sums;   // [A][HW/32][64]
+    float *attn;        // [A][64]
+    size_t bytes;
+};
+static Workspace carve(void *base, int A, int HW) {
+    Workspace w;
+    size_t off = 0;
+    char *b = (char *)base;
+    auto take = [&](size_t bytes) {
+        char *p = b ? b + off : nullptr;
+        off += align_up(bytes, 256);
+        return (float *)p;
+    };
+    w.offset = take((size_t)A * 18 * HW * 4);
+    w.b1 = take((size_t)A * 64 * HW * 4);
+    w.tile_sums = take((size_t)A * (HW / 32) * 64 * 4);
+    w.attn = take((size_t)A * 64 * 4);
+    w.bytes = off;
+    return w;
+}
+static inline size_t packed_off_bytes(int C) { return (size_t)9 * C * 32 * 2 * 2; }   // value + residual planes
+static inline size_t packed_dcn_bytes(int C) { return (size_t)9 * C * 64 * 2; }
+
+}  // namespace me
+}  // namespace gc
+
+using namespace gc;
+
+extern "C" size_t gc_me_param_floats(void) { return me::kTailFloats; }
+extern "C" size_t gc_me_packed_bytes(int C) {
+    return C > 0 ? align_up(me::packed_off_bytes(C), 256) + me::packed_dcn_bytes(C) : 0;
+}
+extern "C" size_t gc_me_workspace_bytes(int total_agents, int H, int W) {
+    if (total_agents <= 0 || H <= 0 || W <= 0) return 0;
+    return me::carve(nullptr, total_agents, H * W).bytes;
+}
+
+extern "C" int gc_me_pack_weights(const float *w_offset, const float *w_dcn, int C, void *packed, void *stream) {
+    GC_REQUIRE(w_offset && w_dcn && packed, GC_EINVAL, "gc_me_pack_weights: null pointer");
+    GC_REQUIRE(C > 0 && C % me::kStageCh == 0, GC_EUNSUPPORTED, "gc_me_pack_weights: C must be a multiple of 64 (got %d)", C);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int chunks = C / me::kStageCh;
+    uint4 *p_off = (uint4 *)packed;
+    uint4 *p_dcn = (uint4 *)((char *)packed + align_up(me::packed_off_bytes(C), 256));
+    const int n_off = 9 * chunks * 8 * 32, n_dcn = 9 * chunks * 8 * 64;
+    me::k_me_pack<<<(n_off + 255) / 256, 256, 0, st>>>(w_offset, 18, 32, C, 1, p_off);
+    GC_LAUNCH_CHECK("k_me_pack(offset1)");
+    me::k_me_pack<<<(n_dcn + 255) / 256, 256, 0, st>>>(w_dcn, 64, 64, C, 0, p_dcn);
+    GC_LAUNCH_CHECK("k_me_pack(dcn1)");
+    return GC_OK;
+}
+
+extern "C" int gc_message_extractor(const float *x, int total_agents, int C, int H, int W, const void *packed,
+                                    const float *params, void *workspace, float *message, void *stream) {
+    GC_REQUIRE(total_agents >= 0 && total_agents <= 65535, GC_EINVAL, "gc_message_extractor: bad agent count");
+    if (total_agents == 0) return GC_OK;
+    GC_REQUIRE(x && packed && params && workspace && message, GC_EINVAL, "gc_message_extractor: null pointer");
+    GC_REQUIRE(C > 0 && C % me::kStageCh == 0, GC_EUNSUPPORTED, "gc_message_extractor: C must be a multiple of 64 (got %d)", C);
+    GC_REQUIRE(H > 0 && W > 0 && (H * W) % me::kPix == 0, GC_EUNSUPPORTED,
+               "gc_message_extractor: H*W must be a multiple of 128 (got %dx%d)", H, W);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int HW = H * W, tiles = HW / me::kPix;
+    const me::Workspace ws = me::carve(workspace, total_agents, HW);
+    const uint4 *p_off = (const uint4 *)packed;
+    const uint4 *p_dcn = (const uint4 *)((const char *)packed + align_up(me::packed_off_bytes(C), 256));
+    static bool attr_done = false;
+    constexpr int kSmemOff = 2 * (2 * me::kABytes + 2 * me::kStageCh * 32 * 2), kSmemDcn = 2 * me::kABytes + 2 * me::kStageCh * 64 * 2;
+    if (!attr_done) {
+        cudaFuncSetAttribute(me::k_me_conv<32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemOff);
+        cudaFuncSetAttribute(me::k_me_conv<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemDcn);
+        attr_done = true;
+    }
+    const dim3 grid(tiles, total_agents);
+    me::k_me_conv<32, false><<<grid, me::kThreads, kSmemOff, st>>>(x, nullptr, p_off, params + me::kOffBias, C, H, W, 18,
+                                                                   ws.offset, nullptr);
+    GC_LAUNCH_CHECK("k_me_conv<offset1>");
+    me::k_me_conv<64, true><<<grid, me::kThreads, kSmemDcn, st>>>(x, ws.offset, p_dcn, params + me::kDcnBias, C, H, W, 64,
+                                                                  ws.b1, ws.tile_sums);
+    GC_LAUNCH_CHECK("k_me_conv<dcn1>");
+    me::k_me_attn<<<total_agents, 64, 0, st>>>(ws.tile_sums, tiles * 4, HW, params, ws.attn);
+    GC_LAUNCH_CHECK("k_me_attn");
+    me::k_me_tail<<<grid, 128, 0, st>>>(ws.b1, ws.attn, params, HW, message);
+    GC_LAUNCH_CHECK("k_me_tail");
+    return GC_OK;
+}

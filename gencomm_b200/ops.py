@@ -308,3 +308,49 @@ def gencomm_sample(feat, cond, agent_offsets, noise0, step_noise, w_host, w_dev,
                                      _stream()),
                "gc_gencomm_sample")
     return out
+
+
+# --------------------------------------------------------------------------------------------
+# (8f rank 1) MessageExtractorv2
+# --------------------------------------------------------------------------------------------
+def me_pack_weights(w_offset, w_dcn):
+    """offset1.weight [18,C,3,3], dcn1.weight [64,C,3,3] (device f32) -> packed bf16 B operands (uint8 blob)."""
+    lib = _lib.load()
+    _chk(w_offset, "offset1.weight", torch.float32, 4)
+    _chk(w_dcn, "dcn1.weight", torch.float32, 4)
+    C = w_offset.shape[1]
+    if tuple(w_offset.shape) != (18, C, 3, 3) or tuple(w_dcn.shape) != (64, C, 3, 3):
+        raise ValueError("me_pack_weights: expected offset1.weight [18,C,3,3] and dcn1.weight [64,C,3,3]")
+    packed = torch.empty(lib.gc_me_packed_bytes(C), dtype=torch.uint8, device=w_offset.device)
+    _lib.check(lib.gc_me_pack_weights(_ptr(w_offset), _ptr(w_dcn), C, _ptr(packed), _stream()), "gc_me_pack_weights")
+    return packed
+
+
+def me_pack_params(sd, prefix="bev_extractor."):
+    """The small fp32 parameters in the order include/gencomm_b200.h documents (one device blob)."""
+    lib = _lib.load()
+    g = lambda k: sd[prefix + k].detach().reshape(-1).float()
+    dev = sd[prefix + "dcn1.bias"].device
+    z = lambda n: torch.zeros(n, dtype=torch.float32, device=dev)
+    blob = torch.cat([g("offset1.bias"), z(14), g("dcn1.bias"), g("attn.1.weight"), g("attn.1.bias"), g("attn.3.weight"),
+                      g("attn.3.bias"), g("fuse.0.weight"), g("fuse.0.bias"), g("fuse.2.weight"), g("fuse.2.bias"), z(6)])
+    if blob.numel() != lib.gc_me_param_floats():
+        raise ValueError("me_pack_params: unexpected parameter shapes")
+    return blob.contiguous()
+
+
+def message_extractor(x, packed, params, workspace=None, out=None):
+    """message = MessageExtractorv2(x); x [sumN,C,H,W] f32 (C % 64 == 0, H*W % 128 == 0) -> [sumN,2,H,W]."""
+    lib = _lib.load()
+    _chk(x, "x", torch.float32, 4)
+    _chk(params, "params", torch.float32, 1)
+    A, C, H, W = x.shape
+    if packed.numel() != lib.gc_me_packed_bytes(C) or params.numel() != lib.gc_me_param_floats():
+        raise ValueError("message_extractor: packed weights / params do not match C")
+    if workspace is None:
+        workspace = torch.empty(lib.gc_me_workspace_bytes(A, H, W), dtype=torch.uint8, device=x.device)
+    if out is None:
+        out = torch.empty(A, 2, H, W, dtype=torch.float32, device=x.device)
+    _lib.check(lib.gc_message_extractor(_ptr(x), A, C, H, W, _ptr(packed), _ptr(params), _ptr(workspace), _ptr(out),
+                                        _stream()), "gc_message_extractor")
+    return out

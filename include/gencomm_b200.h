@@ -183,6 +183,27 @@ int gc_unet_forward(const float *cond, const float *x, int total_agents, int t_i
                     const float *w_host /*[host]*/, const float *w_dev, int C, int H, int W, int T,
                     int precision /* GC_PREC_* */, void *workspace, float *pred, void *stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * (8f rank 1) MessageExtractorv2.forward (models/gencomm_modules/message_extractor_v2.py:114-120)
+ *   = BEVDeformableExtractor.forward (:96-112): offset1 (3x3 conv C->18) -> torchvision DeformConv2d (3x3, C->64,
+ *   padding 1) -> average pool + squeeze/excite -> 1x1 (64->64) + ReLU -> 1x1 (64->2).
+ *   x        [sumN][C][H][W] f32, C % 64 == 0, H*W % 128 == 0
+ *   packed   gc_me_packed_bytes(C) bytes written by gc_me_pack_weights from offset1.weight [18][C][3][3] and
+ *            dcn1.weight [64][C][3][3] (device, f32): the bf16 B operands of the two tcgen05 implicit GEMMs
+ *   params   gc_me_param_floats() floats (device): offset1.bias[18] (padded to 32), dcn1.bias[64],
+ *            attn.1.weight[32][64], attn.1.bias[32], attn.3.weight[64][32], attn.3.bias[64],
+ *            fuse.0.weight[64][64], fuse.0.bias[64], fuse.2.weight[2][64], fuse.2.bias[2] (padded to 8)
+ *   workspace gc_me_workspace_bytes(sumN, H, W) bytes (device)
+ *   message  [sumN][2][H][W] f32
+ *   Arithmetic: the two 3x3 layers use bf16 operands with fp32 accumulation; the rest is fp32.
+ * ------------------------------------------------------------------------------------------- */
+size_t gc_me_param_floats(void);
+size_t gc_me_packed_bytes(int C);
+size_t gc_me_workspace_bytes(int total_agents, int H, int W);
+int gc_me_pack_weights(const float *w_offset, const float *w_dcn, int C, void *packed, void *stream);
+int gc_message_extractor(const float *x, int total_agents, int C, int H, int W, const void *packed,
+                         const float *params, void *workspace, float *message, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

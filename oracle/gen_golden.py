@@ -134,12 +134,33 @@ def gen_gencomm(ns):
           sum(p.numel() for p in model.parameters()))
 
 
+def gen_message_extractor(ns):
+    """MessageExtractorv2 through the reference class (torchvision DeformConv2d on CPU)."""
+    torch.manual_seed(11)
+    C, H, W, N = 64, 4, 64, 3
+    model = ns.MessageExtractorv2(C, 2).eval()
+    with torch.no_grad():   # default inits give ~0.3-pixel offsets; scale them up so the bilinear taps really move
+        model.bev_extractor.offset1.weight.mul_(3.0)
+        model.bev_extractor.offset1.bias.add_(0.3 * torch.randn(18))
+    x = synth.bev_features(1201, N, C, H, W)
+    x[2, :, :, 40:] = 0.0   # a camera-like agent: empty outside its field of view
+    with torch.no_grad():
+        out = model(x)
+        offset = model.bev_extractor.offset1(x)
+        b1 = model.bev_extractor.dcn1(x, offset)
+    sd = {k: v.numpy() for k, v in model.state_dict().items()}
+    np.savez_compressed(os.path.join(OUT, "message_extractor.npz"), x=x.numpy(), ref_out=out.numpy(),
+                        ref_offset=offset.numpy(), ref_b1=b1.numpy(), **{"sd/" + k: v for k, v in sd.items()})
+    print("message_extractor.npz: out", tuple(out.shape), "|offset| max", float(offset.abs().max()))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ns = ref_import.load()
     gen_pillars(ns)
     gen_warp(ns)
     gen_gencomm(ns)
+    gen_message_extractor(ns)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)) // 1024, "KiB")
 

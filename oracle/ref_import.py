@@ -96,6 +96,7 @@ def load():
     from opencood.utils.transformation_utils import normalize_pairwise_tfm
     from opencood.models.gencomm_modules.unet import DiffusionUNet
     from opencood.models.gencomm_modules.cond_diff import GenComm, Config
+    from opencood.models.gencomm_modules.message_extractor_v2 import MessageExtractorv2
     ns.PillarVFE = PillarVFE
     ns.PointPillarScatter = PointPillarScatter
     ns.warp_affine_simple = warp_affine_simple
@@ -106,4 +107,5 @@ def load():
     ns.DiffusionUNet = DiffusionUNet
     ns.GenComm = GenComm
     ns.Config = Config
+    ns.MessageExtractorv2 = MessageExtractorv2
     return ns

@@ -325,3 +325,66 @@ def gencomm_sample(spatial_features, conditions, record_len, sd, noise0, step_no
             mean = sch["posterior_mean_coef1"][t] * x_recon + sch["posterior_mean_coef2"][t] * x  # :273-276
             x = mean + (0.5 * sch["posterior_log_variance_clipped"][t]).exp() * step_noises[k]  # :310-311
     return x
+
+
+# ---------------------------------------------------------------------------------------------
+# MessageExtractorv2: models/gencomm_modules/message_extractor_v2.py:70-120.
+# DeformConv2d is torchvision.ops.deform_conv2d (third-party, present in this image: torchvision 0.26);
+# its arithmetic is restated here from torchvision/csrc/ops/cpu/deform_conv2d_kernel.cpp
+# (bilinear_interpolate + deformable_im2col) and pinned against the reference class in
+# tests/test_oracle_cpu.py (golden produced by the real MessageExtractorv2 through torchvision).
+# ---------------------------------------------------------------------------------------------
+def deform_bilinear(img, h, w):
+    """img [C,H,W]; h, w [P] float sampling positions -> [C,P].  torchvision bilinear_interpolate: zero when the
+    position is <= -1 or >= size; each of the four corners contributes only if it lies inside the image."""
+    C, H, W = img.shape
+    inside = (h > -1) & (h < H) & (w > -1) & (w < W)
+    h_low, w_low = torch.floor(h), torch.floor(w)
+    lh, lw = h - h_low, w - w_low
+    hh, hw = 1 - lh, 1 - lw
+    h_low, w_low = h_low.long(), w_low.long()
+    h_high, w_high = h_low + 1, w_low + 1
+
+    def corner(hi, wi, ok):
+        ok = ok & inside
+        v = img[:, hi.clamp(0, H - 1), wi.clamp(0, W - 1)]
+        return torch.where(ok[None], v, torch.zeros_like(v))
+
+    v1 = corner(h_low, w_low, (h_low >= 0) & (w_low >= 0))
+    v2 = corner(h_low, w_high, (h_low >= 0) & (w_high <= W - 1))
+    v3 = corner(h_high, w_low, (h_high <= H - 1) & (w_low >= 0))
+    v4 = corner(h_high, w_high, (h_high <= H - 1) & (w_high <= W - 1))
+    return (hh * hw)[None] * v1 + (hh * lw)[None] * v2 + (lh * hw)[None] * v3 + (lh * lw)[None] * v4
+
+
+def deform_conv2d_3x3(x, offset, weight, bias):
+    """torchvision.ops.deform_conv2d(x, offset, weight, bias, stride 1, padding 1, dilation 1), 3x3, one offset group.
+    x [N,C,H,W]; offset [N,18,H,W] with channel 2k = dy and 2k+1 = dx of tap k = ky*3+kx; weight [O,C,3,3]."""
+    N, C, H, W = x.shape
+    O = weight.shape[0]
+    ys, xs = torch.meshgrid(torch.arange(H, dtype=x.dtype), torch.arange(W, dtype=x.dtype), indexing="ij")
+    out = torch.empty(N, O, H, W, dtype=x.dtype)
+    for n in range(N):
+        cols = []
+        for k in range(9):
+            ky, kx = k // 3, k % 3
+            h = (ys - 1 + ky + offset[n, 2 * k]).reshape(-1)
+            w = (xs - 1 + kx + offset[n, 2 * k + 1]).reshape(-1)
+            cols.append(deform_bilinear(x[n], h, w))                 # [C, HW]
+        col = torch.stack(cols, dim=1).reshape(C * 9, H * W)          # (c, k) order == weight.view(O, C*9)
+        out[n] = (weight.reshape(O, C * 9) @ col + bias[:, None]).reshape(O, H, W)
+    return out
+
+
+def message_extractor_v2(x, sd, prefix="bev_extractor."):
+    """MessageExtractorv2.forward (message_extractor_v2.py:114-120) -> BEVDeformableExtractor.forward (:96-112).
+    sd: the module's state_dict."""
+    g = lambda k: sd[prefix + k]
+    offset = F.conv2d(x, g("offset1.weight"), g("offset1.bias"), padding=1)                     # :97
+    b1 = deform_conv2d_3x3(x, offset, g("dcn1.weight"), g("dcn1.bias"))                        # :101
+    gap = b1.mean(dim=(2, 3), keepdim=True)                                                     # :108 AdaptiveAvgPool2d(1)
+    a = torch.sigmoid(F.conv2d(F.relu(F.conv2d(gap, g("attn.1.weight"), g("attn.1.bias"))),
+                               g("attn.3.weight"), g("attn.3.bias")))
+    enhanced = b1 * a                                                                           # :109
+    return F.conv2d(F.relu(F.conv2d(enhanced, g("fuse.0.weight"), g("fuse.0.bias"))),           # :111
+                    g("fuse.2.weight"), g("fuse.2.bias")), offset, b1

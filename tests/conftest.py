@@ -52,3 +52,8 @@ def golden_warp():
 @pytest.fixture(scope="session")
 def golden_gencomm():
     return load_golden("gencomm.npz")
+
+
+@pytest.fixture(scope="session")
+def golden_message_extractor():
+    return load_golden("message_extractor.npz")

@@ -66,3 +66,15 @@ def test_modules_keep_reference_state_dict_keys():
     with pytest.raises(NotImplementedError):
         PillarVFE({"use_norm": True, "with_distance": True, "use_absolute_xyz": True, "num_filters": [64]},
                   4, [0.4, 0.4, 4], [-102.4, -51.2, -3, 102.4, 51.2, 1])
+
+
+def test_message_extractor_keeps_reference_state_dict_keys(golden_message_extractor):
+    from gencomm_b200 import MessageExtractorv2
+    m = MessageExtractorv2(64, 2)
+    ref_keys = {k[3:] for k in golden_message_extractor if k.startswith("sd/")}
+    assert set(m.state_dict()) == ref_keys
+    m.load_state_dict({k[3:]: torch.from_numpy(v) for k, v in golden_message_extractor.items() if k.startswith("sd/")})
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m(torch.zeros(1, 64, 4, 32))
+    with pytest.raises(NotImplementedError):
+        MessageExtractorv2(64, 3)

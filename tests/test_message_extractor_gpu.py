@@ -1,0 +1,101 @@
+"""GPU parity of MessageExtractorv2 against the golden vectors of the reference class and the
+oracle restatement.
+
+Tolerance (stated here, as BASELINE.json's north star asks for the bf16 tensor-core paths): the two 3x3 layers use bf16
+operands with fp32 accumulation, everything else is fp32:
+    offsets (plain 3x3)           : max|d| <= 1e-2 * max|ref|,  mean|d| <= 3e-3 * mean|ref|
+    deformable features (dcn1)    : max|d| <= 2e-2 * max|ref|,  mean|d| <= 5e-3 * mean|ref|
+                                    (bf16 rounding of the operands + the bf16 error of the offsets moving the taps;
+                                     measured on the golden fixture, offsets up to 6.8 px: 1.1e-2 / see the assert)
+    message (after the 1x1 tail)  : max|d| <= 2e-2 * max|ref|,  mean|d| <= 1e-2 * mean|ref|
+"""
+import numpy as np
+import pytest
+import torch
+
+from gencomm_b200 import MessageExtractorv2, _lib, ops, synth
+from oracle import ref_ops as R
+
+pytestmark = pytest.mark.gpu
+T = torch.from_numpy
+DEV = "cuda"
+
+
+def _close(got, ref, max_rel, mean_rel, what):
+    d = (got - ref).abs()
+    assert float(d.max()) <= max_rel * float(ref.abs().max()), (what, float(d.max()), float(ref.abs().max()))
+    assert float(d.mean()) <= mean_rel * float(ref.abs().mean()), (what, float(d.mean()), float(ref.abs().mean()))
+
+
+def _run(model, x):
+    """message + the intermediate offset / deformable feature maps (views of the workspace)."""
+    be = model.bev_extractor
+    packed, params = be._blobs()
+    A, C, H, W = x.shape
+    ws = torch.empty(_lib.load().gc_me_workspace_bytes(A, H, W), dtype=torch.uint8, device=x.device)
+    out = ops.message_extractor(x, packed, params, workspace=ws)
+    torch.cuda.synchronize()
+    f = ws.view(torch.float32)
+    n_off = A * 18 * H * W
+    off = f[:n_off].view(A, 18, H, W)
+    start = ((n_off * 4 + 255) // 256) * 256 // 4
+    b1 = f[start:start + A * 64 * H * W].view(A, 64, H, W)
+    return out.cpu(), off.cpu().clone(), b1.cpu().clone()
+
+
+def test_message_extractor_matches_golden(golden_message_extractor):
+    g = golden_message_extractor
+    x = T(g["x"])
+    model = MessageExtractorv2(x.shape[1], 2)
+    model.load_state_dict({k[3:]: T(v) for k, v in g.items() if k.startswith("sd/")})
+    model = model.to(DEV).eval()
+    out, off, b1 = _run(model, x.to(DEV))
+    _close(off, T(g["ref_offset"]), 1e-2, 3e-3, "offset")
+    _close(b1, T(g["ref_b1"]), 2e-2, 5e-3, "dcn1")
+    _close(out, T(g["ref_out"]), 2e-2, 1e-2, "message")
+    out2 = model(x.to(DEV)).cpu()          # the public forward(), cached blobs
+    assert torch.equal(out2, out)
+
+
+@pytest.mark.parametrize("C,H,W,N,scale", [(128, 64, 128, 2, 4.0), (256, 8, 48, 1, 1.0), (64, 2, 64, 3, 8.0)])
+def test_message_extractor_matches_oracle(C, H, W, N, scale):
+    """OPV2V-H (C=128, 64x128) and V2X-Real-like (C=256) shapes, rows that are not a multiple of the 128-pixel tile
+    (W=48), large offsets (taps leave the image) -- against the oracle restatement on the same seeded inputs."""
+    torch.manual_seed(C + H)
+    model = MessageExtractorv2(C, 2).eval()
+    with torch.no_grad():
+        model.bev_extractor.offset1.weight.mul_(scale)
+        model.bev_extractor.offset1.bias.add_(0.5 * torch.randn(18))
+    x = synth.bev_features(77, N, C, H, W)
+    x[-1, :, :, W // 2:] = 0.0
+    ref_out, ref_off, ref_b1 = R.message_extractor_v2(x, {k: v.detach() for k, v in model.state_dict().items()})
+    out, off, b1 = _run(model.to(DEV), x.to(DEV))
+    _close(off, ref_off, 1e-2, 3e-3, "offset")
+    _close(b1, ref_b1, 2e-2, 5e-3, "dcn1")
+    _close(out, ref_out, 2e-2, 1e-2, "message")
+
+
+def test_zero_offsets_reduce_to_a_plain_convolution():
+    """Size-independent property: with offset1 == 0 the deformable layer is an ordinary 3x3 convolution."""
+    torch.manual_seed(3)
+    C, H, W = 64, 16, 64
+    model = MessageExtractorv2(C, 2).eval()
+    with torch.no_grad():
+        model.bev_extractor.offset1.weight.zero_()
+        model.bev_extractor.offset1.bias.zero_()
+    x = synth.bev_features(5, 2, C, H, W)
+    _, off, b1 = _run(model.to(DEV), x.to(DEV))
+    assert not off.any()
+    be = model.bev_extractor.cpu()
+    ref = torch.nn.functional.conv2d(x, be.dcn1.weight.detach(), be.dcn1.bias.detach(), padding=1)
+    _close(b1, ref, 1e-2, 3e-3, "dcn1 == conv2d")
+
+
+def test_message_extractor_argument_errors():
+    model = MessageExtractorv2(64, 2).to(DEV)
+    with pytest.raises(RuntimeError, match="multiple of 128"):
+        model(torch.zeros(1, 64, 3, 10, device=DEV))
+    bad = MessageExtractorv2(48, 2).to(DEV)
+    with pytest.raises(RuntimeError, match="multiple of 64"):
+        bad(torch.zeros(1, 48, 4, 32, device=DEV))
+    assert model(torch.zeros(0, 64, 4, 32, device=DEV)).shape == (0, 2, 4, 32)

@@ -115,3 +115,15 @@ def test_gencomm_sampler_matches_reference(golden_gencomm):
     out = R.gencomm_sample(T(g["feat"]), T(g["cond"]), T(g["record_len"]), _sd(g), T(g["noise0"]),
                            [T(s) for s in g["step_noises"]])
     assert torch.allclose(out, T(g["ref_pred"]), rtol=0, atol=2e-6)
+
+
+def test_message_extractor_restatement_matches_reference(golden_message_extractor):
+    """oracle/ref_ops.message_extractor_v2 (incl. the restated torchvision deform_conv2d) vs the golden outputs of the
+    reference MessageExtractorv2 class (oracle/gen_golden.py::gen_message_extractor)."""
+    g = golden_message_extractor
+    sd = {k[3:]: T(v) for k, v in g.items() if k.startswith("sd/")}
+    out, offset, b1 = R.message_extractor_v2(T(g["x"]), sd)
+    assert torch.allclose(offset, T(g["ref_offset"]), rtol=0, atol=1e-5)
+    assert torch.allclose(b1, T(g["ref_b1"]), rtol=0, atol=1e-5)
+    assert torch.allclose(out, T(g["ref_out"]), rtol=0, atol=1e-6)
+    assert float(T(g["ref_offset"]).abs().max()) > 2.0   # the fixture really moves the sampling taps
