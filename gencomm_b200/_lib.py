@@ -52,7 +52,7 @@ SIGNATURES = {
                                 c_int, c_void_p, c_void_p, c_void_p]),
     "gc_me_param_floats": (c_size_t, []),
     "gc_me_packed_bytes": (c_size_t, [c_int]),
-    "gc_me_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "gc_me_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "gc_me_pack_weights": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "gc_message_extractor": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                      c_void_p]),

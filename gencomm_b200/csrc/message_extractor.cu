@@ -10,11 +10,12 @@
 //
 // Both 3x3 convolutions are real dense contractions (K = 9 C = 1152 at C = 128): they run as ONE tcgen05 implicit-GEMM
 // kernel template, k_me_conv<NOUT, DEFORM>:
-//   * CTA = 128 consecutive pixels (M = 128) of one agent, 256 threads.  Thread (pixel m, channel half h) builds its part
-//     of the A operand: per tap the four bilinear corners + weights are evaluated once (torchvision's
-//     bilinear_interpolate, zero outside the image; the plain convolution is the same code with zero offsets and one
-//     corner), then 32 channels are sampled, rounded to bf16 and stored as 16-byte rows of K-major no-swizzle core
-//     matrices -- the deformable im2col never exists in global memory.
+//   * A pre-pass writes the features once as channel-last bf16 (value + residual planes).
+//   * CTA = 128 consecutive pixels (M = 128) of one agent, 256 threads.  Per tap the four bilinear corners + weights
+//     of every pixel are evaluated once (torchvision's bilinear_interpolate, zero outside the image; the plain
+//     convolution is the same code with one corner of weight 1).  Eight lanes then build one pixel's row of the A
+//     operand: per corner ONE coalesced 16-byte load of 8 channels each, interpolation in fp32, rounding to bf16,
+//     one 16-byte store into K-major no-swizzle core matrices -- the deformable im2col never exists in global memory.
 //   * K is walked in stages of one tap x 64 channels (four K = 16 MMAs), double buffered: the gather of stage s+1
 //     overlaps the MMAs of stage s; stage reuse is guarded by tcgen05.commit -> mbarrier.
 //   * B operand: the weights, pre-packed once to bf16 core-matrix order (gc_me_pack_weights), 8 KB per stage from L2.
@@ -101,25 +102,36 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
 }
 
 constexpr int kPix = 128;            // pixels per CTA = M
-constexpr int kStageCh = 64;         // input channels per stage (four K = 16 MMAs)
 constexpr int kThreads = 256;
-constexpr int kABytes = kStageCh * kPix * 2;   // 16 KB: [8 channel groups][128 pixels][8 bf16]
+// Input channels per stage (SC / 16 MMAs of K = 16): 64 for the deformable layer, 32 for the offset layer (its value +
+// residual planes double the operand bytes; with 64-channel stages only two CTAs fit an SM and the layer was latency
+// bound on its load -> store -> barrier -> MMA chain: 305 us at 28 % issue-active).
+// A operand plane: [SC/8 channel groups][128 pixels][8 bf16], the group stride padded by 16 (32) bytes so that the lanes
+// that build one pixel store to different bank quads (measured without the pad: 8-way conflicts, 32 wavefronts per
+// STS.128, 70 M conflicts per launch).  UMMA no-swizzle K-major: LBO = group stride, SBO = 128 B.
+__host__ __device__ constexpr int a_group_bytes(int SC) { return kPix * 16 + (SC == 64 ? 16 : 32); }
+__host__ __device__ constexpr int a_plane_bytes(int SC) { return (SC / 8) * a_group_bytes(SC); }
+__host__ __device__ constexpr int conv_smem_bytes(int NOUT, bool split, int SC) {
+    return 2 * (split ? 2 : 1) * (a_plane_bytes(SC) + SC * NOUT * 2);
+}
+constexpr int kScOffset = 32, kScDeform = 64;
 
 // ------------------------------------------------------------------------------------------------
 // weights [NOUT_real][C][3][3] f32 -> bf16 B operand, per stage (tap, 64-channel chunk):
-//   [k8 = 8 channel groups][n8 = NOUT/8][8 rows n][8 bf16 k]     (rows >= NOUT_real are zero)
+//   [k8 = SC/8 channel groups][n8 = NOUT/8][8 rows n][8 bf16 k]     (rows >= NOUT_real are zero)
 // ------------------------------------------------------------------------------------------------
 //   split: every stage is followed by its residual plane  lo = bf16(w - float(bf16(w)))  (the "bf16x3" offset layer)
 __device__ __forceinline__ float bf16_residual(float v) { return v - __bfloat162float(__float2bfloat16_rn(v)); }
 
-__global__ void k_me_pack(const float *__restrict__ w, int n_real, int NOUT, int C, int split, uint4 *__restrict__ out) {
-    const int chunks = C / kStageCh;
-    const int per_stage = 8 * NOUT;            // uint4 (8 k values of one row n) per stage and plane
+__global__ void k_me_pack(const float *__restrict__ w, int n_real, int NOUT, int C, int SC, int split,
+                          uint4 *__restrict__ out) {
+    const int chunks = C / SC, groups = SC / 8;
+    const int per_stage = groups * NOUT;       // uint4 (8 k values of one row n) per stage and plane
     const int total = 9 * chunks * per_stage;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
-    const int n = i % NOUT;                // i = ((stage * 8 + k8) * (NOUT/8) + n8) * 8 + (n % 8)  with n = n8 * 8 + n % 8
-    const int k8 = (i / NOUT) % 8;
+    const int n = i % NOUT;                // i = ((stage * groups + k8) * (NOUT/8) + n8) * 8 + (n % 8)  with n = n8 * 8 + n % 8
+    const int k8 = (i / NOUT) % groups;
     const int stage = i / per_stage;
     const int tap = stage / chunks, chunk = stage % chunks;
     uint32_t p[4], q[4];
@@ -128,7 +140,7 @@ __global__ void k_me_pack(const float *__restrict__ w, int n_real, int NOUT, int
         float v[2];
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
-            const int c = chunk * kStageCh + k8 * 8 + 2 * j + e;
+            const int c = chunk * SC + k8 * 8 + 2 * j + e;
             v[e] = n < n_real ? w[((size_t)n * C + c) * 9 + tap] : 0.0f;
         }
         p[j] = pack_bf16(v[0], v[1]);
@@ -144,36 +156,81 @@ __global__ void k_me_pack(const float *__restrict__ w, int n_real, int NOUT, int
 }
 
 // ------------------------------------------------------------------------------------------------
-// 3x3 (deformable) convolution as a tcgen05 implicit GEMM.  grid = (H*W/128, n_agents), 256 threads.
-//   x [A][C][H][W] f32; offset [A][18][H][W] f32 (DEFORM; channel 2k = dy, 2k+1 = dx of tap k); wp: k_me_pack output
-//   out [A][n_store][H][W] f32 (+ bias);  tile_sums [A][tiles*4][NOUT] (DEFORM): channel sums over 32-pixel groups
+// x [A][C][HW] f32 (NCHW)  ->  channel-last bf16 planes  xh = bf16(x),  xl = bf16(x - xh)   [A][HW][C]
+// so that a bilinear corner of 8 channels is ONE 16-byte load and the 8 lanes that sample a pixel read 128 contiguous
+// bytes.  (Measured before: sampling NCHW fp32 directly made the deformable layer L1-gather bound -- 4 loads per
+// (pixel, tap, channel), l1tex 76 % busy, 0.64 ms of the 0.94 ms call.)   grid = (HW/64, C/64, A), 256 threads.
 // ------------------------------------------------------------------------------------------------
-template <int NOUT, bool DEFORM>
+__global__ void __launch_bounds__(256)
+k_me_to_nhwc(const float *__restrict__ x, int C, int HW, uint4 *__restrict__ xh, uint4 *__restrict__ xl) {
+    __shared__ float t[64][65];
+    const int tid = threadIdx.x, p0 = blockIdx.x * 64, c0 = blockIdx.y * 64, a = blockIdx.z;
+    const float *src = x + ((size_t)a * C + c0) * HW + p0;
+    {
+        const int p = tid & 63, c_base = tid >> 6;   // 16 independent loads in flight per thread
+        float v[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) v[k] = (p0 + p < HW) ? __ldg(src + (size_t)(c_base + 4 * k) * HW + p) : 0.0f;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) t[c_base + 4 * k][p] = v[k];
+    }
+    __syncthreads();
+    for (int i = tid; i < 64 * 8; i += 256) {
+        const int p = i >> 3, g = i & 7;
+        if (p0 + p >= HW) continue;
+        float v[8], r[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { v[k] = t[g * 8 + k][p]; r[k] = bf16_residual(v[k]); }
+        const size_t o = ((size_t)a * HW + p0 + p) * (C / 8) + c0 / 8 + g;
+        xh[o] = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+        xl[o] = make_uint4(pack_bf16(r[0], r[1]), pack_bf16(r[2], r[3]), pack_bf16(r[4], r[5]), pack_bf16(r[6], r[7]));
+    }
+}
+
+__device__ __forceinline__ float bf_lo(uint32_t u) { return __uint_as_float(u << 16); }
+__device__ __forceinline__ float bf_hi(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }
+// torchvision bilinear_interpolate: val = hh*hw*v1 + hh*lw*v2 + lh*hw*v3 + lh*lw*v4 (left to right), two channels
+__device__ __forceinline__ uint32_t lerp2(const float4 &w, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    float lo = w.x * bf_lo(a), hi = w.x * bf_hi(a);
+    lo += w.y * bf_lo(b); hi += w.y * bf_hi(b);
+    lo += w.z * bf_lo(c); hi += w.z * bf_hi(c);
+    lo += w.w * bf_lo(d); hi += w.w * bf_hi(d);
+    return pack_bf16(lo, hi);
+}
+
+// ------------------------------------------------------------------------------------------------
+// 3x3 (deformable) convolution as a tcgen05 implicit GEMM.  grid = (H*W/128, n_agents), 256 threads.
+//   xh, xl [A][HW][C] bf16 (k_me_to_nhwc); offset [A][18][H][W] f32 (DEFORM; channel 2k = dy, 2k+1 = dx of tap k);
+//   wp: k_me_pack output;  out [A][n_store][H][W] f32 (+ bias);
+//   tile_sums [A][tiles*4][NOUT] (DEFORM): channel sums over 32-pixel groups
+// ------------------------------------------------------------------------------------------------
+template <int NOUT, bool DEFORM, int SC>
 __global__ void __launch_bounds__(kThreads)
-k_me_conv(const float *__restrict__ x, const float *__restrict__ offset, const uint4 *__restrict__ wp,
-          const float *__restrict__ bias, int C, int H, int W, int n_store, float *__restrict__ out,
-          float *__restrict__ tile_sums) {
+k_me_conv(const uint4 *__restrict__ xh, const uint4 *__restrict__ xl, const float *__restrict__ offset,
+          const uint4 *__restrict__ wp, const float *__restrict__ bias, int C, int H, int W, int n_store,
+          float *__restrict__ out, float *__restrict__ tile_sums) {
     // The plain (offset) layer runs as "bf16x3": A and B are split into a bf16 value and a bf16 residual and three MMAs
     // (hi*hi + lo*hi + hi*lo) rebuild ~16 mantissa bits, because its output positions the deformable layer's taps:
     // a bf16-only offset (rel. error 4e-3) moves a tap by 0.02 px at 5 px, which on high-frequency features costs
     // more accuracy than the deformable layer's own bf16 rounding.
     constexpr bool SPLIT = !DEFORM;
     constexpr int kPlanes = SPLIT ? 2 : 1;
-    constexpr int kBBytes = kStageCh * NOUT * 2 * kPlanes;
+    constexpr int kAGroup = a_group_bytes(SC), kABytes = a_plane_bytes(SC), kGroups = SC / 8;
+    constexpr int kBBytes = SC * NOUT * 2 * kPlanes;
     constexpr int kAStage = kABytes * kPlanes;
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t *a_s = smem;                      // [2][kPlanes][kABytes]
-    uint8_t *b_s = smem + 2 * kAStage;        // [2][kPlanes][kStageCh * NOUT * 2]
+    uint8_t *b_s = smem + 2 * kAStage;        // [2][kPlanes][SC * NOUT * 2]
     __shared__ __align__(8) uint64_t s_empty[2], s_done;
     __shared__ uint32_t s_tmem;
+    __shared__ __align__(16) int4 s_o[kPix];      // pixel index (y*W + x) of the four bilinear corners of the tap
+    __shared__ __align__(16) float4 s_w[kPix];    // their weights (0 for a corner outside the image)
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int m = tid & (kPix - 1), half = tid >> 7;
     const int agent = blockIdx.y, tile = blockIdx.x;
     const int HW = H * W;
-    const int pix = tile * kPix + m;
-    const int py = pix / W, px = pix - py * W;
-    const int chunks = C / kStageCh, stages = 9 * chunks;
+    const int chunks = C / SC, stages = 9 * chunks;
+    const int C8 = C / 8;
 
     if (warp == 0) tmem_alloc<NOUT>(&s_tmem);
     if (tid == 32) {
@@ -186,40 +243,49 @@ k_me_conv(const float *__restrict__ x, const float *__restrict__ offset, const u
     const uint32_t tmem = s_tmem;
     const uint32_t a_base = smem_u32(a_s), b_base = smem_u32(b_s);
     constexpr uint32_t idesc = make_idesc(128, NOUT);
-
-    const float *xa = x + (size_t)agent * C * HW;
-    int o1 = 0, o2 = 0, o3 = 0, o4 = 0;
-    float w1 = 0.f, w2 = 0.f, w3 = 0.f, w4 = 0.f;
+    const uint4 *xh_a = xh + (size_t)agent * HW * C8;
+    const uint4 *xl_a = xl + (size_t)agent * HW * C8;
 
     for (int s = 0; s < stages; ++s) {
         const int b = s & 1;
         const int tap = s / chunks, chunk = s - tap * chunks;
         if (chunk == 0) {
-            // sampling position of this pixel for the tap (torchvision deformable_im2col / bilinear_interpolate)
-            const int ky = tap / 3, kx = tap - 3 * ky;
-            if (DEFORM) {
-                const float *op = offset + ((size_t)agent * 18 + 2 * tap) * HW + pix;
-                const float hh_ = (float)(py - 1 + ky) + __ldg(op);
-                const float ww_ = (float)(px - 1 + kx) + __ldg(op + HW);
-                const bool inside = hh_ > -1.0f && hh_ < (float)H && ww_ > -1.0f && ww_ < (float)W;
-                const float hf = floorf(hh_), wf = floorf(ww_);
-                const int hl = (int)hf, wl = (int)wf, hh = hl + 1, wh = wl + 1;
-                const float lh = hh_ - hf, lw = ww_ - wf, uh = 1.0f - lh, uw = 1.0f - lw;
-                const bool t_ok = inside && hl >= 0, b_ok = inside && hh <= H - 1;
-                const bool l_ok = wl >= 0, r_ok = wh <= W - 1;
-                const int hlc = min(max(hl, 0), H - 1), hhc = min(max(hh, 0), H - 1);
-                const int wlc = min(max(wl, 0), W - 1), whc = min(max(wh, 0), W - 1);
-                o1 = hlc * W + wlc; o2 = hlc * W + whc; o3 = hhc * W + wlc; o4 = hhc * W + whc;
-                w1 = (t_ok && l_ok) ? uh * uw : 0.0f;
-                w2 = (t_ok && r_ok) ? uh * lw : 0.0f;
-                w3 = (b_ok && l_ok) ? lh * uw : 0.0f;
-                w4 = (b_ok && r_ok) ? lh * lw : 0.0f;
-            } else {
-                const int yy = py - 1 + ky, xx = px - 1 + kx;
-                const bool ok = yy >= 0 && yy < H && xx >= 0 && xx < W;
-                o1 = ok ? yy * W + xx : 0;
-                w1 = ok ? 1.0f : 0.0f;
+            // sampling position of every pixel of the tile for this tap (torchvision deformable_im2col /
+            // bilinear_interpolate), once per tap, shared through s_o / s_w.  Every thread is past its staging of the
+            // previous tap (barrier at the end of the previous stage), so the arrays can be overwritten.
+            if (tid < kPix) {
+                const int pix = tile * kPix + tid;
+                const int py = pix / W, px = pix - py * W;
+                const int ky = tap / 3, kx = tap - 3 * ky;
+                int4 o = make_int4(0, 0, 0, 0);
+                float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (DEFORM) {
+                    const float *op = offset + ((size_t)agent * 18 + 2 * tap) * HW + pix;
+                    const float hh_ = (float)(py - 1 + ky) + __ldg(op);
+                    const float ww_ = (float)(px - 1 + kx) + __ldg(op + HW);
+                    const bool inside = hh_ > -1.0f && hh_ < (float)H && ww_ > -1.0f && ww_ < (float)W;
+                    const float hf = floorf(hh_), wf = floorf(ww_);
+                    const int hl = (int)hf, wl = (int)wf, hh = hl + 1, wh = wl + 1;
+                    const float lh = hh_ - hf, lw = ww_ - wf, uh = 1.0f - lh, uw = 1.0f - lw;
+                    const bool t_ok = inside && hl >= 0, b_ok = inside && hh <= H - 1;
+                    const bool l_ok = wl >= 0, r_ok = wh <= W - 1;
+                    const int hlc = min(max(hl, 0), H - 1), hhc = min(max(hh, 0), H - 1);
+                    const int wlc = min(max(wl, 0), W - 1), whc = min(max(wh, 0), W - 1);
+                    o = make_int4(hlc * W + wlc, hlc * W + whc, hhc * W + wlc, hhc * W + whc);
+                    w.x = (t_ok && l_ok) ? uh * uw : 0.0f;
+                    w.y = (t_ok && r_ok) ? uh * lw : 0.0f;
+                    w.z = (b_ok && l_ok) ? lh * uw : 0.0f;
+                    w.w = (b_ok && r_ok) ? lh * lw : 0.0f;
+                } else {
+                    const int yy = py - 1 + ky, xx = px - 1 + kx;
+                    const bool ok = yy >= 0 && yy < H && xx >= 0 && xx < W;
+                    o.x = ok ? yy * W + xx : 0;
+                    w.x = ok ? 1.0f : 0.0f;
+                }
+                s_o[tid] = o;
+                s_w[tid] = w;
             }
+            __syncthreads();
         }
         if (s >= 2) mbar_wait(smem_u32(&s_empty[b]), (uint32_t)((s >> 1) - 1) & 1u);   // MMAs of stage s-2 retired
         // ---- B stage: kBBytes contiguous bytes of the packed weights ----
@@ -228,34 +294,47 @@ k_me_conv(const float *__restrict__ x, const float *__restrict__ offset, const u
             uint4 *dst = reinterpret_cast<uint4 *>(b_s + b * kBBytes);
             for (int i = tid; i < kBBytes / 16; i += kThreads) dst[i] = __ldg(src + i);
         }
-        // ---- A stage: this thread's pixel x 32 channels (4 groups of 8) ----
+        // ---- A stage: 128 pixels x 8 channel groups = 1024 16-byte rows, four per thread.  The eight lanes of a pixel
+        // read 128 contiguous bytes per corner (one full line; spreading a warp over 8 pixels x 4 groups instead was
+        // measured 1.9x slower: twice the L1 tags per request) ----
         {
-            const float *xc = xa + (size_t)(chunk * kStageCh + half * 32) * HW;
-            uint4 *dst = reinterpret_cast<uint4 *>(a_s + b * kAStage) + (half * 4) * kPix + m;
+            uint8_t *dst = a_s + b * kAStage;
+            const int g_loc = tid & (kGroups - 1);
+            const int cg = chunk * kGroups + g_loc;
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-                float v[8];
+            for (int pass = 0; pass < kGroups / 2; pass += 2) {
+                uint4 q[2][4];
+                float4 w[2];
+                int p[2];
 #pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    const float *p = xc + (size_t)(g * 8 + c) * HW;
+                for (int u = 0; u < 2; ++u) {
+                    p[u] = ((pass + u) * kThreads + tid) / kGroups;
+                    const int4 o = s_o[p[u]];
+                    w[u] = s_w[p[u]];
                     if (DEFORM) {
-                        // torchvision: val = hh*hw*v1 + hh*lw*v2 + lh*hw*v3 + lh*lw*v4 (left to right)
-                        float t = w1 * __ldg(p + o1);
-                        t += w2 * __ldg(p + o2);
-                        t += w3 * __ldg(p + o3);
-                        t += w4 * __ldg(p + o4);
-                        v[c] = t;
+                        q[u][0] = __ldg(xh_a + (size_t)o.x * C8 + cg);
+                        q[u][1] = __ldg(xh_a + (size_t)o.y * C8 + cg);
+                        q[u][2] = __ldg(xh_a + (size_t)o.z * C8 + cg);
+                        q[u][3] = __ldg(xh_a + (size_t)o.w * C8 + cg);
                     } else {
-                        v[c] = w1 * __ldg(p + o1);
+                        q[u][0] = __ldg(xh_a + (size_t)o.x * C8 + cg);
+                        q[u][1] = __ldg(xl_a + (size_t)o.x * C8 + cg);
                     }
                 }
-                dst[g * kPix] = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]),
-                                           pack_bf16(v[6], v[7]));
-                if (SPLIT) {
 #pragma unroll
-                    for (int c = 0; c < 8; ++c) v[c] = bf16_residual(v[c]);
-                    dst[kABytes / 16 + g * kPix] = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]),
-                                                              pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+                for (int u = 0; u < 2; ++u) {
+                    uint4 *d = reinterpret_cast<uint4 *>(dst + g_loc * kAGroup) + p[u];
+                    if (DEFORM) {
+                        d[0] = make_uint4(lerp2(w[u], q[u][0].x, q[u][1].x, q[u][2].x, q[u][3].x),
+                                          lerp2(w[u], q[u][0].y, q[u][1].y, q[u][2].y, q[u][3].y),
+                                          lerp2(w[u], q[u][0].z, q[u][1].z, q[u][2].z, q[u][3].z),
+                                          lerp2(w[u], q[u][0].w, q[u][1].w, q[u][2].w, q[u][3].w));
+                    } else {
+                        const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+                        const bool ok = w[u].x != 0.0f;
+                        d[0] = ok ? q[u][0] : z;
+                        d[kABytes / 16] = ok ? q[u][1] : z;
+                    }
                 }
             }
         }
@@ -265,15 +344,15 @@ k_me_conv(const float *__restrict__ x, const float *__restrict__ offset, const u
         if (tid == 0) {
             tc_fence_after();
             const uint32_t a_buf = a_base + (uint32_t)b * kAStage, b_buf = b_base + (uint32_t)b * kBBytes;
-            constexpr uint32_t kBPlane = kStageCh * NOUT * 2;
+            constexpr uint32_t kBPlane = SC * NOUT * 2;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {   // K = 16: channel groups 2j and 2j+1
-                const uint32_t a_off = (uint32_t)(2 * j) * (kPix * 16u), b_off = (uint32_t)(2 * j) * (NOUT * 16u);
-                const uint64_t a_hi = make_desc(a_buf + a_off, kPix * 16u, 128u);
+            for (int j = 0; j < SC / 16; ++j) {   // K = 16: channel groups 2j and 2j+1
+                const uint32_t a_off = (uint32_t)(2 * j) * (uint32_t)kAGroup, b_off = (uint32_t)(2 * j) * (NOUT * 16u);
+                const uint64_t a_hi = make_desc(a_buf + a_off, (uint32_t)kAGroup, 128u);
                 const uint64_t b_hi = make_desc(b_buf + b_off, NOUT * 16u, 128u);
                 mma_bf16(tmem, a_hi, b_hi, idesc, (s > 0 || j > 0) ? 1u : 0u);
                 if (SPLIT) {
-                    const uint64_t a_lo = make_desc(a_buf + kABytes + a_off, kPix * 16u, 128u);
+                    const uint64_t a_lo = make_desc(a_buf + kABytes + a_off, (uint32_t)kAGroup, 128u);
                     const uint64_t b_lo = make_desc(b_buf + kBPlane + b_off, NOUT * 16u, 128u);
                     mma_bf16(tmem, a_lo, b_hi, idesc, 1u);
                     mma_bf16(tmem, a_hi, b_lo, idesc, 1u);
@@ -368,29 +447,35 @@ k_me_tail(const float *__restrict__ b1, const float *__restrict__ attn, const fl
     __syncthreads();
     const int p = blockIdx.x * 128 + tid;
     if (p >= HW) return;
-    float acc[64];
+    float2 acc[32];   // packed fp32 (FFMA2): two output channels per instruction, same roundings as scalar fmaf
 #pragma unroll
-    for (int o = 0; o < 64; ++o) acc[o] = 0.0f;
+    for (int o = 0; o < 32; ++o) acc[o] = make_float2(0.0f, 0.0f);
     const float *src = b1 + (size_t)a * 64 * HW + p;
-#pragma unroll 2
-    for (int c = 0; c < 64; ++c) {
-        const float v = __ldg(src + (size_t)c * HW);
-        const float4 *wr = reinterpret_cast<const float4 *>(&s_w[c][0]);
+#pragma unroll 1
+    for (int c0 = 0; c0 < 64; c0 += 8) {
+        float v8[8];   // eight plane-strided loads in flight (two at a time left the kernel latency bound: 24 % issue-active)
 #pragma unroll
-        for (int o4 = 0; o4 < 16; ++o4) {
-            const float4 w = wr[o4];
-            acc[4 * o4 + 0] = fmaf(w.x, v, acc[4 * o4 + 0]);
-            acc[4 * o4 + 1] = fmaf(w.y, v, acc[4 * o4 + 1]);
-            acc[4 * o4 + 2] = fmaf(w.z, v, acc[4 * o4 + 2]);
-            acc[4 * o4 + 3] = fmaf(w.w, v, acc[4 * o4 + 3]);
+        for (int k = 0; k < 8; ++k) v8[k] = __ldg(src + (size_t)(c0 + k) * HW);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const float2 vv = make_float2(v8[k], v8[k]);
+            const float4 *wr = reinterpret_cast<const float4 *>(&s_w[c0 + k][0]);
+#pragma unroll
+            for (int o4 = 0; o4 < 16; ++o4) {
+                const float4 w = wr[o4];
+                acc[2 * o4 + 0] = __ffma2_rn(make_float2(w.x, w.y), vv, acc[2 * o4 + 0]);
+                acc[2 * o4 + 1] = __ffma2_rn(make_float2(w.z, w.w), vv, acc[2 * o4 + 1]);
+            }
         }
     }
     float r0 = prm[kFuse2B], r1 = prm[kFuse2B + 1];
 #pragma unroll
-    for (int o = 0; o < 64; ++o) {
-        const float h = fmaxf(acc[o] + s_b[o], 0.0f);
-        r0 = fmaf(s_w2[0][o], h, r0);
-        r1 = fmaf(s_w2[1][o], h, r1);
+    for (int o = 0; o < 32; ++o) {
+        const float h0 = fmaxf(acc[o].x + s_b[2 * o], 0.0f), h1 = fmaxf(acc[o].y + s_b[2 * o + 1], 0.0f);
+        r0 = fmaf(s_w2[0][2 * o], h0, r0);
+        r1 = fmaf(s_w2[1][2 * o], h0, r1);
+        r0 = fmaf(s_w2[0][2 * o + 1], h1, r0);
+        r1 = fmaf(s_w2[1][2 * o + 1], h1, r1);
     }
     out[((size_t)a * 2 + 0) * HW + p] = r0;
     out[((size_t)a * 2 + 1) * HW + p] = r1;
@@ -401,9 +486,10 @@ struct Workspace {
     float *b1;          // [A][64][HW]
     float *tile_sums;   // [A][HW/32][64]
     float *attn;        // [A][64]
+    uint4 *xh, *xl;     // [A][HW][C] bf16: value and residual planes of the input, channel-last
     size_t bytes;
 };
-static Workspace carve(void *base, int A, int HW) {
+static Workspace carve(void *base, int A, int C, int HW) {
     Workspace w;
     size_t off = 0;
     char *b = (char *)base;
@@ -416,6 +502,8 @@ static Workspace carve(void *base, int A, int HW) {
     w.b1 = take((size_t)A * 64 * HW * 4);
     w.tile_sums = take((size_t)A * (HW / 32) * 64 * 4);
     w.attn = take((size_t)A * 64 * 4);
+    w.xh = (uint4 *)take((size_t)A * HW * C * 2);
+    w.xl = (uint4 *)take((size_t)A * HW * C * 2);
     w.bytes = off;
     return w;
 }
@@ -431,22 +519,21 @@ extern "C" size_t gc_me_param_floats(void) { return me::kTailFloats; }
 extern "C" size_t gc_me_packed_bytes(int C) {
     return C > 0 ? align_up(me::packed_off_bytes(C), 256) + me::packed_dcn_bytes(C) : 0;
 }
-extern "C" size_t gc_me_workspace_bytes(int total_agents, int H, int W) {
-    if (total_agents <= 0 || H <= 0 || W <= 0) return 0;
-    return me::carve(nullptr, total_agents, H * W).bytes;
+extern "C" size_t gc_me_workspace_bytes(int total_agents, int C, int H, int W) {
+    if (total_agents <= 0 || C <= 0 || H <= 0 || W <= 0) return 0;
+    return me::carve(nullptr, total_agents, C, H * W).bytes;
 }
 
 extern "C" int gc_me_pack_weights(const float *w_offset, const float *w_dcn, int C, void *packed, void *stream) {
     GC_REQUIRE(w_offset && w_dcn && packed, GC_EINVAL, "gc_me_pack_weights: null pointer");
-    GC_REQUIRE(C > 0 && C % me::kStageCh == 0, GC_EUNSUPPORTED, "gc_me_pack_weights: C must be a multiple of 64 (got %d)", C);
+    GC_REQUIRE(C > 0 && C % 64 == 0, GC_EUNSUPPORTED, "gc_me_pack_weights: C must be a multiple of 64 (got %d)", C);
     cudaStream_t st = (cudaStream_t)stream;
-    const int chunks = C / me::kStageCh;
     uint4 *p_off = (uint4 *)packed;
     uint4 *p_dcn = (uint4 *)((char *)packed + align_up(me::packed_off_bytes(C), 256));
-    const int n_off = 9 * chunks * 8 * 32, n_dcn = 9 * chunks * 8 * 64;
-    me::k_me_pack<<<(n_off + 255) / 256, 256, 0, st>>>(w_offset, 18, 32, C, 1, p_off);
+    const int n_off = 9 * (C / 8) * 32, n_dcn = 9 * (C / 8) * 64;
+    me::k_me_pack<<<(n_off + 255) / 256, 256, 0, st>>>(w_offset, 18, 32, C, me::kScOffset, 1, p_off);
     GC_LAUNCH_CHECK("k_me_pack(offset1)");
-    me::k_me_pack<<<(n_dcn + 255) / 256, 256, 0, st>>>(w_dcn, 64, 64, C, 0, p_dcn);
+    me::k_me_pack<<<(n_dcn + 255) / 256, 256, 0, st>>>(w_dcn, 64, 64, C, me::kScDeform, 0, p_dcn);
     GC_LAUNCH_CHECK("k_me_pack(dcn1)");
     return GC_OK;
 }
@@ -456,27 +543,29 @@ extern "C" int gc_message_extractor(const float *x, int total_agents, int C, int
     GC_REQUIRE(total_agents >= 0 && total_agents <= 65535, GC_EINVAL, "gc_message_extractor: bad agent count");
     if (total_agents == 0) return GC_OK;
     GC_REQUIRE(x && packed && params && workspace && message, GC_EINVAL, "gc_message_extractor: null pointer");
-    GC_REQUIRE(C > 0 && C % me::kStageCh == 0, GC_EUNSUPPORTED, "gc_message_extractor: C must be a multiple of 64 (got %d)", C);
+    GC_REQUIRE(C > 0 && C % 64 == 0, GC_EUNSUPPORTED, "gc_message_extractor: C must be a multiple of 64 (got %d)", C);
     GC_REQUIRE(H > 0 && W > 0 && (H * W) % me::kPix == 0, GC_EUNSUPPORTED,
                "gc_message_extractor: H*W must be a multiple of 128 (got %dx%d)", H, W);
     cudaStream_t st = (cudaStream_t)stream;
     const int HW = H * W, tiles = HW / me::kPix;
-    const me::Workspace ws = me::carve(workspace, total_agents, HW);
+    const me::Workspace ws = me::carve(workspace, total_agents, C, HW);
     const uint4 *p_off = (const uint4 *)packed;
     const uint4 *p_dcn = (const uint4 *)((const char *)packed + align_up(me::packed_off_bytes(C), 256));
     static bool attr_done = false;
-    constexpr int kSmemOff = 2 * (2 * me::kABytes + 2 * me::kStageCh * 32 * 2), kSmemDcn = 2 * me::kABytes + 2 * me::kStageCh * 64 * 2;
+    constexpr int kSmemOff = me::conv_smem_bytes(32, true, me::kScOffset), kSmemDcn = me::conv_smem_bytes(64, false, me::kScDeform);
     if (!attr_done) {
-        cudaFuncSetAttribute(me::k_me_conv<32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemOff);
-        cudaFuncSetAttribute(me::k_me_conv<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemDcn);
+        cudaFuncSetAttribute(me::k_me_conv<32, false, me::kScOffset>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemOff);
+        cudaFuncSetAttribute(me::k_me_conv<64, true, me::kScDeform>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemDcn);
         attr_done = true;
     }
     const dim3 grid(tiles, total_agents);
-    me::k_me_conv<32, false><<<grid, me::kThreads, kSmemOff, st>>>(x, nullptr, p_off, params + me::kOffBias, C, H, W, 18,
-                                                                   ws.offset, nullptr);
+    me::k_me_to_nhwc<<<dim3((HW + 63) / 64, C / 64, total_agents), 256, 0, st>>>(x, C, HW, ws.xh, ws.xl);
+    GC_LAUNCH_CHECK("k_me_to_nhwc");
+    me::k_me_conv<32, false, me::kScOffset><<<grid, me::kThreads, kSmemOff, st>>>(ws.xh, ws.xl, nullptr, p_off, params + me::kOffBias, C, H,
+                                                                   W, 18, ws.offset, nullptr);
     GC_LAUNCH_CHECK("k_me_conv<offset1>");
-    me::k_me_conv<64, true><<<grid, me::kThreads, kSmemDcn, st>>>(x, ws.offset, p_dcn, params + me::kDcnBias, C, H, W, 64,
-                                                                  ws.b1, ws.tile_sums);
+    me::k_me_conv<64, true, me::kScDeform><<<grid, me::kThreads, kSmemDcn, st>>>(ws.xh, ws.xl, ws.offset, p_dcn, params + me::kDcnBias, C, H,
+                                                                  W, 64, ws.b1, ws.tile_sums);
     GC_LAUNCH_CHECK("k_me_conv<dcn1>");
     me::k_me_attn<<<total_agents, 64, 0, st>>>(ws.tile_sums, tiles * 4, HW, params, ws.attn);
     GC_LAUNCH_CHECK("k_me_attn");

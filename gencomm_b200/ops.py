@@ -348,7 +348,7 @@ def message_extractor(x, packed, params, workspace=None, out=None):
     if packed.numel() != lib.gc_me_packed_bytes(C) or params.numel() != lib.gc_me_param_floats():
         raise ValueError("message_extractor: packed weights / params do not match C")
     if workspace is None:
-        workspace = torch.empty(lib.gc_me_workspace_bytes(A, H, W), dtype=torch.uint8, device=x.device)
+        workspace = torch.empty(lib.gc_me_workspace_bytes(A, C, H, W), dtype=torch.uint8, device=x.device)
     if out is None:
         out = torch.empty(A, 2, H, W, dtype=torch.float32, device=x.device)
     _lib.check(lib.gc_message_extractor(_ptr(x), A, C, H, W, _ptr(packed), _ptr(params), _ptr(workspace), _ptr(out),

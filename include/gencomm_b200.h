@@ -193,13 +193,13 @@ int gc_unet_forward(const float *cond, const float *x, int total_agents, int t_i
  *   params   gc_me_param_floats() floats (device): offset1.bias[18] (padded to 32), dcn1.bias[64],
  *            attn.1.weight[32][64], attn.1.bias[32], attn.3.weight[64][32], attn.3.bias[64],
  *            fuse.0.weight[64][64], fuse.0.bias[64], fuse.2.weight[2][64], fuse.2.bias[2] (padded to 8)
- *   workspace gc_me_workspace_bytes(sumN, H, W) bytes (device)
+ *   workspace gc_me_workspace_bytes(sumN, C, H, W) bytes (device)
  *   message  [sumN][2][H][W] f32
  *   Arithmetic: the two 3x3 layers use bf16 operands with fp32 accumulation; the rest is fp32.
  * ------------------------------------------------------------------------------------------- */
 size_t gc_me_param_floats(void);
 size_t gc_me_packed_bytes(int C);
-size_t gc_me_workspace_bytes(int total_agents, int H, int W);
+size_t gc_me_workspace_bytes(int total_agents, int C, int H, int W);
 int gc_me_pack_weights(const float *w_offset, const float *w_dcn, int C, void *packed, void *stream);
 int gc_message_extractor(const float *x, int total_agents, int C, int H, int W, const void *packed,
                          const float *params, void *workspace, float *message, void *stream);

@@ -32,7 +32,7 @@ def _run(model, x):
     be = model.bev_extractor
     packed, params = be._blobs()
     A, C, H, W = x.shape
-    ws = torch.empty(_lib.load().gc_me_workspace_bytes(A, H, W), dtype=torch.uint8, device=x.device)
+    ws = torch.empty(_lib.load().gc_me_workspace_bytes(A, C, H, W), dtype=torch.uint8, device=x.device)
     out = ops.message_extractor(x, packed, params, workspace=ws)
     torch.cuda.synchronize()
     f = ws.view(torch.float32)
