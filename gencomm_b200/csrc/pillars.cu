@@ -505,6 +505,8 @@ k_canvas(Src src, int nx, int ny, int C, float *__restrict__ canvas) {
     }
 }
 
+__device__ __forceinline__ float2 dup2(float v) { return make_float2(v, v); }
+
 // ------------------------------------------------------------------------------------------------
 // 4b. persistent canvas writer for the fused front end (round-1q; the default for nx % 4 == 0).
 //
@@ -592,7 +594,6 @@ __device__ __forceinline__ PfnPacked pack_pfn(const PfnLane &wa, const PfnLane &
     return w;
 }
 
-__device__ __forceinline__ float2 dup2(float v) { return make_float2(v, v); }
 
 // Same roundings, same order as pfn_pillar().  p = this lane's point for lane < n, a copy of point 0 otherwise.
 __device__ __forceinline__ float2 pfn_pillar_packed(const PfnPacked &w, float4 p, int n, float inv_n, float cx,
