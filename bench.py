@@ -252,7 +252,7 @@ def message_extractor_extra(dev, frames=8, agents=4, C=128, H=64, W=128, iters=1
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / iters
     flops = 2.0 * A * H * W * (9 * C * (18 + 64) + 64 * 64 + 2 * 64)
-    return {"workload": f"MessageExtractorv2, {frames} frames x {agents} agents, C={C}, {H}x{W}", "launches_per_call": 4,
+    return {"workload": f"MessageExtractorv2, {frames} frames x {agents} agents, C={C}, {H}x{W}", "launches_per_call": 5,
             "ms_per_call": ms, "frames_per_s": frames / (ms * 1e-3), "tflops": flops / (ms * 1e-3) / 1e12,
             "precision_note": "offset1 3x3: bf16x3 (value + residual operands, three tcgen05 MMAs, fp32 accumulation); "
                               "deformable 3x3: bf16 operands, fp32 TMEM accumulation; pool / excite / 1x1 tail fp32"}
@@ -453,10 +453,20 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the secondary GenComm sampler measurement")
     args = ap.parse_args()
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_ours(args)
+    # The contract is ONE JSON line on stdout.  Libraries write to fd 1 behind Python's back (NCCL prints its version
+    # banner there at communicator creation), so fd 1 is pointed at stderr for the whole run and the JSON line goes to a
+    # private duplicate of the original stdout.
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = real_stdout
+    try:
+        if args.impl == "reference":
+            run_reference(args)
+        else:
+            run_ours(args)
+    finally:
+        real_stdout.flush()
 
 
 if __name__ == "__main__":
