@@ -28,6 +28,8 @@
 // reference is written in tests/test_message_extractor_gpu.py.
 #include <cuda_bf16.h>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace gc {
@@ -288,11 +290,15 @@ k_me_conv(const uint4 *__restrict__ xh, const uint4 *__restrict__ xl, const floa
             __syncthreads();
         }
         if (s >= 2) mbar_wait(smem_u32(&s_empty[b]), (uint32_t)((s >> 1) - 1) & 1u);   // MMAs of stage s-2 retired
-        // ---- B stage: kBBytes contiguous bytes of the packed weights ----
+        // ---- B stage: kBBytes contiguous bytes of the packed weights; the loads are issued here and stored after the
+        // first batch of A loads is in flight (one round trip instead of two or three) ----
+        constexpr int kBIter = (kBBytes / 16 + kThreads - 1) / kThreads;
+        uint4 bq[kBIter];
         {
             const uint4 *src = wp + (size_t)s * (kBBytes / 16);
-            uint4 *dst = reinterpret_cast<uint4 *>(b_s + b * kBBytes);
-            for (int i = tid; i < kBBytes / 16; i += kThreads) dst[i] = __ldg(src + i);
+#pragma unroll
+            for (int i = 0; i < kBIter; ++i)
+                bq[i] = (i * kThreads + tid < kBBytes / 16) ? __ldg(src + i * kThreads + tid) : make_uint4(0u, 0u, 0u, 0u);
         }
         // ---- A stage: 128 pixels x 8 channel groups = 1024 16-byte rows, four per thread.  The eight lanes of a pixel
         // read 128 contiguous bytes per corner (one full line; spreading a warp over 8 pixels x 4 groups instead was
@@ -320,6 +326,12 @@ k_me_conv(const uint4 *__restrict__ xh, const uint4 *__restrict__ xl, const floa
                         q[u][0] = __ldg(xh_a + (size_t)o.x * C8 + cg);
                         q[u][1] = __ldg(xl_a + (size_t)o.x * C8 + cg);
                     }
+                }
+                if (pass == 0) {
+                    uint4 *bd = reinterpret_cast<uint4 *>(b_s + b * kBBytes);
+#pragma unroll
+                    for (int i = 0; i < kBIter; ++i)
+                        if (i * kThreads + tid < kBBytes / 16) bd[i * kThreads + tid] = bq[i];
                 }
 #pragma unroll
                 for (int u = 0; u < 2; ++u) {
@@ -388,6 +400,131 @@ k_me_conv(const uint4 *__restrict__ xh, const uint4 *__restrict__ xl, const floa
                     }
                 }
             }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_free<NOUT>(tmem);
+}
+
+// ------------------------------------------------------------------------------------------------
+// offset1 fast path for W % 128 == 0 (every shipped configuration: 64 x 128 maps): a tile is 128 pixels of ONE image
+// row, so the three taps kx = 0, 1, 2 of a kernel row are the same staged pixels shifted by one 16-byte operand row.
+// Stage (ky, 32-channel chunk) = 130 pixels x0-1 .. x0+128 of input row y-1+ky, copied once from the channel-last
+// planes (zero outside the image); the taps are addressed by moving the descriptor start by kx * 16 bytes (the conv_in
+// scheme of denoiser_tc.cu).  3 x C/32 stages of 18 MMAs instead of 9 x C/32 stages of 6: a third of the loads, stores
+// and barriers of the generic kernel (ncu: that one spends the offset layer waiting on its per-stage
+// load -> store -> barrier -> MMA chain).  bf16x3 like the generic path.  grid = (H*W/128, n_agents), 256 threads.
+// ------------------------------------------------------------------------------------------------
+constexpr int kR3Pix = 130;
+constexpr int kR3Group = kR3Pix * 16;                  // 2080 B = 32 (mod 128): the 4-lane pixel rows store conflict-free
+constexpr int kR3Plane = 4 * kR3Group;
+constexpr int kR3BBlk = 32 * 32 * 2 * 2;               // one tap's B: value + residual planes (= one packed stage, SC = 32)
+constexpr int kR3Stage = 2 * kR3Plane + 3 * kR3BBlk;
+constexpr int kR3Smem = 2 * kR3Stage;
+
+__global__ void __launch_bounds__(kThreads)
+k_me_offset_row3(const uint4 *__restrict__ xh, const uint4 *__restrict__ xl, const uint4 *__restrict__ wp,
+                 const float *__restrict__ bias, int C, int H, int W, float *__restrict__ out) {
+    constexpr int NOUT = 32, n_store = 18;
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ __align__(8) uint64_t s_empty[2], s_done;
+    __shared__ uint32_t s_tmem;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int agent = blockIdx.y, tile = blockIdx.x;
+    const int HW = H * W, C8 = C / 8, chunks = C / 32, stages = 3 * chunks;
+    const int pix0 = tile * kPix, py = pix0 / W, x0 = pix0 - py * W;
+
+    if (warp == 0) tmem_alloc<NOUT>(&s_tmem);
+    if (tid == 32) {
+        mbar_init(smem_u32(&s_empty[0]), 1); mbar_init(smem_u32(&s_empty[1]), 1); mbar_init(smem_u32(&s_done), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = s_tmem;
+    const uint32_t s_base = smem_u32(smem);
+    constexpr uint32_t idesc = make_idesc(128, NOUT);
+    const uint4 *xh_a = xh + (size_t)agent * HW * C8;
+    const uint4 *xl_a = xl + (size_t)agent * HW * C8;
+
+    for (int s = 0; s < stages; ++s) {
+        const int b = s & 1;
+        const int ky = s / chunks, chunk = s - ky * chunks;
+        if (s >= 2) mbar_wait(smem_u32(&s_empty[b]), (uint32_t)((s >> 1) - 1) & 1u);   // MMAs of stage s-2 retired
+        uint8_t *a_buf = smem + b * kR3Stage, *b_buf = a_buf + 2 * kR3Plane;
+        // ---- all nine 16-byte loads of this thread are issued before the first store (one L2 round trip per stage;
+        // load -> store pairs in sequence made the layer wait five round trips per stage: ncu, 57 % of the stall
+        // samples on the STS instructions) ----
+        {
+            // B: the three taps of kernel row ky (4 KB each, value + residual): 768 rows, three per thread
+            uint4 bq[3];
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx)
+                bq[kx] = __ldg(wp + (size_t)((ky * 3 + kx) * chunks + chunk) * (kR3BBlk / 16) + tid);
+            // A: 130 pixels x 4 channel groups, value and residual planes
+            const int yy = py - 1 + ky;
+            const bool row_ok = yy >= 0 && yy < H;
+            const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+            uint4 hi[3], lo[3];
+#pragma unroll
+            for (int it = 0; it < 3; ++it) {
+                const int item = it * kThreads + tid;
+                const int p = item >> 2, g = item & 3, xx = x0 - 1 + p;
+                const bool ok = item < kR3Pix * 4 && row_ok && xx >= 0 && xx < W;
+                const size_t idx = ok ? (size_t)(yy * W + xx) * C8 + chunk * 4 + g : 0;
+                hi[it] = ok ? __ldg(xh_a + idx) : z;
+                lo[it] = ok ? __ldg(xl_a + idx) : z;
+            }
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) reinterpret_cast<uint4 *>(b_buf)[kx * (kR3BBlk / 16) + tid] = bq[kx];
+#pragma unroll
+            for (int it = 0; it < 3; ++it) {
+                const int item = it * kThreads + tid;
+                if (item < kR3Pix * 4) {
+                    uint4 *d = reinterpret_cast<uint4 *>(a_buf + (item & 3) * kR3Group) + (item >> 2);
+                    d[0] = hi[it];
+                    d[kR3Plane / 16] = lo[it];
+                }
+            }
+        }
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+            const uint32_t a_addr = s_base + (uint32_t)b * kR3Stage, b_addr = a_addr + 2u * kR3Plane;
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {   // K = 16: channel groups 2j and 2j+1
+                    const uint32_t a_off = (uint32_t)(2 * j) * kR3Group + (uint32_t)kx * 16u;
+                    const uint32_t b_off = (uint32_t)kx * kR3BBlk + (uint32_t)(2 * j) * (NOUT * 16u);
+                    const uint64_t a_hi = make_desc(a_addr + a_off, kR3Group, 128u);
+                    const uint64_t a_lo = make_desc(a_addr + kR3Plane + a_off, kR3Group, 128u);
+                    const uint64_t b_hi = make_desc(b_addr + b_off, NOUT * 16u, 128u);
+                    const uint64_t b_lo = make_desc(b_addr + kR3BBlk / 2 + b_off, NOUT * 16u, 128u);
+                    mma_bf16(tmem, a_hi, b_hi, idesc, (s > 0 || kx > 0 || j > 0) ? 1u : 0u);
+                    mma_bf16(tmem, a_lo, b_hi, idesc, 1u);
+                    mma_bf16(tmem, a_hi, b_lo, idesc, 1u);
+                }
+            }
+            mma_commit(smem_u32(&s_empty[b]));
+            if (s == stages - 1) mma_commit(smem_u32(&s_done));
+        }
+    }
+    mbar_wait(smem_u32(&s_done), 0u);
+    tc_fence_after();
+    {
+        const int q = warp & 3, ch0 = (warp >> 2) * (NOUT / 2);
+        const int p_out = tile * kPix + q * 32 + lane;
+        float v[16];
+        tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)ch0, v);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const int ch = ch0 + i;
+            if (ch < n_store) out[((size_t)agent * n_store + ch) * HW + p_out] = v[i] + __ldg(bias + ch);
         }
     }
     tc_fence_before();
@@ -556,14 +693,22 @@ extern "C" int gc_message_extractor(const float *x, int total_agents, int C, int
     if (!attr_done) {
         cudaFuncSetAttribute(me::k_me_conv<32, false, me::kScOffset>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemOff);
         cudaFuncSetAttribute(me::k_me_conv<64, true, me::kScDeform>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemDcn);
+        cudaFuncSetAttribute(me::k_me_offset_row3, cudaFuncAttributeMaxDynamicSharedMemorySize, me::kR3Smem);
         attr_done = true;
     }
     const dim3 grid(tiles, total_agents);
     me::k_me_to_nhwc<<<dim3((HW + 63) / 64, C / 64, total_agents), 256, 0, st>>>(x, C, HW, ws.xh, ws.xl);
     GC_LAUNCH_CHECK("k_me_to_nhwc");
-    me::k_me_conv<32, false, me::kScOffset><<<grid, me::kThreads, kSmemOff, st>>>(ws.xh, ws.xl, nullptr, p_off, params + me::kOffBias, C, H,
-                                                                   W, 18, ws.offset, nullptr);
-    GC_LAUNCH_CHECK("k_me_conv<offset1>");
+    if (W % me::kPix == 0 && !getenv("GC_ME_GENERIC_OFFSET")) {   // a tile is 128 pixels of one image row
+        me::k_me_offset_row3<<<grid, me::kThreads, me::kR3Smem, st>>>(ws.xh, ws.xl, p_off, params + me::kOffBias, C, H, W,
+                                                                      ws.offset);
+        GC_LAUNCH_CHECK("k_me_offset_row3");
+    } else {
+        me::k_me_conv<32, false, me::kScOffset><<<grid, me::kThreads, kSmemOff, st>>>(ws.xh, ws.xl, nullptr, p_off,
+                                                                                   params + me::kOffBias, C, H, W, 18,
+                                                                                   ws.offset, nullptr);
+        GC_LAUNCH_CHECK("k_me_conv<offset1>");
+    }
     me::k_me_conv<64, true, me::kScDeform><<<grid, me::kThreads, kSmemDcn, st>>>(ws.xh, ws.xl, ws.offset, p_dcn, params + me::kDcnBias, C, H,
                                                                   W, 64, ws.b1, ws.tile_sums);
     GC_LAUNCH_CHECK("k_me_conv<dcn1>");
