@@ -22,7 +22,8 @@
 //   * D: fp32 accumulators in TMEM (NOUT columns), epilogue tcgen05.ld.32x32b (lane = pixel -> coalesced NCHW stores),
 //     bias, and -- for the deformable layer -- the per-tile channel sums the average pool needs (deterministic order).
 // The tail (global average pool -> squeeze/excite -> two 1x1 convolutions) is 1 % of the FLOPs: CUDA-core fp32 kernels,
-// the excitation folded into the first 1x1's weights per agent.
+// the excitation folded into the first 1x1's weights per agent (two threads per pixel with 32 accumulators each were
+// measured slower: 117 -> 167 us, shared-memory weight reads lose their warp-wide broadcast).
 //
 // Arithmetic: bf16 operands, fp32 accumulation for the two 3x3 layers; everything else fp32.  Tolerance vs the fp32
 // reference is written in tests/test_message_extractor_gpu.py.
@@ -192,12 +193,13 @@ k_me_to_nhwc(const float *__restrict__ x, int C, int HW, uint4 *__restrict__ xh,
 __device__ __forceinline__ float bf_lo(uint32_t u) { return __uint_as_float(u << 16); }
 __device__ __forceinline__ float bf_hi(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }
 // torchvision bilinear_interpolate: val = hh*hw*v1 + hh*lw*v2 + lh*hw*v3 + lh*lw*v4 (left to right), two channels
+// (packed fp32: one FMUL2 + three FFMA2 for the two channels of a 32-bit word, same roundings as scalar fmaf)
 __device__ __forceinline__ uint32_t lerp2(const float4 &w, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-    float lo = w.x * bf_lo(a), hi = w.x * bf_hi(a);
-    lo += w.y * bf_lo(b); hi += w.y * bf_hi(b);
-    lo += w.z * bf_lo(c); hi += w.z * bf_hi(c);
-    lo += w.w * bf_lo(d); hi += w.w * bf_hi(d);
-    return pack_bf16(lo, hi);
+    float2 r = __fmul2_rn(make_float2(w.x, w.x), make_float2(bf_lo(a), bf_hi(a)));
+    r = __ffma2_rn(make_float2(w.y, w.y), make_float2(bf_lo(b), bf_hi(b)), r);
+    r = __ffma2_rn(make_float2(w.z, w.z), make_float2(bf_lo(c), bf_hi(c)), r);
+    r = __ffma2_rn(make_float2(w.w, w.w), make_float2(bf_lo(d), bf_hi(d)), r);
+    return pack_bf16(r.x, r.y);
 }
 
 // ------------------------------------------------------------------------------------------------
