@@ -32,77 +32,12 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "umma.cuh"
 
 namespace gc {
 namespace me {
 
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-// K-major, SWIZZLE_NONE shared-memory matrix descriptor (the same encoding denoiser_tc.cu validated on the B200)
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-    uint64_t d = (uint64_t)((saddr >> 4) & 0x3FFFu);
-    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
-    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
-    d |= 1ull << 46;
-    return d;
-}
-// kind::f16 instruction descriptor: D = f32, A = B = bf16, both K-major, dense
-__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
-__device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-        "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void mma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "ME_WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra ME_DONE_%=;\n\t"
-        "bra ME_WAIT_%=;\n\t"
-        "ME_DONE_%=:\n\t"
-        "}" ::"r"(bar), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-template <int COLS>
-__device__ __forceinline__ void tmem_alloc(uint32_t *slot) {   // one full warp
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "n"(COLS) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-template <int COLS>
-__device__ __forceinline__ void tmem_free(uint32_t base) {     // the same warp
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(base), "n"(COLS) : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
-    uint32_t r[16];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
-__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
-    const __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);   // .x = lo (low 16 bits), .y = hi
-    return *reinterpret_cast<const uint32_t *>(&h);
-}
+using namespace umma;
 
 constexpr int kPix = 128;            // pixels per CTA = M
 constexpr int kThreads = 256;
@@ -620,6 +555,119 @@ k_me_tail(const float *__restrict__ b1, const float *__restrict__ attn, const fl
     out[((size_t)a * 2 + 1) * HW + p] = r1;
 }
 
+// The same tail with fuse.0 (64 -> 64) on the tensor cores: one M = 128 pixels, N = 64, K = 64 GEMM per CTA in
+// "bf16x3" (value + residual planes of both operands, three MMAs per K = 16 step, ~16 mantissa bits), the excitation
+// folded into the A operand, ReLU + fuse.2 (64 -> 2) in the TMEM epilogue.  Replaces 2048 FFMA2 + 1024 LDS per pixel
+// (k_me_tail: 117 us, latency bound) by 12 MMAs per 128 pixels.  grid = (H*W/128, n_agents), 128 threads (thread = pixel).
+constexpr int kTtGroup = kPix * 16 + 16;        // [8 channel groups][128 pixels][16 B], padded group stride
+constexpr int kTtPlane = 8 * kTtGroup;
+constexpr int kTtBPlane = 64 * 64 * 2;          // [8 k groups][64 n][16 B]
+constexpr int kTtSmem = 2 * kTtPlane + 2 * kTtBPlane;
+
+__global__ void __launch_bounds__(128)
+k_me_tail_tc(const float *__restrict__ b1, const float *__restrict__ attn, const float *__restrict__ prm, int HW,
+             float *__restrict__ out) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t *a_hi = smem, *a_lo = smem + kTtPlane, *b_hi = smem + 2 * kTtPlane, *b_lo = b_hi + kTtBPlane;
+    __shared__ __align__(8) uint64_t s_done;
+    __shared__ uint32_t s_tmem;
+    __shared__ float s_attn[64], s_b[64], s_w2[2][64];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int a = blockIdx.y, p = blockIdx.x * kPix + tid;
+
+    if (warp == 0) tmem_alloc<64>(&s_tmem);
+    if (tid == 32) {
+        mbar_init(smem_u32(&s_done), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (tid < 64) {
+        s_attn[tid] = attn[a * 64 + tid];
+        s_b[tid] = prm[kFuse1B + tid];
+        s_w2[0][tid] = prm[kFuse2W + tid];
+        s_w2[1][tid] = prm[kFuse2W + 64 + tid];
+    }
+    // B: fuse.0.weight [n][k] -> value / residual planes in core-matrix order [k8][n][8 k]
+    for (int i = tid; i < 64 * 8; i += 128) {
+        const int n = i & 63, k8 = i >> 6;
+        const float4 w0 = __ldg(reinterpret_cast<const float4 *>(prm + kFuse1W + n * 64 + k8 * 8));
+        const float4 w1 = __ldg(reinterpret_cast<const float4 *>(prm + kFuse1W + n * 64 + k8 * 8 + 4));
+        const float v[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+        uint32_t h[4], l[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            h[j] = pack_bf16(v[2 * j], v[2 * j + 1]);
+            l[j] = pack_bf16(bf16_residual(v[2 * j]), bf16_residual(v[2 * j + 1]));
+        }
+        reinterpret_cast<uint4 *>(b_hi)[k8 * 64 + n] = make_uint4(h[0], h[1], h[2], h[3]);
+        reinterpret_cast<uint4 *>(b_lo)[k8 * 64 + n] = make_uint4(l[0], l[1], l[2], l[3]);
+    }
+    // A: this thread's pixel, 64 plane-strided loads in flight
+    float x[64];
+    {
+        const float *src = b1 + (size_t)a * 64 * HW + (p < HW ? p : 0);
+#pragma unroll
+        for (int c = 0; c < 64; ++c) x[c] = __ldg(src + (size_t)c * HW);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+        uint32_t h[4], l[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float v0 = x[8 * g + 2 * j] * s_attn[8 * g + 2 * j], v1 = x[8 * g + 2 * j + 1] * s_attn[8 * g + 2 * j + 1];
+            h[j] = pack_bf16(v0, v1);
+            l[j] = pack_bf16(bf16_residual(v0), bf16_residual(v1));
+        }
+        reinterpret_cast<uint4 *>(a_hi + g * kTtGroup)[tid] = make_uint4(h[0], h[1], h[2], h[3]);
+        reinterpret_cast<uint4 *>(a_lo + g * kTtGroup)[tid] = make_uint4(l[0], l[1], l[2], l[3]);
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    const uint32_t tmem = s_tmem;
+    if (tid == 0) {
+        tc_fence_after();
+        constexpr uint32_t idesc = make_idesc(128, 64);
+        const uint32_t ah = smem_u32(a_hi), al = smem_u32(a_lo), bh = smem_u32(b_hi), bl = smem_u32(b_lo);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {   // K = 16: channel groups 2j and 2j+1
+            const uint32_t a_off = (uint32_t)(2 * j) * kTtGroup, b_off = (uint32_t)(2 * j) * (64 * 16u);
+            const uint64_t d_ah = make_desc(ah + a_off, kTtGroup, 128u), d_al = make_desc(al + a_off, kTtGroup, 128u);
+            const uint64_t d_bh = make_desc(bh + b_off, 64 * 16u, 128u), d_bl = make_desc(bl + b_off, 64 * 16u, 128u);
+            mma_bf16(tmem, d_ah, d_bh, idesc, j > 0 ? 1u : 0u);
+            mma_bf16(tmem, d_al, d_bh, idesc, 1u);
+            mma_bf16(tmem, d_ah, d_bl, idesc, 1u);
+        }
+        mma_commit(smem_u32(&s_done));
+    }
+    mbar_wait(smem_u32(&s_done), 0u);
+    tc_fence_after();
+    {
+        const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
+        float r0 = prm[kFuse2B], r1 = prm[kFuse2B + 1];
+#pragma unroll
+        for (int c16 = 0; c16 < 64; c16 += 16) {
+            float v[16];
+            tmem_ld16(taddr + (uint32_t)c16, v);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const float h = fmaxf(v[i] + s_b[c16 + i], 0.0f);
+                r0 = fmaf(s_w2[0][c16 + i], h, r0);
+                r1 = fmaf(s_w2[1][c16 + i], h, r1);
+            }
+        }
+        if (p < HW) {
+            out[((size_t)a * 2 + 0) * HW + p] = r0;
+            out[((size_t)a * 2 + 1) * HW + p] = r1;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_free<64>(tmem);
+}
+
 struct Workspace {
     float *offset;      // [A][18][HW]
     float *b1;          // [A][64][HW]
@@ -696,6 +744,7 @@ extern "C" int gc_message_extractor(const float *x, int total_agents, int C, int
         cudaFuncSetAttribute(me::k_me_conv<32, false, me::kScOffset>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemOff);
         cudaFuncSetAttribute(me::k_me_conv<64, true, me::kScDeform>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemDcn);
         cudaFuncSetAttribute(me::k_me_offset_row3, cudaFuncAttributeMaxDynamicSharedMemorySize, me::kR3Smem);
+        cudaFuncSetAttribute(me::k_me_tail_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, me::kTtSmem);
         attr_done = true;
     }
     const dim3 grid(tiles, total_agents);
@@ -716,7 +765,12 @@ extern "C" int gc_message_extractor(const float *x, int total_agents, int C, int
     GC_LAUNCH_CHECK("k_me_conv<dcn1>");
     me::k_me_attn<<<total_agents, 64, 0, st>>>(ws.tile_sums, tiles * 4, HW, params, ws.attn);
     GC_LAUNCH_CHECK("k_me_attn");
-    me::k_me_tail<<<grid, 128, 0, st>>>(ws.b1, ws.attn, params, HW, message);
-    GC_LAUNCH_CHECK("k_me_tail");
+    if (!getenv("GC_ME_FP32_TAIL")) {
+        me::k_me_tail_tc<<<grid, 128, me::kTtSmem, st>>>(ws.b1, ws.attn, params, HW, message);
+        GC_LAUNCH_CHECK("k_me_tail_tc");
+    } else {   // CUDA-core fp32 tail (A/B)
+        me::k_me_tail<<<grid, 128, 0, st>>>(ws.b1, ws.attn, params, HW, message);
+        GC_LAUNCH_CHECK("k_me_tail");
+    }
     return GC_OK;
 }
