@@ -56,6 +56,11 @@ SIGNATURES = {
     "gc_me_pack_weights": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "gc_message_extractor": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                      c_void_p]),
+    "gc_enhancer_param_floats": (c_size_t, [c_int]),
+    "gc_enhancer_packed_bytes": (c_size_t, [c_int]),
+    "gc_enhancer_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
+    "gc_enhancer_pack_weights": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
+    "gc_enhancer": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
 }
 
 _lib = None

@@ -1,0 +1,329 @@
+// Implicit-GEMM building blocks on tcgen05 shared by message_extractor.cu and enhancer.cu:
+//   k_me_to_nhwc : NCHW fp32 -> channel-last bf16 value + residual planes
+//   k_me_pack    : weights -> bf16 (value [+ residual]) B operands in UMMA core-matrix order
+//   k_me_conv    : 3x3 (plain or deformable) convolution / 1x1 GEMM over the planes, fp32 accumulation in TMEM
+// See message_extractor.cu for the design notes and the measurements behind the layout choices.
+#pragma once
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace gc {
+namespace me {
+
+using namespace umma;
+
+constexpr int kPix = 128;            // pixels per CTA = M
+constexpr int kThreads = 256;
+// Input channels per stage (SC / 16 MMAs of K = 16): 64 for the deformable layer, 32 for the offset layer (its value +
+// residual planes double the operand bytes; with 64-channel stages only two CTAs fit an SM and the layer was latency
+// bound on its load -> store -> barrier -> MMA chain: 305 us at 28 % issue-active).
+// A operand plane: [SC/8 channel groups][128 pixels][8 bf16], the group stride padded by 16 (32) bytes so that the lanes
+// that build one pixel store to different bank quads (measured without the pad: 8-way conflicts, 32 wavefronts per
+// STS.128, 70 M conflicts per launch).  UMMA no-swizzle K-major: LBO = group stride, SBO = 128 B.
+__host__ __device__ constexpr int a_group_bytes(int SC) { return kPix * 16 + (SC == 64 ? 16 : 32); }
+__host__ __device__ constexpr int a_plane_bytes(int SC) { return (SC / 8) * a_group_bytes(SC); }
+__host__ __device__ constexpr int conv_smem_bytes(int NOUT, bool split, int SC) {
+    return 2 * (split ? 2 : 1) * (a_plane_bytes(SC) + SC * NOUT * 2);
+}
+constexpr int kScOffset = 32, kScDeform = 64;
+
+// ------------------------------------------------------------------------------------------------
+// weights [NOUT_real][C][3][3] f32 -> bf16 B operand, per stage (tap, 64-channel chunk):
+//   [k8 = SC/8 channel groups][n8 = NOUT/8][8 rows n][8 bf16 k]     (rows >= NOUT_real are zero)
+// ------------------------------------------------------------------------------------------------
+//   split: every stage is followed by its residual plane  lo = bf16(w - float(bf16(w)))  (the "bf16x3" offset layer)
+__device__ __forceinline__ float bf16_residual(float v) { return v - __bfloat162float(__float2bfloat16_rn(v)); }
+
+static __global__ void k_me_pack(const float *__restrict__ w, int n_real, int NOUT, int C, int SC, int taps, int split,
+                          uint4 *__restrict__ out) {
+    const int chunks = C / SC, groups = SC / 8;
+    const int per_stage = groups * NOUT;       // uint4 (8 k values of one row n) per stage and plane
+    const int total = taps * chunks * per_stage;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int n = i % NOUT;                // i = ((stage * groups + k8) * (NOUT/8) + n8) * 8 + (n % 8)  with n = n8 * 8 + n % 8
+    const int k8 = (i / NOUT) % groups;
+    const int stage = i / per_stage;
+    const int tap = stage / chunks, chunk = stage % chunks;
+    uint32_t p[4], q[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        float v[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const int c = chunk * SC + k8 * 8 + 2 * j + e;
+            v[e] = n < n_real ? w[((size_t)n * C + c) * taps + tap] : 0.0f;
+        }
+        p[j] = pack_bf16(v[0], v[1]);
+        q[j] = pack_bf16(bf16_residual(v[0]), bf16_residual(v[1]));
+    }
+    const int within = i - stage * per_stage;
+    if (split) {
+        out[(size_t)stage * 2 * per_stage + within] = make_uint4(p[0], p[1], p[2], p[3]);
+        out[(size_t)stage * 2 * per_stage + per_stage + within] = make_uint4(q[0], q[1], q[2], q[3]);
+    } else {
+        out[i] = make_uint4(p[0], p[1], p[2], p[3]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// x [A][C][HW] f32 (NCHW)  ->  channel-last bf16 planes  xh = bf16(x),  xl = bf16(x - xh)   [A][HW][C]
+// so that a bilinear corner of 8 channels is ONE 16-byte load and the 8 lanes that sample a pixel read 128 contiguous
+// bytes.  (Measured before: sampling NCHW fp32 directly made the deformable layer L1-gather bound -- 4 loads per
+// (pixel, tap, channel), l1tex 76 % busy, 0.64 ms of the 0.94 ms call.)   grid = (HW/64, C/64, A), 256 threads.
+// ------------------------------------------------------------------------------------------------
+static __global__ void __launch_bounds__(256)
+k_me_to_nhwc(const float *__restrict__ x, int C, int HW, uint4 *__restrict__ xh, uint4 *__restrict__ xl) {
+    __shared__ float t[64][65];
+    const int tid = threadIdx.x, p0 = blockIdx.x * 64, c0 = blockIdx.y * 64, a = blockIdx.z;
+    const float *src = x + ((size_t)a * C + c0) * HW + p0;
+    {
+        const int p = tid & 63, c_base = tid >> 6;   // 16 independent loads in flight per thread
+        float v[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) v[k] = (p0 + p < HW) ? __ldg(src + (size_t)(c_base + 4 * k) * HW + p) : 0.0f;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) t[c_base + 4 * k][p] = v[k];
+    }
+    __syncthreads();
+    for (int i = tid; i < 64 * 8; i += 256) {
+        const int p = i >> 3, g = i & 7;
+        if (p0 + p >= HW) continue;
+        float v[8], r[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { v[k] = t[g * 8 + k][p]; r[k] = bf16_residual(v[k]); }
+        const size_t o = ((size_t)a * HW + p0 + p) * (C / 8) + c0 / 8 + g;
+        xh[o] = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+        xl[o] = make_uint4(pack_bf16(r[0], r[1]), pack_bf16(r[2], r[3]), pack_bf16(r[4], r[5]), pack_bf16(r[6], r[7]));
+    }
+}
+
+__device__ __forceinline__ float bf_lo(uint32_t u) { return __uint_as_float(u << 16); }
+__device__ __forceinline__ float bf_hi(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }
+// torchvision bilinear_interpolate: val = hh*hw*v1 + hh*lw*v2 + lh*hw*v3 + lh*lw*v4 (left to right), two channels
+// (packed fp32: one FMUL2 + three FFMA2 for the two channels of a 32-bit word, same roundings as scalar fmaf)
+__device__ __forceinline__ uint32_t lerp2(const float4 &w, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    float2 r = __fmul2_rn(make_float2(w.x, w.x), make_float2(bf_lo(a), bf_hi(a)));
+    r = __ffma2_rn(make_float2(w.y, w.y), make_float2(bf_lo(b), bf_hi(b)), r);
+    r = __ffma2_rn(make_float2(w.z, w.z), make_float2(bf_lo(c), bf_hi(c)), r);
+    r = __ffma2_rn(make_float2(w.w, w.w), make_float2(bf_lo(d), bf_hi(d)), r);
+    return pack_bf16(r.x, r.y);
+}
+
+// ------------------------------------------------------------------------------------------------
+// 3x3 (deformable) convolution as a tcgen05 implicit GEMM.  grid = (H*W/128, n_agents), 256 threads.
+//   xh, xl [A][HW][C] bf16 (k_me_to_nhwc); offset [A][18][H][W] f32 (DEFORM; channel 2k = dy, 2k+1 = dx of tap k);
+//   wp: k_me_pack output;  out [A][n_store][H][W] f32 (+ bias);
+//   tile_sums [A][tiles*4][NOUT] (DEFORM): channel sums over 32-pixel groups
+// ------------------------------------------------------------------------------------------------
+// TAPS = 9: 3x3 convolution; TAPS = 1: 1x1 (a plain GEMM over the channel-last planes; used by the Enhancer's linear
+// layers).  EPI = 0: bias; EPI = 1: bias + exact GELU.  c_in = channels contracted (<= C, the channel count of the planes);
+// the n_store output channels go to planes out_ch_off .. of an [A][out_ch_total][HW] f32 tensor.
+__device__ __forceinline__ float gelu_erf(float v) { return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f)); }
+
+template <int NOUT, bool DEFORM, int SC, int TAPS = 9, int EPI = 0>
+__global__ void __launch_bounds__(kThreads)
+k_me_conv(const uint4 *__restrict__ xh, const uint4 *__restrict__ xl, const float *__restrict__ offset,
+          const uint4 *__restrict__ wp, const float *__restrict__ bias, int C, int c_in, int H, int W, int n_store,
+          int out_ch_total, int out_ch_off, float *__restrict__ out, float *__restrict__ tile_sums) {
+    // The plain (offset) layer runs as "bf16x3": A and B are split into a bf16 value and a bf16 residual and three MMAs
+    // (hi*hi + lo*hi + hi*lo) rebuild ~16 mantissa bits, because its output positions the deformable layer's taps:
+    // a bf16-only offset (rel. error 4e-3) moves a tap by 0.02 px at 5 px, which on high-frequency features costs
+    // more accuracy than the deformable layer's own bf16 rounding.
+    constexpr bool SPLIT = !DEFORM;
+    constexpr int kPlanes = SPLIT ? 2 : 1;
+    constexpr int kAGroup = a_group_bytes(SC), kABytes = a_plane_bytes(SC), kGroups = SC / 8;
+    constexpr int kBBytes = SC * NOUT * 2 * kPlanes;
+    constexpr int kAStage = kABytes * kPlanes;
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t *a_s = smem;                      // [2][kPlanes][kABytes]
+    uint8_t *b_s = smem + 2 * kAStage;        // [2][kPlanes][SC * NOUT * 2]
+    __shared__ __align__(8) uint64_t s_empty[2], s_done;
+    __shared__ uint32_t s_tmem;
+    __shared__ __align__(16) int4 s_o[kPix];      // pixel index (y*W + x) of the four bilinear corners of the tap
+    __shared__ __align__(16) float4 s_w[kPix];    // their weights (0 for a corner outside the image)
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int agent = blockIdx.y, tile = blockIdx.x;
+    const int HW = H * W;
+    const int chunks = c_in / SC, stages = TAPS * chunks;
+    const int C8 = C / 8;
+
+    if (warp == 0) tmem_alloc<NOUT>(&s_tmem);
+    if (tid == 32) {
+        mbar_init(smem_u32(&s_empty[0]), 1); mbar_init(smem_u32(&s_empty[1]), 1); mbar_init(smem_u32(&s_done), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = s_tmem;
+    const uint32_t a_base = smem_u32(a_s), b_base = smem_u32(b_s);
+    constexpr uint32_t idesc = make_idesc(128, NOUT);
+    const uint4 *xh_a = xh + (size_t)agent * HW * C8;
+    const uint4 *xl_a = xl + (size_t)agent * HW * C8;
+
+    for (int s = 0; s < stages; ++s) {
+        const int b = s & 1;
+        const int tap = s / chunks, chunk = s - tap * chunks;
+        if (chunk == 0) {
+            // sampling position of every pixel of the tile for this tap (torchvision deformable_im2col /
+            // bilinear_interpolate), once per tap, shared through s_o / s_w.  Every thread is past its staging of the
+            // previous tap (barrier at the end of the previous stage), so the arrays can be overwritten.
+            if (tid < kPix) {
+                const int pix = tile * kPix + tid;
+                const int py = pix / W, px = pix - py * W;
+                const int ky = TAPS == 1 ? 1 : tap / 3, kx = TAPS == 1 ? 1 : tap - 3 * ky;
+                int4 o = make_int4(0, 0, 0, 0);
+                float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (DEFORM) {
+                    const float *op = offset + ((size_t)agent * 18 + 2 * tap) * HW + pix;
+                    const float hh_ = (float)(py - 1 + ky) + __ldg(op);
+                    const float ww_ = (float)(px - 1 + kx) + __ldg(op + HW);
+                    const bool inside = hh_ > -1.0f && hh_ < (float)H && ww_ > -1.0f && ww_ < (float)W;
+                    const float hf = floorf(hh_), wf = floorf(ww_);
+                    const int hl = (int)hf, wl = (int)wf, hh = hl + 1, wh = wl + 1;
+                    const float lh = hh_ - hf, lw = ww_ - wf, uh = 1.0f - lh, uw = 1.0f - lw;
+                    const bool t_ok = inside && hl >= 0, b_ok = inside && hh <= H - 1;
+                    const bool l_ok = wl >= 0, r_ok = wh <= W - 1;
+                    const int hlc = min(max(hl, 0), H - 1), hhc = min(max(hh, 0), H - 1);
+                    const int wlc = min(max(wl, 0), W - 1), whc = min(max(wh, 0), W - 1);
+                    o = make_int4(hlc * W + wlc, hlc * W + whc, hhc * W + wlc, hhc * W + whc);
+                    w.x = (t_ok && l_ok) ? uh * uw : 0.0f;
+                    w.y = (t_ok && r_ok) ? uh * lw : 0.0f;
+                    w.z = (b_ok && l_ok) ? lh * uw : 0.0f;
+                    w.w = (b_ok && r_ok) ? lh * lw : 0.0f;
+                } else {
+                    const int yy = py - 1 + ky, xx = px - 1 + kx;
+                    const bool ok = yy >= 0 && yy < H && xx >= 0 && xx < W;
+                    o.x = ok ? yy * W + xx : 0;
+                    w.x = ok ? 1.0f : 0.0f;
+                }
+                s_o[tid] = o;
+                s_w[tid] = w;
+            }
+            __syncthreads();
+        }
+        if (s >= 2) mbar_wait(smem_u32(&s_empty[b]), (uint32_t)((s >> 1) - 1) & 1u);   // MMAs of stage s-2 retired
+        // ---- B stage: kBBytes contiguous bytes of the packed weights; the loads are issued here and stored after the
+        // first batch of A loads is in flight (one round trip instead of two or three) ----
+        constexpr int kBIter = (kBBytes / 16 + kThreads - 1) / kThreads;
+        uint4 bq[kBIter];
+        {
+            const uint4 *src = wp + (size_t)s * (kBBytes / 16);
+#pragma unroll
+            for (int i = 0; i < kBIter; ++i)
+                bq[i] = (i * kThreads + tid < kBBytes / 16) ? __ldg(src + i * kThreads + tid) : make_uint4(0u, 0u, 0u, 0u);
+        }
+        // ---- A stage: 128 pixels x 8 channel groups = 1024 16-byte rows, four per thread.  The eight lanes of a pixel
+        // read 128 contiguous bytes per corner (one full line; spreading a warp over 8 pixels x 4 groups instead was
+        // measured 1.9x slower: twice the L1 tags per request) ----
+        {
+            uint8_t *dst = a_s + b * kAStage;
+            const int g_loc = tid & (kGroups - 1);
+            const int cg = chunk * kGroups + g_loc;
+#pragma unroll
+            for (int pass = 0; pass < kGroups / 2; pass += 2) {
+                uint4 q[2][4];
+                float4 w[2];
+                int p[2];
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    p[u] = ((pass + u) * kThreads + tid) / kGroups;
+                    const int4 o = s_o[p[u]];
+                    w[u] = s_w[p[u]];
+                    if (DEFORM) {
+                        q[u][0] = __ldg(xh_a + (size_t)o.x * C8 + cg);
+                        q[u][1] = __ldg(xh_a + (size_t)o.y * C8 + cg);
+                        q[u][2] = __ldg(xh_a + (size_t)o.z * C8 + cg);
+                        q[u][3] = __ldg(xh_a + (size_t)o.w * C8 + cg);
+                    } else {
+                        q[u][0] = __ldg(xh_a + (size_t)o.x * C8 + cg);
+                        q[u][1] = __ldg(xl_a + (size_t)o.x * C8 + cg);
+                    }
+                }
+                if (pass == 0) {
+                    uint4 *bd = reinterpret_cast<uint4 *>(b_s + b * kBBytes);
+#pragma unroll
+                    for (int i = 0; i < kBIter; ++i)
+                        if (i * kThreads + tid < kBBytes / 16) bd[i * kThreads + tid] = bq[i];
+                }
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    uint4 *d = reinterpret_cast<uint4 *>(dst + g_loc * kAGroup) + p[u];
+                    if (DEFORM) {
+                        d[0] = make_uint4(lerp2(w[u], q[u][0].x, q[u][1].x, q[u][2].x, q[u][3].x),
+                                          lerp2(w[u], q[u][0].y, q[u][1].y, q[u][2].y, q[u][3].y),
+                                          lerp2(w[u], q[u][0].z, q[u][1].z, q[u][2].z, q[u][3].z),
+                                          lerp2(w[u], q[u][0].w, q[u][1].w, q[u][2].w, q[u][3].w));
+                    } else {
+                        const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+                        const bool ok = w[u].x != 0.0f;
+                        d[0] = ok ? q[u][0] : z;
+                        d[kABytes / 16] = ok ? q[u][1] : z;
+                    }
+                }
+            }
+        }
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+            const uint32_t a_buf = a_base + (uint32_t)b * kAStage, b_buf = b_base + (uint32_t)b * kBBytes;
+            constexpr uint32_t kBPlane = SC * NOUT * 2;
+#pragma unroll
+            for (int j = 0; j < SC / 16; ++j) {   // K = 16: channel groups 2j and 2j+1
+                const uint32_t a_off = (uint32_t)(2 * j) * (uint32_t)kAGroup, b_off = (uint32_t)(2 * j) * (NOUT * 16u);
+                const uint64_t a_hi = make_desc(a_buf + a_off, (uint32_t)kAGroup, 128u);
+                const uint64_t b_hi = make_desc(b_buf + b_off, NOUT * 16u, 128u);
+                mma_bf16(tmem, a_hi, b_hi, idesc, (s > 0 || j > 0) ? 1u : 0u);
+                if (SPLIT) {
+                    const uint64_t a_lo = make_desc(a_buf + kABytes + a_off, (uint32_t)kAGroup, 128u);
+                    const uint64_t b_lo = make_desc(b_buf + kBPlane + b_off, NOUT * 16u, 128u);
+                    mma_bf16(tmem, a_lo, b_hi, idesc, 1u);
+                    mma_bf16(tmem, a_hi, b_lo, idesc, 1u);
+                }
+            }
+            mma_commit(smem_u32(&s_empty[b]));
+            if (s == stages - 1) mma_commit(smem_u32(&s_done));
+        }
+    }
+    mbar_wait(smem_u32(&s_done), 0u);
+    tc_fence_after();
+
+    // ---- epilogue: warp w reads TMEM lanes 32 (w % 4) .. +31 (= pixels) and columns (w / 4) * NOUT/2 .. ----
+    {
+        const int q = warp & 3, ch0 = (warp >> 2) * (NOUT / 2);
+        const int p_out = tile * kPix + q * 32 + lane;
+        const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)ch0;
+#pragma unroll
+        for (int c16 = 0; c16 < NOUT / 2; c16 += 16) {
+            float v[16];
+            tmem_ld16(taddr + (uint32_t)c16, v);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const int ch = ch0 + c16 + i;
+                if (ch < n_store) {
+                    float r = v[i] + (bias ? __ldg(bias + ch) : 0.0f);
+                    if (EPI == 1) r = gelu_erf(r);
+                    out[((size_t)agent * out_ch_total + out_ch_off + ch) * HW + p_out] = r;
+                    if (DEFORM) {
+                        float t = r;
+#pragma unroll
+                        for (int d = 16; d >= 1; d >>= 1) t += __shfl_xor_sync(0xffffffffu, t, d);
+                        if (lane == 0) tile_sums[((size_t)agent * gridDim.x * 4 + tile * 4 + q) * NOUT + ch] = t;
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_free<NOUT>(tmem);
+}
+
+}  // namespace me
+}  // namespace gc

@@ -354,3 +354,52 @@ def message_extractor(x, packed, params, workspace=None, out=None):
     _lib.check(lib.gc_message_extractor(_ptr(x), A, C, H, W, _ptr(packed), _ptr(params), _ptr(workspace), _ptr(out),
                                         _stream()), "gc_message_extractor")
     return out
+
+
+# --------------------------------------------------------------------------------------------
+# (8f rank 1) Enhancer
+# --------------------------------------------------------------------------------------------
+ENHANCER_PARAM_ORDER = ("block_1.norm1.weight", "block_1.norm1.bias", "block_1.norm2.weight", "block_1.norm2.bias",
+                        "block_1.mlp.linear1.0.bias", "block_1.mlp.dwconv.0.weight", "block_1.mlp.dwconv.0.bias",
+                        "block_1.mlp.linear2.0.bias", "split_attn.fc1.weight", "split_attn.bn1.weight",
+                        "split_attn.bn1.bias", "split_attn.fc2.weight")
+
+
+def enhancer_pack(sd):
+    """state_dict (device tensors) -> (packed bf16x3 B operands, fp32 parameter blob)."""
+    lib = _lib.load()
+    w_p = sd["block_1.mlp.partial_conv3.weight"].detach().float().contiguous()
+    w_1 = sd["block_1.mlp.linear1.0.weight"].detach().float().contiguous()
+    w_2 = sd["block_1.mlp.linear2.0.weight"].detach().float().contiguous()
+    for t, n in ((w_p, "partial_conv3.weight"), (w_1, "linear1.0.weight"), (w_2, "linear2.0.weight")):
+        _chk(t, n, torch.float32)
+    C = w_1.shape[1]
+    if tuple(w_p.shape) != (C // 4, C // 4, 3, 3) or tuple(w_1.shape) != (4 * C, C) or tuple(w_2.shape) != (C, 2 * C):
+        raise ValueError("enhancer_pack: unexpected weight shapes")
+    nbytes = lib.gc_enhancer_packed_bytes(C)
+    if nbytes == 0:
+        raise RuntimeError(f"gc_enhancer: C must be 128 or 256 (got {C})")
+    packed = torch.empty(nbytes, dtype=torch.uint8, device=w_1.device)
+    _lib.check(lib.gc_enhancer_pack_weights(_ptr(w_p), _ptr(w_1), _ptr(w_2), C, _ptr(packed), _stream()),
+               "gc_enhancer_pack_weights")
+    params = torch.cat([sd[k].detach().reshape(-1).float() for k in ENHANCER_PARAM_ORDER]).contiguous()
+    if params.numel() != lib.gc_enhancer_param_floats(C):
+        raise ValueError("enhancer_pack: unexpected parameter shapes")
+    return packed, params
+
+
+def enhancer(x, packed, params, workspace=None, out=None):
+    """out = Enhancer(x) for all agents; x [sumN,C,H,W] f32 (C in {128,256}, H*W % 128 == 0)."""
+    lib = _lib.load()
+    _chk(x, "x", torch.float32, 4)
+    _chk(params, "params", torch.float32, 1)
+    A, C, H, W = x.shape
+    if packed.numel() != lib.gc_enhancer_packed_bytes(C) or params.numel() != lib.gc_enhancer_param_floats(C):
+        raise ValueError("enhancer: packed weights / params do not match C")
+    if workspace is None:
+        workspace = torch.empty(lib.gc_enhancer_workspace_bytes(A, C, H, W), dtype=torch.uint8, device=x.device)
+    if out is None:
+        out = torch.empty_like(x)
+    _lib.check(lib.gc_enhancer(_ptr(x), A, C, H, W, _ptr(packed), _ptr(params), _ptr(workspace), _ptr(out), _stream()),
+               "gc_enhancer")
+    return out

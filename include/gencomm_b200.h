@@ -204,6 +204,27 @@ int gc_me_pack_weights(const float *w_offset, const float *w_dcn, int C, void *p
 int gc_message_extractor(const float *x, int total_agents, int C, int H, int W, const void *packed,
                          const float *params, void *workspace, float *message, void *stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * (8f rank 1) Enhancer.forward (models/gencomm_modules/enhancer.py:335-383): Enhancer_block block_1 (:316-333, attention
+ *   disabled in the reference) = x + LN1(x), + FRFN(LN2(.)) (:205-250), then SplitAttn (:286-314).  Per agent; all agents
+ *   of all frames in one call.
+ *   x, out   [sumN][C][H][W] f32, C in {128, 256}, H*W % 128 == 0
+ *   packed   gc_enhancer_packed_bytes(C) bytes written by gc_enhancer_pack_weights from block_1.mlp.partial_conv3.weight
+ *            [C/4][C/4][3][3], block_1.mlp.linear1.0.weight [4C][C], block_1.mlp.linear2.0.weight [C][2C] (device, f32)
+ *   params   gc_enhancer_param_floats(C) floats (device), in this order: block_1.norm1.weight/bias [C], norm2.weight/bias
+ *            [C], mlp.linear1.0.bias [4C], mlp.dwconv.0.weight [2C][9], mlp.dwconv.0.bias [2C], mlp.linear2.0.bias [C],
+ *            split_attn.fc1.weight [C][C], split_attn.bn1.weight/bias [C], split_attn.fc2.weight [C][C]
+ *   workspace gc_enhancer_workspace_bytes(sumN, C, H, W) bytes (device)
+ *   Arithmetic: the three dense layers are tcgen05 GEMMs in bf16x3 (fp32-grade); everything else fp32.
+ * ------------------------------------------------------------------------------------------- */
+size_t gc_enhancer_param_floats(int C);
+size_t gc_enhancer_packed_bytes(int C);
+size_t gc_enhancer_workspace_bytes(int total_agents, int C, int H, int W);
+int gc_enhancer_pack_weights(const float *w_pconv, const float *w_lin1, const float *w_lin2, int C, void *packed,
+                             void *stream);
+int gc_enhancer(const float *x, int total_agents, int C, int H, int W, const void *packed, const float *params,
+                void *workspace, float *out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

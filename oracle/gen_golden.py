@@ -154,6 +154,34 @@ def gen_message_extractor(ns):
     print("message_extractor.npz: out", tuple(out.shape), "|offset| max", float(offset.abs().max()))
 
 
+def gen_enhancer(ns):
+    """Enhancer through the reference class."""
+    torch.manual_seed(13)
+    C, H, W = 128, 4, 64
+    model = ns.Enhancer(C, [8, 8], 4).eval()
+    with torch.no_grad():   # LayerNorm affines default to (1, 0), biases to small values: randomise so they matter
+        for name, p in model.named_parameters():
+            if "norm" in name or "bn1" in name:
+                p.add_(0.2 * torch.randn_like(p))
+            elif name.endswith(".bias"):
+                p.add_(0.1 * torch.randn_like(p))
+    x = synth.bev_features(1301, 3, C, H, W)
+    x[2, :, :, 40:] = 0.0
+    record_len = torch.tensor([2, 1], dtype=torch.int64)
+    affine = torch.randn(2, 5, 5, 2, 3)
+    with torch.no_grad():
+        out = model(x, affine, record_len)
+    import json
+    sd = {k: v.numpy() for k, v in model.state_dict().items()}
+    # tensors of the evaluated parameters; names + shapes only for the ones the reference declares but never uses
+    used = {k: v for k, v in sd.items() if (k.startswith("block_1.") and ".attn." not in k) or k.startswith("split_attn.")}
+    shapes = np.frombuffer(json.dumps({k: list(v.shape) for k, v in sd.items()}).encode(), dtype=np.uint8)
+    np.savez_compressed(os.path.join(OUT, "enhancer.npz"), x=x.numpy(), record_len=record_len.numpy(),
+                        affine=affine.numpy(), ref_out=out.numpy(), sd_shapes_json=shapes,
+                        **{"sd/" + k: v for k, v in used.items()})
+    print("enhancer.npz: out", tuple(out.shape), "keys", len(sd), "stored", len(used))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ns = ref_import.load()
@@ -161,6 +189,7 @@ def main():
     gen_warp(ns)
     gen_gencomm(ns)
     gen_message_extractor(ns)
+    gen_enhancer(ns)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)) // 1024, "KiB")
 

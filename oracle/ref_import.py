@@ -97,6 +97,7 @@ def load():
     from opencood.models.gencomm_modules.unet import DiffusionUNet
     from opencood.models.gencomm_modules.cond_diff import GenComm, Config
     from opencood.models.gencomm_modules.message_extractor_v2 import MessageExtractorv2
+    from opencood.models.gencomm_modules.enhancer import Enhancer
     ns.PillarVFE = PillarVFE
     ns.PointPillarScatter = PointPillarScatter
     ns.warp_affine_simple = warp_affine_simple
@@ -108,4 +109,5 @@ def load():
     ns.GenComm = GenComm
     ns.Config = Config
     ns.MessageExtractorv2 = MessageExtractorv2
+    ns.Enhancer = Enhancer
     return ns

@@ -388,3 +388,39 @@ def message_extractor_v2(x, sd, prefix="bev_extractor."):
     enhanced = b1 * a                                                                           # :109
     return F.conv2d(F.relu(F.conv2d(enhanced, g("fuse.0.weight"), g("fuse.0.bias"))),           # :111
                     g("fuse.2.weight"), g("fuse.2.bias")), offset, b1
+
+
+# ---------------------------------------------------------------------------------------------
+# Enhancer: models/gencomm_modules/enhancer.py:335-383 (Enhancer.forward),
+# :316-333 (Enhancer_block.forward: the attention call is commented out at :326), :205-245 (FRFN),
+# :286-314 (SplitAttn with RadixSoftmax(1, 1) = sigmoid, :276-277).  block_2 / block_3 and every
+# Attention parameter exist in the state_dict but are never evaluated (:369-371).
+# ---------------------------------------------------------------------------------------------
+def enhancer(x, sd):
+    """x [sumN,C,H,W] -> [sumN,C,H,W].  Every step is per agent (record_len / affine_matrix only regroup), so all
+    agents are evaluated at once."""
+    N, C, H, W = x.shape
+    g = lambda k: sd[k]
+    t = x.permute(0, 2, 3, 1).reshape(N, H * W, C)                                          # :318-320
+    x1 = t + F.layer_norm(t, (C,), g("block_1.norm1.weight"), g("block_1.norm1.bias"))      # :322-327 (attention off)
+    y = F.layer_norm(x1, (C,), g("block_1.norm2.weight"), g("block_1.norm2.bias"))          # :328
+    # FRFN.forward, :224-245
+    ys = y.reshape(N, H, W, C).permute(0, 3, 1, 2)
+    c4 = C // 4
+    y1 = F.conv2d(ys[:, :c4], g("block_1.mlp.partial_conv3.weight"), None, padding=1)       # :233
+    ys = torch.cat([y1, ys[:, c4:]], dim=1)
+    u = F.gelu(F.linear(ys.permute(0, 2, 3, 1).reshape(N, H * W, C), g("block_1.mlp.linear1.0.weight"),
+                        g("block_1.mlp.linear1.0.bias")))                                    # :239 (nn.GELU = erf)
+    u1, u2 = u.chunk(2, dim=-1)                                                              # :241
+    u1 = u1.reshape(N, H, W, 2 * C).permute(0, 3, 1, 2)
+    u1 = F.gelu(F.conv2d(u1, g("block_1.mlp.dwconv.0.weight"), g("block_1.mlp.dwconv.0.bias"), padding=1,
+                         groups=2 * C))                                                      # :244
+    v = u1.permute(0, 2, 3, 1).reshape(N, H * W, 2 * C) * u2                                 # :246
+    s = x1 + F.linear(v, g("block_1.mlp.linear2.0.weight"), g("block_1.mlp.linear2.0.bias"))   # :248, :328
+    s = s.reshape(N, H, W, C)
+    # SplitAttn.forward, :300-314
+    gap = s.mean((1, 2), keepdim=True)
+    a = F.relu(F.layer_norm(F.linear(gap, g("split_attn.fc1.weight")), (C,), g("split_attn.bn1.weight"),
+                            g("split_attn.bn1.bias")))
+    a = torch.sigmoid(F.linear(a, g("split_attn.fc2.weight")))
+    return (s * a).permute(0, 3, 1, 2).contiguous()                                          # :374

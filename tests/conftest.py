@@ -57,3 +57,8 @@ def golden_gencomm():
 @pytest.fixture(scope="session")
 def golden_message_extractor():
     return load_golden("message_extractor.npz")
+
+
+@pytest.fixture(scope="session")
+def golden_enhancer():
+    return load_golden("enhancer.npz")

@@ -78,3 +78,14 @@ def test_message_extractor_keeps_reference_state_dict_keys(golden_message_extrac
         m(torch.zeros(1, 64, 4, 32))
     with pytest.raises(NotImplementedError):
         MessageExtractorv2(64, 3)
+
+
+def test_enhancer_keeps_reference_state_dict_keys(golden_enhancer):
+    import json
+    from gencomm_b200 import Enhancer
+    shapes = json.loads(bytes(golden_enhancer["sd_shapes_json"]).decode())
+    m = Enhancer(128, [8, 8], 4)
+    assert {k: list(v.shape) for k, v in m.state_dict().items()} == shapes
+    m.load_state_dict({k[3:]: torch.from_numpy(v) for k, v in golden_enhancer.items() if k.startswith("sd/")}, strict=False)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m(torch.zeros(1, 128, 4, 32))

@@ -127,3 +127,11 @@ def test_message_extractor_restatement_matches_reference(golden_message_extracto
     assert torch.allclose(b1, T(g["ref_b1"]), rtol=0, atol=1e-5)
     assert torch.allclose(out, T(g["ref_out"]), rtol=0, atol=1e-6)
     assert float(T(g["ref_offset"]).abs().max()) > 2.0   # the fixture really moves the sampling taps
+
+
+def test_enhancer_restatement_matches_reference(golden_enhancer):
+    """oracle/ref_ops.enhancer vs the golden output of the reference Enhancer class (gen_golden.py::gen_enhancer)."""
+    g = golden_enhancer
+    sd = {k[3:]: T(v) for k, v in g.items() if k.startswith("sd/")}
+    out = R.enhancer(T(g["x"]), sd)
+    assert torch.allclose(out, T(g["ref_out"]), rtol=0, atol=5e-6)
