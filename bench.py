@@ -258,6 +258,31 @@ def message_extractor_extra(dev, frames=8, agents=4, C=128, H=64, W=128, iters=1
                               "deformable 3x3: bf16 operands, fp32 TMEM accumulation; pool / excite / 1x1 tail fp32"}
 
 
+def enhancer_extra(dev, frames=8, agents=4, C=128, H=64, W=128, iters=10):
+    """Enhancer (enhancer.py:335-383) on the same feature shape, device resident, CUDA events."""
+    import gencomm_b200 as G
+    torch.manual_seed(0)
+    m = G.Enhancer(C, [8, 8], 4).to(dev).eval()
+    A = frames * agents
+    xs = [torch.randn(A, C, H, W, device=dev) for _ in range(3)]
+    for k in range(3):
+        m(xs[k])
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for k in range(iters):
+        m(xs[k % 3])
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    flops = 2.0 * A * H * W * (9 * (C // 4) ** 2 + 4 * C * C + 2 * C * C + 2 * C * 9)
+    return {"workload": f"Enhancer, {frames} frames x {agents} agents, C={C}, {H}x{W}",
+            "launches_per_call": 11 + C // 32 + C // 128, "ms_per_call": ms, "frames_per_s": frames / (ms * 1e-3),
+            "tflops": flops / (ms * 1e-3) / 1e12,
+            "precision_note": "partial_conv3 / linear1 / linear2: bf16x3 tcgen05 GEMMs (fp32-grade); LayerNorms, depth-wise "
+                              "conv + gate, pool / excite fp32"}
+
+
 # ------------------------------------------------------------------------------------------------
 # GPU path
 # ------------------------------------------------------------------------------------------------
@@ -377,6 +402,7 @@ def run_ours(args):
 
     sampler_extra = None
     me_extra = None
+    enh_extra = None
     if rank == 0 and world == 1 and not args.no_extras:
         try:
             sampler_extra = gencomm_sampler_extra(dev)
@@ -386,6 +412,10 @@ def run_ours(args):
             me_extra = message_extractor_extra(dev)
         except Exception as exc:
             me_extra = {"error": repr(exc)}
+        try:
+            enh_extra = enhancer_extra(dev)
+        except Exception as exc:
+            enh_extra = {"error": repr(exc)}
 
     # ---------------- max over ranks, gather of checksums + timings ----------------
     times = torch.tensor([elapsed_ms, e2e_ms], dtype=torch.float64, device=dev)
@@ -434,6 +464,7 @@ def run_ours(args):
             "cpu_baseline": cpu_baseline,
             "gencomm_sampler": sampler_extra,
             "message_extractor": me_extra,
+            "enhancer": enh_extra,
             "checksum": checksum,
         }
         if gathered is not None:
