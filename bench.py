@@ -277,7 +277,7 @@ def enhancer_extra(dev, frames=8, agents=4, C=128, H=64, W=128, iters=10):
     ms = e0.elapsed_time(e1) / iters
     flops = 2.0 * A * H * W * (9 * (C // 4) ** 2 + 4 * C * C + 2 * C * C + 2 * C * 9)
     return {"workload": f"Enhancer, {frames} frames x {agents} agents, C={C}, {H}x{W}",
-            "launches_per_call": 11 + C // 32 + C // 128, "ms_per_call": ms, "frames_per_s": frames / (ms * 1e-3),
+            "launches_per_call": 11 + C // 64 + C // 128, "ms_per_call": ms, "frames_per_s": frames / (ms * 1e-3),
             "tflops": flops / (ms * 1e-3) / 1e12,
             "precision_note": "partial_conv3 / linear1 / linear2: bf16x3 tcgen05 GEMMs (fp32-grade); LayerNorms, depth-wise "
                               "conv + gate, pool / excite fp32"}

@@ -13,7 +13,7 @@
 // kernel of implicit_gemm.cuh in "bf16x3" (value + residual bf16 planes of both operands, three MMAs per K = 16 step,
 // fp32 accumulation in TMEM -- fp32-grade results):
 //   partial_conv3 : k_me_conv<C/4, plain 3x3>           K = 9 C/4
-//   linear1+GELU  : k_me_conv<128, 1x1, GELU> x C/32    K = C,   N = 4C in chunks of 128 TMEM columns
+//   linear1+GELU  : k_me_conv<256, 1x1, GELU> x C/64    K = C,   N = 4C in chunks of 256 TMEM columns
 //   linear2       : k_me_conv<128, 1x1>       x C/128   K = 2C,  N = C
 // fed by k_me_to_nhwc (NCHW fp32 -> channel-last bf16 planes).  LayerNorms, the depth-wise convolution + gate, the
 // pool / excite and the final scale are fp32 CUDA-core kernels (thread = pixel, plane-coalesced).
@@ -62,23 +62,25 @@ k_enh_ln(const float *__restrict__ x, const float *__restrict__ prm, Prm L, int 
     const float *xs = x + (size_t)a * C * HW + p;
     float *x1s = x1 + (size_t)a * C * HW + p, *ys = y + (size_t)a * C * HW + p;
     const float inv_c = 1.0f / (float)C;
-    float s = 0.0f;
-    for (int c = 0; c < C; ++c) s += __ldg(xs + (size_t)c * HW);
+    // three passes over the thread's column of planes instead of five: the variances come from sum / sum of squares
+    // (C values of O(1) magnitude: the cancellation error is ~1e-6 of the variance)
+    float s = 0.0f, q = 0.0f;
+#pragma unroll 8
+    for (int c = 0; c < C; ++c) { const float v = __ldg(xs + (size_t)c * HW); s += v; q = fmaf(v, v, q); }
     const float m0 = s * inv_c;
-    float q = 0.0f;
-    for (int c = 0; c < C; ++c) { const float d = __ldg(xs + (size_t)c * HW) - m0; q = fmaf(d, d, q); }
-    const float r0 = rsqrtf(q * inv_c + 1e-5f);
-    s = 0.0f;
+    const float r0 = rsqrtf(fmaxf(q * inv_c - m0 * m0, 0.0f) + 1e-5f);
+    s = 0.0f; q = 0.0f;
+#pragma unroll 8
     for (int c = 0; c < C; ++c) {
         const float v = __ldg(xs + (size_t)c * HW);
         const float t = v + ((v - m0) * r0 * __ldg(prm + L.n1w + c) + __ldg(prm + L.n1b + c));
         x1s[(size_t)c * HW] = t;
         s += t;
+        q = fmaf(t, t, q);
     }
     const float m1 = s * inv_c;
-    q = 0.0f;
-    for (int c = 0; c < C; ++c) { const float d = x1s[(size_t)c * HW] - m1; q = fmaf(d, d, q); }
-    const float r1 = rsqrtf(q * inv_c + 1e-5f);
+    const float r1 = rsqrtf(fmaxf(q * inv_c - m1 * m1, 0.0f) + 1e-5f);
+#pragma unroll 8
     for (int c = 0; c < C; ++c)
         ys[(size_t)c * HW] = (x1s[(size_t)c * HW] - m1) * r1 * __ldg(prm + L.n2w + c) + __ldg(prm + L.n2b + c);
 }
@@ -111,6 +113,56 @@ k_enh_dw(const float *__restrict__ u, const float *__restrict__ prm, Prm L, int 
         for (int k = 0; k < 9; ++k) acc = fmaf(s_w[c][k], ok[k] ? __ldg(pl + off[k]) : 0.0f, acc);
         const float g = __ldg(ua + (size_t)(2 * C + c0 + c) * HW + p);
         v[((size_t)a * 2 * C + c0 + c) * HW + p] = gelu_erf(acc) * g;
+    }
+}
+
+// The same for W % 128 == 0: thread = one x of a 128-pixel row segment, the CTA walks kDwRows rows with a sliding 3x3
+// window in registers, so every input row is fetched once per CTA (+ 2 halo rows per kDwRows) instead of by three CTAs
+// (first version: 535 us of the 1.74 ms call).  grid = (W/128 * ceil(H/kDwRows), 2C/32, A), 128 threads.
+constexpr int kDwRows = 8;
+__global__ void __launch_bounds__(128)
+k_enh_dw_rows(const float *__restrict__ u, const float *__restrict__ prm, Prm L, int C, int H, int W, float *__restrict__ v) {
+    __shared__ float s_w[32][9], s_b[32];
+    const int a = blockIdx.z, c0 = blockIdx.y * 32, HW = H * W;
+    for (int i = threadIdx.x; i < 32 * 9; i += 128) s_w[i / 9][i % 9] = prm[L.dww + (c0 + i / 9) * 9 + i % 9];
+    if (threadIdx.x < 32) s_b[threadIdx.x] = prm[L.dwb + c0 + threadIdx.x];
+    __syncthreads();
+    const int segs = W / 128, seg = blockIdx.x % segs, r0 = (blockIdx.x / segs) * kDwRows;
+    const int x = seg * 128 + threadIdx.x;
+    const bool lok = x > 0, rok = x + 1 < W;
+    const float *ua = u + (size_t)a * 4 * C * HW;
+    auto row3 = [&](const float *pl, int r, float (&o)[3]) {
+        if (r < 0 || r >= H) { o[0] = o[1] = o[2] = 0.0f; return; }
+        const float *q = pl + (size_t)r * W + x;
+        o[0] = lok ? __ldg(q - 1) : 0.0f;
+        o[1] = __ldg(q);
+        o[2] = rok ? __ldg(q + 1) : 0.0f;
+    };
+    for (int c = 0; c < 32; ++c) {
+        const float *pl = ua + (size_t)(c0 + c) * HW;
+        const float *gl = ua + (size_t)(2 * C + c0 + c) * HW;
+        float *vo = v + ((size_t)a * 2 * C + c0 + c) * HW;
+        float w[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) w[k] = s_w[c][k];
+        const float bias = s_b[c];
+        float top[3], mid[3], bot[3];
+        row3(pl, r0 - 1, top);
+        row3(pl, r0, mid);
+#pragma unroll
+        for (int i = 0; i < kDwRows; ++i) {
+            const int r = r0 + i;
+            if (r < H) {
+                row3(pl, r + 1, bot);
+                float acc = bias;   // tap order ky*3+kx like the reference weight layout
+                acc = fmaf(w[0], top[0], acc); acc = fmaf(w[1], top[1], acc); acc = fmaf(w[2], top[2], acc);
+                acc = fmaf(w[3], mid[0], acc); acc = fmaf(w[4], mid[1], acc); acc = fmaf(w[5], mid[2], acc);
+                acc = fmaf(w[6], bot[0], acc); acc = fmaf(w[7], bot[1], acc); acc = fmaf(w[8], bot[2], acc);
+                vo[(size_t)r * W + x] = gelu_erf(acc) * __ldg(gl + (size_t)r * W + x);
+#pragma unroll
+                for (int k = 0; k < 3; ++k) { top[k] = mid[k]; mid[k] = bot[k]; }
+            }
+        }
     }
 }
 
@@ -214,10 +266,10 @@ static Workspace carve(void *base, int A, int C, int HW) {
 // packed bf16x3 B operands: [partial_conv3][linear1: C/32 chunks of 128 rows][linear2: C/128 chunks of 128 rows]
 constexpr int kSc = 32;
 static inline size_t pk_pconv_bytes(int C) { return (size_t)9 * (C / 4) * (C / 4) * 2 * 2; }      // N = C/4 rows
-static inline size_t pk_lin1_chunk_bytes(int C) { return (size_t)C * 128 * 2 * 2; }
+static inline size_t pk_lin1_chunk_bytes(int C) { return (size_t)C * 256 * 2 * 2; }   // 256 rows per launch
 static inline size_t pk_lin2_chunk_bytes(int C) { return (size_t)2 * C * 128 * 2 * 2; }
 static inline size_t pk_lin1_off(int C) { return align_up(pk_pconv_bytes(C), 256); }
-static inline size_t pk_lin2_off(int C) { return pk_lin1_off(C) + (size_t)(C / 32) * pk_lin1_chunk_bytes(C); }
+static inline size_t pk_lin2_off(int C) { return pk_lin1_off(C) + (size_t)(C / 64) * pk_lin1_chunk_bytes(C); }
 static inline size_t pk_total(int C) { return pk_lin2_off(C) + (size_t)(C / 128) * pk_lin2_chunk_bytes(C); }
 
 template <int NOUT, int TAPS, int EPI>
@@ -259,9 +311,9 @@ extern "C" int gc_enhancer_pack_weights(const float *w_pconv, const float *w_lin
         me::k_me_pack<<<(n + 255) / 256, 256, 0, st>>>(w_pconv, c4, c4, c4, enh::kSc, 9, 1, (uint4 *)pk);
         GC_LAUNCH_CHECK("k_me_pack(partial_conv3)");
     }
-    for (int j = 0; j < C / 32; ++j) {   // linear1.weight [4C][C], rows 128 j ..
-        const int n = (C / 8) * 128;
-        me::k_me_pack<<<(n + 255) / 256, 256, 0, st>>>(w_lin1 + (size_t)j * 128 * C, 128, 128, C, enh::kSc, 1, 1,
+    for (int j = 0; j < C / 64; ++j) {   // linear1.weight [4C][C], rows 256 j ..
+        const int n = (C / 8) * 256;
+        me::k_me_pack<<<(n + 255) / 256, 256, 0, st>>>(w_lin1 + (size_t)j * 256 * C, 256, 256, C, enh::kSc, 1, 1,
                                                       (uint4 *)(pk + enh::pk_lin1_off(C) + j * enh::pk_lin1_chunk_bytes(C)));
         GC_LAUNCH_CHECK("k_me_pack(linear1)");
     }
@@ -302,14 +354,21 @@ extern "C" int gc_enhancer(const float *x, int total_agents, int C, int H, int W
     if (rc) return rc;
     me::k_me_to_nhwc<<<dim3((HW + 63) / 64, C / 64, A), 256, 0, st>>>(ws.y, C, HW, ws.yh, ws.yl);
     GC_LAUNCH_CHECK("k_me_to_nhwc(ycat)");
-    for (int j = 0; j < C / 32; ++j) {   // linear1 + GELU, 128 output channels per launch
-        rc = enh::launch_conv<128, 1, 1>(st, grid, ws.yh, ws.yl,
+    for (int j = 0; j < C / 64; ++j) {   // linear1 + GELU, 256 output channels (= 256 TMEM columns) per launch: the A
+        // operand is staged once per 256 columns (128 per launch was measured first: 4 x 125 us at C = 128)
+        rc = enh::launch_conv<256, 1, 1>(st, grid, ws.yh, ws.yl,
                                          (const uint4 *)(pk + enh::pk_lin1_off(C) + j * enh::pk_lin1_chunk_bytes(C)),
-                                         params + L.l1b + 128 * j, C, C, H, W, 128, 4 * C, 128 * j, ws.u);
+                                         params + L.l1b + 256 * j, C, C, H, W, 256, 4 * C, 256 * j, ws.u);
         if (rc) return rc;
     }
-    enh::k_enh_dw<<<dim3(tiles, 2 * C / 32, A), 128, 0, st>>>(ws.u, params, L, C, H, W, ws.v);
-    GC_LAUNCH_CHECK("k_enh_dw");
+    if (W % 128 == 0 && !getenv("GC_ENH_GENERIC_DW")) {
+        const int row_blocks = (H + enh::kDwRows - 1) / enh::kDwRows;
+        enh::k_enh_dw_rows<<<dim3((W / 128) * row_blocks, 2 * C / 32, A), 128, 0, st>>>(ws.u, params, L, C, H, W, ws.v);
+        GC_LAUNCH_CHECK("k_enh_dw_rows");
+    } else {
+        enh::k_enh_dw<<<dim3(tiles, 2 * C / 32, A), 128, 0, st>>>(ws.u, params, L, C, H, W, ws.v);
+        GC_LAUNCH_CHECK("k_enh_dw");
+    }
     me::k_me_to_nhwc<<<dim3((HW + 63) / 64, 2 * C / 64, A), 256, 0, st>>>(ws.v, 2 * C, HW, ws.vh, ws.vl);
     GC_LAUNCH_CHECK("k_me_to_nhwc(v)");
     for (int j = 0; j < C / 128; ++j) {   // linear2

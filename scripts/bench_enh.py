@@ -44,7 +44,7 @@ def main():
     nbytes = 4.0 * A * hw * 2 * C   # x read once, out written once
     print(json.dumps({"workload": f"Enhancer {A} agents, C={C}, {args.H}x{args.W}", "ms_per_call": ms,
                       "frames_per_s": args.frames / ms * 1e3, "tflops": flops / ms / 1e9,
-                      "mandatory_gbs": nbytes / ms / 1e6, "launches_per_call": 11 + C // 32 + C // 128}))
+                      "mandatory_gbs": nbytes / ms / 1e6, "launches_per_call": 11 + C // 64 + C // 128}))
 
 
 if __name__ == "__main__":
