@@ -17,8 +17,8 @@
 //   linear2       : k_me_conv<128, 1x1>       x C/128   K = 2C,  N = C
 // fed by k_me_to_nhwc (NCHW fp32 -> channel-last bf16 planes).  LayerNorms, the depth-wise convolution + gate, the
 // pool / excite and the final scale are fp32 CUDA-core kernels (thread = pixel, plane-coalesced).
-// This first version keeps every intermediate as an NCHW fp32 tensor between the kernels (15 launches); fusing the
-// epilogues into channel-last bf16 operands is the obvious next step and is listed in DESIGN.md.
+// linear1 writes its GELU'd output channel-last (fp32) and the depth-wise + gate kernel turns it directly into linear2's
+// bf16 operand planes; the other intermediates are still NCHW fp32 tensors between the kernels.
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -85,84 +85,75 @@ k_enh_ln(const float *__restrict__ x, const float *__restrict__ prm, Prm L, int 
         ys[(size_t)c * HW] = (x1s[(size_t)c * HW] - m1) * r1 * __ldg(prm + L.n2w + c) + __ldg(prm + L.n2b + c);
 }
 
-// v[c] = GELU(dwconv3x3(u[c]) + b[c]) * u[2C + c]   for c < 2C (FRFN gate, enhancer.py:241-246).
-// u [A][4C][HW] f32 (already GELU'd by the linear1 epilogue), v [A][2C][HW].  grid = (HW/128, 2C/32, A), 128 threads.
-__global__ void __launch_bounds__(128)
-k_enh_dw(const float *__restrict__ u, const float *__restrict__ prm, Prm L, int C, int H, int W, float *__restrict__ v) {
-    __shared__ float s_w[32][9], s_b[32];
-    const int a = blockIdx.z, c0 = blockIdx.y * 32, HW = H * W;
-    for (int i = threadIdx.x; i < 32 * 9; i += 128) s_w[i / 9][i % 9] = prm[L.dww + (c0 + i / 9) * 9 + i % 9];
-    if (threadIdx.x < 32) s_b[threadIdx.x] = prm[L.dwb + c0 + threadIdx.x];
-    __syncthreads();
-    const int p = blockIdx.x * 128 + threadIdx.x;
-    if (p >= HW) return;
-    const int py = p / W, px = p - py * W;
-    int off[9];
-    bool ok[9];
-#pragma unroll
-    for (int k = 0; k < 9; ++k) {
-        const int yy = py - 1 + k / 3, xx = px - 1 + k % 3;
-        ok[k] = yy >= 0 && yy < H && xx >= 0 && xx < W;
-        off[k] = ok[k] ? yy * W + xx : p;
-    }
-    const float *ua = u + (size_t)a * 4 * C * HW;
-    for (int c = 0; c < 32; ++c) {
-        const float *pl = ua + (size_t)(c0 + c) * HW;
-        float acc = s_b[c];
-#pragma unroll
-        for (int k = 0; k < 9; ++k) acc = fmaf(s_w[c][k], ok[k] ? __ldg(pl + off[k]) : 0.0f, acc);
-        const float g = __ldg(ua + (size_t)(2 * C + c0 + c) * HW + p);
-        v[((size_t)a * 2 * C + c0 + c) * HW + p] = gelu_erf(acc) * g;
-    }
-}
-
-// The same for W % 128 == 0: thread = one x of a 128-pixel row segment, the CTA walks kDwRows rows with a sliding 3x3
-// window in registers, so every input row is fetched once per CTA (+ 2 halo rows per kDwRows) instead of by three CTAs
-// (first version: 535 us of the 1.74 ms call).  grid = (W/128 * ceil(H/kDwRows), 2C/32, A), 128 threads.
+// v[c] = GELU(dwconv3x3(u[c]) + b[c]) * u[2C + c]   for c < 2C (FRFN gate, enhancer.py:241-246), channel-last:
+// u [A][HW][4C] f32 (linear1 epilogue EPI = 2)  ->  v as bf16 value + residual planes [A][HW][2C], i.e. directly the A
+// operand of linear2.  (The first version kept u and v as NCHW fp32 tensors: thread = pixel, 535 us, then 310 us with a
+// sliding 3x3 register window over 8 rows, plus an NCHW -> channel-last conversion of v.)
+// Any W.
+// CTA = 8 pixels of a row x kDwRows rows x 128 channels; thread = (x, channel quad) walks the rows with a sliding 3x3 window
+// of float4 in registers, so every u element is fetched once per CTA (+ halo: 1.56x) instead of by nine pixel threads
+// of different CTAs through L2 (first channel-last version, one thread per (pixel, quad): 422 us).
+// grid = (ceil(W/8) * ceil(H/kDwRows), 2C/128, A), 256 threads.
 constexpr int kDwRows = 8;
-__global__ void __launch_bounds__(128)
-k_enh_dw_rows(const float *__restrict__ u, const float *__restrict__ prm, Prm L, int C, int H, int W, float *__restrict__ v) {
-    __shared__ float s_w[32][9], s_b[32];
-    const int a = blockIdx.z, c0 = blockIdx.y * 32, HW = H * W;
-    for (int i = threadIdx.x; i < 32 * 9; i += 128) s_w[i / 9][i % 9] = prm[L.dww + (c0 + i / 9) * 9 + i % 9];
-    if (threadIdx.x < 32) s_b[threadIdx.x] = prm[L.dwb + c0 + threadIdx.x];
+__global__ void __launch_bounds__(256)
+k_enh_dw_cl(const float *__restrict__ u, const float *__restrict__ prm, Prm L, int C, int H, int W,
+            uint2 *__restrict__ vh, uint2 *__restrict__ vl) {
+    __shared__ __align__(16) float s_dw[10][128];   // [9 taps + bias][128 channels of this CTA]
+    const int C2 = 2 * C, c0 = blockIdx.y * 128, a = blockIdx.z, HW = H * W;
+    for (int i = threadIdx.x; i < 128 * 9; i += 256) s_dw[i % 9][i / 9] = prm[L.dww + (c0 + i / 9) * 9 + i % 9];
+    if (threadIdx.x < 128) s_dw[9][threadIdx.x] = prm[L.dwb + c0 + threadIdx.x];
     __syncthreads();
-    const int segs = W / 128, seg = blockIdx.x % segs, r0 = (blockIdx.x / segs) * kDwRows;
-    const int x = seg * 128 + threadIdx.x;
+    const int xb = (W + 7) / 8;
+    const int x = (blockIdx.x % xb) * 8 + (threadIdx.x >> 5), r0 = (blockIdx.x / xb) * kDwRows;
+    const int q = threadIdx.x & 31;             // channel quad within the CTA's 128 channels
+    if (x >= W) return;
+    const float4 *ub = reinterpret_cast<const float4 *>(u + (size_t)a * HW * 4 * C) + (c0 >> 2) + q;   // + pixel * C (float4)
     const bool lok = x > 0, rok = x + 1 < W;
-    const float *ua = u + (size_t)a * 4 * C * HW;
-    auto row3 = [&](const float *pl, int r, float (&o)[3]) {
-        if (r < 0 || r >= H) { o[0] = o[1] = o[2] = 0.0f; return; }
-        const float *q = pl + (size_t)r * W + x;
-        o[0] = lok ? __ldg(q - 1) : 0.0f;
-        o[1] = __ldg(q);
-        o[2] = rok ? __ldg(q + 1) : 0.0f;
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    auto row3 = [&](int r, float4 (&o)[3]) {
+        if (r < 0 || r >= H) { o[0] = o[1] = o[2] = z; return; }
+        const float4 *p = ub + (size_t)(r * W + x) * C;
+        o[0] = lok ? __ldg(p - C) : z;
+        o[1] = __ldg(p);
+        o[2] = rok ? __ldg(p + C) : z;
     };
-    for (int c = 0; c < 32; ++c) {
-        const float *pl = ua + (size_t)(c0 + c) * HW;
-        const float *gl = ua + (size_t)(2 * C + c0 + c) * HW;
-        float *vo = v + ((size_t)a * 2 * C + c0 + c) * HW;
-        float w[9];
+    float4 w[9];
 #pragma unroll
-        for (int k = 0; k < 9; ++k) w[k] = s_w[c][k];
-        const float bias = s_b[c];
-        float top[3], mid[3], bot[3];
-        row3(pl, r0 - 1, top);
-        row3(pl, r0, mid);
+    for (int k = 0; k < 9; ++k) w[k] = *reinterpret_cast<const float4 *>(&s_dw[k][4 * q]);
+    const float4 bias = *reinterpret_cast<const float4 *>(&s_dw[9][4 * q]);
+    float4 top[3], mid[3], bot[3];
+    row3(r0 - 1, top);
+    row3(r0, mid);
+#pragma unroll 1
+    for (int i = 0; i < kDwRows; ++i) {
+        const int r = r0 + i;
+        if (r >= H) break;
+        row3(r + 1, bot);
+        float4 acc = bias;   // tap order ky*3+kx like the reference weight layout
 #pragma unroll
-        for (int i = 0; i < kDwRows; ++i) {
-            const int r = r0 + i;
-            if (r < H) {
-                row3(pl, r + 1, bot);
-                float acc = bias;   // tap order ky*3+kx like the reference weight layout
-                acc = fmaf(w[0], top[0], acc); acc = fmaf(w[1], top[1], acc); acc = fmaf(w[2], top[2], acc);
-                acc = fmaf(w[3], mid[0], acc); acc = fmaf(w[4], mid[1], acc); acc = fmaf(w[5], mid[2], acc);
-                acc = fmaf(w[6], bot[0], acc); acc = fmaf(w[7], bot[1], acc); acc = fmaf(w[8], bot[2], acc);
-                vo[(size_t)r * W + x] = gelu_erf(acc) * __ldg(gl + (size_t)r * W + x);
-#pragma unroll
-                for (int k = 0; k < 3; ++k) { top[k] = mid[k]; mid[k] = bot[k]; }
-            }
+        for (int k = 0; k < 3; ++k) {
+            acc.x = fmaf(w[k].x, top[k].x, acc.x); acc.y = fmaf(w[k].y, top[k].y, acc.y);
+            acc.z = fmaf(w[k].z, top[k].z, acc.z); acc.w = fmaf(w[k].w, top[k].w, acc.w);
         }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            acc.x = fmaf(w[3 + k].x, mid[k].x, acc.x); acc.y = fmaf(w[3 + k].y, mid[k].y, acc.y);
+            acc.z = fmaf(w[3 + k].z, mid[k].z, acc.z); acc.w = fmaf(w[3 + k].w, mid[k].w, acc.w);
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            acc.x = fmaf(w[6 + k].x, bot[k].x, acc.x); acc.y = fmaf(w[6 + k].y, bot[k].y, acc.y);
+            acc.z = fmaf(w[6 + k].z, bot[k].z, acc.z); acc.w = fmaf(w[6 + k].w, bot[k].w, acc.w);
+        }
+        const size_t pa = (size_t)a * HW + (size_t)r * W + x;
+        const float4 g = __ldg(ub + (size_t)(r * W + x) * C + (C2 >> 2));
+        const float r0v = gelu_erf(acc.x) * g.x, r1v = gelu_erf(acc.y) * g.y, r2v = gelu_erf(acc.z) * g.z,
+                    r3v = gelu_erf(acc.w) * g.w;
+        const size_t o = pa * (C2 >> 2) + (c0 >> 2) + q;
+        vh[o] = make_uint2(pack_bf16(r0v, r1v), pack_bf16(r2v, r3v));
+        vl[o] = make_uint2(pack_bf16(bf16_residual(r0v), bf16_residual(r1v)), pack_bf16(bf16_residual(r2v), bf16_residual(r3v)));
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { top[k] = mid[k]; mid[k] = bot[k]; }
     }
 }
 
@@ -234,7 +225,7 @@ k_enh_scale(const float *__restrict__ s, const float *__restrict__ attn, int HW,
 }
 
 struct Workspace {
-    float *x1, *y, *u, *v, *s, *gap, *attn;
+    float *x1, *y, *u, *s, *gap, *attn;
     uint4 *yh, *yl, *vh, *vl;
     size_t bytes;
 };
@@ -251,7 +242,6 @@ static Workspace carve(void *base, int A, int C, int HW) {
     w.x1 = (float *)take(plane * C);
     w.y = (float *)take(plane * C);
     w.u = (float *)take(plane * 4 * C);
-    w.v = (float *)take(plane * 2 * C);
     w.s = (float *)take(plane * C);
     w.gap = (float *)take((size_t)A * C * 4);
     w.attn = (float *)take((size_t)A * C * 4);
@@ -356,21 +346,16 @@ extern "C" int gc_enhancer(const float *x, int total_agents, int C, int H, int W
     GC_LAUNCH_CHECK("k_me_to_nhwc(ycat)");
     for (int j = 0; j < C / 64; ++j) {   // linear1 + GELU, 256 output channels (= 256 TMEM columns) per launch: the A
         // operand is staged once per 256 columns (128 per launch was measured first: 4 x 125 us at C = 128)
-        rc = enh::launch_conv<256, 1, 1>(st, grid, ws.yh, ws.yl,
+        rc = enh::launch_conv<256, 1, 2>(st, grid, ws.yh, ws.yl,
                                          (const uint4 *)(pk + enh::pk_lin1_off(C) + j * enh::pk_lin1_chunk_bytes(C)),
                                          params + L.l1b + 256 * j, C, C, H, W, 256, 4 * C, 256 * j, ws.u);
         if (rc) return rc;
     }
-    if (W % 128 == 0 && !getenv("GC_ENH_GENERIC_DW")) {
-        const int row_blocks = (H + enh::kDwRows - 1) / enh::kDwRows;
-        enh::k_enh_dw_rows<<<dim3((W / 128) * row_blocks, 2 * C / 32, A), 128, 0, st>>>(ws.u, params, L, C, H, W, ws.v);
-        GC_LAUNCH_CHECK("k_enh_dw_rows");
-    } else {
-        enh::k_enh_dw<<<dim3(tiles, 2 * C / 32, A), 128, 0, st>>>(ws.u, params, L, C, H, W, ws.v);
-        GC_LAUNCH_CHECK("k_enh_dw");
+    {   // depth-wise 3x3 + GELU + gate on the channel-last u, straight into linear2's bf16 operand planes
+        const dim3 g3(((W + 7) / 8) * ((H + enh::kDwRows - 1) / enh::kDwRows), 2 * C / 128, A);
+        enh::k_enh_dw_cl<<<g3, 256, 0, st>>>(ws.u, params, L, C, H, W, (uint2 *)ws.vh, (uint2 *)ws.vl);
+        GC_LAUNCH_CHECK("k_enh_dw_cl");
     }
-    me::k_me_to_nhwc<<<dim3((HW + 63) / 64, 2 * C / 64, A), 256, 0, st>>>(ws.v, 2 * C, HW, ws.vh, ws.vl);
-    GC_LAUNCH_CHECK("k_me_to_nhwc(v)");
     for (int j = 0; j < C / 128; ++j) {   // linear2
         rc = enh::launch_conv<128, 1, 0>(st, grid, ws.vh, ws.vl,
                                          (const uint4 *)(pk + enh::pk_lin2_off(C) + j * enh::pk_lin2_chunk_bytes(C)),

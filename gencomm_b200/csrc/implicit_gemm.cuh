@@ -119,7 +119,7 @@ __device__ __forceinline__ uint32_t lerp2(const float4 &w, uint32_t a, uint32_t 
 //   tile_sums [A][tiles*4][NOUT] (DEFORM): channel sums over 32-pixel groups
 // ------------------------------------------------------------------------------------------------
 // TAPS = 9: 3x3 convolution; TAPS = 1: 1x1 (a plain GEMM over the channel-last planes; used by the Enhancer's linear
-// layers).  EPI = 0: bias; EPI = 1: bias + exact GELU.  c_in = channels contracted (<= C, the channel count of the planes);
+// layers).  EPI = 0: bias; EPI = 1: bias + exact GELU; EPI = 2: bias + GELU written channel-last (all NOUT columns).  c_in = channels contracted (<= C, the channel count of the planes);
 // the n_store output channels go to planes out_ch_off .. of an [A][out_ch_total][HW] f32 tensor.
 __device__ __forceinline__ float gelu_erf(float v) { return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f)); }
 
@@ -303,6 +303,14 @@ k_me_conv(const uint4 *__restrict__ xh, const uint4 *__restrict__ xl, const floa
         for (int c16 = 0; c16 < NOUT / 2; c16 += 16) {
             float v[16];
             tmem_ld16(taddr + (uint32_t)c16, v);
+            if (EPI == 2) {   // bias + GELU, fp32 channel-last [A][HW][out_ch_total]: 64 contiguous bytes per lane
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = gelu_erf(v[i] + (bias ? __ldg(bias + ch0 + c16 + i) : 0.0f));
+                float4 *dst = reinterpret_cast<float4 *>(out + ((size_t)agent * HW + p_out) * out_ch_total + out_ch_off + ch0 + c16);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                continue;
+            }
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
                 const int ch = ch0 + c16 + i;
