@@ -184,7 +184,7 @@ def run_reference(args):
             break
     fps = done / total
     sample = (f"{done} frames timed (K = {args.steps} requested, 150 s cap), 1 frame per step (4 agents x 100k pts), "
-              f"torch CPU threads={torch.get_num_threads()}")"
+              f"torch CPU threads={torch.get_num_threads()}")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
         "steps": done, "warmup": args.warmup, "ms_per_step": 1e3 * total / done,
