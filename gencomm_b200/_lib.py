@@ -61,6 +61,16 @@ SIGNATURES = {
     "gc_enhancer_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "gc_enhancer_pack_weights": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "gc_enhancer": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "gc_double_conv_packed_bytes": (c_size_t, [c_int, c_int]),
+    "gc_double_conv_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int, c_int]),
+    "gc_double_conv_pack": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "gc_double_conv": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                               c_void_p, c_void_p]),
+    "gc_det_heads_packed_bytes": (c_size_t, [c_int, c_int]),
+    "gc_det_heads_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
+    "gc_det_heads_pack": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "gc_det_heads": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                             c_void_p]),
 }
 
 _lib = None

@@ -119,7 +119,8 @@ __device__ __forceinline__ uint32_t lerp2(const float4 &w, uint32_t a, uint32_t 
 //   tile_sums [A][tiles*4][NOUT] (DEFORM): channel sums over 32-pixel groups
 // ------------------------------------------------------------------------------------------------
 // TAPS = 9: 3x3 convolution; TAPS = 1: 1x1 (a plain GEMM over the channel-last planes; used by the Enhancer's linear
-// layers).  EPI = 0: bias; EPI = 1: bias + exact GELU; EPI = 2: bias + GELU written channel-last (all NOUT columns).  c_in = channels contracted (<= C, the channel count of the planes);
+// layers).  EPI = 0: bias; EPI = 1: bias + exact GELU; EPI = 2: bias + GELU written channel-last (all NOUT columns);
+// EPI = 3: bias + ReLU.  c_in = channels contracted (<= C, the channel count of the planes);
 // the n_store output channels go to planes out_ch_off .. of an [A][out_ch_total][HW] f32 tensor.
 __device__ __forceinline__ float gelu_erf(float v) { return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f)); }
 
@@ -127,7 +128,8 @@ template <int NOUT, bool DEFORM, int SC, int TAPS = 9, int EPI = 0>
 __global__ void __launch_bounds__(kThreads)
 k_me_conv(const uint4 *__restrict__ xh, const uint4 *__restrict__ xl, const float *__restrict__ offset,
           const uint4 *__restrict__ wp, const float *__restrict__ bias, int C, int c_in, int H, int W, int n_store,
-          int out_ch_total, int out_ch_off, float *__restrict__ out, float *__restrict__ tile_sums) {
+          int out_ch_total, int out_ch_off, float *__restrict__ out, float *__restrict__ tile_sums, int H_in = 0,
+          int W_in = 0, int stride = 1) {
     // The plain (offset) layer runs as "bf16x3": A and B are split into a bf16 value and a bf16 residual and three MMAs
     // (hi*hi + lo*hi + hi*lo) rebuild ~16 mantissa bits, because its output positions the deformable layer's taps:
     // a bf16-only offset (rel. error 4e-3) moves a tap by 0.02 px at 5 px, which on high-frequency features costs
@@ -162,8 +164,10 @@ k_me_conv(const uint4 *__restrict__ xh, const uint4 *__restrict__ xl, const floa
     const uint32_t tmem = s_tmem;
     const uint32_t a_base = smem_u32(a_s), b_base = smem_u32(b_s);
     constexpr uint32_t idesc = make_idesc(128, NOUT);
-    const uint4 *xh_a = xh + (size_t)agent * HW * C8;
-    const uint4 *xl_a = xl + (size_t)agent * HW * C8;
+    // plain convolutions may be strided: H x W is the output grid, Hi x Wi the input grid the planes are laid out over
+    const int Hi = H_in > 0 ? H_in : H, Wi = W_in > 0 ? W_in : W;
+    const uint4 *xh_a = xh + (size_t)agent * Hi * Wi * C8;
+    const uint4 *xl_a = xl + (size_t)agent * Hi * Wi * C8;
 
     for (int s = 0; s < stages; ++s) {
         const int b = s & 1;
@@ -196,9 +200,9 @@ k_me_conv(const uint4 *__restrict__ xh, const uint4 *__restrict__ xl, const floa
                     w.z = (b_ok && l_ok) ? lh * uw : 0.0f;
                     w.w = (b_ok && r_ok) ? lh * lw : 0.0f;
                 } else {
-                    const int yy = py - 1 + ky, xx = px - 1 + kx;
-                    const bool ok = yy >= 0 && yy < H && xx >= 0 && xx < W;
-                    o.x = ok ? yy * W + xx : 0;
+                    const int yy = py * stride - 1 + ky, xx = px * stride - 1 + kx;
+                    const bool ok = yy >= 0 && yy < Hi && xx >= 0 && xx < Wi;
+                    o.x = ok ? yy * Wi + xx : 0;
                     w.x = ok ? 1.0f : 0.0f;
                 }
                 s_o[tid] = o;
@@ -317,6 +321,7 @@ k_me_conv(const uint4 *__restrict__ xh, const uint4 *__restrict__ xl, const floa
                 if (ch < n_store) {
                     float r = v[i] + (bias ? __ldg(bias + ch) : 0.0f);
                     if (EPI == 1) r = gelu_erf(r);
+                    if (EPI == 3) r = fmaxf(r, 0.0f);
                     out[((size_t)agent * out_ch_total + out_ch_off + ch) * HW + p_out] = r;
                     if (DEFORM) {
                         float t = r;

@@ -403,3 +403,59 @@ def enhancer(x, packed, params, workspace=None, out=None):
     _lib.check(lib.gc_enhancer(_ptr(x), A, C, H, W, _ptr(packed), _ptr(params), _ptr(workspace), _ptr(out), _stream()),
                "gc_enhancer")
     return out
+
+
+# --------------------------------------------------------------------------------------------
+# (8f rank 2, first slice) DoubleConv (shrink header) and the shared detection heads
+# --------------------------------------------------------------------------------------------
+def double_conv_pack(w1, b1, w2, b2):
+    lib = _lib.load()
+    w1, w2 = w1.detach().float().contiguous(), w2.detach().float().contiguous()
+    _chk(w1, "double_conv.0.weight", torch.float32, 4)
+    _chk(w2, "double_conv.2.weight", torch.float32, 4)
+    c_out, c_in = w1.shape[0], w1.shape[1]
+    if tuple(w1.shape[2:]) != (3, 3) or tuple(w2.shape) != (c_out, c_out, 3, 3):
+        raise NotImplementedError("gencomm_b200 DoubleConv: 3x3 kernels (the shipped shrink headers)")
+    packed = torch.empty(max(lib.gc_double_conv_packed_bytes(c_in, c_out), 1), dtype=torch.uint8, device=w1.device)
+    _lib.check(lib.gc_double_conv_pack(_ptr(w1), _ptr(w2), c_in, c_out, _ptr(packed), _stream()), "gc_double_conv_pack")
+    bias = torch.cat([b1.detach().float().reshape(-1), b2.detach().float().reshape(-1)]).contiguous()
+    return packed, bias
+
+
+def double_conv(x, packed, bias, c_out, stride, workspace=None):
+    lib = _lib.load()
+    _chk(x, "x", torch.float32, 4)
+    A, c_in, H, W = x.shape
+    Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
+    if workspace is None:
+        workspace = torch.empty(max(lib.gc_double_conv_workspace_bytes(A, c_in, H, W, stride, c_out), 1), dtype=torch.uint8,
+                                device=x.device)
+    out = torch.empty(A, c_out, Ho, Wo, dtype=torch.float32, device=x.device)
+    _lib.check(lib.gc_double_conv(_ptr(x), A, c_in, H, W, int(stride), int(c_out), _ptr(packed), _ptr(bias), _ptr(workspace),
+                                  _ptr(out), _stream()), "gc_double_conv")
+    return out
+
+
+def det_heads_pack(weights, biases):
+    """weights: 1x1 conv weights [n_i, C, 1, 1] (cls, reg, dir); returns (packed, bias, splits)."""
+    lib = _lib.load()
+    w = torch.cat([t.detach().float().reshape(t.shape[0], -1) for t in weights]).contiguous()
+    _chk(w, "head weights", torch.float32, 2)
+    n_out, C = w.shape
+    packed = torch.empty(max(lib.gc_det_heads_packed_bytes(C, n_out), 1), dtype=torch.uint8, device=w.device)
+    _lib.check(lib.gc_det_heads_pack(_ptr(w), C, n_out, _ptr(packed), _stream()), "gc_det_heads_pack")
+    bias = torch.cat([b.detach().float().reshape(-1) for b in biases]).contiguous()
+    return packed, bias, [t.shape[0] for t in weights]
+
+
+def det_heads(x, packed, bias, workspace=None):
+    lib = _lib.load()
+    _chk(x, "x", torch.float32, 4)
+    B, C, H, W = x.shape
+    n_out = bias.numel()
+    if workspace is None:
+        workspace = torch.empty(max(lib.gc_det_heads_workspace_bytes(B, C, H, W), 1), dtype=torch.uint8, device=x.device)
+    out = torch.empty(B, n_out, H, W, dtype=torch.float32, device=x.device)
+    _lib.check(lib.gc_det_heads(_ptr(x), B, C, H, W, n_out, _ptr(packed), _ptr(bias), _ptr(workspace), _ptr(out), _stream()),
+               "gc_det_heads")
+    return out

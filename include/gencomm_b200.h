@@ -225,6 +225,27 @@ int gc_enhancer_pack_weights(const float *w_pconv, const float *w_lin1, const fl
 int gc_enhancer(const float *x, int total_agents, int C, int H, int W, const void *packed, const float *params,
                 void *workspace, float *out, void *stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * (8f rank 2, first slice) DoubleConv / DownsampleConv (models/sub_modules/downsample_conv.py:7-50):
+ *   out = ReLU(conv3x3(ReLU(conv3x3_stride_s(x) + b1)) + b2), padding 1, stride s in {1, 2}
+ *   x [sumN][c_in][H][W] f32 -> out [sumN][c_out][Ho][Wo], Ho = (H - 1) / s + 1; c_in, c_out % 64 == 0, c_out <= 256,
+ *   Ho*Wo % 128 == 0.  packed: gc_double_conv_pack(double_conv.0.weight [c_out][c_in][3][3], double_conv.2.weight
+ *   [c_out][c_out][3][3]); bias [2][c_out] (device).  tcgen05 implicit GEMMs in bf16x3 (fp32-grade).
+ * Shared detection heads (models/heter_model_baseline.py:130-135): cls_head, reg_head, dir_head = three 1x1 Conv2d on
+ *   the fused feature, evaluated as one GEMM: w [n_out][C] = their weights concatenated, n_out <= 64, bias [n_out];
+ *   x [B][C][H][W] -> out [B][n_out][H][W].
+ * ------------------------------------------------------------------------------------------- */
+size_t gc_double_conv_packed_bytes(int c_in, int c_out);
+size_t gc_double_conv_workspace_bytes(int total_agents, int c_in, int H, int W, int stride, int c_out);
+int gc_double_conv_pack(const float *w1, const float *w2, int c_in, int c_out, void *packed, void *stream);
+int gc_double_conv(const float *x, int total_agents, int c_in, int H, int W, int stride, int c_out, const void *packed,
+                   const float *bias, void *workspace, float *out, void *stream);
+size_t gc_det_heads_packed_bytes(int C, int n_out);
+size_t gc_det_heads_workspace_bytes(int n_frames, int C, int H, int W);
+int gc_det_heads_pack(const float *w, int C, int n_out, void *packed, void *stream);
+int gc_det_heads(const float *x, int n_frames, int C, int H, int W, int n_out, const void *packed, const float *bias,
+                 void *workspace, float *out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -182,6 +182,27 @@ def gen_enhancer(ns):
     print("enhancer.npz: out", tuple(out.shape), "keys", len(sd), "stored", len(used))
 
 
+def gen_det_tail(ns):
+    """DownsampleConv (shrink header, stride 2 like the GenComm stage-1 yaml) through the reference class, and the three
+    1x1 heads (plain nn.Conv2d in heter_model_baseline.py:130-135)."""
+    torch.manual_seed(17)
+    cfg = {"kernal_size": [3], "stride": [2], "padding": [1], "dim": [64], "input_dim": 64}
+    model = ns.DownsampleConv(cfg).eval()
+    x = synth.bev_features(1401, 2, 64, 16, 32)
+    with torch.no_grad():
+        out = model(x)
+    heads = [torch.nn.Conv2d(64, n, 1) for n in (2, 14, 4)]
+    with torch.no_grad():
+        hout = [h(out) for h in heads]
+    sd = {k: v.numpy() for k, v in model.state_dict().items()}
+    np.savez_compressed(os.path.join(OUT, "det_tail.npz"), x=x.numpy(), ref_out=out.numpy(),
+                        **{"sd/" + k: v for k, v in sd.items()},
+                        **{f"head{i}/weight": h.weight.detach().numpy() for i, h in enumerate(heads)},
+                        **{f"head{i}/bias": h.bias.detach().numpy() for i, h in enumerate(heads)},
+                        **{f"head{i}/out": o.numpy() for i, o in enumerate(hout)})
+    print("det_tail.npz: out", tuple(out.shape))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ns = ref_import.load()
@@ -190,6 +211,7 @@ def main():
     gen_gencomm(ns)
     gen_message_extractor(ns)
     gen_enhancer(ns)
+    gen_det_tail(ns)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)) // 1024, "KiB")
 

@@ -98,6 +98,7 @@ def load():
     from opencood.models.gencomm_modules.cond_diff import GenComm, Config
     from opencood.models.gencomm_modules.message_extractor_v2 import MessageExtractorv2
     from opencood.models.gencomm_modules.enhancer import Enhancer
+    from opencood.models.sub_modules.downsample_conv import DownsampleConv
     ns.PillarVFE = PillarVFE
     ns.PointPillarScatter = PointPillarScatter
     ns.warp_affine_simple = warp_affine_simple
@@ -110,4 +111,5 @@ def load():
     ns.Config = Config
     ns.MessageExtractorv2 = MessageExtractorv2
     ns.Enhancer = Enhancer
+    ns.DownsampleConv = DownsampleConv
     return ns

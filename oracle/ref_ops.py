@@ -424,3 +424,19 @@ def enhancer(x, sd):
                             g("split_attn.bn1.bias")))
     a = torch.sigmoid(F.linear(a, g("split_attn.fc2.weight")))
     return (s * a).permute(0, 3, 1, 2).contiguous()                                          # :374
+
+
+# ---------------------------------------------------------------------------------------------
+# DownsampleConv (models/sub_modules/downsample_conv.py:7-50) and the shared heads
+# (models/heter_model_baseline.py:130-135, applied at :165-167): plain torch convolutions.
+# ---------------------------------------------------------------------------------------------
+def downsample_conv(x, sd, strides):
+    """sd: state_dict of DownsampleConv; strides: config['stride'] (kernel 3, padding 1)."""
+    for i, s in enumerate(strides):
+        x = F.relu(F.conv2d(x, sd[f"layers.{i}.double_conv.0.weight"], sd[f"layers.{i}.double_conv.0.bias"], stride=s, padding=1))
+        x = F.relu(F.conv2d(x, sd[f"layers.{i}.double_conv.2.weight"], sd[f"layers.{i}.double_conv.2.bias"], padding=1))
+    return x
+
+
+def det_heads(x, cls_w, cls_b, reg_w, reg_b, dir_w, dir_b):
+    return F.conv2d(x, cls_w, cls_b), F.conv2d(x, reg_w, reg_b), F.conv2d(x, dir_w, dir_b)

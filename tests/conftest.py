@@ -62,3 +62,8 @@ def golden_message_extractor():
 @pytest.fixture(scope="session")
 def golden_enhancer():
     return load_golden("enhancer.npz")
+
+
+@pytest.fixture(scope="session")
+def golden_det_tail():
+    return load_golden("det_tail.npz")

@@ -89,3 +89,13 @@ def test_enhancer_keeps_reference_state_dict_keys(golden_enhancer):
     m.load_state_dict({k[3:]: torch.from_numpy(v) for k, v in golden_enhancer.items() if k.startswith("sd/")}, strict=False)
     with pytest.raises(RuntimeError, match="CUDA"):
         m(torch.zeros(1, 128, 4, 32))
+
+
+def test_downsample_conv_keeps_reference_state_dict_keys(golden_det_tail):
+    from gencomm_b200 import DetectionHeads, DownsampleConv
+    m = DownsampleConv({"kernal_size": [3], "stride": [2], "padding": [1], "dim": [64], "input_dim": 64})
+    assert set(m.state_dict()) == {k[3:] for k in golden_det_tail if k.startswith("sd/")}
+    assert set(DetectionHeads(64, 2).state_dict()) == {"cls_head.weight", "cls_head.bias", "reg_head.weight",
+                                                       "reg_head.bias", "dir_head.weight", "dir_head.bias"}
+    with pytest.raises(NotImplementedError):
+        DownsampleConv({"kernal_size": [5], "stride": [1], "padding": [2], "dim": [64], "input_dim": 64})

@@ -135,3 +135,13 @@ def test_enhancer_restatement_matches_reference(golden_enhancer):
     sd = {k[3:]: T(v) for k, v in g.items() if k.startswith("sd/")}
     out = R.enhancer(T(g["x"]), sd)
     assert torch.allclose(out, T(g["ref_out"]), rtol=0, atol=5e-6)
+
+
+def test_downsample_conv_restatement_matches_reference(golden_det_tail):
+    g = golden_det_tail
+    sd = {k[3:]: T(v) for k, v in g.items() if k.startswith("sd/")}
+    out = R.downsample_conv(T(g["x"]), sd, [2])
+    assert torch.allclose(out, T(g["ref_out"]), rtol=0, atol=1e-6)
+    heads = R.det_heads(out, *[T(g[f"head{i}/{k}"]) for i in range(3) for k in ("weight", "bias")])
+    for i, h in enumerate(heads):
+        assert torch.allclose(h, T(g[f"head{i}/out"]), rtol=0, atol=1e-6)
