@@ -15,5 +15,6 @@ from .gencomm import Config, DiffusionUNet, GenComm  # noqa: F401
 from .message_extractor import BEVDeformableExtractor, MessageExtractorv2  # noqa: F401
 from .enhancer import Enhancer  # noqa: F401
 from .det_tail import DetectionHeads, DoubleConv, DownsampleConv  # noqa: F401
+from .backbone import BaseBEVBackbone  # noqa: F401
 
 __version__ = "0.1.0"

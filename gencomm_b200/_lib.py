@@ -71,6 +71,11 @@ SIGNATURES = {
     "gc_det_heads_pack": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "gc_det_heads": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                              c_void_p]),
+    "gc_conv_packed_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "gc_conv_pack": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "gc_to_planes": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "gc_conv_planes": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
+                               c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
 }
 
 _lib = None

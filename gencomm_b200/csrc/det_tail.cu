@@ -152,3 +152,93 @@ extern "C" int gc_det_heads(const float *x, int n_frames, int C, int H, int W, i
     return dt::launch_n<1, 0>(n_out, st, dim3(H * W / me::kPix, n_frames), xh, xl, (const uint4 *)packed, bias, C, H, W, out, H,
                               W, 1);
 }
+
+// ------------------------------------------------------------------------------------------------
+// Generic layer entry points over the channel-last bf16 planes (used by the host mirror of BaseBEVBackbone,
+// models/sub_modules/base_bev_backbone.py:96-124): conv3x3 (stride 1/2, pad 1) or 1x1, folded-BN bias, ReLU, written
+// either as the next layer's planes or as NCHW fp32 (optionally pixel-shuffled = one phase of a ConvTranspose2d whose
+// kernel equals its stride).
+// ------------------------------------------------------------------------------------------------
+namespace gc {
+namespace dt {
+
+template <int NOUT, int TAPS, int EPI>
+static int launch_layer(cudaStream_t st, dim3 grid, const uint4 *xh, const uint4 *xl, const uint4 *wp, const float *bias, int C,
+                        int Ho, int Wo, int n_out, int out_total, int out_off, float *out, uint4 *oh, uint4 *ol, int H_in,
+                        int W_in, int stride, int up, int up_dy, int up_dx) {
+    constexpr int kSmem = conv_smem_bytes(NOUT, true, kSc);
+    static bool done = false;
+    if (!done) {
+        cudaFuncSetAttribute(k_me_conv<NOUT, false, kSc, TAPS, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+        done = true;
+    }
+    k_me_conv<NOUT, false, kSc, TAPS, EPI><<<grid, kThreads, kSmem, st>>>(xh, xl, nullptr, wp, bias, C, C, Ho, Wo, n_out, out_total,
+                                                                       out_off, out, nullptr, H_in, W_in, stride, oh, ol, up,
+                                                                       up_dy, up_dx);
+    GC_LAUNCH_CHECK("k_me_conv (layer)");
+    return GC_OK;
+}
+template <int TAPS, int EPI, class... Args>
+static int launch_layer_n(int n, Args... args) {
+    if (n <= 64) return launch_layer<64, TAPS, EPI>(args...);
+    if (n <= 128) return launch_layer<128, TAPS, EPI>(args...);
+    return launch_layer<256, TAPS, EPI>(args...);
+}
+
+}  // namespace dt
+}  // namespace gc
+
+extern "C" size_t gc_conv_packed_bytes(int taps, int c_in, int n_out) {
+    return (taps == 1 || taps == 9) && c_in > 0 && n_out > 0 ? dt::packed_conv_bytes(taps, c_in, n_out < 64 ? 64 : n_out) : 0;
+}
+extern "C" int gc_conv_pack(const float *w /* [n_out][c_in][taps] */, int taps, int c_in, int n_out, void *packed, void *stream) {
+    GC_REQUIRE(w && packed, GC_EINVAL, "gc_conv_pack: null pointer");
+    GC_REQUIRE((taps == 1 || taps == 9) && c_in > 0 && c_in % 32 == 0 && n_out > 0 && n_out <= 256, GC_EUNSUPPORTED,
+               "gc_conv_pack: taps in {1,9}, c_in %% 32 == 0, n_out <= 256 (got %d, %d, %d)", taps, c_in, n_out);
+    const int n = dt::pad_n(n_out < 64 ? 64 : n_out), t = taps * (c_in / 8) * n;
+    me::k_me_pack<<<(t + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w, n_out, n, c_in, dt::kSc, taps, 1, (uint4 *)packed);
+    GC_LAUNCH_CHECK("k_me_pack(layer)");
+    return GC_OK;
+}
+extern "C" int gc_to_planes(const float *x, int total_agents, int C, int HW, void *xh, void *xl, void *stream) {
+    GC_REQUIRE(total_agents >= 0 && C > 0 && C % 64 == 0 && HW > 0, GC_EUNSUPPORTED, "gc_to_planes: C must be a multiple of 64");
+    if (total_agents == 0) return GC_OK;
+    GC_REQUIRE(x && xh && xl, GC_EINVAL, "gc_to_planes: null pointer");
+    me::k_me_to_nhwc<<<dim3((HW + 63) / 64, C / 64, total_agents), 256, 0, (cudaStream_t)stream>>>(x, C, HW, (uint4 *)xh, (uint4 *)xl);
+    GC_LAUNCH_CHECK("k_me_to_nhwc");
+    return GC_OK;
+}
+extern "C" int gc_conv_planes(const void *xh, const void *xl, int total_agents, int c_in, int H_in, int W_in, int stride, int taps,
+                              int n_out, const void *packed, const float *bias, void *oh, void *ol, float *out_nchw,
+                              int out_ch_total, int out_ch_off, int up, int up_dy, int up_dx, void *stream) {
+    GC_REQUIRE(total_agents >= 0 && total_agents <= 65535, GC_EINVAL, "gc_conv_planes: bad agent count");
+    if (total_agents == 0) return GC_OK;
+    GC_REQUIRE(xh && xl && packed && ((oh && ol) || out_nchw), GC_EINVAL, "gc_conv_planes: null pointer");
+    GC_REQUIRE((taps == 1 || taps == 9) && c_in > 0 && c_in % 32 == 0 && n_out >= 8 && n_out <= 256 && n_out % 8 == 0,
+               GC_EUNSUPPORTED, "gc_conv_planes: taps in {1,9}, c_in %% 32 == 0, n_out %% 8 == 0, n_out <= 256");
+    GC_REQUIRE((stride == 1 || stride == 2) && (taps == 9 || stride == 1) && up >= 1 && up_dy >= 0 && up_dy < up && up_dx >= 0 &&
+                   up_dx < up,
+               GC_EUNSUPPORTED, "gc_conv_planes: bad stride / up-sampling phase");
+    const int Ho = taps == 9 ? (H_in - 1) / stride + 1 : H_in, Wo = taps == 9 ? (W_in - 1) / stride + 1 : W_in;
+    GC_REQUIRE(Ho > 0 && Wo > 0 && (Ho * Wo) % me::kPix == 0, GC_EUNSUPPORTED,
+               "gc_conv_planes: output H*W must be a multiple of 128 (got %dx%d)", Ho, Wo);
+    GC_REQUIRE(out_ch_total >= out_ch_off + n_out && out_ch_total % 8 == 0 && out_ch_off % 8 == 0, GC_EINVAL,
+               "gc_conv_planes: bad output channel window");
+    cudaStream_t st = (cudaStream_t)stream;
+    const dim3 grid(Ho * Wo / me::kPix, total_agents);
+    const uint4 *a = (const uint4 *)xh, *b = (const uint4 *)xl, *wp = (const uint4 *)packed;
+    if (oh) {
+        GC_REQUIRE(up == 1 && n_out % 16 == 0, GC_EUNSUPPORTED,
+                   "gc_conv_planes: plane outputs need n_out %% 16 == 0 and no up-sampling");
+        if (taps == 9)
+            return dt::launch_layer_n<9, 5>(n_out, st, grid, a, b, wp, bias, c_in, Ho, Wo, n_out, out_ch_total, out_ch_off,
+                                            (float *)nullptr, (uint4 *)oh, (uint4 *)ol, H_in, W_in, stride, 1, 0, 0);
+        return dt::launch_layer_n<1, 5>(n_out, st, grid, a, b, wp, bias, c_in, Ho, Wo, n_out, out_ch_total, out_ch_off,
+                                        (float *)nullptr, (uint4 *)oh, (uint4 *)ol, H_in, W_in, stride, 1, 0, 0);
+    }
+    if (taps == 9)
+        return dt::launch_layer_n<9, 3>(n_out, st, grid, a, b, wp, bias, c_in, Ho, Wo, n_out, out_ch_total, out_ch_off, out_nchw,
+                                        (uint4 *)nullptr, (uint4 *)nullptr, H_in, W_in, stride, up, up_dy, up_dx);
+    return dt::launch_layer_n<1, 3>(n_out, st, grid, a, b, wp, bias, c_in, Ho, Wo, n_out, out_ch_total, out_ch_off, out_nchw,
+                                    (uint4 *)nullptr, (uint4 *)nullptr, H_in, W_in, stride, up, up_dy, up_dx);
+}

@@ -120,7 +120,7 @@ __device__ __forceinline__ uint32_t lerp2(const float4 &w, uint32_t a, uint32_t 
 // ------------------------------------------------------------------------------------------------
 // TAPS = 9: 3x3 convolution; TAPS = 1: 1x1 (a plain GEMM over the channel-last planes; used by the Enhancer's linear
 // layers).  EPI = 0: bias; EPI = 1: bias + exact GELU; EPI = 2: bias + GELU written channel-last (all NOUT columns);
-// EPI = 3: bias + ReLU.  c_in = channels contracted (<= C, the channel count of the planes);
+// EPI = 3: bias + ReLU; EPI = 5: bias + ReLU written as channel-last bf16 value + residual planes (oh, ol).  c_in = channels contracted (<= C, the channel count of the planes);
 // the n_store output channels go to planes out_ch_off .. of an [A][out_ch_total][HW] f32 tensor.
 __device__ __forceinline__ float gelu_erf(float v) { return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f)); }
 
@@ -129,7 +129,8 @@ __global__ void __launch_bounds__(kThreads)
 k_me_conv(const uint4 *__restrict__ xh, const uint4 *__restrict__ xl, const float *__restrict__ offset,
           const uint4 *__restrict__ wp, const float *__restrict__ bias, int C, int c_in, int H, int W, int n_store,
           int out_ch_total, int out_ch_off, float *__restrict__ out, float *__restrict__ tile_sums, int H_in = 0,
-          int W_in = 0, int stride = 1) {
+          int W_in = 0, int stride = 1, uint4 *__restrict__ oh = nullptr, uint4 *__restrict__ ol = nullptr, int up = 1,
+          int up_dy = 0, int up_dx = 0) {
     // The plain (offset) layer runs as "bf16x3": A and B are split into a bf16 value and a bf16 residual and three MMAs
     // (hi*hi + lo*hi + hi*lo) rebuild ~16 mantissa bits, because its output positions the deformable layer's taps:
     // a bf16-only offset (rel. error 4e-3) moves a tap by 0.02 px at 5 px, which on high-frequency features costs
@@ -303,10 +304,32 @@ k_me_conv(const uint4 *__restrict__ xh, const uint4 *__restrict__ xl, const floa
         const int q = warp & 3, ch0 = (warp >> 2) * (NOUT / 2);
         const int p_out = tile * kPix + q * 32 + lane;
         const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)ch0;
+        // NCHW stores may be "pixel-shuffled": output pixel (y * up + up_dy, x * up + up_dx) of an up-sampled grid -- one
+        // phase of a ConvTranspose2d with kernel == stride == up evaluated as a 1x1 GEMM over the input pixels
+        const int pyo = p_out / W, pxo = p_out - pyo * W;
+        const size_t hw_store = (size_t)HW * up * up;
+        const size_t p_store = (size_t)(pyo * up + up_dy) * (W * up) + pxo * up + up_dx;
 #pragma unroll
         for (int c16 = 0; c16 < NOUT / 2; c16 += 16) {
             float v[16];
             tmem_ld16(taddr + (uint32_t)c16, v);
+            if (EPI == 5) {   // bias + ReLU -> channel-last bf16 value + residual planes [A][HW][out_ch_total]: the next
+                              // layer's A operand, no fp32 NCHW round trip and no layout conversion between layers
+                uint32_t h[8], l[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float a = fmaxf(v[2 * i] + (bias ? __ldg(bias + ch0 + c16 + 2 * i) : 0.0f), 0.0f);
+                    const float b = fmaxf(v[2 * i + 1] + (bias ? __ldg(bias + ch0 + c16 + 2 * i + 1) : 0.0f), 0.0f);
+                    h[i] = pack_bf16(a, b);
+                    l[i] = pack_bf16(bf16_residual(a), bf16_residual(b));
+                }
+                if (ch0 + c16 < n_store) {
+                    const size_t o = ((size_t)agent * HW + p_out) * (out_ch_total >> 3) + ((out_ch_off + ch0 + c16) >> 3);
+                    oh[o] = make_uint4(h[0], h[1], h[2], h[3]); oh[o + 1] = make_uint4(h[4], h[5], h[6], h[7]);
+                    ol[o] = make_uint4(l[0], l[1], l[2], l[3]); ol[o + 1] = make_uint4(l[4], l[5], l[6], l[7]);
+                }
+                continue;
+            }
             if (EPI == 2) {   // bias + GELU, fp32 channel-last [A][HW][out_ch_total]: 64 contiguous bytes per lane
 #pragma unroll
                 for (int i = 0; i < 16; ++i) v[i] = gelu_erf(v[i] + (bias ? __ldg(bias + ch0 + c16 + i) : 0.0f));
@@ -322,7 +345,7 @@ k_me_conv(const uint4 *__restrict__ xh, const uint4 *__restrict__ xl, const floa
                     float r = v[i] + (bias ? __ldg(bias + ch) : 0.0f);
                     if (EPI == 1) r = gelu_erf(r);
                     if (EPI == 3) r = fmaxf(r, 0.0f);
-                    out[((size_t)agent * out_ch_total + out_ch_off + ch) * HW + p_out] = r;
+                    out[((size_t)agent * out_ch_total + out_ch_off + ch) * hw_store + p_store] = r;
                     if (DEFORM) {
                         float t = r;
 #pragma unroll

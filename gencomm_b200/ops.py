@@ -459,3 +459,52 @@ def det_heads(x, packed, bias, workspace=None):
     _lib.check(lib.gc_det_heads(_ptr(x), B, C, H, W, n_out, _ptr(packed), _ptr(bias), _ptr(workspace), _ptr(out), _stream()),
                "gc_det_heads")
     return out
+
+
+# --------------------------------------------------------------------------------------------
+# (8f rank 2) layer primitives over channel-last bf16 planes (BaseBEVBackbone)
+# --------------------------------------------------------------------------------------------
+def conv_pack(w):
+    """w [n_out, c_in, k, k] f32 (k in {1, 3}, BatchNorm folded) -> packed bf16x3 B operand."""
+    lib = _lib.load()
+    w = w.detach().float().contiguous()
+    _chk(w, "conv weight", torch.float32, 4)
+    n_out, c_in, k, _ = w.shape
+    taps = k * k
+    nbytes = lib.gc_conv_packed_bytes(taps, c_in, n_out)
+    if nbytes == 0:
+        raise NotImplementedError("gencomm_b200 conv layers: 1x1 or 3x3 kernels")
+    packed = torch.empty(nbytes, dtype=torch.uint8, device=w.device)
+    _lib.check(lib.gc_conv_pack(_ptr(w), taps, c_in, n_out, _ptr(packed), _stream()), "gc_conv_pack")
+    return packed
+
+
+def to_planes(x):
+    """x [A,C,H,W] f32 -> (xh, xl) channel-last bf16 value + residual planes (uint8 blobs)."""
+    lib = _lib.load()
+    _chk(x, "x", torch.float32, 4)
+    A, C, H, W = x.shape
+    xh = torch.empty(max(A * H * W * C * 2, 1), dtype=torch.uint8, device=x.device)
+    xl = torch.empty_like(xh)
+    _lib.check(lib.gc_to_planes(_ptr(x), A, C, H * W, _ptr(xh), _ptr(xl), _stream()), "gc_to_planes")
+    return xh, xl
+
+
+def conv_planes(planes, A, c_in, H_in, W_in, packed, bias, n_out, taps, stride=1, out_nchw=None, out_ch_off=0, up=1,
+                up_dy=0, up_dx=0):
+    """ReLU(conv(planes) + bias).  Returns the output planes (xh, xl) when out_nchw is None, else writes into out_nchw
+    [A, C_total, Ho*up, Wo*up] at channel offset out_ch_off and phase (up_dy, up_dx)."""
+    lib = _lib.load()
+    xh, xl = planes
+    Ho, Wo = ((H_in - 1) // stride + 1, (W_in - 1) // stride + 1) if taps == 9 else (H_in, W_in)
+    if out_nchw is None:
+        oh = torch.empty(max(A * Ho * Wo * n_out * 2, 1), dtype=torch.uint8, device=xh.device)
+        ol = torch.empty_like(oh)
+        _lib.check(lib.gc_conv_planes(_ptr(xh), _ptr(xl), A, c_in, H_in, W_in, stride, taps, n_out, _ptr(packed), _ptr(bias),
+                                      _ptr(oh), _ptr(ol), None, n_out, 0, 1, 0, 0, _stream()), "gc_conv_planes")
+        return (oh, ol), Ho, Wo
+    _chk(out_nchw, "out", torch.float32, 4)
+    _lib.check(lib.gc_conv_planes(_ptr(xh), _ptr(xl), A, c_in, H_in, W_in, stride, taps, n_out, _ptr(packed), _ptr(bias), None,
+                                  None, _ptr(out_nchw), out_nchw.shape[1], out_ch_off, up, up_dy, up_dx, _stream()),
+               "gc_conv_planes")
+    return None, Ho, Wo

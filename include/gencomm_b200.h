@@ -246,6 +246,23 @@ int gc_det_heads_pack(const float *w, int C, int n_out, void *packed, void *stre
 int gc_det_heads(const float *x, int n_frames, int C, int H, int W, int n_out, const void *packed, const float *bias,
                  void *workspace, float *out, void *stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * (8f rank 2) Layer primitives behind BaseBEVBackbone.forward (models/sub_modules/base_bev_backbone.py:96-124):
+ *   gc_to_planes   x [A][C][HW] f32 -> channel-last bf16 value + residual planes (2 x A*HW*C*2 bytes), C % 64 == 0
+ *   gc_conv_pack   w [n_out][c_in][taps] f32 (taps = 9: 3x3, row-major ky,kx; taps = 1: 1x1; BatchNorm already folded)
+ *   gc_conv_planes ReLU(conv(planes) + bias): 3x3 with padding 1 and stride 1|2, or 1x1; written as the next layer's
+ *                  planes (oh, ol: [A][Ho*Wo][out_ch_total] bf16, channels out_ch_off..) or as NCHW fp32 out_nchw
+ *                  [A][out_ch_total][Ho*up][Wo*up] at pixel (y*up + up_dy, x*up + up_dx) -- one phase of a
+ *                  ConvTranspose2d whose kernel equals its stride `up` (up = 1: an ordinary NCHW store).
+ *   Output H*W must be a multiple of 128; n_out <= 256.  bf16x3 tcgen05 GEMMs (fp32-grade).
+ * ------------------------------------------------------------------------------------------- */
+size_t gc_conv_packed_bytes(int taps, int c_in, int n_out);
+int gc_conv_pack(const float *w, int taps, int c_in, int n_out, void *packed, void *stream);
+int gc_to_planes(const float *x, int total_agents, int C, int HW, void *xh, void *xl, void *stream);
+int gc_conv_planes(const void *xh, const void *xl, int total_agents, int c_in, int H_in, int W_in, int stride, int taps,
+                   int n_out, const void *packed, const float *bias, void *oh, void *ol, float *out_nchw,
+                   int out_ch_total, int out_ch_off, int up, int up_dy, int up_dx, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

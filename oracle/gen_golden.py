@@ -203,6 +203,33 @@ def gen_det_tail(ns):
     print("det_tail.npz: out", tuple(out.shape))
 
 
+BACKBONE_CFG = {"layer_nums": [1, 1, 2], "layer_strides": [2, 2, 2], "num_filters": [64, 64, 128],
+                "upsample_strides": [1, 2, 4], "num_upsample_filter": [64, 64, 64]}
+
+
+def backbone_input():
+    return synth.bev_features(1501, 1, 64, 64, 128, sparsity=0.7)
+
+
+def gen_backbone(ns):
+    """BaseBEVBackbone through the reference class (eval mode, randomised BatchNorm statistics)."""
+    torch.manual_seed(19)
+    model = ns.BaseBEVBackbone(BACKBONE_CFG, 64).eval()
+    with torch.no_grad():
+        for m in model.modules():
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.running_mean.normal_(0, 0.1); m.running_var.uniform_(0.5, 1.5)
+                m.weight.add_(0.2 * torch.randn_like(m.weight)); m.bias.add_(0.1 * torch.randn_like(m.bias))
+    x = backbone_input()
+    with torch.no_grad():
+        out = model({"spatial_features": x})["spatial_features_2d"]
+    sd = {k: v.numpy() for k, v in model.state_dict().items()}
+    # the input is regenerated from its seed (backbone_input); every 4th output channel is stored to keep the fixture small
+    np.savez_compressed(os.path.join(OUT, "backbone.npz"), ref_out_c4=out[:, ::4].numpy(), x_checksum=np.float64(x.double().sum()),
+                        **{"sd/" + k: v for k, v in sd.items()})
+    print("backbone.npz: out", tuple(out.shape), "keys", len(sd))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ns = ref_import.load()
@@ -212,6 +239,7 @@ def main():
     gen_message_extractor(ns)
     gen_enhancer(ns)
     gen_det_tail(ns)
+    gen_backbone(ns)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)) // 1024, "KiB")
 

@@ -99,6 +99,7 @@ def load():
     from opencood.models.gencomm_modules.message_extractor_v2 import MessageExtractorv2
     from opencood.models.gencomm_modules.enhancer import Enhancer
     from opencood.models.sub_modules.downsample_conv import DownsampleConv
+    from opencood.models.sub_modules.base_bev_backbone import BaseBEVBackbone
     ns.PillarVFE = PillarVFE
     ns.PointPillarScatter = PointPillarScatter
     ns.warp_affine_simple = warp_affine_simple
@@ -112,4 +113,5 @@ def load():
     ns.MessageExtractorv2 = MessageExtractorv2
     ns.Enhancer = Enhancer
     ns.DownsampleConv = DownsampleConv
+    ns.BaseBEVBackbone = BaseBEVBackbone
     return ns

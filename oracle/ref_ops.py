@@ -440,3 +440,21 @@ def downsample_conv(x, sd, strides):
 
 def det_heads(x, cls_w, cls_b, reg_w, reg_b, dir_w, dir_b):
     return F.conv2d(x, cls_w, cls_b), F.conv2d(x, reg_w, reg_b), F.conv2d(x, dir_w, dir_b)
+
+
+# ---------------------------------------------------------------------------------------------
+# BaseBEVBackbone.forward (models/sub_modules/base_bev_backbone.py:96-124), eval mode: per level
+# ZeroPad2d(1) + Conv2d(3x3, stride s, no bias) + BN(eps 1e-3) + ReLU, n x [Conv2d(3x3, pad 1) + BN + ReLU];
+# deblock = ConvTranspose2d(kernel = stride = u, no bias) + BN + ReLU; the deblock outputs are concatenated.
+# ---------------------------------------------------------------------------------------------
+def bev_backbone(x, sd, layer_nums, layer_strides, upsample_strides):
+    def bn(t, prefix):
+        return F.batch_norm(t, sd[prefix + ".running_mean"], sd[prefix + ".running_var"], sd[prefix + ".weight"],
+                            sd[prefix + ".bias"], training=False, eps=1e-3)
+    ups = []
+    for i, (n, s, u) in enumerate(zip(layer_nums, layer_strides, upsample_strides)):
+        x = F.relu(bn(F.conv2d(F.pad(x, (1, 1, 1, 1)), sd[f"blocks.{i}.1.weight"], None, stride=s), f"blocks.{i}.2"))
+        for k in range(n):
+            x = F.relu(bn(F.conv2d(x, sd[f"blocks.{i}.{4 + 3 * k}.weight"], None, padding=1), f"blocks.{i}.{5 + 3 * k}"))
+        ups.append(F.relu(bn(F.conv_transpose2d(x, sd[f"deblocks.{i}.0.weight"], None, stride=u), f"deblocks.{i}.1")))
+    return torch.cat(ups, dim=1)

@@ -67,3 +67,18 @@ def golden_enhancer():
 @pytest.fixture(scope="session")
 def golden_det_tail():
     return load_golden("det_tail.npz")
+
+
+@pytest.fixture(scope="session")
+def golden_backbone():
+    return load_golden("backbone.npz")
+
+
+BACKBONE_CFG = {"layer_nums": [1, 1, 2], "layer_strides": [2, 2, 2], "num_filters": [64, 64, 128],
+                "upsample_strides": [1, 2, 4], "num_upsample_filter": [64, 64, 64]}
+
+
+def backbone_input():
+    """The input of tests/golden/backbone.npz (oracle/gen_golden.py::backbone_input), regenerated from its seed."""
+    from gencomm_b200 import synth
+    return synth.bev_features(1501, 1, 64, 64, 128, sparsity=0.7)

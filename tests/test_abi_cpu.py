@@ -99,3 +99,13 @@ def test_downsample_conv_keeps_reference_state_dict_keys(golden_det_tail):
                                                        "reg_head.bias", "dir_head.weight", "dir_head.bias"}
     with pytest.raises(NotImplementedError):
         DownsampleConv({"kernal_size": [5], "stride": [1], "padding": [2], "dim": [64], "input_dim": 64})
+
+
+def test_bev_backbone_keeps_reference_state_dict_keys(golden_backbone):
+    from conftest import BACKBONE_CFG
+    from gencomm_b200 import BaseBEVBackbone
+    m = BaseBEVBackbone(BACKBONE_CFG, 64)
+    assert set(m.state_dict()) == {k[3:] for k in golden_backbone if k.startswith("sd/")}
+    assert m.num_bev_features == 192
+    with pytest.raises(NotImplementedError):
+        BaseBEVBackbone({**BACKBONE_CFG, "upsample_strides": [1, 2, 0.5]}, 64)

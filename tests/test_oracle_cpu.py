@@ -145,3 +145,13 @@ def test_downsample_conv_restatement_matches_reference(golden_det_tail):
     heads = R.det_heads(out, *[T(g[f"head{i}/{k}"]) for i in range(3) for k in ("weight", "bias")])
     for i, h in enumerate(heads):
         assert torch.allclose(h, T(g[f"head{i}/out"]), rtol=0, atol=1e-6)
+
+
+def test_bev_backbone_restatement_matches_reference(golden_backbone):
+    from conftest import BACKBONE_CFG, backbone_input
+    g = golden_backbone
+    x = backbone_input()
+    assert abs(float(x.double().sum()) - float(g["x_checksum"])) < 1e-6
+    sd = {k[3:]: T(v) for k, v in g.items() if k.startswith("sd/")}
+    out = R.bev_backbone(x, sd, BACKBONE_CFG["layer_nums"], BACKBONE_CFG["layer_strides"], BACKBONE_CFG["upsample_strides"])
+    assert torch.allclose(out[:, ::4], T(g["ref_out_c4"]), rtol=0, atol=1e-6)
