@@ -454,7 +454,7 @@ def run_ours(args):
                        "points_per_agent": POINTS, "grid": [pipe.nx, pipe.ny], "fusion": FUSION,
                        "l2": f"{n_sets} distinct input sets cycled; per-step canvas traffic "
                              f"{pipe.scatter_bytes() / 1e6:.0f} MB >> 126 MB L2 (inputs larger than L2)",
-                       "not_in_step": "cuDNN backbone/shrink/heads (out of scope, SURVEY 2.1)"},
+                       "not_in_step": "backbone/shrink/heads (SURVEY 8f rank 2; built, measured separately: scripts/bench_backbone.py, bench_det_tail.py)"},
             "clocks": clocks,
             "e2e": {"value": frames / (e2e_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / K,
