@@ -17,4 +17,31 @@ from .enhancer import Enhancer  # noqa: F401
 from .det_tail import DetectionHeads, DoubleConv, DownsampleConv  # noqa: F401
 from .backbone import BaseBEVBackbone  # noqa: F401
 
+from .heter_model_baseline_w_gencomm_stage1 import HeterModelBaselineWGenComm  # noqa: F401
+from .heter_model_baseline_w_gencomm_stage2 import HeterModelBaselineWDiffCommStage2  # noqa: F401
+
+
+def create_model(hypes):
+    """``train_utils.create_model`` (tools/train_utils.py:255-288) over this package: resolves
+    ``gencomm_b200.<core_method>`` and the class whose lower-cased name is ``core_method`` without underscores."""
+    import importlib
+    name = hypes['model']['core_method']
+    try:
+        lib = importlib.import_module(f"{__name__}.{name}")
+    except ModuleNotFoundError as e:
+        raise NotImplementedError(f"gencomm_b200 has no model {name!r} (GenComm stage 1 / stage 2 detectors only)") from e
+    target = name.replace('_', '').lower()
+    for attr, cls in lib.__dict__.items():
+        if attr.lower() == target:
+            return cls(hypes['model']['args'])
+    # Reference quirk: the shipped yamls name the FILE (heter_model_baseline_w_gencomm_stage1 / _stage2) while the classes
+    # are called HeterModelBaselineWGenComm / HeterModelBaselineWDiffCommStage2, which the name rule above cannot match.
+    # Fall back to the one model class the module itself defines.
+    own = [c for c in lib.__dict__.values() if isinstance(c, type) and c.__module__ == lib.__name__
+           and not c.__name__.startswith('_')]
+    if len(own) == 1:
+        return own[0](hypes['model']['args'])
+    raise NotImplementedError(f"no class matching {target!r} in {lib.__name__}")
+
+
 __version__ = "0.1.0"

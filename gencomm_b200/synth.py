@@ -110,3 +110,73 @@ def pfn_weights(seed=0):
         "bn_mean": torch.randn(64, generator=g) * 0.1,
         "bn_var": torch.rand(64, generator=g) + 0.5,
     }
+
+
+def fill_state_dict(state_dict, seed=0):
+    """Deterministic, architecture-independent weights for a whole model: every tensor is drawn from a generator seeded
+    by (seed, crc32(key)), so the reference model (golden generation) and the drop-in model (tests) get bit-identical
+    parameters from their shared ``state_dict`` keys without a multi-MB weight fixture.  Convolution / linear weights
+    are scaled to keep activations O(1) through the ReLU stacks; normalisation statistics are non-trivial."""
+    import zlib
+    out = {}
+    for key, ref in state_dict.items():
+        g = torch.Generator().manual_seed((int(seed) * 1_000_003 + zlib.crc32(key.encode())) & 0x7FFFFFFF)
+        shape, leaf = tuple(ref.shape), key.rsplit(".", 1)[-1]
+        if not ref.dtype.is_floating_point:
+            out[key] = ref.clone()                                        # num_batches_tracked, integer buffers
+        elif leaf == "running_var":
+            out[key] = torch.rand(shape, generator=g) + 0.5
+        elif leaf == "running_mean":
+            out[key] = 0.1 * torch.randn(shape, generator=g)
+        elif ref.dim() >= 2:
+            fan_in = ref[0].numel()
+            if "deblocks" in key:                                         # ConvTranspose2d [c_in, c_out, k, k]: one tap per output
+                fan_in = ref.shape[0]
+            gain = 2.0 if any(s in key for s in ("backbone_", "shrinker_", "shrink_conv")) else 1.0
+            if "offset" in key:
+                gain = 0.05                                               # deformable offsets stay within a few cells
+            out[key] = torch.randn(shape, generator=g) * (gain / max(fan_in, 1)) ** 0.5
+        elif leaf == "weight":
+            out[key] = 1.0 + 0.2 * torch.randn(shape, generator=g)        # norm scales
+        elif leaf == "bias":
+            out[key] = 0.1 * torch.randn(shape, generator=g)
+        else:                                                             # schedule buffers and other constants stay
+            out[key] = ref.clone()
+        out[key] = out[key].to(ref.dtype)
+    return out
+
+
+def gencomm_stage1_args(fusion="att"):
+    """``model.args`` of hypes_yaml/opv2v/GenComm_yamls/gencomm/stage1/m1_att.yaml:93-170 (LiDAR PointPillars agents,
+    OPV2V-H range, C=128 at 64x128) as a fresh dict (the constructors write ``grid_size`` into it)."""
+    rng = list(OPV2V_H_RANGE)
+    return {
+        "ego_modality": "m1", "lidar_range": rng,
+        "m1": {"core_method": "point_pillar", "sensor_type": "lidar",
+               "encoder_args": {"voxel_size": [0.4, 0.4, 4], "lidar_range": rng,
+                                "pillar_vfe": {"use_norm": True, "with_distance": False, "use_absolute_xyz": True,
+                                               "num_filters": [64]},
+                                "point_pillar_scatter": {"num_features": 64}},
+               "backbone_args": {"layer_nums": [3, 5, 8], "layer_strides": [2, 2, 2], "num_filters": [64, 128, 256],
+                                 "upsample_strides": [1, 2, 4], "num_upsample_filter": [128, 128, 128]},
+               "aligner_args": {"core_method": "identity"},
+               "shrink_header": {"kernal_size": [3], "stride": [2], "padding": [1], "dim": [128], "input_dim": 384}},
+        "enhancer": {"in_ch": 128}, "message_extractor": {"in_ch": 128, "out_ch": 2},
+        "fusion_method": fusion, "att": {"feat_dim": 128}, "in_head": 128, "anchor_number": 2,
+        "dir_args": {"dir_offset": 0.7853, "num_bins": 2, "anchor_yaw": [0, 90]}, "gmatch": True,
+        "gencomm": {"model": {"embed_dim": 130, "in_channels": 128, "out_ch": 128, "ch": 8, "ch_mult": [1, 1],
+                              "num_res_blocks": 2, "attn_resolutions": [16], "dropout": 0.0, "resamp_with_conv": True},
+                    "diffusion": {"beta_schedule": "linear", "beta_start": 0.0005, "beta_end": 0.02,
+                                  "num_diffusion_timesteps": 3}},
+    }
+
+
+def heter_frames(seed, record_len, n_points=30_000, max_cav=5):
+    """Host inputs of a batch of collaborative frames for the full detector: per-agent clouds (list of [P,4] f32) and
+    ``pairwise_t_matrix`` [B,L,L,4,4] f64; agents stay within ~40 m so their canvases overlap after the warp."""
+    clouds, pws = [], []
+    for f, n in enumerate(record_len):
+        for a in range(int(n)):
+            clouds.append(lidar_points(seed + f, a, n_points))
+        pws.append(pairwise_t_matrix(seed + f, int(n), max_cav, spread=(40.0, 15.0)))
+    return clouds, np.stack(pws)

@@ -230,6 +230,54 @@ def gen_backbone(ns):
     print("backbone.npz: out", tuple(out.shape), "keys", len(sd))
 
 
+HETER_RECORD_LEN = [2, 1]
+HETER_SEED, HETER_POINTS, HETER_WSEED = 4100, 30_000, 11
+
+
+def heter_inputs():
+    """Inputs of tests/golden/heter_model.npz, regenerated from seeds (also used by the tests)."""
+    clouds, pairwise = synth.heter_frames(HETER_SEED, HETER_RECORD_LEN, HETER_POINTS)
+    voxels = ref_ops.collate_voxels([ref_ops.voxelize(c, synth.OPV2V_H_RANGE, [0.4, 0.4, 4.0]) for c in clouds])
+    n = len(clouds)
+    noise0, steps = synth.sampler_noise(HETER_SEED, n, 128, 64, 128, T=3)
+    return voxels, torch.from_numpy(pairwise), torch.tensor(HETER_RECORD_LEN, dtype=torch.int64), noise0, steps
+
+
+def gen_heter_model(ns):
+    """The UNMODIFIED HeterModelBaselineWGenComm (stage-1 detector, m1_att.yaml model args) on two frames (2 + 1 agents)
+    of the full OPV2V-H grid.  Weights: synth.fill_state_dict (regenerated in the tests from the shared state_dict
+    keys, so the key list itself is pinned); sampler noise injected in the reference's draw order."""
+    import opencood.models.gencomm_modules.cond_diff as cd
+    from opencood.models.heter_model_baseline_w_gencomm_stage1 import HeterModelBaselineWGenComm
+    args = synth.gencomm_stage1_args("att")
+    model = HeterModelBaselineWGenComm(args).eval()
+    model.load_state_dict(synth.fill_state_dict(model.state_dict(), HETER_WSEED))
+    voxels, pairwise, record_len, n0, steps = heter_inputs()
+    data = {"inputs_m1": voxels, "agent_modality_list": ["m1"] * int(record_len.sum()), "pairwise_t_matrix": pairwise,
+            "record_len": record_len}
+    C, H, W = 128, 64, 128
+    queue = [n0, torch.zeros(1, C, H, W), torch.zeros(1, C, H, W)]
+    step_queue = list(steps)
+    orig_randn_like, orig_noise_like = torch.randn_like, cd.noise_like
+    torch.randn_like = lambda t, *a, **k: queue.pop(0).to(t)
+    cd.noise_like = lambda shape, device, repeat=False: step_queue.pop(0)
+    try:
+        with torch.no_grad():
+            out = model(data)
+    finally:
+        torch.randn_like, cd.noise_like = orig_randn_like, orig_noise_like
+    assert not queue and not step_queue
+    keys = sorted(model.state_dict().keys())
+    np.savez_compressed(os.path.join(OUT, "heter_model.npz"), state_dict_keys=np.array(keys),
+                        n_pillars=np.int64(voxels["voxel_coords"].shape[0]),
+                        cls_preds=out["cls_preds"].numpy(), reg_preds=out["reg_preds"].numpy(),
+                        dir_preds=out["dir_preds"].numpy(), message=out["message"].numpy(),
+                        gt_feature_c8=out["gt_feature"][:, ::8].numpy(), pred_feature_c8=out["pred_feature"][:, ::8].numpy())
+    print("heter_model.npz: cls", tuple(out["cls_preds"].shape), "pillars", voxels["voxel_coords"].shape[0],
+          "|cls| max", float(out["cls_preds"].abs().max()), "|gt| max", float(out["gt_feature"].abs().max()),
+          "|pred| max", float(out["pred_feature"].abs().max()))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ns = ref_import.load()
@@ -240,6 +288,7 @@ def main():
     gen_enhancer(ns)
     gen_det_tail(ns)
     gen_backbone(ns)
+    gen_heter_model(ns)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)) // 1024, "KiB")
 

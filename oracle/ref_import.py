@@ -15,6 +15,9 @@ image and irrelevant to the hot path.  They are replaced 
 * ``pyquaternion.Quaternion``          (transformation_utils.py:13)
 * ``shapely.geometry.Polygon``         (utils/common_utils.py:12)
 * ``timm.models.layers``               (cond_diff.py:20, DropPath & friends; unused on the eval path)
+* ``efficientnet_pytorch.EfficientNet`` (lss_submodule.py:7, camera encoder; only needed to import heter_encoders.py
+  for the full-detector golden, the LiDAR path never touches it); ``termcolor`` and ``spconv`` (sparse-conv classes
+  of the SECOND encoder, sparse_backbone_3d.py:2-9) are stubbed for the same import and never called
 """
 import os
 import sys
@@ -58,7 +61,7 @@ def install_stubs():
     _stub("matplotlib.cm")
     _stub("matplotlib.colors")
     _stub("pyquaternion", Quaternion=_Anything)
-    geo = _stub("shapely.geometry", Polygon=_Anything)
+    geo = _stub("shapely.geometry", Polygon=_Anything, Point=_Anything, MultiPoint=_Anything)
     _stub("shapely", geometry=geo)
 
     class DropPath(nn.Module):  # identity at eval; never instantiated by GenComm's eval path
@@ -79,6 +82,10 @@ def install_stubs():
                    PatchEmbed=_Anything, to_ntuple=lambda n: to_2tuple)
     models = _stub("timm.models", layers=layers)
     _stub("timm", models=models)
+    _stub("termcolor", colored=lambda s, *a, **k: s)       # sparse_backbone_3d.py:2 (SECOND encoder, unused here)
+    _stub("spconv", **{n: _Anything for n in ("SparseSequential", "SubMConv3d", "SparseConv3d", "SparseInverseConv3d",
+                                              "SparseConvTensor")})   # sparse_backbone_3d.py:3-9, import-time only
+    _stub("efficientnet_pytorch", EfficientNet=_Anything)   # camera encoder import of heter_encoders.py (lss_submodule.py:7)
 
 
 def load():

@@ -458,3 +458,44 @@ def bev_backbone(x, sd, layer_nums, layer_strides, upsample_strides):
             x = F.relu(bn(F.conv2d(x, sd[f"blocks.{i}.{4 + 3 * k}.weight"], None, padding=1), f"blocks.{i}.{5 + 3 * k}"))
         ups.append(F.relu(bn(F.conv_transpose2d(x, sd[f"deblocks.{i}.0.weight"], None, stride=u), f"deblocks.{i}.1")))
     return torch.cat(ups, dim=1)
+
+
+# ---------------------------------------------------------------------------------------------
+# HeterModelBaselineWGenComm.forward (models/heter_model_baseline_w_gencomm_stage1.py:174-297), eval mode, one LiDAR
+# point_pillar modality, att / max fusion: the composition of the restatements above, in the reference's order.
+# ---------------------------------------------------------------------------------------------
+def heter_gencomm_forward(sd, args, voxels, pairwise_t_matrix, record_len, noise0, step_noises, modality="m1",
+                          mask_generated=False):
+    """sd: the full model's state_dict; args: its ``model.args``; voxels: the collated ``inputs_m1`` dict.
+    Returns cls_preds / reg_preds / dir_preds / gt_feature / pred_feature / message like the reference."""
+    sub = lambda prefix: {k[len(prefix):]: v for k, v in sd.items() if k.startswith(prefix)}
+    setting = args[modality]
+    enc, rng = setting["encoder_args"], args["lidar_range"]
+    H, W = rng[4] - rng[1], rng[3] - rng[0]                                                      # :94-95
+    affine = normalize_pairwise_tfm(pairwise_t_matrix, H, W, 1)                                 # :177
+    p = sub(f"encoder_{modality}.pillar_vfe.pfn_layers.0.")                                     # heter_encoders.py:39-51
+    pf = pillar_vfe(voxels["voxel_features"], voxels["voxel_num_points"], voxels["voxel_coords"], p["linear.weight"],
+                    p["norm.weight"], p["norm.bias"], p["norm.running_mean"], p["norm.running_var"],
+                    enc["voxel_size"], enc["lidar_range"])
+    g = grid_size(enc["lidar_range"], enc["voxel_size"])
+    n_agents = int(sum(int(n) for n in record_len))
+    feature = scatter(pf, voxels["voxel_coords"], int(g[0]), int(g[1]), n_agents)
+    b = setting["backbone_args"]
+    feature = bev_backbone(feature, sub(f"backbone_{modality}."), b["layer_nums"], b["layer_strides"],
+                           b["upsample_strides"])                                               # :192
+    feature = downsample_conv(feature, sub(f"shrinker_{modality}."), setting["shrink_header"]["stride"])  # :193
+    message = message_extractor_v2(feature, sub(f"message_extractor_{modality}."))[0]           # :194
+    T = args["gencomm"]["diffusion"]["num_diffusion_timesteps"]
+    pred = gencomm_sample(feature, message, record_len, sub("gencomm.denoiser."), noise0, step_noises, T)  # :258
+    x = pred
+    if mask_generated:   # stage 2 'trick' (heter_model_baseline_w_gencomm_stage2.py:284-285,293-294)
+        x = pred * torch.any(feature, dim=1).to(torch.uint8).unsqueeze(1)
+    x = enhancer(x, sub("enhancer.")) if "enhancer" in args else x                              # :278-279
+    fuse = att_fusion if args["fusion_method"] == "att" else max_fusion
+    fused = fuse(x, record_len, affine)                                                         # :281
+    if "shrink_header" in args:
+        fused = downsample_conv(fused, sub("shrink_conv."), args["shrink_header"]["stride"])    # :283-284
+    cls, reg, dr = det_heads(fused, sd["cls_head.weight"], sd["cls_head.bias"], sd["reg_head.weight"],
+                             sd["reg_head.bias"], sd["dir_head.weight"], sd["dir_head.bias"])   # :287-289
+    return {"cls_preds": cls, "reg_preds": reg, "dir_preds": dr, "gt_feature": feature, "pred_feature": pred,
+            "message": message}

@@ -82,3 +82,15 @@ def backbone_input():
     """The input of tests/golden/backbone.npz (oracle/gen_golden.py::backbone_input), regenerated from its seed."""
     from gencomm_b200 import synth
     return synth.bev_features(1501, 1, 64, 64, 128, sparsity=0.7)
+
+
+@pytest.fixture(scope="session")
+def golden_heter_model():
+    return load_golden("heter_model.npz")
+
+
+@pytest.fixture(scope="session")
+def heter_inputs():
+    """(voxels, pairwise, record_len, noise0, step_noises) of tests/golden/heter_model.npz, regenerated from seeds."""
+    from oracle import gen_golden
+    return gen_golden.heter_inputs()

@@ -155,3 +155,49 @@ def test_bev_backbone_restatement_matches_reference(golden_backbone):
     sd = {k[3:]: T(v) for k, v in g.items() if k.startswith("sd/")}
     out = R.bev_backbone(x, sd, BACKBONE_CFG["layer_nums"], BACKBONE_CFG["layer_strides"], BACKBONE_CFG["upsample_strides"])
     assert torch.allclose(out[:, ::4], T(g["ref_out_c4"]), rtol=0, atol=1e-6)
+
+
+def test_heter_model_restatement_matches_reference(golden_heter_model, heter_inputs):
+    """The composed oracle (voxels -> ... -> heads) against the UNMODIFIED HeterModelBaselineWGenComm on the full
+    OPV2V-H grid (2 + 1 agents); the weights are regenerated from the reference's own state_dict key list."""
+    from gencomm_b200 import HeterModelBaselineWGenComm, synth
+    from oracle import gen_golden
+    g = golden_heter_model
+    model = HeterModelBaselineWGenComm(synth.gencomm_stage1_args("att"))
+    assert sorted(model.state_dict().keys()) == list(g["state_dict_keys"])      # a reference checkpoint loads as is
+    sd = synth.fill_state_dict(model.state_dict(), gen_golden.HETER_WSEED)
+    voxels, pairwise, record_len, n0, steps = heter_inputs
+    assert voxels["voxel_coords"].shape[0] == int(g["n_pillars"])
+    out = R.heter_gencomm_forward(sd, synth.gencomm_stage1_args("att"), voxels, pairwise, record_len, n0, steps)
+    for k in ("cls_preds", "reg_preds", "dir_preds", "message"):
+        ref = T(g[k])
+        assert float((out[k] - ref).abs().max()) <= 1e-5 * float(ref.abs().max()), k
+    for k in ("gt_feature", "pred_feature"):
+        ref = T(g[k + "_c8"])
+        assert float((out[k][:, ::8] - ref).abs().max()) <= 1e-5 * float(ref.abs().max()), k
+
+
+def test_create_model_resolves_the_gencomm_detectors():
+    """train_utils.create_model (tools/train_utils.py:255-288) over gencomm_b200, incl. the yaml / class-name quirk."""
+    import pytest
+    import gencomm_b200 as G
+    from gencomm_b200 import synth
+    m1 = G.create_model({"model": {"core_method": "heter_model_baseline_w_gencomm_stage1",
+                                   "args": synth.gencomm_stage1_args("max")}})
+    assert type(m1).__name__ == "HeterModelBaselineWGenComm" and isinstance(m1.fusion_net, G.MaxFusion)
+    a2 = synth.gencomm_stage1_args("att")
+    a2["diffcomm"] = a2.pop("gencomm")
+    a2["trick"] = True
+    m2 = G.create_model({"model": {"core_method": "heter_model_baseline_w_gencomm_stage2", "args": a2}})
+    assert type(m2).__name__ == "HeterModelBaselineWDiffCommStage2" and m2.trick
+    assert set(m2.state_dict().keys()) == set(m1.state_dict().keys())
+    with pytest.raises(NotImplementedError):
+        G.create_model({"model": {"core_method": "point_pillar_v2vnet", "args": {}}})
+    cam = synth.gencomm_stage1_args("att")
+    cam["m2"] = dict(cam["m1"], sensor_type="camera", core_method="lift_splat_shoot")
+    with pytest.raises(NotImplementedError, match="LiDAR"):
+        G.HeterModelBaselineWGenComm(cam)
+    bad = synth.gencomm_stage1_args("att")
+    bad["fusion_method"] = "v2xvit"
+    with pytest.raises(NotImplementedError, match="fusion_method"):
+        G.HeterModelBaselineWGenComm(bad)
