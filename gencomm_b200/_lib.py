@@ -23,6 +23,13 @@ class VoxelGeom(ctypes.Structure):
                 ("max_voxels", ctypes.c_int32)]
 
 
+class PostParams(ctypes.Structure):
+    """gcPostParams"""
+    _fields_ = [("score_threshold", ctypes.c_float), ("nms_thresh", ctypes.c_float), ("dir_offset", ctypes.c_float),
+                ("num_bins", ctypes.c_int32), ("order_hwl", ctypes.c_int32), ("top", ctypes.c_int32),
+                ("gt_range", ctypes.c_double * 6)]
+
+
 _F3 = ctypes.c_float * 3
 _GEOM_P = ctypes.POINTER(VoxelGeom)
 
@@ -76,6 +83,9 @@ SIGNATURES = {
     "gc_to_planes": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "gc_conv_planes": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                                c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "gc_postprocess_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "gc_postprocess": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                               ctypes.POINTER(PostParams), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
 }
 
 _lib = None

@@ -508,3 +508,47 @@ def conv_planes(planes, A, c_in, H_in, W_in, packed, bias, n_out, taps, stride=1
                                   None, _ptr(out_nchw), out_nchw.shape[1], out_ch_off, up, up_dy, up_dx, _stream()),
                "gc_conv_planes")
     return None, Ho, Wo
+
+
+# --------------------------------------------------------------------------------------------
+# (8f rank 3) decode + rotated NMS
+# --------------------------------------------------------------------------------------------
+def make_post_params(score_threshold, nms_thresh, dir_offset, num_bins, order, gt_range, top=1000):
+    if order not in ("hwl", "lhw"):
+        raise ValueError(f"unknown bbx order {order!r}")        # the reference sys.exit()s (voxel_postprocessor.py:119)
+    p = _lib.PostParams()
+    p.score_threshold, p.nms_thresh, p.dir_offset = float(score_threshold), float(nms_thresh), float(dir_offset)
+    p.num_bins, p.order_hwl, p.top = int(num_bins), int(order == "hwl"), int(top)
+    for j in range(6):
+        p.gt_range[j] = float(gt_range[j])
+    return p
+
+
+def postprocess(cls_preds, reg_preds, dir_preds, anchors, params, tfm=None, workspace=None):
+    """cls [B,A,H,W], reg [B,7A,H,W], dir [B,A*bins,H,W] | None, anchors [H,W,A,7] f32, tfm [B,4,4] f32 | None ->
+    (boxes [B,top,8,3], scores [B,top], counts [B] i32); rows >= counts[b] are unspecified.  Asynchronous."""
+    lib = _lib.load()
+    _chk(cls_preds, "cls_preds", torch.float32, 4)
+    _chk(reg_preds, "reg_preds", torch.float32, 4)
+    _chk(anchors, "anchors", torch.float32, 4)
+    B, A, H, W = cls_preds.shape
+    if tuple(reg_preds.shape) != (B, 7 * A, H, W) or tuple(anchors.shape) != (H, W, A, 7):
+        raise ValueError("postprocess: reg_preds must be [B,7A,H,W] and anchors [H,W,A,7]")
+    if dir_preds is not None:
+        _chk(dir_preds, "dir_preds", torch.float32, 4)
+        if tuple(dir_preds.shape) != (B, A * params.num_bins, H, W):
+            raise ValueError("postprocess: dir_preds must be [B,A*num_bins,H,W]")
+    if tfm is not None:
+        _chk(tfm, "transformation_matrix", torch.float32, 3)
+        if tuple(tfm.shape) != (B, 4, 4):
+            raise ValueError("postprocess: transformation_matrix must be [B,4,4]")
+    dev = cls_preds.device
+    if workspace is None:
+        workspace = torch.empty(max(lib.gc_postprocess_workspace_bytes(B, A * H * W), 1), dtype=torch.uint8, device=dev)
+    boxes = torch.empty(B, params.top, 8, 3, dtype=torch.float32, device=dev)
+    scores = torch.empty(B, params.top, dtype=torch.float32, device=dev)
+    counts = torch.empty(B, dtype=torch.int32, device=dev)
+    _lib.check(lib.gc_postprocess(_ptr(cls_preds), _ptr(reg_preds), _ptr(dir_preds) if dir_preds is not None else None,
+                                  _ptr(anchors), _ptr(tfm) if tfm is not None else None, B, A, H, W, ctypes.byref(params),
+                                  _ptr(workspace), _ptr(boxes), _ptr(scores), _ptr(counts), _stream()), "gc_postprocess")
+    return boxes, scores, counts

@@ -180,3 +180,24 @@ def heter_frames(seed, record_len, n_points=30_000, max_cav=5):
             clouds.append(lidar_points(seed + f, a, n_points))
         pws.append(pairwise_t_matrix(seed + f, int(n), max_cav, spread=(40.0, 15.0)))
     return clouds, np.stack(pws)
+
+
+def postprocess_params(score_threshold=0.2, nms_thresh=0.15):
+    """``postprocess`` block of m1_att.yaml:66-89 with the fields yaml_utils.load_point_pillar_params adds (:71-80)."""
+    rng = list(OPV2V_H_RANGE)
+    return {"core_method": "VoxelPostprocessor", "gt_range": rng, "order": "hwl", "max_num": 150, "nms_thresh": nms_thresh,
+            "anchor_args": {"cav_lidar_range": rng, "l": 3.9, "w": 1.6, "h": 1.56, "r": [0, 90], "feature_stride": 4,
+                            "num": 2, "vw": 0.4, "vh": 0.4, "W": 512, "H": 256},
+            "target_args": {"pos_threshold": 0.6, "neg_threshold": 0.45, "score_threshold": score_threshold},
+            "dir_args": {"dir_offset": 0.7853, "num_bins": 2, "anchor_yaw": [0, 90]}}
+
+
+def head_outputs(seed, H=64, W=128, A=2, bins=2, bias=-3.0, smooth=5):
+    """Synthetic detector head maps of one frame: cls [1,A,H,W] (spatially smooth so that positives cluster and the NMS
+    has overlapping boxes to suppress; ``bias`` sets the candidate count), reg [1,7A,H,W], dir [1,A*bins,H,W]."""
+    g = torch.Generator().manual_seed(int(seed))
+    raw = torch.randn(1, A, H + smooth - 1, W + smooth - 1, generator=g)
+    cls = torch.nn.functional.avg_pool2d(raw, smooth, stride=1) * (1.2 * smooth) + bias
+    reg = 0.3 * torch.randn(1, 7 * A, H, W, generator=g)
+    dr = torch.randn(1, A * bins, H, W, generator=g)
+    return cls.contiguous(), reg, dr

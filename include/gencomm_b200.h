@@ -263,6 +263,31 @@ int gc_conv_planes(const void *xh, const void *xl, int total_agents, int c_in, i
                    int n_out, const void *packed, const float *bias, void *oh, void *ol, float *out_nchw,
                    int out_ch_total, int out_ch_off, int up, int up_dy, int up_dx, void *stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * (8f rank 3) VoxelPostprocessor.post_process (data_utils/post_processor/voxel_postprocessor.py:1084-1244) for the
+ * ego output of an intermediate-fusion model, batched over frames: sigmoid + score threshold, delta_to_boxes3d
+ * (:1351-1396), direction-classifier fix (:1156-1172), boxes_to_corners_3d + project_box3d (utils/box_utils.py:152-203,
+ * :278-316), remove_large_pred_bbx / remove_bbx_abnormal_z (:1062-1112), nms_rotated (:915-960; polygon IoU of
+ * utils/common_utils.py:230-252 as float64 convex clipping), mask_boxes_outside_range_numpy (:384-421).
+ *   cls [B][A][H][W], reg [B][7A][H][W], dir [B][A*num_bins][H][W] (or NULL), anchors [H][W][A][7] f32
+ *   (generate_anchor_box, :68-121), tfm [B][4][4] f32 row-major (cav -> ego, NULL = identity).
+ *   -> boxes [B][top][8][3] f32, scores [B][top] f32 in NMS pick order (highest score first), counts [B] i32.
+ *   Score ties are broken larger-anchor-index first.  No host synchronisation.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct gcPostParams {
+    float score_threshold; /* target_args.score_threshold */
+    float nms_thresh;      /* nms_thresh */
+    float dir_offset;      /* dir_args.dir_offset */
+    int32_t num_bins;      /* dir_args.num_bins */
+    int32_t order_hwl;     /* order == 'hwl' (PointPillars) : 1, 'lhw' : 0 */
+    int32_t top;           /* candidates entering the NMS (the reference uses 1000; <= 1024) */
+    double gt_range[6];    /* gt_range: xmin, ymin, zmin, xmax, ymax, zmax */
+} gcPostParams;
+size_t gc_postprocess_workspace_bytes(int n_frames, int n_anchors /* A*H*W */);
+int gc_postprocess(const float *cls, const float *reg, const float *dir, const float *anchors, const float *tfm, int n_frames,
+                   int A, int H, int W, const gcPostParams *params, void *workspace, float *boxes, float *scores, int *counts,
+                   void *stream);
+
 #ifdef __cplusplus
 }
 #endif

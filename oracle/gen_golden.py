@@ -278,6 +278,36 @@ def gen_heter_model(ns):
           "|pred| max", float(out["pred_feature"].abs().max()))
 
 
+POSTPROCESS_CASES = {"mid": (1, -3.0, False), "cap": (2, -1.0, False), "few": (4, -4.5, True), "none": (3, -9.0, False)}
+
+
+def postprocess_transform(moved):
+    """ego -> ego is the identity (intermediate fusion); ``moved`` exercises project_box3d with a rigid transform."""
+    return torch.from_numpy(synth.pose_matrix(1.5, -0.75, 3.0)).float() if moved else torch.eye(4)
+
+
+def gen_postprocess(ns):
+    """The UNMODIFIED VoxelPostprocessor.generate_anchor_box / post_process (decode, direction fix, corners, projection,
+    size / z filters, rotated NMS, range mask) on synthetic head maps.  The polygon area inside nms_rotated comes from
+    the convex-clipping stand-in for shapely (oracle/ref_import.py::_ConvexPolygon): everything else is reference code."""
+    from opencood.data_utils.post_processor.voxel_postprocessor import VoxelPostprocessor
+    params = synth.postprocess_params()
+    pp = VoxelPostprocessor(params, train=False)
+    anchors = pp.generate_anchor_box()
+    out = {"anchors": anchors}
+    for name, (seed, bias, moved) in POSTPROCESS_CASES.items():
+        cls, reg, dr = synth.head_outputs(seed, bias=bias)
+        data = {"ego": {"transformation_matrix": postprocess_transform(moved), "anchor_box": torch.from_numpy(anchors)}}
+        res = {"ego": {"cls_preds": cls.clone(), "reg_preds": reg.clone(), "dir_preds": dr.clone()}}
+        boxes, scores = pp.post_process(data, res)
+        n = 0 if boxes is None else boxes.shape[0]
+        out[f"{name}/count"] = np.int64(n)
+        out[f"{name}/boxes"] = np.zeros((0, 8, 3), np.float32) if boxes is None else boxes.numpy()
+        out[f"{name}/scores"] = np.zeros((0,), np.float32) if boxes is None else scores.numpy()
+        print("postprocess", name, "candidates", int((torch.sigmoid(cls) > 0.2).sum()), "kept", n)
+    np.savez_compressed(os.path.join(OUT, "postprocess.npz"), **out)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ns = ref_import.load()
@@ -289,6 +319,7 @@ def main():
     gen_det_tail(ns)
     gen_backbone(ns)
     gen_heter_model(ns)
+    gen_postprocess(ns)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)) // 1024, "KiB")
 

@@ -13,7 +13,10 @@ image and irrelevant to the hot path.  They are replaced 
 * ``icecream.ic``                      (debug print; torch_transformation_utils.py:11)
 * ``matplotlib`` / ``matplotlib.pyplot`` (plotting;    torch_transformation_utils.py:10)
 * ``pyquaternion.Quaternion``          (transformation_utils.py:13)
-* ``shapely.geometry.Polygon``         (utils/common_utils.py:12)
+* ``shapely.geometry.Polygon``         (utils/common_utils.py:12; a functional convex-quad stand-in, see _ConvexPolygon,
+  so that the reference's own post_process / nms_rotated can run for the decode + NMS golden)
+* ``opencood.utils.box_overlaps`` (Cython extension, label generation only) and ``opencood.visualization.vis_utils``
+  (open3d / matplotlib) -- imported by voxel_postprocessor.py:20-21, never called by post_process
 * ``timm.models.layers``               (cond_diff.py:20, DropPath & friends; unused on the eval path)
 * ``efficientnet_pytorch.EfficientNet`` (lss_submodule.py:7, camera encoder; only needed to import heter_encoders.py
   for the full-detector golden, the LiDAR path never touches it); ``termcolor`` and ``spconv`` (sparse-conv classes
@@ -50,6 +53,30 @@ class _Anything:
         return _Anything()
 
 
+class _ConvexPolygon:
+    """Functional stand-in for ``shapely.geometry.Polygon`` restricted to what ``box_utils.nms_rotated`` uses
+    (``common_utils.convert_format`` / ``compute_iou``: ``a.intersection(b).area``, ``a.union(b).area``) on convex quads.
+    shapely (GEOS) is absent from this image, so the reference's NMS runs on the oracle's own polygon clipping
+    (oracle/ref_ops.py::convex_intersection_area): everything in post_process EXCEPT the polygon area is reference code."""
+
+    def __init__(self, pts=None, area=None):
+        import numpy as np
+        self.pts = None if pts is None else np.asarray([(float(x), float(y)) for x, y in pts], dtype=np.float64)
+        self._area = area
+
+    @property
+    def area(self):
+        from oracle import ref_ops
+        return self._area if self.pts is None else abs(ref_ops._quad_area(self.pts))
+
+    def intersection(self, other):
+        from oracle import ref_ops
+        return _ConvexPolygon(area=ref_ops.convex_intersection_area(self.pts, other.pts))
+
+    def union(self, other):
+        return _ConvexPolygon(area=self.area + other.area - self.intersection(other).area)
+
+
 def install_stubs():
     import torch.nn as nn
 
@@ -61,7 +88,7 @@ def install_stubs():
     _stub("matplotlib.cm")
     _stub("matplotlib.colors")
     _stub("pyquaternion", Quaternion=_Anything)
-    geo = _stub("shapely.geometry", Polygon=_Anything, Point=_Anything, MultiPoint=_Anything)
+    geo = _stub("shapely.geometry", Polygon=_ConvexPolygon, Point=_Anything, MultiPoint=_Anything)
     _stub("shapely", geometry=geo)
 
     class DropPath(nn.Module):  # identity at eval; never instantiated by GenComm's eval path
@@ -85,7 +112,9 @@ def install_stubs():
     _stub("termcolor", colored=lambda s, *a, **k: s)       # sparse_backbone_3d.py:2 (SECOND encoder, unused here)
     _stub("spconv", **{n: _Anything for n in ("SparseSequential", "SubMConv3d", "SparseConv3d", "SparseInverseConv3d",
                                               "SparseConvTensor")})   # sparse_backbone_3d.py:3-9, import-time only
-    _stub("efficientnet_pytorch", EfficientNet=_Anything)   # camera encoder import of heter_encoders.py (lss_submodule.py:7)
+    _stub("efficientnet_pytorch", EfficientNet=_Anything)
+    _stub("opencood.utils.box_overlaps", bbox_overlaps=_Anything())
+    _stub("opencood.visualization.vis_utils")   # camera encoder import of heter_encoders.py (lss_submodule.py:7)
 
 
 def load():

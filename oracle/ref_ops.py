@@ -33,6 +33,8 @@ def _lib():
             raise RuntimeError(f"{path} missing: run `make -C oracle` (or __graft_entry__.build())")
         _LIB = ctypes.CDLL(path)
         _LIB.gc_ref_voxelize.restype = ctypes.c_int
+        _LIB.gc_ref_nms_rotated.restype = ctypes.c_int
+        _LIB.gc_ref_quad_iou.restype = ctypes.c_float
     return _LIB
 
 
@@ -499,3 +501,174 @@ def heter_gencomm_forward(sd, args, voxels, pairwise_t_matrix, record_len, noise
                              sd["reg_head.bias"], sd["dir_head.weight"], sd["dir_head.bias"])   # :287-289
     return {"cls_preds": cls, "reg_preds": reg, "dir_preds": dr, "gt_feature": feature, "pred_feature": pred,
             "message": message}
+
+
+# ---------------------------------------------------------------------------------------------
+# decode + rotated NMS.  VoxelPostprocessor.generate_anchor_box
+# (data_utils/post_processor/voxel_postprocessor.py:68-121), .delta_to_boxes3d (:1351-1396), .post_process (:1084-1244),
+# box_utils.boxes_to_corners_3d (utils/box_utils.py:152-203), project_box3d (:278-316), corner_to_standup_box_torch
+# (:251-275), remove_large_pred_bbx (:1062-1091), remove_bbx_abnormal_z (:1094-1112), nms_rotated (:915-960),
+# mask_boxes_outside_range_numpy (:423-462), common_utils.limit_period (utils/common_utils.py:104-113).
+# The polygon IoU of nms_rotated lives in third-party shapely (GEOS; absent from this image, version unpinned:
+# "parity unpinned" for that one function) -- restated below as convex clipping in float64.
+# ---------------------------------------------------------------------------------------------
+def generate_anchor_box(anchor_args, order="hwl"):
+    """anchor_args: {cav_lidar_range, l, w, h, r (degrees), num, vw, vh, W, H, feature_stride} -> [H/fs, W/fs, A, 7] f64."""
+    import math
+    a = anchor_args
+    r = [math.radians(e) for e in a["r"]]
+    fs = a.get("feature_stride", 2)
+    rng = a["cav_lidar_range"]
+    x = np.linspace(rng[0] + a["vw"], rng[3] - a["vw"], a["W"] // fs)                            # :98
+    y = np.linspace(rng[1] + a["vh"], rng[4] - a["vh"], a["H"] // fs)                            # :99
+    cx, cy = np.meshgrid(x, y)
+    cx = np.tile(cx[..., np.newaxis], len(r))
+    cy = np.tile(cy[..., np.newaxis], len(r))
+    cz = np.ones_like(cx) * -1.0
+    w, l, h = np.ones_like(cx) * a["w"], np.ones_like(cx) * a["l"], np.ones_like(cx) * a["h"]
+    r_ = np.ones_like(cx)
+    for i in range(len(r)):
+        r_[..., i] = r[i]
+    if order == "hwl":
+        return np.stack([cx, cy, cz, h, w, l, r_], axis=-1)                                      # :113
+    return np.stack([cx, cy, cz, l, h, w, r_], axis=-1)
+
+
+def delta_to_boxes3d(deltas, anchors):
+    """deltas [N, 7A, H, W] f32, anchors [H, W, A, 7] -> [N, H*W*A, 7] f32 (:1351-1396)."""
+    N = deltas.shape[0]
+    d = deltas.permute(0, 2, 3, 1).contiguous().view(N, -1, 7)
+    an = anchors.view(-1, 7).float()
+    ad = torch.sqrt(an[:, 4] ** 2 + an[:, 5] ** 2)
+    b = torch.zeros_like(d)
+    b[..., 0] = d[..., 0] * ad + an[:, 0]
+    b[..., 1] = d[..., 1] * ad + an[:, 1]
+    b[..., 2] = d[..., 2] * an[:, 3] + an[:, 2]
+    b[..., 3:6] = torch.exp(d[..., 3:6]) * an[:, 3:6]
+    b[..., 6] = d[..., 6] + an[:, 6]
+    return b
+
+
+def limit_period(val, offset=0.5, period=2 * np.pi):
+    return val - torch.floor(val / period + offset) * period                                     # common_utils.py:112
+
+
+def boxes_to_corners_3d(boxes3d, order):
+    b = boxes3d[:, [0, 1, 2, 5, 4, 3, 6]] if order == "hwl" else boxes3d
+    template = b.new_tensor(([1, -1, -1], [1, 1, -1], [-1, 1, -1], [-1, -1, -1],
+                             [1, -1, 1], [1, 1, 1], [-1, 1, 1], [-1, -1, 1])) / 2
+    c = b[:, None, 3:6].repeat(1, 8, 1) * template[None]
+    cosa, sina = torch.cos(b[:, 6]), torch.sin(b[:, 6])
+    zeros, ones = torch.zeros_like(cosa), torch.ones_like(cosa)
+    rot = torch.stack((cosa, sina, zeros, -sina, cosa, zeros, zeros, zeros, ones), dim=1).view(-1, 3, 3)
+    c = torch.matmul(c, rot)                                                                     # common_utils.py:159
+    return c + b[:, None, 0:3]
+
+
+def _quad_area(p):
+    x, y = p[:, 0], p[:, 1]
+    return 0.5 * float(np.sum(x * np.roll(y, -1) - np.roll(x, -1) * y))
+
+
+def convex_intersection_area(p, q):
+    """Area of the intersection of two convex polygons ([n,2] float64, any orientation): Sutherland-Hodgman clipping
+    of p against the edges of q (what shapely's ``a.intersection(b).area`` returns for convex quads)."""
+    p, q = np.asarray(p, np.float64), np.asarray(q, np.float64)
+    if _quad_area(p) < 0:
+        p = p[::-1]
+    if _quad_area(q) < 0:
+        q = q[::-1]
+    out = [tuple(v) for v in p]
+    for i in range(len(q)):
+        a, b = q[i], q[(i + 1) % len(q)]
+        ex, ey = b[0] - a[0], b[1] - a[1]
+        inp, out = out, []
+        if not inp:
+            break
+        side = [ex * (v[1] - a[1]) - ey * (v[0] - a[0]) for v in inp]      # >= 0: inside (left of the CCW edge)
+        for k in range(len(inp)):
+            cur, nxt = inp[k], inp[(k + 1) % len(inp)]
+            sc, sn = side[k], side[(k + 1) % len(inp)]
+            if sc >= 0:
+                out.append(cur)
+            if (sc >= 0) != (sn >= 0):
+                t = sc / (sc - sn)
+                out.append((cur[0] + t * (nxt[0] - cur[0]), cur[1] + t * (nxt[1] - cur[1])))
+    if len(out) < 3:
+        return 0.0
+    return abs(_quad_area(np.asarray(out, np.float64)))
+
+
+def polygon_iou(p, q):
+    inter = convex_intersection_area(p, q)
+    union = abs(_quad_area(np.asarray(p, np.float64))) + abs(_quad_area(np.asarray(q, np.float64))) - inter
+    return np.float32(inter / union) if union != 0 else np.float32("nan")
+
+
+def nms_rotated_py(boxes, scores, threshold, top=1000):
+    """boxes [N,8,3] (or [N,4,2]) -> picked indices, highest score first (box_utils.py:915-960), pure Python / numpy
+    (slow: small cases only).  Ties in the score are ordered larger-index-first (numpy's ``argsort()[::-1]`` with a
+    stable sort; the reference's quicksort leaves tie order unspecified)."""
+    if boxes.shape[0] == 0:
+        return np.array([], dtype=np.int32)
+    quad = boxes.numpy()[:, :4, :2].astype(np.float64)
+    s = scores.numpy()
+    ixs = s.argsort(kind="stable")[::-1][:top]
+    pick = []
+    while len(ixs) > 0:
+        i = ixs[0]
+        pick.append(i)
+        iou = np.array([polygon_iou(quad[i], quad[j]) for j in ixs[1:]], dtype=np.float32)
+        remove = np.where(iou > threshold)[0] + 1
+        ixs = np.delete(ixs, remove)
+        ixs = np.delete(ixs, 0)
+    return np.array(pick, dtype=np.int32)
+
+
+def nms_rotated(boxes, scores, threshold, top=1000):
+    """Same algorithm through the C restatement (oracle/nms_ref.c); pinned against nms_rotated_py in the tests."""
+    n = int(boxes.shape[0])
+    if n == 0:
+        return np.array([], dtype=np.int32)
+    quad = np.ascontiguousarray(boxes.numpy()[:, :4, :2].astype(np.float64))
+    s = np.ascontiguousarray(scores.numpy(), dtype=np.float32)
+    pick = np.empty((min(n, top),), np.int32)
+    k = _lib().gc_ref_nms_rotated(_p(quad), _p(s), ctypes.c_int(n), ctypes.c_float(threshold), ctypes.c_int(top), _p(pick))
+    return pick[:k].copy()
+
+
+def post_process(cls_preds, reg_preds, dir_preds, anchor_box, transformation_matrix, params):
+    """One frame (batch 1), ego only.  params: {'order','target_args':{'score_threshold'},'dir_args':{'dir_offset',
+    'num_bins'},'nms_thresh','gt_range'}.  Returns (pred_box3d [K,8,3] f32, scores [K] f32) or (None, None)."""
+    prob = torch.sigmoid(cls_preds.permute(0, 2, 3, 1)).reshape(1, -1)                           # :1130-1132
+    batch_box3d = delta_to_boxes3d(reg_preds, anchor_box)                                       # :1139
+    mask = torch.gt(prob, params["target_args"]["score_threshold"]).view(1, -1)
+    assert batch_box3d.shape[0] == 1
+    boxes3d = batch_box3d[0][mask[0]]
+    scores = prob[0][mask[0]]
+    if len(boxes3d) == 0:
+        return None, None
+    dir_offset, num_bins = params["dir_args"]["dir_offset"], params["dir_args"]["num_bins"]
+    dm = dir_preds.permute(0, 2, 3, 1).contiguous().reshape(1, -1, num_bins)[mask]               # :1162-1163
+    dir_labels = torch.max(dm, dim=-1)[1]
+    period = 2 * np.pi / num_bins
+    dir_rot = limit_period(boxes3d[..., 6] - dir_offset, 0, period)                              # :1168-1170
+    boxes3d[..., 6] = dir_rot + dir_offset + period * dir_labels.to(dm.dtype)                    # :1171
+    boxes3d[..., 6] = limit_period(boxes3d[..., 6], 0.5, 2 * np.pi)                              # :1172
+    corners = boxes_to_corners_3d(boxes3d, params["order"])                                     # :1184
+    Tm = torch.as_tensor(transformation_matrix).to(corners.dtype)
+    hom = torch.cat((corners.transpose(1, 2), torch.ones((corners.shape[0], 1, 8))), dim=1)
+    proj = torch.matmul(Tm, hom)[:, :3, :].transpose(1, 2)                                       # box_utils.py:303-314
+    mx, mn = proj.max(dim=1)[0], proj.min(dim=1)[0]
+    x_len, y_len = mx[:, 0] - mn[:, 0], mx[:, 1] - mn[:, 1]
+    z_len = mx[:, 1] - mn[:, 1]                                          # sic: the reference uses axis 1 again (:1084-1086)
+    keep1 = torch.logical_and(torch.logical_and(x_len <= 6, y_len <= 6), z_len)                  # :1088-1089
+    keep2 = torch.logical_and(mn[:, 2] >= -3, mx[:, 2] <= 1)                                     # :1108-1110
+    keep = torch.logical_and(keep1, keep2)
+    proj, scores = proj[keep], scores[keep]
+    pick = nms_rotated(proj, scores, params["nms_thresh"])                                       # :1217
+    proj, scores = proj[pick], scores[pick]
+    lim = np.asarray(params["gt_range"], dtype=np.float64)
+    pn = proj.numpy()
+    inside = ((pn >= lim[0:3]) & (pn <= lim[3:6])).all(axis=2).sum(axis=1) >= 8                  # box_utils.py:456-458
+    return torch.from_numpy(pn[inside]), scores[torch.from_numpy(inside)]

@@ -94,3 +94,8 @@ def heter_inputs():
     """(voxels, pairwise, record_len, noise0, step_noises) of tests/golden/heter_model.npz, regenerated from seeds."""
     from oracle import gen_golden
     return gen_golden.heter_inputs()
+
+
+@pytest.fixture(scope="session")
+def golden_postprocess():
+    return load_golden("postprocess.npz")

@@ -201,3 +201,41 @@ def test_create_model_resolves_the_gencomm_detectors():
     bad["fusion_method"] = "v2xvit"
     with pytest.raises(NotImplementedError, match="fusion_method"):
         G.HeterModelBaselineWGenComm(bad)
+
+
+def test_postprocess_restatement_matches_reference(golden_postprocess):
+    """Decode + rotated NMS: the oracle against the UNMODIFIED VoxelPostprocessor.post_process
+    (bit-exact boxes / scores / order), incl. the top-1000 cap, a rigid cav -> ego transform and the empty frame."""
+    from gencomm_b200 import VoxelPostprocessor, synth
+    from oracle import gen_golden
+    g = golden_postprocess
+    params = synth.postprocess_params()
+    anchors = R.generate_anchor_box(params["anchor_args"], params["order"])
+    assert np.array_equal(anchors, g["anchors"])
+    assert np.array_equal(VoxelPostprocessor(params, train=False).generate_anchor_box(), g["anchors"])   # host mirror
+    for name, (seed, bias, moved) in gen_golden.POSTPROCESS_CASES.items():
+        cls, reg, dr = synth.head_outputs(seed, bias=bias)
+        boxes, scores = R.post_process(cls, reg, dr, T(anchors), gen_golden.postprocess_transform(moved), params)
+        if int(g[f"{name}/count"]) == 0:
+            assert boxes is None and scores is None
+            continue
+        assert torch.equal(boxes, T(g[f"{name}/boxes"])), name
+        assert torch.equal(scores, T(g[f"{name}/scores"])), name
+
+
+def test_nms_c_restatement_matches_python_restatement():
+    """oracle/nms_ref.c against the numpy / Python restatement of nms_rotated + polygon IoU on a small clustered case."""
+    g = torch.Generator().manual_seed(5)
+    n = 120
+    centre = torch.rand(n, 1, 2, generator=g) * 12.0
+    yaw = torch.rand(n, generator=g) * 3.1416
+    half = torch.tensor([[1.95, -0.8], [1.95, 0.8], [-1.95, 0.8], [-1.95, -0.8]])
+    rot = torch.stack([torch.stack([yaw.cos(), -yaw.sin()], -1), torch.stack([yaw.sin(), yaw.cos()], -1)], -2)
+    quad = torch.einsum("nij,kj->nki", rot, half) + centre
+    boxes = torch.cat([quad, torch.zeros(n, 4, 1)], dim=-1)
+    scores = torch.rand(n, generator=g)
+    scores[7] = scores[3]                                            # a tie: larger index first
+    a = R.nms_rotated(boxes, scores, 0.15)
+    b = R.nms_rotated_py(boxes, scores, 0.15)
+    assert np.array_equal(a, b) and 5 < len(a) < n
+    assert abs(float(R.polygon_iou(quad[0].numpy(), quad[0].numpy())) - 1.0) < 1e-6
