@@ -3,8 +3,8 @@
 Collaborative frames are independent units (the reference processes them one by one,
 tools/inference.py:131-227), so the path shards with NO data-path collective: global frame f runs on
 rank ``f % world``.  The only exchange is an end-of-run ``all_gather`` of small per-frame summaries
-(top-K responses of the fused map as a detection proxy until decode/NMS exists, plus per-stage
-timings), a few KB per rank: latency-bound, NVLink bandwidth is irrelevant.
+(``gather_detections``: count + boxes + scores per frame from ``VoxelPostprocessor``; ``gather_summaries``: top-K
+responses of the fused map for the head-less bench step, plus per-stage timings), KBs per rank: latency-bound, NVLink bandwidth is irrelevant.
 
 Works with any ``torch.distributed`` backend (NCCL on the GPU box, gloo in the CPU tests).
 """
@@ -76,3 +76,51 @@ def gather_summaries(local, n_frames, device, k=TOPK, n_timings=0):
     if not torch.equal(owner, expect):
         raise RuntimeError("frame ownership does not follow frame_idx % world")
     return values, indices, timings, owner
+
+
+def gather_detections(local, n_frames, device, k_max=1000):
+    """All-gather per-frame detections (``count i32, boxes [k_max,8,3] f32, scores [k_max] f32`` zero
+    padded; the NMS caps a frame at top 1000, utils/box_utils.py:941).
+
+    local: {global_frame_idx: (boxes [K,8,3] | None, scores [K] | None)} for this rank's frames (the return value of
+    ``VoxelPostprocessor.post_process``).  Returns {frame: (boxes [K,8,3], scores [K])} for ALL frames on every rank
+    (empty tensors for frames without detections).  One collective of per_rank * (2 + 25 k_max) floats per rank.
+    """
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    per_rank = (int(n_frames) + world - 1) // world
+    width = 2 + 25 * k_max                              # frame id, count, boxes, scores
+    buf = torch.zeros((per_rank, width), dtype=torch.float32, device=device)
+    buf[:, 0] = -1.0
+    if len(local) > per_rank:
+        raise RuntimeError(f"rank owns {len(local)} frames, more than ceil(n_frames / world) = {per_rank}")
+    for row, f in enumerate(sorted(local)):
+        boxes, scores = local[f]
+        k = 0 if boxes is None else int(boxes.shape[0])
+        if k > k_max:
+            raise ValueError(f"frame {f}: {k} detections exceed k_max = {k_max}")
+        buf[row, 0], buf[row, 1] = float(f), float(k)
+        if k:
+            buf[row, 2:2 + 24 * k] = boxes.to(device=device, dtype=torch.float32).reshape(-1)
+            buf[row, 2 + 24 * k_max:2 + 24 * k_max + k] = scores.to(device=device, dtype=torch.float32)
+    if world > 1:
+        parts = [torch.empty_like(buf) for _ in range(world)]
+        dist.all_gather(parts, buf)
+    else:
+        parts = [buf]
+    out = {}
+    for r, p in enumerate(parts):
+        p = p.cpu()
+        for row in p:
+            f = int(row[0])
+            if f < 0:
+                continue
+            if f in out:
+                raise RuntimeError(f"frame {f} reported twice (second time by rank {r})")
+            if f % world != r:
+                raise RuntimeError("frame ownership does not follow frame_idx % world")
+            k = int(row[1])
+            out[f] = (row[2:2 + 24 * k].reshape(k, 8, 3).clone(), row[2 + 24 * k_max:2 + 24 * k_max + k].clone())
+    missing = [f for f in range(int(n_frames)) if f not in out]
+    if missing:
+        raise RuntimeError(f"frames {missing} were not processed by any rank")
+    return out

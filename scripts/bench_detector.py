@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Whole-detector microbench: HeterModelBaselineWGenComm (stage-1 GenComm detector, m1_att.yaml model args) from raw
-LiDAR points to cls / reg / dir maps, F frames of N agents per call, per-stage CUDA-event breakdown.
+LiDAR points to decoded, NMS-filtered boxes, F frames of N agents per call, per-stage CUDA-event breakdown.
 
     python scripts/bench_detector.py [--frames 8] [--agents 4] [--points 100000] [--iters 5] [--fusion att]
 """
@@ -47,13 +47,23 @@ def main():
         mod = getattr(m, name)
         mod.register_forward_pre_hook(lambda _m, _i, label=label: marks.append((label, 0, _ev())))
         mod.register_forward_hook(lambda _m, _i, _o, label=label: marks.append((label, 1, _ev())))
-    for _ in range(2):
+    pp = G.VoxelPostprocessor(synth.postprocess_params(score_threshold=0.6), train=False)
+    anchors = torch.from_numpy(pp.generate_anchor_box()).float().cuda()
+
+    def run():
         out = m(dict(data))
+        marks.append(("postprocess", 0, _ev()))
+        det = pp.post_process_batch(out["cls_preds"], out["reg_preds"], out["dir_preds"], anchors)
+        marks.append(("postprocess", 1, _ev()))
+        return out, det
+
+    for _ in range(2):
+        out, det = run()
     torch.cuda.synchronize()
     marks.clear()
     e0, e1 = _ev(sync=False), None
     for _ in range(args.iters):
-        out = m(dict(data))
+        out, det = run()
     e1 = _ev(sync=False)
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / args.iters
@@ -65,7 +75,7 @@ def main():
     print(json.dumps({"workload": f"HeterModelBaselineWGenComm m1_att, {F} frames x {N} agents x {args.points} points, "
                                   f"OPV2V-H grid, {args.fusion} fusion, sampler {args.precision}",
                       "ms_per_call": ms, "frames_per_s": F / ms * 1e3, "stage_ms": {k: round(v, 3) for k, v in per.items()},
-                      "cls_preds": list(out["cls_preds"].shape)}))
+                      "cls_preds": list(out["cls_preds"].shape), "detections_per_frame": det[2].tolist()}))
 
 
 def _ev(sync=False):

@@ -110,6 +110,24 @@ def test_stage2_detector_max_fusion_trick_matches_oracle(heter_inputs):
     _close(out["pred_feature"].cpu(), ref["pred_feature"], "stage2 pred_feature", 2e-2, 1e-2)
 
 
+def test_detector_outputs_through_gpu_postprocess_match_oracle_postprocess(heter_inputs):
+    """points -> detector -> decode + NMS entirely on the GPU; the oracle post-processes the same head maps on the host
+    (both frames of the batch in one gc_postprocess call)."""
+    m = _model()
+    out = m(_data(heter_inputs))
+    params = synth.postprocess_params(score_threshold=0.6)
+    pp = G.VoxelPostprocessor(params, train=False)
+    anchors = pp.generate_anchor_box()
+    boxes, scores, counts = pp.post_process_batch(out["cls_preds"], out["reg_preds"], out["dir_preds"], anchors)
+    for f in range(2):
+        ref_b, ref_s = R.post_process(out["cls_preds"][f:f + 1].cpu(), out["reg_preds"][f:f + 1].cpu(),
+                                      out["dir_preds"][f:f + 1].cpu(), T(anchors), torch.eye(4), params)
+        k = int(counts[f])
+        assert ref_b is not None and k == ref_b.shape[0] and k > 10, (f, k)
+        assert float((boxes[f, :k].cpu() - ref_b).abs().max()) <= 1e-4
+        assert float((scores[f, :k].cpu() - ref_s).abs().max()) <= 1e-6
+
+
 def test_detector_is_inference_only():
     m = _model()
     m.train()

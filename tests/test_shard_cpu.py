@@ -70,3 +70,39 @@ def test_missing_frame_is_reported():
         assert "not processed" in str(e)
     else:
         raise AssertionError("missing frame went unnoticed")
+
+
+def fake_detections(frame):
+    """Ragged per-frame detections incl. an empty frame (post_process returns (None, None) there)."""
+    k = (frame * 3) % 5
+    if k == 0:
+        return None, None
+    g = torch.Generator().manual_seed(99 + frame)
+    return torch.randn(k, 8, 3, generator=g), torch.rand(k, generator=g)
+
+
+def _det_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        local = {f: fake_detections(f) for f in shard.frames_for_rank(N_FRAMES, rank, world)}
+        out[rank] = shard.gather_detections(local, N_FRAMES, torch.device("cpu"), k_max=6)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_world2_gloo_detection_gather():
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_det_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    single = shard.gather_detections({f: fake_detections(f) for f in range(N_FRAMES)}, N_FRAMES, torch.device("cpu"), k_max=6)
+    for rank in (0, 1):
+        got = out[rank]
+        assert sorted(got.keys()) == list(range(N_FRAMES))
+        for f in range(N_FRAMES):
+            boxes, scores = fake_detections(f)
+            k = 0 if boxes is None else boxes.shape[0]
+            assert got[f][0].shape == (k, 8, 3) and got[f][1].shape == (k,)
+            if k:
+                assert torch.equal(got[f][0], boxes) and torch.equal(got[f][1], scores)
+            assert torch.equal(got[f][0], single[f][0]) and torch.equal(got[f][1], single[f][1])
