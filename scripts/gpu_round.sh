@@ -21,3 +21,13 @@ timeout 900 ncu --set full --clock-control none --import-source on -k regex:"k_c
 ls -la $OUT
 echo "== fuse microbench"
 timeout 600 python scripts/bench_fuse.py --quick 2>&1 | tee $OUT/bench_fuse_$TAG.txt
+echo "== component microbenches"
+timeout 200 python scripts/bench_detector.py 2>&1 | tail -1 | tee $OUT/bench_detector_$TAG.json
+timeout 200 python scripts/bench_backbone.py --torch 2>&1 | tail -1 | tee $OUT/bench_backbone_$TAG.json
+timeout 100 python scripts/bench_postprocess.py --cpu 2>&1 | tail -1 | tee $OUT/bench_postprocess_$TAG.json
+timeout 100 python scripts/bench_det_tail.py 2>&1 | tail -1 | tee $OUT/bench_det_tail_$TAG.json
+timeout 100 python scripts/bench_me.py 2>&1 | tail -1 | tee $OUT/bench_me_$TAG.json
+timeout 100 python scripts/bench_enh.py 2>&1 | tail -1 | tee $OUT/bench_enh_$TAG.json
+echo "== ncu: backbone conv + postprocess kernels"
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:"k_me_conv|k_post_nms|k_post_decode" -s 60 -c 8 \
+    -f -o $OUT/prof_det_$TAG python scripts/bench_detector.py --frames 2 --iters 1 > $OUT/ncu_det_$TAG.log 2>&1
