@@ -143,8 +143,11 @@ k_me_conv(const uint4 *__restrict__ xh, const uint4 *__restrict__ xl, const floa
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t *a_s = smem;                      // [2][kPlanes][kABytes]
     uint8_t *b_s = smem + 2 * kAStage;        // [2][kPlanes][SC * NOUT * 2]
-    __shared__ __align__(8) uint64_t s_empty[2], s_done;
+    __shared__ __align__(8) uint64_t s_empty[2], s_done, s_full[2];
     __shared__ uint32_t s_tmem;
+    // B stages arrive by one 1-D bulk copy (TMA) per stage instead of LDG + STS by every thread: the packed weights of a
+    // stage are kBBytes contiguous bytes in global memory and land in the same order in shared memory.
+    constexpr bool kBulkB = true;
     __shared__ __align__(16) int4 s_o[kPix];      // pixel index (y*W + x) of the four bilinear corners of the tap
     __shared__ __align__(16) float4 s_w[kPix];    // their weights (0 for a corner outside the image)
 
@@ -157,6 +160,7 @@ k_me_conv(const uint4 *__restrict__ xh, const uint4 *__restrict__ xl, const floa
     if (warp == 0) tmem_alloc<NOUT>(&s_tmem);
     if (tid == 32) {
         mbar_init(smem_u32(&s_empty[0]), 1); mbar_init(smem_u32(&s_empty[1]), 1); mbar_init(smem_u32(&s_done), 1);
+        mbar_init(smem_u32(&s_full[0]), 1); mbar_init(smem_u32(&s_full[1]), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     tc_fence_before();
@@ -214,9 +218,11 @@ k_me_conv(const uint4 *__restrict__ xh, const uint4 *__restrict__ xl, const floa
         if (s >= 2) mbar_wait(smem_u32(&s_empty[b]), (uint32_t)((s >> 1) - 1) & 1u);   // MMAs of stage s-2 retired
         // ---- B stage: kBBytes contiguous bytes of the packed weights; the loads are issued here and stored after the
         // first batch of A loads is in flight (one round trip instead of two or three) ----
-        constexpr int kBIter = (kBBytes / 16 + kThreads - 1) / kThreads;
+        constexpr int kBIter = kBulkB ? 1 : (kBBytes / 16 + kThreads - 1) / kThreads;
         uint4 bq[kBIter];
-        {
+        if (kBulkB) {
+            if (tid == 0) bulk_load(smem_u32(b_s + b * kBBytes), wp + (size_t)s * (kBBytes / 16), kBBytes, smem_u32(&s_full[b]));
+        } else {
             const uint4 *src = wp + (size_t)s * (kBBytes / 16);
 #pragma unroll
             for (int i = 0; i < kBIter; ++i)
@@ -249,7 +255,7 @@ k_me_conv(const uint4 *__restrict__ xh, const uint4 *__restrict__ xl, const floa
                         q[u][1] = __ldg(xl_a + (size_t)o.x * C8 + cg);
                     }
                 }
-                if (pass == 0) {
+                if (!kBulkB && pass == 0) {
                     uint4 *bd = reinterpret_cast<uint4 *>(b_s + b * kBBytes);
 #pragma unroll
                     for (int i = 0; i < kBIter; ++i)
@@ -276,6 +282,7 @@ k_me_conv(const uint4 *__restrict__ xh, const uint4 *__restrict__ xl, const floa
         tc_fence_before();
         __syncthreads();
         if (tid == 0) {
+            if (kBulkB) mbar_wait(smem_u32(&s_full[b]), (uint32_t)(s >> 1) & 1u);   // the stage's weights have landed
             tc_fence_after();
             const uint32_t a_buf = a_base + (uint32_t)b * kAStage, b_buf = b_base + (uint32_t)b * kBBytes;
             constexpr uint32_t kBPlane = SC * NOUT * 2;
