@@ -26,7 +26,7 @@ static int launch(cudaStream_t st, dim3 grid, const uint4 *xh, const uint4 *xl, 
         cudaFuncSetAttribute(k_me_conv<NOUT, false, kSc, TAPS, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
         done = true;
     }
-    k_me_conv<NOUT, false, kSc, TAPS, EPI><<<grid, kThreads, kSmem, st>>>(xh, xl, nullptr, wp, bias, C, C, H, W, n_store,
+    k_me_conv<NOUT, false, kSc, TAPS, EPI><<<grid, conv_block_threads(false), kSmem, st>>>(xh, xl, nullptr, wp, bias, C, C, H, W, n_store,
                                                                        n_store, 0, out, nullptr, H_in, W_in, stride);
     GC_LAUNCH_CHECK("k_me_conv (det_tail)");
     return GC_OK;
@@ -172,7 +172,7 @@ static int launch_layer(cudaStream_t st, dim3 grid, const uint4 *xh, const uint4
         cudaFuncSetAttribute(k_me_conv<NOUT, false, kSc, TAPS, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
         done = true;
     }
-    k_me_conv<NOUT, false, kSc, TAPS, EPI><<<grid, kThreads, kSmem, st>>>(xh, xl, nullptr, wp, bias, C, C, Ho, Wo, n_out, out_total,
+    k_me_conv<NOUT, false, kSc, TAPS, EPI><<<grid, conv_block_threads(false), kSmem, st>>>(xh, xl, nullptr, wp, bias, C, C, Ho, Wo, n_out, out_total,
                                                                        out_off, out, nullptr, H_in, W_in, stride, oh, ol, up,
                                                                        up_dy, up_dx);
     GC_LAUNCH_CHECK("k_me_conv (layer)");

@@ -271,7 +271,7 @@ static int launch_conv(cudaStream_t st, dim3 grid, const uint4 *xh, const uint4 
         cudaFuncSetAttribute(k_me_conv<NOUT, false, kSc, TAPS, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
         done = true;
     }
-    k_me_conv<NOUT, false, kSc, TAPS, EPI><<<grid, kThreads, kSmem, st>>>(xh, xl, nullptr, wp, bias, C, c_in, H, W, n_store,
+    k_me_conv<NOUT, false, kSc, TAPS, EPI><<<grid, conv_block_threads(false), kSmem, st>>>(xh, xl, nullptr, wp, bias, C, c_in, H, W, n_store,
                                                                        out_total, out_off, out, nullptr);
     GC_LAUNCH_CHECK("k_me_conv (enhancer)");
     return GC_OK;

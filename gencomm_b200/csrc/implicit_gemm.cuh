@@ -15,7 +15,10 @@ namespace me {
 using namespace umma;
 
 constexpr int kPix = 128;            // pixels per CTA = M
-constexpr int kThreads = 256;
+constexpr int kThreads = 256;          // threads that stage operands and run the epilogue
+// Plain (non-deformable) layers add one warp that only feeds the tensor core: it issues the weight (B) bulk copies one
+// stage ahead and the MMAs, so the 256 operand threads never meet at a block-wide barrier inside the K loop.
+__host__ __device__ constexpr int conv_block_threads(bool deform) { return deform ? kThreads : kThreads + 32; }
 // Input channels per stage (SC / 16 MMAs of K = 16): 64 for the deformable layer, 32 for the offset layer (its value +
 // residual planes double the operand bytes; with 64-channel stages only two CTAs fit an SM and the layer was latency
 // bound on its load -> store -> barrier -> MMA chain: 305 us at 28 % issue-active).
@@ -125,7 +128,7 @@ __device__ __forceinline__ uint32_t lerp2(const float4 &w, uint32_t a, uint32_t 
 __device__ __forceinline__ float gelu_erf(float v) { return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f)); }
 
 template <int NOUT, bool DEFORM, int SC, int TAPS = 9, int EPI = 0>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(conv_block_threads(DEFORM))
 k_me_conv(const uint4 *__restrict__ xh, const uint4 *__restrict__ xl, const float *__restrict__ offset,
           const uint4 *__restrict__ wp, const float *__restrict__ bias, int C, int c_in, int H, int W, int n_store,
           int out_ch_total, int out_ch_off, float *__restrict__ out, float *__restrict__ tile_sums, int H_in = 0,
@@ -143,7 +146,7 @@ k_me_conv(const uint4 *__restrict__ xh, const uint4 *__restrict__ xl, const floa
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t *a_s = smem;                      // [2][kPlanes][kABytes]
     uint8_t *b_s = smem + 2 * kAStage;        // [2][kPlanes][SC * NOUT * 2]
-    __shared__ __align__(8) uint64_t s_empty[2], s_done, s_full[2];
+    __shared__ __align__(8) uint64_t s_empty[2], s_done, s_full[2], s_afull[2];
     __shared__ uint32_t s_tmem;
     // B stages arrive by one 1-D bulk copy (TMA) per stage instead of LDG + STS by every thread: the packed weights of a
     // stage are kBBytes contiguous bytes in global memory and land in the same order in shared memory.
@@ -161,6 +164,7 @@ k_me_conv(const uint4 *__restrict__ xh, const uint4 *__restrict__ xl, const floa
     if (tid == 32) {
         mbar_init(smem_u32(&s_empty[0]), 1); mbar_init(smem_u32(&s_empty[1]), 1); mbar_init(smem_u32(&s_done), 1);
         mbar_init(smem_u32(&s_full[0]), 1); mbar_init(smem_u32(&s_full[1]), 1);
+        mbar_init(smem_u32(&s_afull[0]), kThreads); mbar_init(smem_u32(&s_afull[1]), kThreads);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     tc_fence_before();
@@ -174,6 +178,84 @@ k_me_conv(const uint4 *__restrict__ xh, const uint4 *__restrict__ xl, const floa
     const uint4 *xh_a = xh + (size_t)agent * Hi * Wi * C8;
     const uint4 *xl_a = xl + (size_t)agent * Hi * Wi * C8;
 
+    if constexpr (!DEFORM) {
+        // ---- plain 3x3 / 1x1 path: warp-specialised, no block-wide barrier in the K loop ----
+        static_assert(SC == 32, "the plain path stages 32 channels (4 groups) per stage");
+        constexpr uint32_t kBPlane = SC * NOUT * 2;
+        if (warp == kThreads / 32) {
+            // feeder warp (one lane): B(s+1) bulk copy as soon as its buffer is free, then the MMAs of stage s
+            if (lane == 0) {
+                bulk_load(smem_u32(b_s), wp, kBBytes, smem_u32(&s_full[0]));
+                for (int s = 0; s < stages; ++s) {
+                    const int b = s & 1;
+                    if (s + 1 < stages) {
+                        const int b1 = (s + 1) & 1;
+                        if (s + 1 >= 2) mbar_wait(smem_u32(&s_empty[b1]), (uint32_t)(((s + 1) >> 1) - 1) & 1u);
+                        bulk_load(smem_u32(b_s + b1 * kBBytes), wp + (size_t)(s + 1) * (kBBytes / 16), kBBytes, smem_u32(&s_full[b1]));
+                    }
+                    mbar_wait(smem_u32(&s_afull[b]), (uint32_t)(s >> 1) & 1u);
+                    mbar_wait(smem_u32(&s_full[b]), (uint32_t)(s >> 1) & 1u);
+                    tc_fence_after();
+                    const uint32_t a_buf = a_base + (uint32_t)b * kAStage, b_buf = b_base + (uint32_t)b * kBBytes;
+#pragma unroll
+                    for (int j = 0; j < SC / 16; ++j) {
+                        const uint32_t a_off = (uint32_t)(2 * j) * (uint32_t)kAGroup, b_off = (uint32_t)(2 * j) * (NOUT * 16u);
+                        const uint64_t a_hi = make_desc(a_buf + a_off, (uint32_t)kAGroup, 128u);
+                        const uint64_t b_hi = make_desc(b_buf + b_off, NOUT * 16u, 128u);
+                        const uint64_t a_lo = make_desc(a_buf + kABytes + a_off, (uint32_t)kAGroup, 128u);
+                        const uint64_t b_lo = make_desc(b_buf + kBPlane + b_off, NOUT * 16u, 128u);
+                        mma_bf16(tmem, a_hi, b_hi, idesc, (s > 0 || j > 0) ? 1u : 0u);
+                        mma_bf16(tmem, a_lo, b_hi, idesc, 1u);
+                        mma_bf16(tmem, a_hi, b_lo, idesc, 1u);
+                    }
+                    mma_commit(smem_u32(&s_empty[b]));
+                    if (s == stages - 1) mma_commit(smem_u32(&s_done));
+                }
+            }
+        } else {
+            // operand threads: two pixels (tid / 4 and 64 + tid / 4) of channel group tid & 3, value + residual plane;
+            // the rows of stage s + 1 are in flight (registers) while stage s is stored
+            const int g_loc = tid & 3;
+            int py[2], px[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int pix = tile * kPix + u * 64 + (tid >> 2);
+                py[u] = pix / W;
+                px[u] = pix - py[u] * W;
+            }
+            auto issue = [&](int s, uint4 (&q)[2][2]) {
+                const int tap = s / chunks, chunk = s - tap * chunks;
+                const int ky = TAPS == 1 ? 1 : tap / 3, kx = TAPS == 1 ? 1 : tap - 3 * ky;
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int yy = py[u] * stride - 1 + ky, xx = px[u] * stride - 1 + kx;
+                    const bool ok = yy >= 0 && yy < Hi && xx >= 0 && xx < Wi;
+                    const size_t o = (size_t)(ok ? yy * Wi + xx : 0) * C8 + chunk * kGroups + g_loc;
+                    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+                    q[u][0] = ok ? __ldg(xh_a + o) : z;
+                    q[u][1] = ok ? __ldg(xl_a + o) : z;
+                }
+            };
+            uint4 qa[2][2], qb[2][2];
+            issue(0, qa);
+            for (int s = 0; s < stages; ++s) {
+                const int b = s & 1;
+                if (s + 1 < stages) issue(s + 1, qb);
+                if (s >= 2) mbar_wait(smem_u32(&s_empty[b]), (uint32_t)((s >> 1) - 1) & 1u);   // MMAs of stage s-2 retired
+                uint8_t *dst = a_s + b * kAStage;
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    uint4 *d = reinterpret_cast<uint4 *>(dst + g_loc * kAGroup) + (u * 64 + (tid >> 2));
+                    d[0] = qa[u][0];
+                    d[kABytes / 16] = qa[u][1];
+                }
+                fence_async_smem();
+                mbar_arrive(smem_u32(&s_afull[b]));
+#pragma unroll
+                for (int u = 0; u < 2; ++u) { qa[u][0] = qb[u][0]; qa[u][1] = qb[u][1]; }
+            }
+        }
+    } else
     for (int s = 0; s < stages; ++s) {
         const int b = s & 1;
         const int tap = s / chunks, chunk = s - tap * chunks;
@@ -307,7 +389,7 @@ k_me_conv(const uint4 *__restrict__ xh, const uint4 *__restrict__ xl, const floa
     tc_fence_after();
 
     // ---- epilogue: warp w reads TMEM lanes 32 (w % 4) .. +31 (= pixels) and columns (w / 4) * NOUT/2 .. ----
-    {
+    if (warp < kThreads / 32) {
         const int q = warp & 3, ch0 = (warp >> 2) * (NOUT / 2);
         const int p_out = tile * kPix + q * 32 + lane;
         const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)ch0;

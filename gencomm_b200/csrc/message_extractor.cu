@@ -448,7 +448,7 @@ extern "C" int gc_message_extractor(const float *x, int total_agents, int C, int
                                                                       ws.offset);
         GC_LAUNCH_CHECK("k_me_offset_row3");
     } else {
-        me::k_me_conv<32, false, me::kScOffset><<<grid, me::kThreads, kSmemOff, st>>>(ws.xh, ws.xl, nullptr, p_off,
+        me::k_me_conv<32, false, me::kScOffset><<<grid, me::conv_block_threads(false), kSmemOff, st>>>(ws.xh, ws.xl, nullptr, p_off,
                                                                                    params + me::kOffBias, C, C, H, W, 18, 18,
                                                                                    0, ws.offset, nullptr);
         GC_LAUNCH_CHECK("k_me_conv<offset1>");
