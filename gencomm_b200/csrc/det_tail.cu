@@ -9,6 +9,8 @@
 // both operands, fp32 accumulation in TMEM: fp32-grade results): strided / plain 3x3 with a bias + ReLU epilogue, and
 // ONE 1x1 GEMM for the three heads (their weight matrices concatenated, N <= 64).
 #include "common.cuh"
+#include <stdlib.h>
+
 #include "implicit_gemm.cuh"
 
 namespace gc {
@@ -162,21 +164,36 @@ extern "C" int gc_det_heads(const float *x, int n_frames, int C, int H, int W, i
 namespace gc {
 namespace dt {
 
+template <int NOUT, int TAPS, int EPI, int MT>
+static int launch_layer_mt(cudaStream_t st, dim3 grid, const uint4 *xh, const uint4 *xl, const uint4 *wp, const float *bias, int C,
+                           int Ho, int Wo, int n_out, int out_total, int out_off, float *out, uint4 *oh, uint4 *ol, int H_in,
+                           int W_in, int stride, int up, int up_dy, int up_dx) {
+    constexpr int kSmem = conv_smem_bytes(NOUT, true, kSc, MT);
+    static bool done = false;
+    if (!done) {
+        cudaFuncSetAttribute(k_me_conv<NOUT, false, kSc, TAPS, EPI, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+        done = true;
+    }
+    grid.x /= MT;
+    k_me_conv<NOUT, false, kSc, TAPS, EPI, MT><<<grid, conv_block_threads(false), kSmem, st>>>(
+        xh, xl, nullptr, wp, bias, C, C, Ho, Wo, n_out, out_total, out_off, out, nullptr, H_in, W_in, stride, oh, ol, up, up_dy, up_dx);
+    GC_LAUNCH_CHECK("k_me_conv (layer)");
+    return GC_OK;
+}
+// 3x3 plane-to-plane layers (the backbone's bulk) can run two 128-pixel tiles per CTA on one weight stage (half the weight
+// traffic from L2).  Measured on the B200: backbone 7.89 ms vs 7.66 ms with one tile -- no gain, so it is opt-in.
 template <int NOUT, int TAPS, int EPI>
 static int launch_layer(cudaStream_t st, dim3 grid, const uint4 *xh, const uint4 *xl, const uint4 *wp, const float *bias, int C,
                         int Ho, int Wo, int n_out, int out_total, int out_off, float *out, uint4 *oh, uint4 *ol, int H_in,
                         int W_in, int stride, int up, int up_dy, int up_dx) {
-    constexpr int kSmem = conv_smem_bytes(NOUT, true, kSc);
-    static bool done = false;
-    if (!done) {
-        cudaFuncSetAttribute(k_me_conv<NOUT, false, kSc, TAPS, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
-        done = true;
+    static const bool two = getenv("GC_CONV_MT2") != nullptr;   // measured: no gain, opt-in for A/B
+    if constexpr (TAPS == 9 && EPI == 5) {
+        if (two && grid.x % 2 == 0 && (long long)grid.x * grid.y >= 2 * 148)
+            return launch_layer_mt<NOUT, TAPS, EPI, 2>(st, grid, xh, xl, wp, bias, C, Ho, Wo, n_out, out_total, out_off, out, oh, ol,
+                                                       H_in, W_in, stride, up, up_dy, up_dx);
     }
-    k_me_conv<NOUT, false, kSc, TAPS, EPI><<<grid, conv_block_threads(false), kSmem, st>>>(xh, xl, nullptr, wp, bias, C, C, Ho, Wo, n_out, out_total,
-                                                                       out_off, out, nullptr, H_in, W_in, stride, oh, ol, up,
-                                                                       up_dy, up_dx);
-    GC_LAUNCH_CHECK("k_me_conv (layer)");
-    return GC_OK;
+    return launch_layer_mt<NOUT, TAPS, EPI, 1>(st, grid, xh, xl, wp, bias, C, Ho, Wo, n_out, out_total, out_off, out, oh, ol, H_in,
+                                               W_in, stride, up, up_dy, up_dx);
 }
 template <int TAPS, int EPI, class... Args>
 static int launch_layer_n(int n, Args... args) {

@@ -27,8 +27,9 @@ __host__ __device__ constexpr int conv_block_threads(bool deform) { return defor
 // STS.128, 70 M conflicts per launch).  UMMA no-swizzle K-major: LBO = group stride, SBO = 128 B.
 __host__ __device__ constexpr int a_group_bytes(int SC) { return kPix * 16 + (SC == 64 ? 16 : 32); }
 __host__ __device__ constexpr int a_plane_bytes(int SC) { return (SC / 8) * a_group_bytes(SC); }
-__host__ __device__ constexpr int conv_smem_bytes(int NOUT, bool split, int SC) {
-    return 2 * (split ? 2 : 1) * (a_plane_bytes(SC) + SC * NOUT * 2);
+// MT = 128-pixel M tiles per CTA that share one B (weight) stage (plain layers only)
+__host__ __device__ constexpr int conv_smem_bytes(int NOUT, bool split, int SC, int MT = 1) {
+    return 2 * (split ? 2 : 1) * (MT * a_plane_bytes(SC) + SC * NOUT * 2);
 }
 constexpr int kScOffset = 32, kScDeform = 64;
 
@@ -127,7 +128,7 @@ __device__ __forceinline__ uint32_t lerp2(const float4 &w, uint32_t a, uint32_t 
 // the n_store output channels go to planes out_ch_off .. of an [A][out_ch_total][HW] f32 tensor.
 __device__ __forceinline__ float gelu_erf(float v) { return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f)); }
 
-template <int NOUT, bool DEFORM, int SC, int TAPS = 9, int EPI = 0>
+template <int NOUT, bool DEFORM, int SC, int TAPS = 9, int EPI = 0, int MT = 1>
 __global__ void __launch_bounds__(conv_block_threads(DEFORM))
 k_me_conv(const uint4 *__restrict__ xh, const uint4 *__restrict__ xl, const float *__restrict__ offset,
           const uint4 *__restrict__ wp, const float *__restrict__ bias, int C, int c_in, int H, int W, int n_store,
@@ -142,7 +143,9 @@ k_me_conv(const uint4 *__restrict__ xh, const uint4 *__restrict__ xl, const floa
     constexpr int kPlanes = SPLIT ? 2 : 1;
     constexpr int kAGroup = a_group_bytes(SC), kABytes = a_plane_bytes(SC), kGroups = SC / 8;
     constexpr int kBBytes = SC * NOUT * 2 * kPlanes;
-    constexpr int kAStage = kABytes * kPlanes;
+    static_assert(MT == 1 || (!DEFORM && MT == 2 && NOUT * MT <= 512), "two M tiles per CTA: plain layers, <= 512 TMEM columns");
+    constexpr int kATile = kABytes * kPlanes;   // one 128-pixel tile: value (+ residual) plane
+    constexpr int kAStage = kATile * MT;
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t *a_s = smem;                      // [2][kPlanes][kABytes]
     uint8_t *b_s = smem + 2 * kAStage;        // [2][kPlanes][SC * NOUT * 2]
@@ -160,7 +163,7 @@ k_me_conv(const uint4 *__restrict__ xh, const uint4 *__restrict__ xl, const floa
     const int chunks = c_in / SC, stages = TAPS * chunks;
     const int C8 = C / 8;
 
-    if (warp == 0) tmem_alloc<NOUT>(&s_tmem);
+    if (warp == 0) tmem_alloc<NOUT * MT>(&s_tmem);
     if (tid == 32) {
         mbar_init(smem_u32(&s_empty[0]), 1); mbar_init(smem_u32(&s_empty[1]), 1); mbar_init(smem_u32(&s_done), 1);
         mbar_init(smem_u32(&s_full[0]), 1); mbar_init(smem_u32(&s_full[1]), 1);
@@ -196,17 +199,21 @@ k_me_conv(const uint4 *__restrict__ xh, const uint4 *__restrict__ xl, const floa
                     mbar_wait(smem_u32(&s_afull[b]), (uint32_t)(s >> 1) & 1u);
                     mbar_wait(smem_u32(&s_full[b]), (uint32_t)(s >> 1) & 1u);
                     tc_fence_after();
-                    const uint32_t a_buf = a_base + (uint32_t)b * kAStage, b_buf = b_base + (uint32_t)b * kBBytes;
+                    const uint32_t b_buf = b_base + (uint32_t)b * kBBytes;
 #pragma unroll
-                    for (int j = 0; j < SC / 16; ++j) {
-                        const uint32_t a_off = (uint32_t)(2 * j) * (uint32_t)kAGroup, b_off = (uint32_t)(2 * j) * (NOUT * 16u);
-                        const uint64_t a_hi = make_desc(a_buf + a_off, (uint32_t)kAGroup, 128u);
-                        const uint64_t b_hi = make_desc(b_buf + b_off, NOUT * 16u, 128u);
-                        const uint64_t a_lo = make_desc(a_buf + kABytes + a_off, (uint32_t)kAGroup, 128u);
-                        const uint64_t b_lo = make_desc(b_buf + kBPlane + b_off, NOUT * 16u, 128u);
-                        mma_bf16(tmem, a_hi, b_hi, idesc, (s > 0 || j > 0) ? 1u : 0u);
-                        mma_bf16(tmem, a_lo, b_hi, idesc, 1u);
-                        mma_bf16(tmem, a_hi, b_lo, idesc, 1u);
+                    for (int t = 0; t < MT; ++t) {
+                        const uint32_t a_buf = a_base + (uint32_t)b * kAStage + (uint32_t)t * kATile, acc = tmem + (uint32_t)(t * NOUT);
+#pragma unroll
+                        for (int j = 0; j < SC / 16; ++j) {
+                            const uint32_t a_off = (uint32_t)(2 * j) * (uint32_t)kAGroup, b_off = (uint32_t)(2 * j) * (NOUT * 16u);
+                            const uint64_t a_hi = make_desc(a_buf + a_off, (uint32_t)kAGroup, 128u);
+                            const uint64_t b_hi = make_desc(b_buf + b_off, NOUT * 16u, 128u);
+                            const uint64_t a_lo = make_desc(a_buf + kABytes + a_off, (uint32_t)kAGroup, 128u);
+                            const uint64_t b_lo = make_desc(b_buf + kBPlane + b_off, NOUT * 16u, 128u);
+                            mma_bf16(acc, a_hi, b_hi, idesc, (s > 0 || j > 0) ? 1u : 0u);
+                            mma_bf16(acc, a_lo, b_hi, idesc, 1u);
+                            mma_bf16(acc, a_hi, b_lo, idesc, 1u);
+                        }
                     }
                     mma_commit(smem_u32(&s_empty[b]));
                     if (s == stages - 1) mma_commit(smem_u32(&s_done));
@@ -216,18 +223,19 @@ k_me_conv(const uint4 *__restrict__ xh, const uint4 *__restrict__ xl, const floa
             // operand threads: two pixels (tid / 4 and 64 + tid / 4) of channel group tid & 3, value + residual plane;
             // the rows of stage s + 1 are in flight (registers) while stage s is stored
             const int g_loc = tid & 3;
-            int py[2], px[2];
+            constexpr int kU = 2 * MT;      // pixels per thread: u * 64 + tid / 4 of the CTA's MT * 128 pixels
+            int py[kU], px[kU];
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                const int pix = tile * kPix + u * 64 + (tid >> 2);
+            for (int u = 0; u < kU; ++u) {
+                const int pix = tile * (kPix * MT) + u * 64 + (tid >> 2);
                 py[u] = pix / W;
                 px[u] = pix - py[u] * W;
             }
-            auto issue = [&](int s, uint4 (&q)[2][2]) {
+            auto issue = [&](int s, uint4 (&q)[kU][2]) {
                 const int tap = s / chunks, chunk = s - tap * chunks;
                 const int ky = TAPS == 1 ? 1 : tap / 3, kx = TAPS == 1 ? 1 : tap - 3 * ky;
 #pragma unroll
-                for (int u = 0; u < 2; ++u) {
+                for (int u = 0; u < kU; ++u) {
                     const int yy = py[u] * stride - 1 + ky, xx = px[u] * stride - 1 + kx;
                     const bool ok = yy >= 0 && yy < Hi && xx >= 0 && xx < Wi;
                     const size_t o = (size_t)(ok ? yy * Wi + xx : 0) * C8 + chunk * kGroups + g_loc;
@@ -236,23 +244,29 @@ k_me_conv(const uint4 *__restrict__ xh, const uint4 *__restrict__ xl, const floa
                     q[u][1] = ok ? __ldg(xl_a + o) : z;
                 }
             };
-            uint4 qa[2][2], qb[2][2];
-            issue(0, qa);
-            for (int s = 0; s < stages; ++s) {
+            // three register sets rotate: the rows of stages s + 1 and s + 2 are in flight while stage s is stored
+            uint4 q0[kU][2], q1[kU][2], q2[kU][2];
+            auto step = [&](int s, uint4 (&cur)[kU][2], uint4 (&ahead)[kU][2]) {
+                if (s >= stages) return;
                 const int b = s & 1;
-                if (s + 1 < stages) issue(s + 1, qb);
+                if (s + 2 < stages) issue(s + 2, ahead);
                 if (s >= 2) mbar_wait(smem_u32(&s_empty[b]), (uint32_t)((s >> 1) - 1) & 1u);   // MMAs of stage s-2 retired
                 uint8_t *dst = a_s + b * kAStage;
 #pragma unroll
-                for (int u = 0; u < 2; ++u) {
-                    uint4 *d = reinterpret_cast<uint4 *>(dst + g_loc * kAGroup) + (u * 64 + (tid >> 2));
-                    d[0] = qa[u][0];
-                    d[kABytes / 16] = qa[u][1];
+                for (int u = 0; u < kU; ++u) {   // pixel u * 64 + tid / 4 lives in tile u / 2, row (u % 2) * 64 + tid / 4
+                    uint4 *d = reinterpret_cast<uint4 *>(dst + (u >> 1) * kATile + g_loc * kAGroup) + ((u & 1) * 64 + (tid >> 2));
+                    d[0] = cur[u][0];
+                    d[kABytes / 16] = cur[u][1];
                 }
                 fence_async_smem();
                 mbar_arrive(smem_u32(&s_afull[b]));
-#pragma unroll
-                for (int u = 0; u < 2; ++u) { qa[u][0] = qb[u][0]; qa[u][1] = qb[u][1]; }
+            };
+            issue(0, q0);
+            if (stages > 1) issue(1, q1);
+            for (int s = 0; s < stages; s += 3) {
+                step(s, q0, q2);
+                step(s + 1, q1, q0);
+                step(s + 2, q2, q1);
             }
         }
     } else
@@ -389,10 +403,12 @@ k_me_conv(const uint4 *__restrict__ xh, const uint4 *__restrict__ xl, const floa
     tc_fence_after();
 
     // ---- epilogue: warp w reads TMEM lanes 32 (w % 4) .. +31 (= pixels) and columns (w / 4) * NOUT/2 .. ----
-    if (warp < kThreads / 32) {
+    if (warp < kThreads / 32)
+#pragma unroll 1
+    for (int mt = 0; mt < MT; ++mt) {
         const int q = warp & 3, ch0 = (warp >> 2) * (NOUT / 2);
-        const int p_out = tile * kPix + q * 32 + lane;
-        const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)ch0;
+        const int p_out = tile * (kPix * MT) + mt * kPix + q * 32 + lane;
+        const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * NOUT + ch0);
         // NCHW stores may be "pixel-shuffled": output pixel (y * up + up_dy, x * up + up_dx) of an up-sampled grid -- one
         // phase of a ConvTranspose2d with kernel == stride == up evaluated as a 1x1 GEMM over the input pixels
         const int pyo = p_out / W, pxo = p_out - pyo * W;
@@ -447,7 +463,7 @@ k_me_conv(const uint4 *__restrict__ xh, const uint4 *__restrict__ xl, const floa
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) tmem_free<NOUT>(tmem);
+    if (warp == 0) tmem_free<NOUT * MT>(tmem);
 }
 
 }  // namespace me
