@@ -29,5 +29,5 @@ timeout 100 python scripts/bench_det_tail.py 2>&1 | tail -1 | tee $OUT/bench_det
 timeout 100 python scripts/bench_me.py 2>&1 | tail -1 | tee $OUT/bench_me_$TAG.json
 timeout 100 python scripts/bench_enh.py 2>&1 | tail -1 | tee $OUT/bench_enh_$TAG.json
 echo "== ncu: backbone conv + postprocess kernels"
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:"k_me_conv|k_post_nms|k_post_decode" -s 60 -c 8 \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:"k_me_conv" -s 60 -c 6 \
     -f -o $OUT/prof_det_$TAG python scripts/bench_detector.py --frames 2 --iters 1 > $OUT/ncu_det_$TAG.log 2>&1
