@@ -17,6 +17,7 @@ from .enhancer import Enhancer  # noqa: F401
 from .det_tail import DetectionHeads, DoubleConv, DownsampleConv  # noqa: F401
 from .backbone import BaseBEVBackbone  # noqa: F401
 from .postprocess import VoxelPostprocessor  # noqa: F401
+from .lss import VoxelPooling, gen_dx_bx, voxel_pooling  # noqa: F401
 
 from .heter_model_baseline_w_gencomm_stage1 import HeterModelBaselineWGenComm  # noqa: F401
 from .heter_model_baseline_w_gencomm_stage2 import HeterModelBaselineWDiffCommStage2  # noqa: F401

@@ -1,0 +1,60 @@
+// LSS voxel pooling ("splat"): LiftSplatShoot.voxel_pooling (opencood/models/heter_encoders.py:161-217)
+// -- the camera agents' counterpart of the pillar scatter.  The reference flattens the B*N*D*H*W frustum points, computes
+// an integer voxel per point, filters, argsorts by voxel rank, runs the "cumsum trick" (utils/camera_utils.py:209-217) and
+// index_puts the per-voxel sums into a [B, C, Z, Y, X] grid that is then concatenated over Z.  Here one pass does it:
+// a warp per frustum point computes the voxel with the reference's fp32 arithmetic (sub, div, truncation toward zero like
+// .long()) and adds its C-vector into out[b][z*C + c][y][x] with fp32 reductions in L2 (red.global.add.f32) -- no sort, no
+// prefix sum, no [Nprime, C] gather copies.  HBM-bound: Nprime*C*4 bytes read once, the grid written once (memset) plus the
+// touched cells.  Summation order differs from the reference (whose cumsum differences carry ~1e-7 * |running sum| of
+// cancellation noise): tolerance-bounded, indices exact.
+#include "common.cuh"
+
+namespace gc {
+
+__global__ void __launch_bounds__(256)
+k_lss_splat(const float *__restrict__ geom, const float *__restrict__ x, long long n_points, long long per_batch, int C,
+            float3 lo /* bx - dx/2 (fp32, computed like the reference) */, float3 dx, int3 nx, float *__restrict__ out) {
+    const long long p = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (p >= n_points) return;
+    const float gx = __ldg(geom + 3 * p), gy = __ldg(geom + 3 * p + 1), gz = __ldg(geom + 3 * p + 2);
+    // ((geom - (bx - dx/2)) / dx).long(): fp32 subtract, fp32 divide, truncation toward zero
+    const float fx = __fdiv_rn(__fsub_rn(gx, lo.x), dx.x), fy = __fdiv_rn(__fsub_rn(gy, lo.y), dx.y), fz = __fdiv_rn(__fsub_rn(gz, lo.z), dx.z);
+    if (!(fx > -1.0f && fx < (float)nx.x && fy > -1.0f && fy < (float)nx.y && fz > -1.0f && fz < (float)nx.z)) return;  // also NaN
+    const int ix = (int)fx, iy = (int)fy, iz = (int)fz;          // trunc: (-1, 0) -> 0 like the reference
+    if (ix < 0 || ix >= nx.x || iy < 0 || iy >= nx.y || iz < 0 || iz >= nx.z) return;
+    const long long b = p / per_batch;
+    const size_t plane = (size_t)nx.y * nx.x;
+    float *dst = out + ((size_t)b * nx.z * C + (size_t)iz * C) * plane + (size_t)iy * nx.x + ix;
+    const float *src = x + (size_t)p * C;
+    for (int c = lane; c < C; c += 32) {
+        const float v = __ldg(src + c);
+        if (v != 0.0f) atomicAdd(dst + (size_t)c * plane, v);     // result unused -> RED.E.ADD.F32
+    }
+}
+
+}  // namespace gc
+
+using namespace gc;
+
+extern "C" int gc_lss_voxel_pooling(const float *geom, const float *x, long long n_points, int n_batch, int C, const float *dx,
+                                    const float *bx, const int *nx, float *out, void *stream) {
+    GC_REQUIRE(n_points >= 0 && n_batch > 0 && C > 0 && dx && bx && nx && out, GC_EINVAL, "gc_lss_voxel_pooling: bad arguments");
+    GC_REQUIRE(n_points % n_batch == 0, GC_EINVAL, "gc_lss_voxel_pooling: points must split evenly over the batch (B*N*D*H*W)");
+    GC_REQUIRE(nx[0] > 0 && nx[1] > 0 && nx[2] > 0, GC_EINVAL, "gc_lss_voxel_pooling: bad grid");
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t out_bytes = (size_t)n_batch * nx[2] * C * nx[1] * nx[0] * sizeof(float);
+    cudaError_t e = cudaMemsetAsync(out, 0, out_bytes, st);
+    GC_REQUIRE(e == cudaSuccess, (int)e, "gc_lss_voxel_pooling: memset: %s", cudaGetErrorString(e));
+    if (n_points == 0) return GC_OK;
+    GC_REQUIRE(geom && x, GC_EINVAL, "gc_lss_voxel_pooling: null pointer");
+    // bx - dx / 2. in fp32, the reference's tensor arithmetic (heter_encoders.py:174)
+    float3 lo, d;
+    lo.x = bx[0] - dx[0] / 2.0f; lo.y = bx[1] - dx[1] / 2.0f; lo.z = bx[2] - dx[2] / 2.0f;
+    d.x = dx[0]; d.y = dx[1]; d.z = dx[2];
+    const long long blocks = (n_points + 7) / 8;
+    GC_REQUIRE(blocks < (1ll << 31), GC_EUNSUPPORTED, "gc_lss_voxel_pooling: too many points");
+    k_lss_splat<<<(unsigned)blocks, 256, 0, st>>>(geom, x, n_points, n_points / n_batch, C, lo, d, make_int3(nx[0], nx[1], nx[2]), out);
+    GC_LAUNCH_CHECK("k_lss_splat");
+    return GC_OK;
+}

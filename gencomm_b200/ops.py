@@ -552,3 +552,26 @@ def postprocess(cls_preds, reg_preds, dir_preds, anchors, params, tfm=None, work
                                   _ptr(anchors), _ptr(tfm) if tfm is not None else None, B, A, H, W, ctypes.byref(params),
                                   _ptr(workspace), _ptr(boxes), _ptr(scores), _ptr(counts), _stream()), "gc_postprocess")
     return boxes, scores, counts
+
+
+# --------------------------------------------------------------------------------------------
+# (8f rank 4) LSS voxel pooling
+# --------------------------------------------------------------------------------------------
+def lss_voxel_pooling(geom_feats, x, dx, bx, nx):
+    """geom_feats [B,N,D,H,W,3] f32, x [B,N,D,H,W,C] f32 (cuda); dx / bx / nx: the three-element tensors of gen_dx_bx
+    (host or device) -> [B, nz*C, ny, nx] f32."""
+    lib = _lib.load()
+    _chk(geom_feats, "geom_feats", torch.float32, 6)
+    _chk(x, "x", torch.float32, 6)
+    if geom_feats.shape[:5] != x.shape[:5] or geom_feats.shape[5] != 3:
+        raise ValueError("lss_voxel_pooling: geom_feats must be [B,N,D,H,W,3] and x [B,N,D,H,W,C]")
+    B, C = x.shape[0], x.shape[5]
+    dxh = np.ascontiguousarray(torch.as_tensor(dx).detach().cpu().numpy(), dtype=np.float32)
+    bxh = np.ascontiguousarray(torch.as_tensor(bx).detach().cpu().numpy(), dtype=np.float32)
+    nxh = np.ascontiguousarray(torch.as_tensor(nx).detach().cpu().numpy(), dtype=np.int32)
+    out = torch.empty(B, int(nxh[2]) * C, int(nxh[1]), int(nxh[0]), dtype=torch.float32, device=x.device)
+    n = x.numel() // C
+    _lib.check(lib.gc_lss_voxel_pooling(_ptr(geom_feats), _ptr(x), n, B, C, dxh.ctypes.data_as(ctypes.c_void_p),
+                                        bxh.ctypes.data_as(ctypes.c_void_p), nxh.ctypes.data_as(ctypes.c_void_p), _ptr(out),
+                                        _stream()), "gc_lss_voxel_pooling")
+    return out

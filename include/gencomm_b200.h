@@ -288,6 +288,16 @@ int gc_postprocess(const float *cls, const float *reg, const float *dir, const f
                    int A, int H, int W, const gcPostParams *params, void *workspace, float *boxes, float *scores, int *counts,
                    void *stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * (8f rank 4) LiftSplatShoot.voxel_pooling (models/heter_encoders.py:161-217; cumsum trick utils/camera_utils.py:209-217):
+ * geom [Nprime][3] f32 (ego-frame xyz of the B*N*D*H*W frustum points, batch-major), x [Nprime][C] f32, dx / bx [3] f32 and
+ * nx [3] i32 from gen_dx_bx (camera_utils.py:129-134) -> out [B][nz*C][ny][nx] f32 (zeroed here; the reference's
+ * `torch.cat(final.unbind(dim=2), 1)` layout).  Voxel indices are the reference's (fp32 sub / div, truncation); sums are
+ * fp32 reductions in L2 (order differs from the reference's cumsum differences: tolerance-bounded).
+ * ------------------------------------------------------------------------------------------- */
+int gc_lss_voxel_pooling(const float *geom, const float *x, long long n_points, int n_batch, int C, const float *dx,
+                         const float *bx, const int *nx, float *out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -308,6 +308,27 @@ def gen_postprocess(ns):
     np.savez_compressed(os.path.join(OUT, "postprocess.npz"), **out)
 
 
+def gen_lss_pool(ns):
+    """The UNMODIFIED LiftSplatShoot.voxel_pooling (heter_encoders.py:161-217), called unbound on a stand-in ``self`` that
+    only carries dx / bx / nx / use_quickcumsum (building the class needs the EfficientNet image encoder)."""
+    import types
+    from opencood.models.heter_encoders import LiftSplatShoot
+    out = {}
+    for name, conf, kw in (("z1", synth.LSS_GRID_CONF, {}),
+                           ("z2", dict(synth.LSS_GRID_CONF, zbound=[-10, 10, 10.0], xbound=[-20.0, 20.0, 0.8]), {"B": 1, "N": 3})):
+        dx, bx, nx = ref_ops.gen_dx_bx(conf["xbound"], conf["ybound"], conf["zbound"])
+        geom, x = synth.lss_frustum(31, grid_conf=conf, **kw)
+        for quick in (False, True):
+            me = types.SimpleNamespace(dx=dx, bx=bx, nx=nx, use_quickcumsum=quick)
+            res = LiftSplatShoot.voxel_pooling(me, geom, x)
+        nz = torch.nonzero(res.abs().sum(1))          # occupied cells only: the grid is sparse
+        out[f"{name}/shape"] = np.array(res.shape)
+        out[f"{name}/cells"] = nz.numpy().astype(np.int32)
+        out[f"{name}/values"] = res[nz[:, 0], :, nz[:, 1], nz[:, 2]].numpy()
+        print("lss_pool", name, tuple(res.shape), "occupied cells", nz.shape[0])
+    np.savez_compressed(os.path.join(OUT, "lss_pool.npz"), **out)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ns = ref_import.load()
@@ -320,6 +341,7 @@ def main():
     gen_backbone(ns)
     gen_heter_model(ns)
     gen_postprocess(ns)
+    gen_lss_pool(ns)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)) // 1024, "KiB")
 

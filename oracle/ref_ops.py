@@ -672,3 +672,56 @@ def post_process(cls_preds, reg_preds, dir_preds, anchor_box, transformation_mat
     pn = proj.numpy()
     inside = ((pn >= lim[0:3]) & (pn <= lim[3:6])).all(axis=2).sum(axis=1) >= 8                  # box_utils.py:456-458
     return torch.from_numpy(pn[inside]), scores[torch.from_numpy(inside)]
+
+
+# ---------------------------------------------------------------------------------------------
+# LiftSplatShoot.voxel_pooling (models/heter_encoders.py:161-217) with cumsum_trick
+# (utils/camera_utils.py:209-217) and gen_dx_bx (:129-134).
+# ---------------------------------------------------------------------------------------------
+def gen_dx_bx(xbound, ybound, zbound):
+    dx = torch.Tensor([row[2] for row in [xbound, ybound, zbound]])
+    bx = torch.Tensor([row[0] + row[2] / 2.0 for row in [xbound, ybound, zbound]])
+    nx = torch.LongTensor([(row[1] - row[0]) / row[2] for row in [xbound, ybound, zbound]])
+    return dx, bx, nx
+
+
+def lss_voxel_index(geom_feats, dx, bx, nx):
+    """-> (voxel [Nprime,4] i64 (x, y, z, batch), kept [Nprime] bool), heter_encoders.py:174-185."""
+    B = geom_feats.shape[0]
+    n = geom_feats.numel() // 3
+    g = ((geom_feats - (bx - dx / 2.)) / dx).long().view(n, 3)                                   # :174-175
+    batch_ix = torch.cat([torch.full([n // B, 1], ix, dtype=torch.long) for ix in range(B)])     # :176-177
+    g = torch.cat((g, batch_ix), 1)
+    kept = (g[:, 0] >= 0) & (g[:, 0] < nx[0]) & (g[:, 1] >= 0) & (g[:, 1] < nx[1]) & (g[:, 2] >= 0) & (g[:, 2] < nx[2])
+    return g, kept
+
+
+def lss_voxel_pooling(geom_feats, x, dx, bx, nx):
+    """The reference algorithm in the reference's order (sort by rank, fp32 cumsum differences)."""
+    B, N, D, H, W, C = x.shape
+    xf = x.reshape(-1, C)
+    g, kept = lss_voxel_index(geom_feats, dx, bx, nx)
+    xf, g = xf[kept], g[kept]
+    ranks = g[:, 0] * (nx[1] * nx[2] * B) + g[:, 1] * (nx[2] * B) + g[:, 2] * B + g[:, 3]        # :190-193
+    sorts = ranks.argsort()
+    xf, g, ranks = xf[sorts], g[sorts], ranks[sorts]
+    xf = xf.cumsum(0)                                                                           # camera_utils.py:210-215
+    k = torch.ones(xf.shape[0], dtype=torch.bool)
+    k[:-1] = ranks[1:] != ranks[:-1]
+    xf, g = xf[k], g[k]
+    xf = torch.cat((xf[:1], xf[1:] - xf[:-1]))
+    final = torch.zeros((B, C, int(nx[2]), int(nx[1]), int(nx[0])))
+    final[g[:, 3], :, g[:, 2], g[:, 1], g[:, 0]] = xf                                           # :210-211
+    return torch.cat(final.unbind(dim=2), 1)                                                    # :214
+
+
+def lss_voxel_pooling_exact(geom_feats, x, dx, bx, nx):
+    """Same voxel assignment, per-voxel sums accumulated in float64 (the value both the reference's cumsum differences
+    and the kernel's fp32 reductions approximate)."""
+    B, C = x.shape[0], x.shape[-1]
+    xf = x.reshape(-1, C).double()
+    g, kept = lss_voxel_index(geom_feats, dx, bx, nx)
+    xf, g = xf[kept], g[kept]
+    final = torch.zeros((B, int(nx[2]), int(nx[1]), int(nx[0]), C), dtype=torch.float64)
+    final.index_put_((g[:, 3], g[:, 2], g[:, 1], g[:, 0]), xf, accumulate=True)
+    return final.permute(0, 1, 4, 2, 3).reshape(B, int(nx[2]) * C, int(nx[1]), int(nx[0]))

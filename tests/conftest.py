@@ -99,3 +99,20 @@ def heter_inputs():
 @pytest.fixture(scope="session")
 def golden_postprocess():
     return load_golden("postprocess.npz")
+
+
+@pytest.fixture(scope="session")
+def golden_lss_pool():
+    return load_golden("lss_pool.npz")
+
+
+LSS_CASES = {"z1": (None, {}), "z2": ({"zbound": [-10, 10, 10.0], "xbound": [-20.0, 20.0, 0.8]}, {"B": 1, "N": 3})}
+
+
+def lss_case(name):
+    """(geom_feats, x, grid_conf) of tests/golden/lss_pool.npz case `name`, regenerated from its seed."""
+    from gencomm_b200 import synth
+    over, kw = LSS_CASES[name]
+    conf = dict(synth.LSS_GRID_CONF, **(over or {}))
+    geom, x = synth.lss_frustum(31, grid_conf=conf, **kw)
+    return geom, x, conf

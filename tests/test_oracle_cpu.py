@@ -239,3 +239,21 @@ def test_nms_c_restatement_matches_python_restatement():
     b = R.nms_rotated_py(boxes, scores, 0.15)
     assert np.array_equal(a, b) and 5 < len(a) < n
     assert abs(float(R.polygon_iou(quad[0].numpy(), quad[0].numpy())) - 1.0) < 1e-6
+
+
+def test_lss_voxel_pooling_restatement_matches_reference(golden_lss_pool):
+    """the restated LiftSplatShoot.voxel_pooling against the unmodified reference method (bit-exact:
+    same sort, same fp32 cumsum differences), and the float64 per-voxel sums it approximates."""
+    from conftest import LSS_CASES, lss_case
+    g = golden_lss_pool
+    for name in LSS_CASES:
+        geom, x, conf = lss_case(name)
+        dx, bx, nx = R.gen_dx_bx(conf["xbound"], conf["ybound"], conf["zbound"])
+        out = R.lss_voxel_pooling(geom, x, dx, bx, nx)
+        assert list(out.shape) == g[f"{name}/shape"].tolist()
+        cells = T(g[f"{name}/cells"]).long()
+        assert torch.equal(out[cells[:, 0], :, cells[:, 1], cells[:, 2]], T(g[f"{name}/values"])), name
+        assert int((out.abs().sum(1) != 0).sum()) == cells.shape[0]          # nothing outside the recorded cells
+        exact = R.lss_voxel_pooling_exact(geom, x, dx, bx, nx)
+        # the reference's cumsum differences carry cancellation noise ~1e-7 * |running sum|
+        assert float((out.double() - exact).abs().max()) <= 2e-4, name
