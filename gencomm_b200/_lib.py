@@ -83,8 +83,9 @@ SIGNATURES = {
     "gc_to_planes": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "gc_conv_planes": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                                c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "gc_lss_pool_workspace_bytes": (c_size_t, [c_int, c_int, c_void_p]),
     "gc_lss_voxel_pooling": (c_int, [c_void_p, c_void_p, ctypes.c_longlong, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
-                                     c_void_p]),
+                                     c_void_p, c_void_p]),
     "gc_postprocess_workspace_bytes": (c_size_t, [c_int, c_int]),
     "gc_postprocess": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                ctypes.POINTER(PostParams), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),

@@ -33,18 +33,69 @@ k_lss_splat(const float *__restrict__ geom, const float *__restrict__ x, long lo
     }
 }
 
+
+// Vector variant (C % 4 == 0, workspace given): the grid is accumulated channel-last ([B][nz][ny][nx][C]) so that a point
+// issues C/4 128-bit reductions (red.global.add.v4.f32) instead of C scalar ones -- the scalar kernel is bound by the L2
+// reduction rate (151 M RED per call at the OPV2V camera shape: 0.71 ms whatever the collision rate) -- and a tiled
+// transpose writes the NCHW result.
+__device__ __forceinline__ void red_add_v4(float *addr, float4 v) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+__global__ void __launch_bounds__(256)
+k_lss_splat_cl(const float *__restrict__ geom, const float4 *__restrict__ x, long long n_points, long long per_batch, int C4,
+               float3 lo, float3 dx, int3 nx, float *__restrict__ grid_cl) {
+    const long long p = (long long)blockIdx.x * (blockDim.x >> 4) + (threadIdx.x >> 4);     // 16 lanes per point
+    const int l16 = threadIdx.x & 15;
+    if (p >= n_points) return;
+    const float gx = __ldg(geom + 3 * p), gy = __ldg(geom + 3 * p + 1), gz = __ldg(geom + 3 * p + 2);
+    const float fx = __fdiv_rn(__fsub_rn(gx, lo.x), dx.x), fy = __fdiv_rn(__fsub_rn(gy, lo.y), dx.y), fz = __fdiv_rn(__fsub_rn(gz, lo.z), dx.z);
+    if (!(fx > -1.0f && fx < (float)nx.x && fy > -1.0f && fy < (float)nx.y && fz > -1.0f && fz < (float)nx.z)) return;
+    const int ix = (int)fx, iy = (int)fy, iz = (int)fz;
+    if (ix < 0 || ix >= nx.x || iy < 0 || iy >= nx.y || iz < 0 || iz >= nx.z) return;
+    const long long b = p / per_batch;
+    const size_t cell = (((size_t)b * nx.z + iz) * nx.y + iy) * nx.x + ix;
+    float *dst = grid_cl + cell * (size_t)(4 * C4);
+    const float4 *src = x + (size_t)p * C4;
+    for (int c = l16; c < C4; c += 16) red_add_v4(dst + 4 * c, __ldg(src + c));
+}
+
+// grid_cl [R = B*nz*ny][nx][C]  ->  out [B][nz*C][ny][nx]; one CTA per (row r, 32-cell x 32-channel tile)
+__global__ void __launch_bounds__(256)
+k_lss_to_nchw(const float *__restrict__ grid_cl, int C, int nz, int ny, int nxx, float *__restrict__ out) {
+    __shared__ float t[32][33];
+    const int r = blockIdx.z, x0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int k = ty; k < 32; k += 8) {
+        const int xx = x0 + k, c = c0 + tx;
+        t[k][tx] = (xx < nxx && c < C) ? __ldg(grid_cl + ((size_t)r * nxx + xx) * C + c) : 0.0f;
+    }
+    __syncthreads();
+    const int y = r % ny, z = (r / ny) % nz, b = r / (ny * nz);
+    for (int k = ty; k < 32; k += 8) {
+        const int c = c0 + k, xx = x0 + tx;
+        if (c < C && xx < nxx) out[(((size_t)b * nz * C + (size_t)z * C + c) * ny + y) * nxx + xx] = t[tx][k];
+    }
+}
+
 }  // namespace gc
 
 using namespace gc;
 
+extern "C" size_t gc_lss_pool_workspace_bytes(int n_batch, int C, const int *nx) {
+    if (n_batch <= 0 || C <= 0 || C % 4 != 0 || !nx || nx[0] <= 0 || nx[1] <= 0 || nx[2] <= 0) return 0;
+    return (size_t)n_batch * nx[2] * nx[1] * nx[0] * C * sizeof(float);
+}
+
 extern "C" int gc_lss_voxel_pooling(const float *geom, const float *x, long long n_points, int n_batch, int C, const float *dx,
-                                    const float *bx, const int *nx, float *out, void *stream) {
+                                    const float *bx, const int *nx, void *workspace, float *out, void *stream) {
     GC_REQUIRE(n_points >= 0 && n_batch > 0 && C > 0 && dx && bx && nx && out, GC_EINVAL, "gc_lss_voxel_pooling: bad arguments");
     GC_REQUIRE(n_points % n_batch == 0, GC_EINVAL, "gc_lss_voxel_pooling: points must split evenly over the batch (B*N*D*H*W)");
     GC_REQUIRE(nx[0] > 0 && nx[1] > 0 && nx[2] > 0, GC_EINVAL, "gc_lss_voxel_pooling: bad grid");
     cudaStream_t st = (cudaStream_t)stream;
     const size_t out_bytes = (size_t)n_batch * nx[2] * C * nx[1] * nx[0] * sizeof(float);
-    cudaError_t e = cudaMemsetAsync(out, 0, out_bytes, st);
+    const bool vec = workspace != nullptr && C % 4 == 0 && n_points > 0 && (size_t)n_batch * nx[2] * nx[1] <= 65535;
+    cudaError_t e = cudaMemsetAsync(vec ? workspace : (void *)out, 0, out_bytes, st);
     GC_REQUIRE(e == cudaSuccess, (int)e, "gc_lss_voxel_pooling: memset: %s", cudaGetErrorString(e));
     if (n_points == 0) return GC_OK;
     GC_REQUIRE(geom && x, GC_EINVAL, "gc_lss_voxel_pooling: null pointer");
@@ -52,9 +103,21 @@ extern "C" int gc_lss_voxel_pooling(const float *geom, const float *x, long long
     float3 lo, d;
     lo.x = bx[0] - dx[0] / 2.0f; lo.y = bx[1] - dx[1] / 2.0f; lo.z = bx[2] - dx[2] / 2.0f;
     d.x = dx[0]; d.y = dx[1]; d.z = dx[2];
+    const int3 n3 = make_int3(nx[0], nx[1], nx[2]);
+    if (vec) {
+        const long long blocks = (n_points + 15) / 16;
+        GC_REQUIRE(blocks < (1ll << 31), GC_EUNSUPPORTED, "gc_lss_voxel_pooling: too many points");
+        k_lss_splat_cl<<<(unsigned)blocks, 256, 0, st>>>(geom, (const float4 *)x, n_points, n_points / n_batch, C / 4, lo, d, n3,
+                                                        (float *)workspace);
+        GC_LAUNCH_CHECK("k_lss_splat_cl");
+        k_lss_to_nchw<<<dim3((nx[0] + 31) / 32, (C + 31) / 32, n_batch * nx[2] * nx[1]), 256, 0, st>>>((const float *)workspace, C, nx[2],
+                                                                                                   nx[1], nx[0], out);
+        GC_LAUNCH_CHECK("k_lss_to_nchw");
+        return GC_OK;
+    }
     const long long blocks = (n_points + 7) / 8;
     GC_REQUIRE(blocks < (1ll << 31), GC_EUNSUPPORTED, "gc_lss_voxel_pooling: too many points");
-    k_lss_splat<<<(unsigned)blocks, 256, 0, st>>>(geom, x, n_points, n_points / n_batch, C, lo, d, make_int3(nx[0], nx[1], nx[2]), out);
+    k_lss_splat<<<(unsigned)blocks, 256, 0, st>>>(geom, x, n_points, n_points / n_batch, C, lo, d, n3, out);
     GC_LAUNCH_CHECK("k_lss_splat");
     return GC_OK;
 }

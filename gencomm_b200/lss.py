@@ -35,7 +35,8 @@ class VoxelPooling(nn.Module):
         self.dx = nn.Parameter(dx, requires_grad=False)      # heter_encoders.py:99-101 keeps them as frozen parameters
         self.bx = nn.Parameter(bx, requires_grad=False)
         self.nx = nn.Parameter(nx, requires_grad=False)
+        self._host = (dx.clone(), bx.clone(), nx.clone())    # host copies for the launch (no device -> host sync per call)
 
     @torch.no_grad()
     def forward(self, geom_feats, x):
-        return voxel_pooling(geom_feats, x, self.dx, self.bx, self.nx)
+        return voxel_pooling(geom_feats, x, *self._host)

@@ -557,7 +557,7 @@ def postprocess(cls_preds, reg_preds, dir_preds, anchors, params, tfm=None, work
 # --------------------------------------------------------------------------------------------
 # (8f rank 4) LSS voxel pooling
 # --------------------------------------------------------------------------------------------
-def lss_voxel_pooling(geom_feats, x, dx, bx, nx):
+def lss_voxel_pooling(geom_feats, x, dx, bx, nx, vector=True):
     """geom_feats [B,N,D,H,W,3] f32, x [B,N,D,H,W,C] f32 (cuda); dx / bx / nx: the three-element tensors of gen_dx_bx
     (host or device) -> [B, nz*C, ny, nx] f32."""
     lib = _lib.load()
@@ -571,7 +571,10 @@ def lss_voxel_pooling(geom_feats, x, dx, bx, nx):
     nxh = np.ascontiguousarray(torch.as_tensor(nx).detach().cpu().numpy(), dtype=np.int32)
     out = torch.empty(B, int(nxh[2]) * C, int(nxh[1]), int(nxh[0]), dtype=torch.float32, device=x.device)
     n = x.numel() // C
+    nxp = nxh.ctypes.data_as(ctypes.c_void_p)
+    ws_bytes = lib.gc_lss_pool_workspace_bytes(B, C, nxp) if vector else 0
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device) if ws_bytes else None
     _lib.check(lib.gc_lss_voxel_pooling(_ptr(geom_feats), _ptr(x), n, B, C, dxh.ctypes.data_as(ctypes.c_void_p),
-                                        bxh.ctypes.data_as(ctypes.c_void_p), nxh.ctypes.data_as(ctypes.c_void_p), _ptr(out),
-                                        _stream()), "gc_lss_voxel_pooling")
+                                        bxh.ctypes.data_as(ctypes.c_void_p), nxp, _ptr(ws) if ws is not None else None,
+                                        _ptr(out), _stream()), "gc_lss_voxel_pooling")
     return out

@@ -207,9 +207,10 @@ LSS_GRID_CONF = {"xbound": [-51.2, 51.2, 0.4], "ybound": [-51.2, 51.2, 0.4], "zb
                  "ddiscr": [2, 50, 48]}     # the camera grid of the OPV2V-H LSS agents (m2 yaml blocks): 256 x 256 x 1
 
 
-def lss_frustum(seed, B=2, N=2, D=12, H=8, W=11, C=16, grid_conf=None, zsplit=False):
+def lss_frustum(seed, B=2, N=2, D=12, H=8, W=11, C=16, grid_conf=None, coarse_frac=0.5):
     """Synthetic frustum: geom_feats [B,N,D,H,W,3] (ego-frame xyz; ~10 % outside the grid, some within one cell below the
-    lower bound, where the reference's truncation keeps them) and features x [B,N,D,H,W,C]."""
+    lower bound, where the reference's truncation keeps them) and features x [B,N,D,H,W,C].  ``coarse_frac`` of the
+    points are snapped onto a 3 m lattice (many points per cell: exercises the accumulation)."""
     conf = grid_conf or LSS_GRID_CONF
     g = torch.Generator().manual_seed(int(seed))
     shape = (B, N, D, H, W)
@@ -217,7 +218,7 @@ def lss_frustum(seed, B=2, N=2, D=12, H=8, W=11, C=16, grid_conf=None, zsplit=Fa
     ys = (torch.rand(shape, generator=g) * 1.12 - 0.06) * (conf["ybound"][1] - conf["ybound"][0]) + conf["ybound"][0]
     zs = (torch.rand(shape, generator=g) * 1.2 - 0.1) * (conf["zbound"][1] - conf["zbound"][0]) + conf["zbound"][0]
     # camera rays hit the same cells many times: quantise half of the points onto a coarse lattice
-    coarse = torch.rand(shape, generator=g) < 0.5
+    coarse = torch.rand(shape, generator=g) < coarse_frac
     xs = torch.where(coarse, torch.round(xs / 3.0) * 3.0 + 0.1, xs)
     ys = torch.where(coarse, torch.round(ys / 3.0) * 3.0 + 0.1, ys)
     geom = torch.stack([xs, ys, zs], dim=-1).float()

@@ -293,10 +293,12 @@ int gc_postprocess(const float *cls, const float *reg, const float *dir, const f
  * geom [Nprime][3] f32 (ego-frame xyz of the B*N*D*H*W frustum points, batch-major), x [Nprime][C] f32, dx / bx [3] f32 and
  * nx [3] i32 from gen_dx_bx (camera_utils.py:129-134) -> out [B][nz*C][ny][nx] f32 (zeroed here; the reference's
  * `torch.cat(final.unbind(dim=2), 1)` layout).  Voxel indices are the reference's (fp32 sub / div, truncation); sums are
- * fp32 reductions in L2 (order differs from the reference's cumsum differences: tolerance-bounded).
+ * fp32 reductions in L2 (order differs from the reference's cumsum differences: tolerance-bounded).  With a workspace
+ * (channel-last accumulation grid) and C % 4 == 0 the reductions are 128-bit (red.global.add.v4.f32) + one transpose.
  * ------------------------------------------------------------------------------------------- */
+size_t gc_lss_pool_workspace_bytes(int n_batch, int C, const int *nx); /* 0 when C % 4 != 0 (scalar path, no workspace) */
 int gc_lss_voxel_pooling(const float *geom, const float *x, long long n_points, int n_batch, int C, const float *dx,
-                         const float *bx, const int *nx, float *out, void *stream);
+                         const float *bx, const int *nx, void *workspace /* or NULL */, float *out, void *stream);
 
 #ifdef __cplusplus
 }

@@ -39,5 +39,12 @@ def test_voxel_pooling_function_form_and_empty_input():
     a = G.voxel_pooling(geom.to(DEV), x.to(DEV), dx, bx, nx)
     b = G.VoxelPooling(conf).to(DEV)(geom.to(DEV), x.to(DEV))
     assert a.shape == b.shape and float((a - b).abs().max()) <= 1e-5       # atomics: run-to-run order may differ
+    # scalar-reduction path (no workspace; also taken when C % 4 != 0) against the 128-bit-reduction path
+    from gencomm_b200 import ops
+    c = ops.lss_voxel_pooling(geom.to(DEV), x.to(DEV), dx, bx, nx, vector=False)
+    assert float((a - c).abs().max()) <= 1e-5
+    x3 = x[..., :3].contiguous()
+    d3 = G.voxel_pooling(geom.to(DEV), x3.to(DEV), dx, bx, nx)
+    assert float((d3 - a[:, :3]).abs().max()) <= 1e-5
     far = torch.full_like(geom, 1.0e4)
     assert float(G.voxel_pooling(far.to(DEV), x.to(DEV), dx, bx, nx).abs().max()) == 0.0
