@@ -150,6 +150,11 @@ class HeterModelBaselineWGenComm(_HeadsMixin, nn.Module):
         for m in self.modality_name_list:
             if m not in counts:
                 continue
+            inp = data_dict[f'inputs_{m}']
+            if 'points' not in inp and 'batch_size' not in inp:
+                # the agent count is known on the host: spares PointPillarScatter's `.item()` sync (point_pillar_scatter.py:45)
+                data_dict = dict(data_dict)
+                data_dict[f'inputs_{m}'] = dict(inp, batch_size=counts[m])
             feature = getattr(self, f"encoder_{m}")(data_dict, m)
             backbone = getattr(self, f"backbone_{m}")
             if not isinstance(backbone, nn.Identity):

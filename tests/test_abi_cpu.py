@@ -109,3 +109,25 @@ def test_bev_backbone_keeps_reference_state_dict_keys(golden_backbone):
     assert m.num_bev_features == 192
     with pytest.raises(NotImplementedError):
         BaseBEVBackbone({**BACKBONE_CFG, "upsample_strides": [1, 2, 0.5]}, 64)
+
+
+def test_postprocessor_and_lss_host_logic():
+    """Host-side mirrors that need no GPU: argument errors, anchor generation shape, gen_dx_bx."""
+    import pytest
+    import torch
+    import gencomm_b200 as G
+    from gencomm_b200 import ops, synth
+    params = synth.postprocess_params()
+    pp = G.VoxelPostprocessor(params, train=False)
+    assert pp.generate_anchor_box().shape == (64, 128, 2, 7)
+    with pytest.raises(NotImplementedError, match="one cav"):
+        pp.post_process({"a": {}, "b": {}}, {"a": {}, "b": {}})
+    with pytest.raises(ValueError, match="order"):
+        ops.make_post_params(0.2, 0.15, 0.78, 2, "xyz", params["gt_range"])
+    bad = dict(params, order="whl")
+    with pytest.raises(ValueError, match="order"):
+        G.VoxelPostprocessor(bad, train=False).generate_anchor_box()
+    dx, bx, nx = G.gen_dx_bx([-51.2, 51.2, 0.4], [-51.2, 51.2, 0.4], [-10, 10, 20.0])
+    assert nx.tolist() == [256, 256, 1] and torch.allclose(bx, torch.tensor([-51.0, -51.0, 0.0]))
+    with pytest.raises(RuntimeError, match="CUDA tensor"):          # no CPU path
+        G.voxel_pooling(torch.zeros(1, 1, 1, 1, 1, 3), torch.zeros(1, 1, 1, 1, 1, 4), dx, bx, nx)
