@@ -244,12 +244,12 @@ k_me_conv(const uint4 *__restrict__ xh, const uint4 *__restrict__ xl, const floa
                     q[u][1] = ok ? __ldg(xl_a + o) : z;
                 }
             };
-            // three register sets rotate: the rows of stages s + 1 and s + 2 are in flight while stage s is stored
-            uint4 q0[kU][2], q1[kU][2], q2[kU][2];
+            // four register sets rotate: the rows of stages s + 1 .. s + 3 are in flight while stage s is stored
+            uint4 q0[kU][2], q1[kU][2], q2[kU][2], q3[kU][2];
             auto step = [&](int s, uint4 (&cur)[kU][2], uint4 (&ahead)[kU][2]) {
                 if (s >= stages) return;
                 const int b = s & 1;
-                if (s + 2 < stages) issue(s + 2, ahead);
+                if (s + 3 < stages) issue(s + 3, ahead);
                 if (s >= 2) mbar_wait(smem_u32(&s_empty[b]), (uint32_t)((s >> 1) - 1) & 1u);   // MMAs of stage s-2 retired
                 uint8_t *dst = a_s + b * kAStage;
 #pragma unroll
@@ -263,10 +263,12 @@ k_me_conv(const uint4 *__restrict__ xh, const uint4 *__restrict__ xl, const floa
             };
             issue(0, q0);
             if (stages > 1) issue(1, q1);
-            for (int s = 0; s < stages; s += 3) {
-                step(s, q0, q2);
+            if (stages > 2) issue(2, q2);
+            for (int s = 0; s < stages; s += 4) {
+                step(s, q0, q3);
                 step(s + 1, q1, q0);
                 step(s + 2, q2, q1);
+                step(s + 3, q3, q2);
             }
         }
     } else
