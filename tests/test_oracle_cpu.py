@@ -257,3 +257,32 @@ def test_lss_voxel_pooling_restatement_matches_reference(golden_lss_pool):
         exact = R.lss_voxel_pooling_exact(geom, x, dx, bx, nx)
         # the reference's cumsum differences carry cancellation noise ~1e-7 * |running sum|
         assert float((out.double() - exact).abs().max()) <= 2e-4, name
+
+
+def test_quad_iou_properties():
+    """Domain properties of the restated polygon IoU (oracle/nms_ref.c): symmetry, identity, disjointness, containment,
+    orientation independence and a closed-form case (two axis-aligned boxes shifted by half their length)."""
+    import ctypes
+    lib = R._lib()
+    def iou(p, q):
+        p = np.ascontiguousarray(p, np.float64); q = np.ascontiguousarray(q, np.float64)
+        return float(lib.gc_ref_quad_iou(R._p(p), R._p(q)))
+    rng = np.random.default_rng(3)
+    def box(cx, cy, l, w, yaw):
+        c, s = np.cos(yaw), np.sin(yaw)
+        pts = np.array([[l / 2, -w / 2], [l / 2, w / 2], [-l / 2, w / 2], [-l / 2, -w / 2]])
+        return pts @ np.array([[c, s], [-s, c]]) + [cx, cy]
+    a = box(0, 0, 4, 2, 0.0)
+    assert abs(iou(a, box(2, 0, 4, 2, 0.0)) - (4.0 / 12.0)) < 1e-6          # overlap 2x2 = 4, union 8 + 8 - 4
+    assert iou(a, box(10, 0, 4, 2, 0.3)) == 0.0                              # disjoint
+    assert abs(iou(a, box(0, 0, 2, 1, 0.0)) - 0.25) < 1e-6                   # contained: 2 / 8
+    for _ in range(200):
+        p = box(*rng.uniform(-3, 3, 2), *rng.uniform(1, 5, 2), rng.uniform(-3.2, 3.2))
+        q = box(*rng.uniform(-3, 3, 2), *rng.uniform(1, 5, 2), rng.uniform(-3.2, 3.2))
+        v = iou(p, q)
+        assert 0.0 <= v <= 1.0 + 1e-6
+        assert abs(v - iou(q, p)) < 1e-6                                      # symmetric
+        assert abs(v - iou(p[::-1], q)) < 1e-6                                # orientation of the corner order
+        assert abs(v - iou(p + 7.5, q + 7.5)) < 1e-5                          # translation
+        assert abs(iou(p, p) - 1.0) < 1e-6
+        assert abs(v - float(R.polygon_iou(p, q))) < 1e-6                     # C vs Python restatement
