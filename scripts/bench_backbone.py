@@ -47,13 +47,16 @@ def main():
     out = {"workload": f"BaseBEVBackbone m1, {args.agents} agents, 64x256x512 -> 384x128x256", "ms_per_call": ms,
            "agents_per_s": args.agents / ms * 1e3, "tflops": fl * args.agents / ms / 1e9, "launches_per_call": 1 + 19 + 21}
     if args.torch:
-        import torch.nn.functional as F
         torch.backends.cudnn.allow_tf32 = False
         torch.backends.cuda.matmul.allow_tf32 = False
-        sd = {k: v for k, v in m.state_dict().items()}
-        sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-        from oracle import ref_ops as R   # the torch restatement, run on the GPU for a cuDNN fp32 comparison
-        f = lambda: R.bev_backbone(x, sd, CFG["layer_nums"], CFG["layer_strides"], CFG["upsample_strides"])
+
+        @torch.no_grad()
+        def f():   # the module tree holds the reference's own torch layers (blocks / deblocks): this is the cuDNN path
+            y, ups = x, []
+            for blk, deb in zip(m.blocks, m.deblocks):
+                y = blk(y)
+                ups.append(deb(y))
+            return torch.cat(ups, dim=1)
         for _ in range(2):
             f()
         torch.cuda.synchronize()

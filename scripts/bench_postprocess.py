@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Microbench of the GPU decode + rotated NMS (gc_postprocess) on synthetic head maps, beside the oracle on the host.
+"""Microbench of the GPU decode + rotated NMS (gc_postprocess) on synthetic head maps.
 
     python scripts/bench_postprocess.py [--frames 8] [--bias -3.0] [--iters 20]
 """
@@ -7,7 +7,6 @@ import argparse
 import json
 import os
 import sys
-import time
 
 import torch
 
@@ -20,7 +19,6 @@ def main():
     ap.add_argument("--frames", type=int, default=8)
     ap.add_argument("--bias", type=float, default=-3.0)
     ap.add_argument("--iters", type=int, default=20)
-    ap.add_argument("--cpu", action="store_true", help="also time the oracle (C NMS + torch decode) on one frame")
     args = ap.parse_args()
     pp = VoxelPostprocessor(synth.postprocess_params(), train=False)
     anchors = torch.from_numpy(pp.generate_anchor_box()).float().cuda()
@@ -39,11 +37,6 @@ def main():
     out = {"workload": f"decode + rotated NMS, {args.frames} frames, 64x128x2 anchors, bias {args.bias}",
            "candidates_per_frame": [int((torch.sigmoid(h[0]) > 0.2).sum()) for h in heads][:4],
            "kept_per_frame": counts.tolist()[:4], "ms_per_call": ms, "frames_per_s": args.frames / ms * 1e3}
-    if args.cpu:
-        from oracle import ref_ops as R
-        t = time.time()
-        R.post_process(heads[0][0], heads[0][1], heads[0][2], anchors.cpu(), torch.eye(4), synth.postprocess_params())
-        out["oracle_cpu_ms_per_frame"] = (time.time() - t) * 1e3
     print(json.dumps(out))
 
 

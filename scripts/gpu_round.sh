@@ -24,7 +24,7 @@ timeout 600 python scripts/bench_fuse.py --quick 2>&1 | tee $OUT/bench_fuse_$TAG
 echo "== component microbenches"
 timeout 200 python scripts/bench_detector.py 2>&1 | tail -1 | tee $OUT/bench_detector_$TAG.json
 timeout 200 python scripts/bench_backbone.py --torch 2>&1 | tail -1 | tee $OUT/bench_backbone_$TAG.json
-timeout 100 python scripts/bench_postprocess.py --cpu 2>&1 | tail -1 | tee $OUT/bench_postprocess_$TAG.json
+timeout 100 python scripts/bench_postprocess.py 2>&1 | tail -1 | tee $OUT/bench_postprocess_$TAG.json
 timeout 100 python scripts/bench_det_tail.py 2>&1 | tail -1 | tee $OUT/bench_det_tail_$TAG.json
 timeout 100 python scripts/bench_me.py 2>&1 | tail -1 | tee $OUT/bench_me_$TAG.json
 timeout 100 python scripts/bench_enh.py 2>&1 | tail -1 | tee $OUT/bench_enh_$TAG.json
