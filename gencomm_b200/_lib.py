@@ -52,11 +52,12 @@ SIGNATURES = {
                                           c_void_p]),
     "gc_gencomm_host_weight_floats": (c_size_t, [c_int]),
     "gc_gencomm_device_weight_floats": (c_size_t, [c_int]),
+    "gc_gencomm_cluster_weight_floats": (c_size_t, [c_int]),
     "gc_gencomm_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "gc_gencomm_sample": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
-                                  c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
-    "gc_unet_forward": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
-                                c_int, c_void_p, c_void_p, c_void_p]),
+                                  c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "gc_unet_forward": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                                c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "gc_me_param_floats": (c_size_t, []),
     "gc_me_packed_bytes": (c_size_t, [c_int]),
     "gc_me_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),

@@ -22,6 +22,7 @@
 // boundary tensors; the sampler arithmetic (q_posterior + noise) is fused into conv_out's
 // epilogue, q_sample is one elementwise kernel.  28 launches per step, 0 host syncs.
 #include "common.cuh"
+#include "denoiser_cluster.cuh"
 #include "denoiser_tc.cuh"
 
 namespace gc {
@@ -447,9 +448,23 @@ struct HostTail {     // trailing part of the host weight blob, after T * kC8Lay
 static int unet_eval(cudaStream_t st, int A, int C, int H, int W, const float *cond, UnetWorkspace &ws,
                      const C8Params *prm, const HostTail &tail, const float *w_in, const float *w_out,
                      const float *b_out, int mode, float c1, float c2, float sigma, const float *noise, float *pred,
-                     int precision) {
+                     int precision, const float *rec_dev) {
     Act *p = ws.p, *q = ws.q;
     g_precision = precision;
+    // cluster-resident middle (denoiser_cluster.cu): conv_in -> ONE launch for the 26 width-8 layers -> conv_out
+    if ((precision & GC_PREC_CLUSTER) && rec_dev != nullptr && (precision & GC_PREC_BF16_TC) == GC_PREC_BF16_TC &&
+        unet_cluster_eligible(C, H, W) && conv_in_tc_eligible(C, H, W) && conv_out_tc_eligible(C, H, W)) {
+        Bias8 bi;
+        for (int i = 0; i < 8; ++i) bi.b[i] = tail.conv_in_bias[i];
+        p[0].tiles = conv_in_tc_tiles(H, W);
+        if (int rc = conv_in_tc(st, A, cond, ws.x, ws.tc_packed, bi, C, H, W, p[0].data, p[0].stats)) return rc;
+        if (int rc = unet_middle_cluster(st, A, p[0].data, rec_dev, p[11].data, p[11].stats)) return rc;
+        p[11].tiles = kCl;
+        Affine8 aff;
+        for (int i = 0; i < 8; ++i) { aff.gamma[i] = tail.norm_out_gamma[i]; aff.beta[i] = tail.norm_out_beta[i]; }
+        return conv_out_tc(st, A, p[11].data, p[11].stats, p[11].tiles, ws.tc_packed, b_out, aff, C, H, W, mode, c1, c2, sigma,
+                           noise, ws.x, pred, 0);
+    }
     Bias8 bi;
     for (int i = 0; i < 8; ++i) bi.b[i] = tail.conv_in_bias[i];
     const dim3 gridP((W + kTW - 1) / kTW, (H + kTH - 1) / kTH, A);
@@ -497,6 +512,8 @@ extern "C" size_t gc_gencomm_host_weight_floats(int T) {
     return (size_t)T * kC8Layers * (sizeof(C8Params) / 4) + sizeof(HostTail) / 4;
 }
 
+extern "C" size_t gc_gencomm_cluster_weight_floats(int T) { return (size_t)T * kClLayers * kClRecFloats; }
+
 extern "C" size_t gc_gencomm_device_weight_floats(int C) {
     return (size_t)(C + 2) * 72 + (size_t)C * 72 + (size_t)C;
 }
@@ -516,8 +533,8 @@ static int check_unet_args(int A, int C, int H, int W, int T) {
 
 // One denoiser evaluation x0 = UNet(cat[cond, x], t) for tests/diagnostics: writes pred [A][C][H][W].
 extern "C" int gc_unet_forward(const float *cond, const float *x, int total_agents, int t_index, const float *w_host,
-                               const float *w_dev, int C, int H, int W, int T, int precision, void *workspace,
-                               float *pred, void *stream) {
+                               const float *w_dev, const float *w_cluster_dev, int C, int H, int W, int T, int precision,
+                               void *workspace, float *pred, void *stream) {
     if (int rc = check_unet_args(total_agents, C, H, W, T)) return rc;
     GC_REQUIRE(cond && x && w_host && w_dev && workspace && pred, GC_EINVAL, "gc_unet_forward: null pointer");
     GC_REQUIRE(t_index >= 0 && t_index < T, GC_EINVAL, "gc_unet_forward: bad timestep");
@@ -530,13 +547,14 @@ extern "C" int gc_unet_forward(const float *cond, const float *x, int total_agen
     if (precision & GC_PREC_BF16_TC)
         if (int rc = conv_tc_pack_weights(st, w_in, w_out, C, ws.tc_packed)) return rc;
     return unet_eval(st, total_agents, C, H, W, cond, ws, prm, tail, w_in, w_out, b_out, 0, 0.f, 0.f, 0.f, nullptr, pred,
-                     precision);
+                     precision, w_cluster_dev ? w_cluster_dev + (size_t)t_index * kClLayers * kClRecFloats : nullptr);
 }
 
 extern "C" int gc_gencomm_sample(const float *feat, const float *cond, const int32_t *agent_offsets, int n_frames,
                                  int total_agents, const float *noise0, const float *step_noise,
-                                 const float *w_host, const float *w_dev, const float *schedule_host, int C, int H,
-                                 int W, int T, int precision, void *workspace, float *pred, void *stream) {
+                                 const float *w_host, const float *w_dev, const float *w_cluster_dev,
+                                 const float *schedule_host, int C, int H, int W, int T, int precision, void *workspace,
+                                 float *pred, void *stream) {
     if (int rc = check_unet_args(total_agents, C, H, W, T)) return rc;
     GC_REQUIRE(feat && cond && agent_offsets && noise0 && w_host && w_dev && schedule_host && workspace && pred,
                GC_EINVAL, "gc_gencomm_sample: null pointer");
@@ -561,7 +579,8 @@ extern "C" int gc_gencomm_sample(const float *feat, const float *cond, const int
         const float *s = schedule_host + (size_t)t * 5;
         const float *nz = t > 0 ? step_noise + (size_t)(T - 1 - t) * total_agents * per_agent : nullptr;
         int rc = unet_eval(st, total_agents, C, H, W, cond, ws, prm, tail, w_in, w_out, b_out, t > 0 ? 1 : 0, s[2], s[3],
-                           s[4], nz, pred, precision);
+                           s[4], nz, pred, precision,
+                           w_cluster_dev ? w_cluster_dev + (size_t)t * kClLayers * kClRecFloats : nullptr);
         if (rc) return rc;
     }
     return GC_OK;

@@ -103,6 +103,33 @@ def pack_unet(sd, C, T, ch=8):
     return host, dev
 
 
+CL_REC_FLOATS = 1712     # kClRecFloats in csrc/denoiser_cluster.cuh
+_DOWN_LAYER = 4          # index of down.0.downsample among the 26 records (CUDA-core layer of the cluster kernel)
+
+
+def pack_unet_cluster(host, T):
+    """Host blob of pack_unet -> the per-layer records of the cluster kernel (csrc/denoiser_cluster.cuh): the tf32 B
+    operand of the input-row-stationary formulation [kx][cin group][k half][block j][cout][4 cin], block j = tap row
+    ky = 2 - j (block 3 zero), then bias, GroupNorm affine and nin_shortcut.  Returns a float32 numpy array."""
+    recs = np.asarray(host[:T * N_C8_LAYERS * C8_FLOATS], dtype=np.float32).reshape(T * N_C8_LAYERS, C8_FLOATS)
+    out = np.zeros((T * N_C8_LAYERS, CL_REC_FLOATS), dtype=np.float32)
+    for i, rec in enumerate(recs):
+        w = rec[:1152].reshape(3, 3, 2, 2, 4, 8)                     # [ky][kx][cg][half][cin4][cout]
+        if i % N_C8_LAYERS == _DOWN_LAYER:
+            out[i, :576] = rec[:1152].reshape(9, 16, 8)[:, :8, :].reshape(-1)   # [tap][cin 8][cout 8]
+        else:
+            b = np.zeros((3, 2, 2, 4, 8, 4), dtype=np.float32)       # [kx][cg][half][j][cout][cin4]
+            for j in range(3):
+                b[:, :, :, j] = w[2 - j].transpose(0, 1, 2, 4, 3)
+            out[i, :1536] = b.reshape(-1)
+        out[i, 1536:1544] = rec[1152:1160]
+        out[i, 1544:1560] = rec[1160:1176]
+        out[i, 1560:1576] = rec[1176:1192]
+        out[i, 1576:1704] = rec[1192:1320]
+        out[i, 1704:1712] = rec[1320:1328]
+    return out.reshape(-1)
+
+
 def make_schedule(T, linear_start=5e-3, linear_end=5e-2):
     """cond_diff.py:196-236 + MDD_utils.py:208-212; returns (buffers dict like the reference, [T,5] float32 table)."""
     betas = (torch.linspace(linear_start ** 0.5, linear_end ** 0.5, T, dtype=torch.float64) ** 2).numpy()
@@ -192,24 +219,34 @@ class DiffusionUNet(nn.Module):
         self.norm_out = _gn(8)
         self.conv_out = nn.Conv2d(8, m.out_ch, 3, 1, 1)
         self._packed = None
-        self.precision = ops.PREC_TC_ALL   # see GenComm.precision
+        self.precision = ops.PREC_CLUSTER_ALL   # see GenComm.precision
 
     def packed(self, T, device):
-        """(host blob, device blob) for T steps, rebuilt when any parameter changes."""
+        """(host blob, device blob, cluster-kernel device blob) for T steps, rebuilt when any parameter changes
+        (call ``invalidate()`` after writing parameters through ``.data``, which does not bump the version)."""
         key = (T, str(device)) + tuple((p.data_ptr(), p._version) for p in self.parameters())
         if self._packed is None or self._packed[0] != key:
             host, dev = pack_unet(self.state_dict(), self.out_ch, T)
-            self._packed = (key, host, dev.to(device))
-        return self._packed[1], self._packed[2]
+            cl = torch.from_numpy(pack_unet_cluster(host, T))
+            self._packed = (key, host, dev.to(device), cl.to(device))
+        return self._packed[1], self._packed[2], self._packed[3]
+
+    def invalidate(self):
+        """Drop the packed-weight cache (in-place parameter updates through ``.data`` are not detected)."""
+        self._packed = None
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        self._packed = None
+        return super()._load_from_state_dict(*args, **kwargs)
 
     def forward(self, x, t):
         if self.training:
             raise RuntimeError("gencomm_b200 DiffusionUNet is inference-only: call .eval()")
         tv = int(t.flatten()[0].item()) if isinstance(t, torch.Tensor) else int(t)
         T = max(tv + 1, 3)
-        host, dev = self.packed(T, x.device)
+        host, dev, cl = self.packed(T, x.device)
         cond, xt = x[:, :2].contiguous(), x[:, 2:].contiguous()
-        return ops.unet_forward(cond, xt, tv, host, dev, T, precision=self.precision)
+        return ops.unet_forward(cond, xt, tv, host, dev, T, precision=self.precision, w_cluster=cl)
 
 
 class GenComm(nn.Module):
@@ -221,6 +258,9 @@ class GenComm(nn.Module):
     ``precision``: ``'bf16'`` runs conv_in / conv_out as bf16 tcgen05 implicit GEMMs with fp32
     accumulation where the shape allows (W % 128 == 0, C % 64 == 0) and everything else in fp32;
     ``'tc'`` additionally runs the full-resolution width-8 middle layers as tf32 tcgen05 implicit GEMMs;
+    ``'cluster'`` (the default) is ``'tc'`` with the 26 width-8 layers of an evaluation fused into one launch of
+    8-CTA thread-block clusters, one per agent, activations resident in distributed shared memory
+    (csrc/denoiser_cluster.cu; 64 x 128 maps, other shapes fall back to ``'tc'``);
     ``'fp32'`` keeps every layer in fp32 (parity path, <= 1e-4 of the reference).
     """
 
@@ -238,12 +278,14 @@ class GenComm(nn.Module):
 
     @property
     def precision(self):
-        return {ops.PREC_F32: 'fp32', ops.PREC_BF16_TC: 'bf16', ops.PREC_TC_ALL: 'tc'}.get(self.denoiser.precision, 'custom')
+        return {ops.PREC_F32: 'fp32', ops.PREC_BF16_TC: 'bf16', ops.PREC_TC_ALL: 'tc',
+                ops.PREC_CLUSTER_ALL: 'cluster'}.get(self.denoiser.precision, 'custom')
 
     @precision.setter
     def precision(self, value):
         if isinstance(value, str):
-            value = {'fp32': ops.PREC_F32, 'bf16': ops.PREC_BF16_TC, 'tc': ops.PREC_TC_ALL}[value]
+            value = {'fp32': ops.PREC_F32, 'bf16': ops.PREC_BF16_TC, 'tc': ops.PREC_TC_ALL,
+                     'cluster': ops.PREC_CLUSTER_ALL}[value]
         self.denoiser.precision = int(value)
 
     def forward(self, spatial_features, conditions, record_len=None, noise=None):
@@ -265,12 +307,12 @@ class GenComm(nn.Module):
             n0, steps = noise
             steps = torch.stack(list(steps)) if not isinstance(steps, torch.Tensor) else steps
             t1n = t2n = None
-        host, wdev = self.denoiser.packed(T, dev)
+        host, wdev, wcl = self.denoiser.packed(T, dev)
         ws_bytes = _lib.load().gc_gencomm_workspace_bytes(A, C, H, W)
         if self._ws is None or self._ws.numel() < ws_bytes or self._ws.device != dev:
             self._ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         pred = ops.gencomm_sample(x, conditions.contiguous(), off, n0.contiguous(), steps.contiguous(), host, wdev,
-                                  self._table, T, self._ws, precision=self.denoiser.precision)
+                                  self._table, T, self._ws, precision=self.denoiser.precision, w_cluster=wcl)
         out = {'pred_feature': pred}
         if t1n is not None:   # visualisation-only samples of the first frame's ego (cond_diff.py:368-371)
             ego = x[:1]

@@ -14,7 +14,7 @@ from . import _lib
 FUSE_WARP_ONLY, FUSE_MAX, FUSE_ATT = 0, 1, 2
 # denoiser arithmetic (include/gencomm_b200.h GC_PREC_*)
 PREC_F32, PREC_TC_CONV_IN, PREC_TC_CONV_OUT, PREC_BF16_TC, PREC_TC_MATERIALIZE = 0, 1, 2, 3, 4
-PREC_TC_MIDDLE, PREC_TC_ALL = 8, 11
+PREC_TC_MIDDLE, PREC_TC_ALL, PREC_CLUSTER, PREC_CLUSTER_ALL = 8, 11, 16, 27
 MAX_POINTS_PER_PILLAR = 32
 MAX_AGENTS_PER_FRAME = 8
 
@@ -261,7 +261,16 @@ def _check_blobs(lib, w_host, w_dev, C, T):
         raise ValueError("packed denoiser weights do not match (C, T)")
 
 
-def unet_forward(cond, x, t_index, w_host, w_dev, T, workspace=None, precision=0):
+def _cluster_ptr(lib, w_cluster, T):
+    if w_cluster is None:
+        return None
+    _chk(w_cluster, "w_cluster", torch.float32, 1)
+    if w_cluster.numel() != lib.gc_gencomm_cluster_weight_floats(T):
+        raise ValueError("packed cluster-kernel denoiser weights do not match T")
+    return _ptr(w_cluster)
+
+
+def unet_forward(cond, x, t_index, w_host, w_dev, T, workspace=None, precision=0, w_cluster=None):
     """pred = UNet(cat[cond, x], t_index) for all agents; cond [A,2,H,W], x [A,C,H,W] f32."""
     lib = _lib.load()
     _chk(cond, "cond", torch.float32, 4)
@@ -274,13 +283,14 @@ def unet_forward(cond, x, t_index, w_host, w_dev, T, workspace=None, precision=0
     if workspace is None:
         workspace = torch.empty(lib.gc_gencomm_workspace_bytes(A, C, H, W), dtype=torch.uint8, device=x.device)
     pred = torch.empty_like(x)
-    _lib.check(lib.gc_unet_forward(_ptr(cond), _ptr(x), A, int(t_index), _host_ptr(w_host), _ptr(w_dev), C, H, W, int(T),
+    _lib.check(lib.gc_unet_forward(_ptr(cond), _ptr(x), A, int(t_index), _host_ptr(w_host), _ptr(w_dev),
+                                   _cluster_ptr(lib, w_cluster, T), C, H, W, int(T),
                                    int(precision), _ptr(workspace), _ptr(pred), _stream()), "gc_unet_forward")
     return pred
 
 
 def gencomm_sample(feat, cond, agent_offsets, noise0, step_noise, w_host, w_dev, schedule, T, workspace=None, out=None,
-                   precision=0):
+                   precision=0, w_cluster=None):
     """GenComm eval sampler; feat [sumN,C,H,W], cond [sumN,2,H,W], noise0 like feat, step_noise [>=T-1,sumN,C,H,W]."""
     lib = _lib.load()
     _chk(feat, "feat", torch.float32, 4)
@@ -304,6 +314,7 @@ def gencomm_sample(feat, cond, agent_offsets, noise0, step_noise, w_host, w_dev,
         out = torch.empty_like(feat)
     _lib.check(lib.gc_gencomm_sample(_ptr(feat), _ptr(cond), _ptr(agent_offsets), agent_offsets.numel() - 1, A,
                                      _ptr(noise0), _ptr(step_noise) if T > 1 else None, _host_ptr(w_host), _ptr(w_dev),
+                                     _cluster_ptr(lib, w_cluster, T),
                                      _host_ptr(schedule), C, H, W, int(T), int(precision), _ptr(workspace), _ptr(out),
                                      _stream()),
                "gc_gencomm_sample")

@@ -48,6 +48,10 @@ extern "C" {
 #define GC_PREC_TC_MATERIALIZE 4 /* validation: explicit im2col operand instead of overlapping windows */
 #define GC_PREC_TC_MIDDLE 8    /* full-resolution width-8 middle layers as tf32 tcgen05 implicit GEMMs */
 #define GC_PREC_TC_ALL 11      /* conv_in/conv_out bf16 + middle layers tf32 */
+#define GC_PREC_CLUSTER 16     /* with GC_PREC_BF16_TC, H x W = 64 x 128 and w_cluster_dev != NULL: the 26 width-8 layers of
+                                  an evaluation run in ONE launch, one thread-block cluster of 8 CTAs per agent, activations
+                                  resident in (distributed) shared memory, tf32 tcgen05 (csrc/denoiser_cluster.cu) */
+#define GC_PREC_CLUSTER_ALL 27 /* GC_PREC_TC_ALL | GC_PREC_CLUSTER: the module default; ineligible shapes fall back to TC_ALL */
 
 int gc_version(void);
 const char *gc_last_error(void);
@@ -164,24 +168,28 @@ int gc_normalize_pairwise_tfm(const double *pairwise, int n, double H, double W,
  *          timestep-embedding projection of that step, GroupNorm affine, nin_shortcut), then
  *          conv_in.bias[8], norm_out.weight[8], norm_out.bias[8]
  *   w_dev  [device] gc_gencomm_device_weight_floats(C) floats: conv_in [C+2][9][8], conv_out [C][9][8], conv_out.bias [C]
+ *   w_cluster_dev [device, may be NULL] gc_gencomm_cluster_weight_floats(T) floats: the same T x 26 conv records in the
+ *          layout the cluster kernel bulk-copies into shared memory (csrc/denoiser_cluster.cuh), packed by
+ *          gencomm_b200/gencomm.py::pack_unet_cluster; NULL disables GC_PREC_CLUSTER
  *   schedule_host [host] [T][5]: sqrt_alphas_cumprod, sqrt_one_minus_alphas_cumprod,
  *          posterior_mean_coef1, posterior_mean_coef2, exp(0.5*posterior_log_variance_clipped)
  *   workspace: gc_gencomm_workspace_bytes(sumN, C, H, W) bytes (device)
  * ------------------------------------------------------------------------------------------- */
 size_t gc_gencomm_host_weight_floats(int T);
 size_t gc_gencomm_device_weight_floats(int C);
+size_t gc_gencomm_cluster_weight_floats(int T);
 size_t gc_gencomm_workspace_bytes(int total_agents, int C, int H, int W);
 
 int gc_gencomm_sample(const float *feat, const float *cond, const int32_t *agent_offsets, int n_frames,
                       int total_agents, const float *noise0, const float *step_noise,
-                      const float *w_host /*[host]*/, const float *w_dev, const float *schedule_host /*[host]*/,
-                      int C, int H, int W, int T, int precision /* GC_PREC_* */, void *workspace, float *pred,
-                      void *stream);
+                      const float *w_host /*[host]*/, const float *w_dev, const float *w_cluster_dev /* or NULL */,
+                      const float *schedule_host /*[host]*/, int C, int H, int W, int T, int precision /* GC_PREC_* */,
+                      void *workspace, float *pred, void *stream);
 
 /* One denoiser evaluation pred = UNet(cat[cond, x], t_index) for all agents (diagnostics / tests). */
 int gc_unet_forward(const float *cond, const float *x, int total_agents, int t_index,
-                    const float *w_host /*[host]*/, const float *w_dev, int C, int H, int W, int T,
-                    int precision /* GC_PREC_* */, void *workspace, float *pred, void *stream);
+                    const float *w_host /*[host]*/, const float *w_dev, const float *w_cluster_dev /* or NULL */, int C,
+                    int H, int W, int T, int precision /* GC_PREC_* */, void *workspace, float *pred, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
  * (8f rank 1) MessageExtractorv2.forward (models/gencomm_modules/message_extractor_v2.py:114-120)

@@ -36,7 +36,7 @@ def main():
     n0, steps = synth.sampler_noise(40, A, C, H, W, T=3)
     noise = (n0.cuda(), torch.stack(steps).cuda())
     rl = torch.full((a.frames,), a.agents, dtype=torch.int64)
-    for name in (("tc", "bf16", "fp32") if a.precision == "both" else (a.precision,)):
+    for name in (("cluster", "tc", "bf16", "fp32") if a.precision == "both" else (a.precision,)):
         m.precision = name
         for _ in range(3):
             m(feat, cond, rl, noise=noise)

@@ -155,3 +155,40 @@ def test_default_noise_path_and_api():
     feat2 = feat.clone(); feat2[1] += 5.0
     b = m(feat2, cond, torch.tensor([2, 1], device=DEV), noise=noise)["pred_feature"]
     assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("C,record_len", [(128, [4]), (256, [5]), (64, [3, 1, 2]), (64, [20])])
+def test_sampler_cluster_resident_path(C, record_len):
+    """'cluster' (the module default): the 26 width-8 layers of an evaluation in one launch of 8-CTA clusters, one per
+    agent, activations in distributed shared memory (csrc/denoiser_cluster.cu).  Same tolerance as the other
+    tensor-core paths; [20] exceeds the number of co-resident clusters (grid-stride over agents)."""
+    from gencomm_b200 import ops
+    H, W = 64, 128
+    A = sum(record_len)
+    m, sd = random_model(C, seed=C + 7)
+    feat = synth.bev_features(33, A, C, H, W)
+    cond = synth.bev_features(33, A, 2, H, W, salt=4)
+    n0, steps = synth.sampler_noise(33, A, C, H, W, T=3)
+    rl = torch.tensor(record_len, dtype=torch.int64)
+    ref = R.gencomm_sample(feat, cond, rl, sd, n0, steps)
+    args = (feat.to(DEV), cond.to(DEV), rl.to(DEV))
+    noise = (n0.to(DEV), torch.stack(steps).to(DEV))
+    m.precision = "tc"
+    out_tc = m(*args, noise=noise)["pred_feature"]
+    m.precision = "cluster"
+    out = m(*args, noise=noise)["pred_feature"]
+    emax = rel_err(out.cpu(), ref)
+    emean = ((out.cpu() - ref).abs().mean() / ref.abs().mean()).item()
+    print(f"gencomm cluster C={C} N={record_len}: max-rel {emax:.2e} mean-rel {emean:.2e}; vs tc {rel_err(out, out_tc):.2e}")
+    assert emax <= TOL_BF16_MAX and emean <= TOL_BF16_MEAN
+    assert not torch.equal(out, out_tc), "cluster path not taken"
+    assert rel_err(out, out_tc) <= 1e-2
+    out2 = m(*args, noise=noise)["pred_feature"]
+    assert torch.equal(out, out2), "cluster path is not deterministic"
+    # one denoiser evaluation, every timestep
+    x = torch.cat([cond, feat], dim=1)
+    for t in (2, 1, 0):
+        r = R.unet_forward(x, torch.full((A,), float(t)), sd)
+        m.precision = ops.PREC_CLUSTER_ALL
+        o = m.denoiser(x.to(DEV), torch.full((A,), t, device=DEV))
+        assert rel_err(o.cpu(), r) <= TOL_BF16_MAX, t
