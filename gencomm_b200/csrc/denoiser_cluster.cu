@@ -20,6 +20,7 @@
 // row and channel group instead of 9, and the staged row is read in place for the three kx taps (descriptor start
 // address shifted by one 16-byte pixel).  TMEM columns are zeroed with tcgen05.st before the first MMA.
 #include <cooperative_groups.h>
+#include <stddef.h>
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -51,7 +52,7 @@ constexpr int kSmemBytes = kOffMisc + 1024;
 struct Misc {
     float ga[16], gb[16];
     float part[8][8];
-    uint64_t mma_bar[2], rec_bar[2];
+    uint64_t mma_bar[2], done_bar[2], rec_bar[2];
     uint32_t tmem;
 };
 static_assert(sizeof(Misc) <= 1024, "Misc does not fit its slot");
@@ -160,6 +161,36 @@ __device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64
         "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
 
+__device__ __forceinline__ float lds1(uint32_t saddr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(saddr));
+    return v;
+}
+__device__ __forceinline__ void sts1(uint32_t saddr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(saddr), "f"(v) : "memory"); }
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+
+// tcgen05.mma / commit issued by ONE elected lane of a converged warp.  Every operand is warp-uniform, so ptxas keeps
+// the descriptors in uniform registers; a `tid == 0` branch instead makes it wrap each MMA in a lane-serialising
+// R2UR loop (measured on the B200: 88 cycles per MMA, profiles/r02b_*).
+__device__ __forceinline__ void mma_tf32_elect(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred pe, pa;\n\t"
+        "setp.eq.b32 pa, 0, 0;\n\t"
+        "elect.sync _|pe, 0xffffffff;\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, pa;\n\t"
+        "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc) : "memory");
+}
+__device__ __forceinline__ void commit_elect(uint32_t bar) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred pe;\n\t"
+        "elect.sync _|pe, 0xffffffff;\n\t"
+        "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
+        "}" ::"r"(bar) : "memory");
+}
+
 // x * sigmoid(x) = h + h * tanh(h), h = x / 2: one MUFU per element (tanh.approx, rel. error 2^-11 = the tf32 operand grid)
 __device__ __forceinline__ float swish_tanh(float u) {
     const float h = 0.5f * u;
@@ -170,32 +201,34 @@ __device__ __forceinline__ float swish_tanh(float u) {
 
 struct Ctx {
     uint32_t smem;        // shared::cta address of the carve-up base
-    Misc *misc;
     uint32_t rank;        // CTA rank in the cluster = row band
     uint32_t tmem;
-    uint32_t ph_mma[2], ph_rec[2];   // mbarrier phase parities (uniform across the CTA)
+    uint32_t ph_mma[2], ph_done[2], ph_rec[2];   // mbarrier phase parities (uniform across the CTA)
     int tid, warp, lane;
-    int dbg;              // timing experiments (GC_CL_DEBUG): 1 skip MMAs, 2 skip staging, 4 skip epilogue math, 8 skip cluster barriers, 16 skip record loads
+    int dbg;              // timing experiments (GC_CL_DEBUG): 1 skip MMAs, 2 skip staging, 4 skip epilogue math, 8 skip cluster barriers
 };
+#define MISC_ADDR(c, member) ((c).smem + kOffMisc + (uint32_t)offsetof(Misc, member))
 
 // ------------------------------------------------------------------------------------------------
 // Stage the rows [i0, i1) of a tensor-core layer's operand: GroupNorm + swish of the raw input (own band or the
 // neighbour's halo row through DSMEM), zero x-halo columns, fp32 (tf32) pixel halves into the operand planes.
+// KMAX = ceil(rows * (PXW + 2) / 256) items per thread.
 // ------------------------------------------------------------------------------------------------
-template <int CG, bool HALF, bool UP, bool GN>
+template <int CG, bool HALF, bool UP, bool GN, int KMAX>
 __device__ __forceinline__ void stage_rows(const Ctx &c, const LayerCfg &L, int i0, int i1) {
     constexpr int PXW = HALF ? 64 : 128, RW = PXW + 2, R = HALF ? 4 : 8, HRES = HALF ? 32 : 64;
     constexpr int SPXW = UP ? 64 : PXW, SR = UP ? 4 : R;             // source tensor geometry
     constexpr int PROWS = CG == 1 ? 10 : 5;                          // slot rows per operand plane
-    constexpr int KMAX = CG == 1 ? (HALF ? 2 : 3) : 2;               // items per thread (5 x 130 / 256, 6 x 66 / 256, 2 x 130 / 256)
     const int nitems = (i1 - i0) * RW;
     const int y0 = (int)c.rank * R;
     float4 v[KMAX][CG][2];
     int slot_px[KMAX];
+    bool inside[KMAX];
 #pragma unroll
     for (int k = 0; k < KMAX; ++k) {
         const int it = c.tid + k * kThreads;
         slot_px[k] = -1;
+        inside[k] = false;
 #pragma unroll
         for (int g = 0; g < CG; ++g) v[k][g][0] = v[k][g][1] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (it >= nitems) continue;
@@ -204,6 +237,7 @@ __device__ __forceinline__ void stage_rows(const Ctx &c, const LayerCfg &L, int 
         const int slot = CG == 1 ? i : (((i >> 1) & 1) * 2 + (i & 1));
         slot_px[k] = slot * kRowPx + px;
         if (px < 1 || px > PXW) continue;                         // x halo: zeros (padding applies after the activation)
+        inside[k] = true;
         const int sx = UP ? ((px - 1) >> 1) : (px - 1);
         int sy = UP ? ((gy >> 1) - (int)c.rank * SR) : (i - 1);   // source row relative to this CTA's band
         uint32_t srank = c.rank;
@@ -215,22 +249,30 @@ __device__ __forceinline__ void stage_rows(const Ctx &c, const LayerCfg &L, int 
             v[k][g][1] = ld_cluster4(a + SPXW * 16u);
         }
     }
+    float4 ga[CG][2], gb[CG][2];
+    if (GN) {
+#pragma unroll
+        for (int g = 0; g < CG; ++g) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                ga[g][h] = lds4(MISC_ADDR(c, ga) + (uint32_t)(g * 8 + h * 4) * 4u);
+                gb[g][h] = lds4(MISC_ADDR(c, gb) + (uint32_t)(g * 8 + h * 4) * 4u);
+            }
+        }
+    }
 #pragma unroll
     for (int k = 0; k < KMAX; ++k) {
         if (slot_px[k] < 0) continue;
-        const int px = slot_px[k] % kRowPx;
-        const bool inside = px >= 1 && px <= PXW;
 #pragma unroll
         for (int g = 0; g < CG; ++g) {
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 float4 u = v[k][g][h];
-                if (GN && inside) {
-                    const float *ga = c.misc->ga + g * 8 + h * 4, *gb = c.misc->gb + g * 8 + h * 4;
-                    u.x = swish_tanh(fmaf(u.x, ga[0], gb[0]));
-                    u.y = swish_tanh(fmaf(u.y, ga[1], gb[1]));
-                    u.z = swish_tanh(fmaf(u.z, ga[2], gb[2]));
-                    u.w = swish_tanh(fmaf(u.w, ga[3], gb[3]));
+                if (GN && inside[k]) {
+                    u.x = swish_tanh(fmaf(u.x, ga[g][h].x, gb[g][h].x));
+                    u.y = swish_tanh(fmaf(u.y, ga[g][h].y, gb[g][h].y));
+                    u.z = swish_tanh(fmaf(u.z, ga[g][h].z, gb[g][h].z));
+                    u.w = swish_tanh(fmaf(u.w, ga[g][h].w, gb[g][h].w));
                 }
                 sts4(c.smem + kOffOper + (uint32_t)(((g * 2 + h) * PROWS) * kRowPx + slot_px[k]) * 16u, u);
             }
@@ -246,15 +288,15 @@ __device__ __forceinline__ void push_stats(const Ctx &c, float (&q8)[8], int out
         for (int m = 16; m >= 1; m >>= 1) q8[i] += __shfl_xor_sync(0xffffffffu, q8[i], m);
     }
     if (c.lane == 0) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) c.misc->part[c.warp][i] = q8[i];
+        sts4(MISC_ADDR(c, part) + (uint32_t)c.warp * 32u, make_float4(q8[0], q8[1], q8[2], q8[3]));
+        sts4(MISC_ADDR(c, part) + (uint32_t)c.warp * 32u + 16u, make_float4(q8[4], q8[5], q8[6], q8[7]));
     }
     __syncthreads();
     if (c.tid < 64) {
         const int vi = c.tid & 7, peer = c.tid >> 3;
         float t = 0.0f;
 #pragma unroll
-        for (int w = 0; w < 8; ++w) t += c.misc->part[w][vi];
+        for (int w = 0; w < 8; ++w) t += lds1(MISC_ADDR(c, part) + (uint32_t)(w * 8 + vi) * 4u);
         st_cluster(mapa(c.smem + kOffStats + (uint32_t)(((out_buf * kCl) + (int)c.rank) * 8 + vi) * 4u, (uint32_t)peer), t);
         if (gstats != nullptr && peer == 0) gstats[c.rank * 8 + vi] = t;
     }
@@ -262,114 +304,136 @@ __device__ __forceinline__ void push_stats(const Ctx &c, float (&q8)[8], int out
 
 // GroupNorm(4 groups) coefficients of the layer input from the cluster-wide partial sums (fixed order -> every CTA
 // of the cluster computes identical values).  unet.py:36-37: eps 1e-6, biased variance.
-__device__ __forceinline__ void gn_coeffs(const Ctx &c, const LayerCfg &L, const float *rec) {
+__device__ __forceinline__ void gn_coeffs(const Ctx &c, const LayerCfg &L, uint32_t rec_saddr) {
     if (c.tid < L.cin) {
         const int ch = c.tid, cc = ch & 7;
-        const float *st = reinterpret_cast<const float *>(reinterpret_cast<const char *>(c.misc) - kOffMisc + kOffStats) +
-                          (size_t)(ch < 8 ? L.in_a : L.in_b) * kCl * 8;
+        const uint32_t st = c.smem + kOffStats + (uint32_t)((ch < 8 ? L.in_a : L.in_b) * kCl * 8) * 4u;
         float s = 0.0f, ss = 0.0f;
         if (L.cin == 8) {
             const int p = cc >> 1;
 #pragma unroll
-            for (int r = 0; r < kCl; ++r) { s += st[r * 8 + 2 * p]; ss += st[r * 8 + 2 * p + 1]; }
+            for (int r = 0; r < kCl; ++r) { s += lds1(st + (uint32_t)(r * 8 + 2 * p) * 4u); ss += lds1(st + (uint32_t)(r * 8 + 2 * p + 1) * 4u); }
         } else {
             const int p = (cc >> 2) * 2;
 #pragma unroll
             for (int r = 0; r < kCl; ++r) {
-                s += st[r * 8 + 2 * p] + st[r * 8 + 2 * p + 2];
-                ss += st[r * 8 + 2 * p + 1] + st[r * 8 + 2 * p + 3];
+                s += lds1(st + (uint32_t)(r * 8 + 2 * p) * 4u) + lds1(st + (uint32_t)(r * 8 + 2 * p + 2) * 4u);
+                ss += lds1(st + (uint32_t)(r * 8 + 2 * p + 1) * 4u) + lds1(st + (uint32_t)(r * 8 + 2 * p + 3) * 4u);
             }
         }
-        const float cnt = (L.half ? 32.0f * 64.0f : 64.0f * 128.0f) * (L.cin == 8 ? 2.0f : 4.0f);
-        const float mean = s / cnt;
-        const float var = fmaxf(ss / cnt - mean * mean, 0.0f);
+        const float inv_cnt = 1.0f / ((L.half ? 32.0f * 64.0f : 64.0f * 128.0f) * (L.cin == 8 ? 2.0f : 4.0f));
+        const float mean = s * inv_cnt;
+        const float var = fmaxf(ss * inv_cnt - mean * mean, 0.0f);
         const float rstd = rsqrtf(var + 1e-6f);
-        const float gamma = rec[kClRecGamma + ch], beta = rec[kClRecBeta + ch];
-        c.misc->ga[ch] = gamma * rstd;
-        c.misc->gb[ch] = beta - mean * gamma * rstd;
+        const float gamma = lds1(rec_saddr + (uint32_t)(kClRecGamma + ch) * 4u), beta = lds1(rec_saddr + (uint32_t)(kClRecBeta + ch) * 4u);
+        sts1(MISC_ADDR(c, ga) + (uint32_t)ch * 4u, gamma * rstd);
+        sts1(MISC_ADDR(c, gb) + (uint32_t)ch * 4u, beta - mean * gamma * rstd);
     }
 }
 
 // ------------------------------------------------------------------------------------------------
-// One tensor-core layer: stage -> MMAs (pipelined in row groups) -> epilogue (bias, residual / nin_shortcut, raw
-// output into this CTA's band, GroupNorm partial sums to the cluster).
+// One tensor-core layer as a two-phase pipeline over the band's output rows (A = upper half, B = lower half):
+//   stage rows of A -> [MMAs of A | stage the remaining rows] -> [MMAs of B | epilogue A] -> epilogue B
+// Epilogue: bias, residual / nin_shortcut, raw output into this CTA's band, GroupNorm partial sums to the cluster.
 // ------------------------------------------------------------------------------------------------
 template <int CG, bool HALF, bool UP, bool GN>
-__device__ __forceinline__ void conv_layer(Ctx &c, const LayerCfg &L, const float *rec, uint32_t rec_saddr, float *gout,
-                                           float *gstats) {
-    constexpr int PXW = HALF ? 64 : 128, R = HALF ? 4 : 8, NR = R + 2, HRES = HALF ? 32 : 64;
-    constexpr int PROWS = CG == 1 ? 10 : 5, GR = CG == 1 ? 5 : 2, NG = (NR + GR - 1) / GR;
+__device__ __forceinline__ void conv_layer(Ctx &c, const LayerCfg &L, uint32_t rec_saddr, float *gout, float *gstats) {
+    constexpr int PXW = HALF ? 64 : 128, RW = PXW + 2, R = HALF ? 4 : 8, NR = R + 2, HRES = HALF ? 32 : 64;
+    constexpr int NRA = R / 2 + 2;                                    // input rows feeding the output rows of phase A
+    constexpr int PROWS = CG == 1 ? 10 : 5;
+    constexpr int NG = CG == 1 ? 2 : NR / 2;                          // staging groups: cin 8: A | B; cin 16: pairs of rows
+    constexpr int GA = CG == 1 ? 0 : NRA / 2 - 1;                     // group whose completion finishes phase A
     constexpr uint32_t kPlane = PROWS * kRowPx * 16u;
     const int y0 = (int)c.rank * R;
 
-    // zero the accumulator columns (8 (NR + 3) of them); ordered before the MMAs by the first group's barrier
-    if (c.warp < 4) {
-        const uint32_t ta = c.tmem + ((uint32_t)(c.warp * 32) << 16);
 #pragma unroll
-        for (int j = 0; j < NR + 3; ++j) tmem_zero8(ta + 8u * j);
-        tmem_wait_st();
-    }
-#pragma unroll 1
     for (int g = 0; g < NG; ++g) {
-        const int i0 = g * GR, i1 = min(NR, i0 + GR);
+        const int i0 = CG == 1 ? (g == 0 ? 0 : NRA) : 2 * g, i1 = CG == 1 ? (g == 0 ? NRA : NR) : 2 * g + 2;
         if (CG == 2 && g >= 2) {   // the slots of group g were read by the MMAs of group g - 2
-            mbar_wait(smem_u32(&c.misc->mma_bar[g & 1]), c.ph_mma[g & 1]);
+            mbar_wait(MISC_ADDR(c, mma_bar) + (uint32_t)(g & 1) * 8u, c.ph_mma[g & 1]);
             c.ph_mma[g & 1] ^= 1u;
         }
-        if (!(c.dbg & 2)) stage_rows<CG, HALF, UP, GN>(c, L, i0, i1);
+        if (!(c.dbg & 2)) {
+            if (CG == 1) {
+                if (g == 0) stage_rows<CG, HALF, UP, GN, (NRA * RW + kThreads - 1) / kThreads>(c, L, i0, i1);
+                else stage_rows<CG, HALF, UP, GN, ((NR - NRA) * RW + kThreads - 1) / kThreads>(c, L, i0, i1);
+            } else {
+                stage_rows<CG, HALF, UP, GN, (2 * RW + kThreads - 1) / kThreads>(c, L, i0, i1);
+            }
+        }
         fence_async_smem();
         tc_fence_before();
         __syncthreads();
-        if (c.tid == 0) {
+        if (c.warp == 0) {         // warp-uniform branch; one elected lane issues
             tc_fence_after();
             constexpr uint32_t idesc = make_idesc_tf32(128, 32);
-            for (int i = i0; i < ((c.dbg & 1) ? i0 : i1); ++i) {
+            const int iend = (c.dbg & 1) ? i0 : i1;
+            for (int i = i0; i < iend; ++i) {
                 const int gy = y0 - 1 + i;
                 if (gy < 0 || gy >= HRES) continue;
                 const int slot = CG == 1 ? i : (((i >> 1) & 1) * 2 + (i & 1));
 #pragma unroll
                 for (int cgi = 0; cgi < CG; ++cgi) {
+                    const uint64_t a0 = make_desc(c.smem + kOffOper + (uint32_t)(cgi * 2) * kPlane + (uint32_t)(slot * kRowPx) * 16u, kPlane, 128u);
+                    const uint64_t b0 = make_desc(rec_saddr + (uint32_t)(cgi * 2 * 4 * 8) * 16u, 512u, 128u);
 #pragma unroll
-                    for (int kx = 0; kx < 3; ++kx) {
-                        const uint64_t adesc = make_desc(c.smem + kOffOper + (uint32_t)(cgi * 2) * kPlane + (uint32_t)(slot * kRowPx + kx) * 16u,
-                                                         kPlane, 128u);
-                        const uint64_t bdesc = make_desc(rec_saddr + (uint32_t)((kx * 2 + cgi) * 2 * 4 * 8) * 16u, 512u, 128u);
-                        mma_tf32(c.tmem + 8u * i, adesc, bdesc, idesc, 1u);
-                    }
+                    for (int kx = 0; kx < 3; ++kx)   // +1 in the descriptor's address field = one 16-byte pixel; B: 2048 B per kx
+                        mma_tf32_elect(c.tmem + 8u * i, a0 + (uint64_t)kx, b0 + (uint64_t)(kx * 128), idesc);
                 }
             }
-            mma_commit(smem_u32(&c.misc->mma_bar[g & 1]));
+            if (CG == 2) commit_elect(MISC_ADDR(c, mma_bar) + (uint32_t)(g & 1) * 8u);
+            if (g == GA) commit_elect(MISC_ADDR(c, done_bar));
+            if (g == NG - 1) commit_elect(MISC_ADDR(c, done_bar) + 8u);
         }
     }
-    // every commit is awaited exactly once by every thread: the last min(NG, 2) groups are still outstanding
+    if (CG == 2) {   // consume the two ring commits nobody waited for (keeps the phase bookkeeping in step)
 #pragma unroll
-    for (int g = (NG >= 2 ? NG - 2 : 0); g < NG; ++g) {
-        mbar_wait(smem_u32(&c.misc->mma_bar[g & 1]), c.ph_mma[g & 1]);
-        c.ph_mma[g & 1] ^= 1u;
+        for (int g = NG - 2; g < NG; ++g) {
+            mbar_wait(MISC_ADDR(c, mma_bar) + (uint32_t)(g & 1) * 8u, c.ph_mma[g & 1]);
+            c.ph_mma[g & 1] ^= 1u;
+        }
     }
-    tc_fence_after();
 
-    // ---- epilogue: thread = pixel x of NROW consecutive output rows ----
-    constexpr int NROW = R / 2;                        // 4 (full) / 2 (half) rows per thread
+    // ---- epilogue, phase by phase: thread = pixel x of NROW consecutive output rows ----
+    constexpr int NROW = R / 4;                        // 2 (full) / 1 (half) rows per thread and phase
     const int q = c.warp & 3, hsel = c.warp >> 2;
-    const int px = q * 32 + c.lane, r0 = hsel * NROW;
+    const int px = q * 32 + c.lane;
     float q8[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) q8[i] = 0.0f;
-    if (px < PXW && !(c.dbg & 4)) {                    // warp-uniform (half resolution: lane quarters 2, 3 idle)
+    float bias[8];
+    {
+        const float4 b0 = lds4(rec_saddr + kClRecBias * 4u), b1 = lds4(rec_saddr + kClRecBias * 4u + 16u);
+        bias[0] = b0.x; bias[1] = b0.y; bias[2] = b0.z; bias[3] = b0.w; bias[4] = b1.x; bias[5] = b1.y; bias[6] = b1.z; bias[7] = b1.w;
+    }
+    const uint32_t out_base = c.smem + kOffF + buf_off(L.out);
+    const uint32_t ra_base = c.smem + kOffF + buf_off(L.res_a), rb_base = c.smem + kOffF + buf_off(L.res_b);
+#pragma unroll
+    for (int ph = 0; ph < 2; ++ph) {
+        mbar_wait(MISC_ADDR(c, done_bar) + (uint32_t)ph * 8u, c.ph_done[ph]);
+        c.ph_done[ph] ^= 1u;
+        tc_fence_after();
+        if (px >= PXW || (c.dbg & 4)) continue;        // warp-uniform (half resolution: lane quarters 2, 3 idle)
+        const int r0 = ph * (R / 2) + hsel * NROW;
         float acc[NROW * 8];
         const uint32_t ta = c.tmem + ((uint32_t)(q * 32) << 16) + 8u * (r0 + 2);
+        if (NROW == 2) {
+            tmem_ld16_nowait(ta, acc);
+        } else {
+            uint32_t rr[8];
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                         : "=r"(rr[0]), "=r"(rr[1]), "=r"(rr[2]), "=r"(rr[3]), "=r"(rr[4]), "=r"(rr[5]), "=r"(rr[6]), "=r"(rr[7])
+                         : "r"(ta));
 #pragma unroll
-        for (int j = 0; j < NROW * 8; j += 16) tmem_ld16_nowait(ta + j, acc + j);
+            for (int i = 0; i < 8; ++i) acc[i] = __uint_as_float(rr[i]);
+        }
         tmem_wait_ld();
-        const uint32_t out_base = c.smem + kOffF + buf_off(L.out);
-        const uint32_t ra_base = c.smem + kOffF + buf_off(L.res_a), rb_base = c.smem + kOffF + buf_off(L.res_b);
 #pragma unroll
         for (int r = 0; r < NROW; ++r) {
             float *a = acc + r * 8;
             const uint32_t poff = (uint32_t)(((r0 + r) * 2) * PXW + px) * 16u;
 #pragma unroll
-            for (int o = 0; o < 8; ++o) a[o] += rec[kClRecBias + o];
+            for (int o = 0; o < 8; ++o) a[o] += bias[o];
             if (L.res != kNone) {
                 const float4 a0 = lds4(ra_base + poff), a1 = lds4(ra_base + poff + PXW * 16u);
                 if (L.res == kIdent) {
@@ -379,13 +443,19 @@ __device__ __forceinline__ void conv_layer(Ctx &c, const LayerCfg &L, const floa
                     const float4 b0 = lds4(rb_base + poff), b1 = lds4(rb_base + poff + PXW * 16u);
                     const float xr[16] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w,
                                           b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                    const float4 n0 = lds4(rec_saddr + kClRecNinB * 4u), n1 = lds4(rec_saddr + kClRecNinB * 4u + 16u);
+                    float sh[8] = {n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, n1.z, n1.w};
 #pragma unroll
-                    for (int o = 0; o < 8; ++o) {
-                        float sh = rec[kClRecNinB + o];
-#pragma unroll
-                        for (int ci = 0; ci < 16; ++ci) sh = fmaf(xr[ci], rec[kClRecNinW + ci * 8 + o], sh);
-                        a[o] += sh;
+                    for (int ci = 0; ci < 16; ++ci) {
+                        const float4 w0 = lds4(rec_saddr + (uint32_t)(kClRecNinW + ci * 8) * 4u);
+                        const float4 w1 = lds4(rec_saddr + (uint32_t)(kClRecNinW + ci * 8 + 4) * 4u);
+                        sh[0] = fmaf(xr[ci], w0.x, sh[0]); sh[1] = fmaf(xr[ci], w0.y, sh[1]);
+                        sh[2] = fmaf(xr[ci], w0.z, sh[2]); sh[3] = fmaf(xr[ci], w0.w, sh[3]);
+                        sh[4] = fmaf(xr[ci], w1.x, sh[4]); sh[5] = fmaf(xr[ci], w1.y, sh[5]);
+                        sh[6] = fmaf(xr[ci], w1.z, sh[6]); sh[7] = fmaf(xr[ci], w1.w, sh[7]);
                     }
+#pragma unroll
+                    for (int o = 0; o < 8; ++o) a[o] += sh[o];
                 }
             }
             const float4 o0 = make_float4(a[0], a[1], a[2], a[3]), o1 = make_float4(a[4], a[5], a[6], a[7]);
@@ -408,11 +478,13 @@ __device__ __forceinline__ void conv_layer(Ctx &c, const LayerCfg &L, const floa
 }
 
 // down.0.downsample (unet.py:59-78): pad (0,1,0,1) + 3x3 stride 2, no GroupNorm, on CUDA cores (thread = output pixel).
-__device__ __forceinline__ void down_layer(Ctx &c, const LayerCfg &L, const float *rec) {
+__device__ __forceinline__ void down_layer(Ctx &c, const LayerCfg &L, uint32_t rec_saddr) {
     const int r = c.tid >> 6, ox = c.tid & 63;
     float acc[8];
-#pragma unroll
-    for (int o = 0; o < 8; ++o) acc[o] = rec[kClRecBias + o];
+    {
+        const float4 b0 = lds4(rec_saddr + kClRecBias * 4u), b1 = lds4(rec_saddr + kClRecBias * 4u + 16u);
+        acc[0] = b0.x; acc[1] = b0.y; acc[2] = b0.z; acc[3] = b0.w; acc[4] = b1.x; acc[5] = b1.y; acc[6] = b1.z; acc[7] = b1.w;
+    }
 #pragma unroll
     for (int ky = 0; ky < 3; ++ky) {
         int sy = 2 * r + ky;                              // full-resolution row relative to this CTA's band (0..8)
@@ -426,10 +498,10 @@ __device__ __forceinline__ void down_layer(Ctx &c, const LayerCfg &L, const floa
             const uint32_t a = mapa(c.smem + kOffF + buf_off(L.in_a) + (uint32_t)((sy * 2) * 128 + sx) * 16u, srank);
             const float4 v0 = ld_cluster4(a), v1 = ld_cluster4(a + 128u * 16u);
             const float vv[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-            const float4 *w = reinterpret_cast<const float4 *>(rec + (ky * 3 + kx) * 64);   // [tap][cin][cout]
+            const uint32_t w = rec_saddr + (uint32_t)((ky * 3 + kx) * 64) * 4u;   // [tap][cin][cout]
 #pragma unroll
             for (int ci = 0; ci < 8; ++ci) {
-                const float4 w0 = w[ci * 2], w1 = w[ci * 2 + 1];
+                const float4 w0 = lds4(w + (uint32_t)(ci * 8) * 4u), w1 = lds4(w + (uint32_t)(ci * 8 + 4) * 4u);
                 acc[0] = fmaf(vv[ci], w0.x, acc[0]); acc[1] = fmaf(vv[ci], w0.y, acc[1]);
                 acc[2] = fmaf(vv[ci], w0.z, acc[2]); acc[3] = fmaf(vv[ci], w0.w, acc[3]);
                 acc[4] = fmaf(vv[ci], w1.x, acc[4]); acc[5] = fmaf(vv[ci], w1.y, acc[5]);
@@ -449,39 +521,49 @@ __device__ __forceinline__ void down_layer(Ctx &c, const LayerCfg &L, const floa
     push_stats(c, q8, L.out, nullptr);
 }
 
-// The 26 middle layers of one UNet evaluation.  rec_g: this step's layer records in global memory.
+// The 26 middle layers of one UNet evaluation.  rec_g: this step's layer records in global memory.  On entry every
+// thread has ARRIVED at the cluster barrier that publishes the input tensor (F0 + its statistics); on exit likewise for
+// the output of layer 25.
 __device__ __forceinline__ void middle_layers(Ctx &c, const float *rec_g, float *gout, float *gstats) {
-    if (c.tid == 0) bulk_load(c.smem + kOffRec, rec_g, kClRecBytes, smem_u32(&c.misc->rec_bar[0]));
+    if (c.tid == 0) bulk_load(c.smem + kOffRec, rec_g, kClRecBytes, MISC_ADDR(c, rec_bar));
 #pragma unroll 1
     for (int l = 0; l < kClLayers; ++l) {
         const LayerCfg L = c_layers[l];
-        // one cluster barrier per layer: the producer's raw rows + statistics are visible, and every CTA is done
-        // reading what this layer is about to overwrite
-        if (!(c.dbg & 8)) cluster_sync_all(); else __syncthreads();
         const int rb = l & 1;
+        // record of the next layer: its buffer was last read during layer l - 1, which this CTA has finished
         if (c.tid == 0 && l + 1 < kClLayers)
             bulk_load(c.smem + kOffRec + (uint32_t)((rb ^ 1) * kClRecBytes), rec_g + (size_t)(l + 1) * kClRecFloats, kClRecBytes,
-                      smem_u32(&c.misc->rec_bar[rb ^ 1]));
-        mbar_wait(smem_u32(&c.misc->rec_bar[rb]), c.ph_rec[rb]);
+                      MISC_ADDR(c, rec_bar) + (uint32_t)(rb ^ 1) * 8u);
+        // zero the accumulator columns (every thread finished reading TMEM before it arrived at the cluster barrier)
+        if (L.kind != kDownK && c.warp < 4) {
+            const uint32_t ta = c.tmem + ((uint32_t)(c.warp * 32) << 16);
+#pragma unroll
+            for (int j = 0; j < 13; ++j) tmem_zero8(ta + 8u * j);
+            tmem_wait_st();
+        }
+        mbar_wait(MISC_ADDR(c, rec_bar) + (uint32_t)rb * 8u, c.ph_rec[rb]);
         c.ph_rec[rb] ^= 1u;
+        // one cluster barrier per layer: the producer's raw rows + statistics are visible, and every CTA is done
+        // reading what this layer is about to overwrite
+        if (!(c.dbg & 8)) cluster_wait(); else __syncthreads();
         const uint32_t rec_saddr = c.smem + kOffRec + (uint32_t)(rb * kClRecBytes);
-        const float *rec = reinterpret_cast<const float *>(reinterpret_cast<const char *>(c.misc) - kOffMisc + kOffRec + rb * kClRecBytes);
         if (L.gn) {
-            gn_coeffs(c, L, rec);
+            gn_coeffs(c, L, rec_saddr);
             __syncthreads();
         }
         const bool last = l == kClLayers - 1;
         if (L.kind == kDownK) {
-            down_layer(c, L, rec);
+            down_layer(c, L, rec_saddr);
         } else if (L.kind == kUpK) {
-            conv_layer<1, false, true, false>(c, L, rec, rec_saddr, nullptr, nullptr);
+            conv_layer<1, false, true, false>(c, L, rec_saddr, nullptr, nullptr);
         } else if (L.half) {
-            if (L.cin == 8) conv_layer<1, true, false, true>(c, L, rec, rec_saddr, nullptr, nullptr);
-            else conv_layer<2, true, false, true>(c, L, rec, rec_saddr, nullptr, nullptr);
+            if (L.cin == 8) conv_layer<1, true, false, true>(c, L, rec_saddr, nullptr, nullptr);
+            else conv_layer<2, true, false, true>(c, L, rec_saddr, nullptr, nullptr);
         } else {
-            if (L.cin == 8) conv_layer<1, false, false, true>(c, L, rec, rec_saddr, last ? gout : nullptr, last ? gstats : nullptr);
-            else conv_layer<2, false, false, true>(c, L, rec, rec_saddr, nullptr, nullptr);
+            if (L.cin == 8) conv_layer<1, false, false, true>(c, L, rec_saddr, last ? gout : nullptr, last ? gstats : nullptr);
+            else conv_layer<2, false, false, true>(c, L, rec_saddr, nullptr, nullptr);
         }
+        if (!(c.dbg & 8)) cluster_arrive();
     }
 }
 
@@ -495,24 +577,29 @@ k_unet_middle_cluster(const float *__restrict__ h0, const float *__restrict__ re
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     Ctx c;
     c.smem = smem_u32(smem_raw);
-    c.misc = reinterpret_cast<Misc *>(smem_raw + kOffMisc);
-    c.tid = threadIdx.x; c.warp = c.tid >> 5; c.lane = c.tid & 31;
+    c.tid = threadIdx.x;
+    c.warp = __shfl_sync(0xffffffffu, c.tid >> 5, 0);   // provably warp-uniform (the MMA warp branches on it)
+    c.lane = c.tid & 31;
     c.rank = blockIdx.x % kCl;
     c.dbg = dbg;
-    c.ph_mma[0] = c.ph_mma[1] = c.ph_rec[0] = c.ph_rec[1] = 0u;
+    c.ph_mma[0] = c.ph_mma[1] = c.ph_done[0] = c.ph_done[1] = c.ph_rec[0] = c.ph_rec[1] = 0u;
     const int n_clusters = gridDim.x / kCl, cluster_id = blockIdx.x / kCl;
+    Misc *misc = reinterpret_cast<Misc *>(smem_raw + kOffMisc);
 
-    if (c.warp == 0) tmem_alloc512(&c.misc->tmem);
+    if (c.warp == 0) tmem_alloc512(&misc->tmem);
     if (c.tid == 32) {
-        mbar_init(smem_u32(&c.misc->mma_bar[0]), 1); mbar_init(smem_u32(&c.misc->mma_bar[1]), 1);
-        mbar_init(smem_u32(&c.misc->rec_bar[0]), 1); mbar_init(smem_u32(&c.misc->rec_bar[1]), 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(MISC_ADDR(c, mma_bar) + 8u * i, 1); mbar_init(MISC_ADDR(c, done_bar) + 8u * i, 1);
+            mbar_init(MISC_ADDR(c, rec_bar) + 8u * i, 1);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    c.tmem = c.misc->tmem;
-    cluster_sync_all();
+    c.tmem = __shfl_sync(0xffffffffu, misc->tmem, 0);
+    cluster_arrive();
+    cluster_wait();
 
     for (int agent = cluster_id; agent < n_agents; agent += n_clusters) {
         // ---- load this CTA's band of h0 into F0 and publish its GroupNorm partial sums ----
@@ -542,9 +629,10 @@ k_unet_middle_cluster(const float *__restrict__ h0, const float *__restrict__ re
             }
             push_stats(c, q8, F0, nullptr);
         }
+        cluster_arrive();
         middle_layers(c, rec_g, out + (size_t)agent * 64 * 128 * 8, stats_out + (size_t)agent * kCl * 8);
         // the next agent's load overwrites F0, which the neighbours read as a halo during layer 24
-        cluster_sync_all();
+        cluster_wait();
     }
     tc_fence_before();
     __syncthreads();

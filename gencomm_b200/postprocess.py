@@ -80,9 +80,12 @@ class VoxelPostprocessor:
         (cav_id, out), = output_dict.items()
         assert cav_id in data_dict
         cav = data_dict[cav_id]
+        # key handling exactly as the reference (:1122-1127): 'psm' renames cls_preds; the 'rm' / 'dm' renames test the
+        # OUTER dict ('rm' in output_dict), where they can only match a cav id -- kept, so psm/rm/dm-style models read
+        # 'reg_preds' and get the direction fix only when 'dir_preds' itself is present
         cls = out['psm'] if 'psm' in out else out['cls_preds']
-        reg = out['rm'] if 'rm' in out else out['reg_preds']
-        dr = out.get('dm', out.get('dir_preds'))
+        reg = out['rm'] if 'rm' in output_dict else out['reg_preds']
+        dr = out['dm'] if 'dm' in output_dict else out.get('dir_preds')
         assert cls.shape[0] == 1                                      # batch size 1 during testing (:1153)
         if 'iou_preds' in out:
             raise NotImplementedError("gencomm_b200 VoxelPostprocessor: iou_preds rescoring is not on the GenComm path")
