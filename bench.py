@@ -1,13 +1,16 @@
 #!/usr/bin/env python
-"""bench.py -- 4-agent OPV2V-H-shape frames/s through the in-scope hot path (BASELINE.json config[1]:
-PointPillars voxelize+PFN+scatter -> 256x256x64 BEV canvas -> warp + AttFusion), one process per GPU.
+"""bench.py -- 4-agent OPV2V-H-shape GenComm frames/s, raw points -> NMS-filtered boxes (BASELINE.json configs[2]:
+PointPillars front end -> BaseBEVBackbone -> shrink -> MessageExtractorv2 -> GenComm 3-step diffusion sampler ->
+Enhancer -> warp + AttFusion -> heads -> decode + rotated NMS), one process per GPU.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--shape opv2v_h|v2xreal]
 
-A "step" is one pass of the hot path over a batch of F synthetic frames (F x 4 agents x 100 k points).
-Frames are independent, so ranks shard them with no data-path collective (weak scaling); NCCL is
-used only to agree on the max-over-ranks time and to all-gather per-rank checksums and timings.
-Rank 0 prints ONE JSON line (contract: see the task statement / DESIGN.md section 6).
+A "step" is one pass of the whole frame path over F synthetic frames per GPU (F x 4 agents x 100 k points; --shape v2xreal:
+configs[3], 5 agents, C = 256).  Frames are independent, so ranks shard them (weak scaling); the path's one exchange step
+-- the all-gather of the padded per-frame detections -- runs over NCCL inside the timed region when N > 1.
+Secondary sections of the same line: the configs[1] HBM step (voxelize + PFN + scatter -> 256x256x64 canvas -> warp +
+AttFusion) with its per-kernel roofline figures, the configs[3]-shaped frame, component microbenches.
+Rank 0 prints ONE JSON line (contract: see the task statement / DESIGN.md section 7).
 """
 import argparse
 import json
@@ -23,11 +26,18 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-N_AGENTS = 4
 POINTS = 100_000
 FUSION = "att"
-METRIC = "4-agent OPV2V-H-shape frames/s (voxelize+PFN+scatter -> 256x256x64 BEV -> warp+AttFusion)"
-WORKLOAD = "configs[1]: PointPillars + AttFusion, 4 agents x 100k pts, 256x256x64 BEV, single B200"
+SHAPES = {
+    "opv2v_h": {"agents": 4, "metric": "4-agent OPV2V-H-shape GenComm frames/s (raw points -> NMS-filtered boxes)",
+                "workload": "configs[2]: GenComm stage-1 detector (m1_att.yaml model args), 4 LiDAR agents x 100k pts, "
+                            "OPV2V-H grid 512x256, C=128 at 64x128, T=3 diffusion sampler, AttFusion, decode + rotated NMS"},
+    "v2xreal": {"agents": 5, "metric": "5-agent V2X-Real-shape GenComm frames/s (raw points -> NMS-filtered boxes)",
+                "workload": "configs[3]: GenComm detector at the V2X-Real shape (5 LiDAR agents x 100k pts, z +-15 m, "
+                            "C=256 at 64x128, T=3 sampler, AttFusion, decode + rotated NMS), frames sharded over the GPUs, "
+                            "NCCL all-gather of detections"},
+}
+HBM_WORKLOAD = "configs[1]: PointPillars + AttFusion, 4 agents x 100k pts, 256x256x64 BEV (voxelize+PFN+scatter -> warp+AttFusion)"
 
 
 def env_int(name, default):
@@ -143,65 +153,237 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons), "how": self.how}
 
 
+def load_tensor_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        if "bf16_tflops_sustained" in d:
+            return float(d["bf16_tflops_sustained"]), "measured (MEASURED_PEAKS.json bf16_tflops_sustained: kernel timed inside a long step)"
+    return 2250.0, "fallback (nominal dense bf16, B200_PROFILING.md)"
+
+
+def kernel_traffic(kernel):
+    """ncu DRAM bytes per launch of `kernel` from the committed capture (profiles/traffic.json), or None when the capture
+    is stale: every entry records the sha1 of the source file the kernel lived in when it was profiled."""
+    import hashlib
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(path):
+        return None
+    with open(path) as f:
+        entry = json.load(f).get(kernel)
+    if not isinstance(entry, dict):
+        return None
+    src = os.path.join(ROOT, entry.get("source", ""))
+    if not os.path.exists(src):
+        return None
+    with open(src, "rb") as f:
+        if hashlib.sha1(f.read()).hexdigest() != entry.get("source_sha1"):
+            return None
+    return entry.get("dram_bytes_per_launch")
+
+
+def bind_to_gpu_numa(local_rank):
+    """Pin this process (and the pinned host buffers it allocates afterwards, first touch) to the CPUs of the NUMA node its
+    GPU hangs off.  Without it every rank runs on node 0 and the host side of the copies serialises (round 1: e2e scaled
+    1.6x on 8 GPUs).  Returns a description for the JSON line."""
+    try:
+        prop = torch.cuda.get_device_properties(local_rank)
+        bus = f"{prop.pci_domain_id:04x}:{prop.pci_bus_id:02x}:{prop.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return {"numa_node": None, "note": "no NUMA affinity reported for the GPU"}
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+        return {"numa_node": node, "cpus": len(allowed) if allowed else 0, "pci": bus}
+    except Exception as exc:   # best effort
+        return {"numa_node": None, "note": repr(exc)}
+
+
 # ------------------------------------------------------------------------------------------------
 # CPU path (the oracle = restatement of the reference's algorithm; test/bench infrastructure only)
 # ------------------------------------------------------------------------------------------------
-def cpu_frame(R, synth, lidar_range, frame, pfn):
-    """One 4-agent frame through the reference's CPU algorithm; returns the fused map."""
-    clouds = [synth.lidar_points(frame, a, POINTS, lidar_range=lidar_range) for a in range(N_AGENTS)]
-    pw = synth.pairwise_t_matrix(frame, N_AGENTS, 5, spread=(0.3 * (lidar_range[3] - lidar_range[0]),
-                                                             0.3 * (lidar_range[4] - lidar_range[1])))
-    t0 = time.perf_counter()
-    batch = R.collate_voxels([R.voxelize(c, lidar_range, synth.VOXEL_SIZE, 32, 70000) for c in clouds])
-    feats = R.pillar_vfe(batch["voxel_features"], batch["voxel_num_points"], batch["voxel_coords"], pfn["weight"],
-                         pfn["bn_weight"], pfn["bn_bias"], pfn["bn_mean"], pfn["bn_var"], synth.VOXEL_SIZE, lidar_range)
-    g = R.grid_size(lidar_range, synth.VOXEL_SIZE)
-    canvas = R.scatter(feats, batch["voxel_coords"], int(g[0]), int(g[1]), N_AGENTS)
-    theta = R.normalize_pairwise_tfm(torch.from_numpy(pw[None]), lidar_range[4] - lidar_range[1],
-                                     lidar_range[3] - lidar_range[0], 1)
-    fused = R.att_fusion(canvas, torch.tensor([N_AGENTS]), theta)
-    return time.perf_counter() - t0, fused
+_CPU_STAGES = ("voxelize", "pillar_vfe", "scatter", "bev_backbone", "downsample_conv", "message_extractor_v2",
+               "gencomm_sample", "enhancer", "att_fusion", "det_heads", "post_process")
+
+
+class CpuFrame:
+    """One GenComm frame through the reference's CPU algorithm (oracle/ref_ops.py restates every stage with file:line
+    citations; pinned to the unmodified reference classes by tests/golden): voxelize -> PillarVFE -> scatter -> backbone ->
+    shrink -> MessageExtractorv2 -> GenComm (T=3) -> Enhancer -> warp + AttFusion -> heads -> decode + rotated NMS.
+    Per-stage wall-clock through timing wrappers around the oracle's own stage functions."""
+
+    def __init__(self, shape, device="cpu"):
+        import gencomm_b200 as G
+        from gencomm_b200 import synth
+        from oracle import ref_ops as R
+        self.R, self.synth, self.shape, self.device = R, synth, shape, torch.device(device)
+        self.n_agents = SHAPES[shape]["agents"]
+        self.args = synth.gencomm_v2xreal_args(FUSION) if shape == "v2xreal" else synth.gencomm_stage1_args(FUSION)
+        m = G.HeterModelBaselineWGenComm(self.args)        # parameter container only: key names + shapes (no kernels run)
+        self.sd = {k: v.to(self.device) for k, v in synth.fill_state_dict(m.state_dict(), 11).items()}
+        self.rng = list(self.args["lidar_range"])
+        self.vs = self.args["m1"]["encoder_args"]["voxel_size"]
+        self.pp = synth.postprocess_params(score_threshold=0.6)
+        self.pp["gt_range"] = list(self.rng)
+        self.pp["anchor_args"]["cav_lidar_range"] = list(self.rng)
+        self.anchors = torch.from_numpy(R.generate_anchor_box(self.pp["anchor_args"], self.pp["order"])).float()
+        self._cur = {}
+        self._wrapped = {}
+        for name in _CPU_STAGES:
+            if hasattr(R, name):
+                self._wrap(name)
+
+    def _wrap(self, name):
+        fn = getattr(self.R, name)
+        self._wrapped[name] = fn
+
+        def timed(*a, **k):
+            if self.device.type == "cuda":
+                torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            out = fn(*a, **k)
+            if self.device.type == "cuda":
+                torch.cuda.synchronize()
+            self._cur[name] = self._cur.get(name, 0.0) + time.perf_counter() - t0
+            return out
+        setattr(self.R, name, timed)
+
+    def close(self):
+        for name, fn in self._wrapped.items():
+            setattr(self.R, name, fn)
+
+    def run(self, frame):
+        R, synth, N, dev = self.R, self.synth, self.n_agents, self.device
+        clouds = [synth.lidar_points(frame, a, POINTS, lidar_range=self.rng) for a in range(N)]
+        pw = torch.from_numpy(synth.pairwise_t_matrix(frame, N, 5, spread=(40.0, 15.0))[None])
+        C = int(self.args["in_head"])
+        n0, steps = synth.sampler_noise(frame, N, C, 64, 128, T=3)
+        self._cur = {}
+        if dev.type == "cuda":
+            torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        vox = R.collate_voxels([R.voxelize(c, self.rng, self.vs, 32, 70000) for c in clouds])   # CPU (spconv is a CPU op)
+        vox = {k: v.to(dev) for k, v in vox.items()}
+        out = R.heter_gencomm_forward(self.sd, self.args, vox, pw.to(dev), torch.tensor([N]), n0.to(dev),
+                                      [s.to(dev) for s in steps])
+        boxes, scores = R.post_process(out["cls_preds"].cpu(), out["reg_preds"].cpu(), out["dir_preds"].cpu(), self.anchors,
+                                       np.eye(4, dtype=np.float32), self.pp)
+        if dev.type == "cuda":
+            torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        self._cur["frame"] = dt
+        return dt, (0 if boxes is None else int(boxes.shape[0]))
+
+    def timed_frames(self, warmup, frames, seed0, budget_s):
+        """warmup untimed frames, then up to `frames` timed ones (stops early once budget_s of timed work is spent).
+        Returns (per-frame seconds, {stage: {median_ms, p90_ms}})."""
+        for w in range(warmup):
+            self.run(10_000 + seed0 + w)
+        tot, ts, per = 0.0, [], []
+        for k in range(frames):
+            dt, _ = self.run(20_000 + seed0 + k)
+            ts.append(dt)
+            per.append(dict(self._cur))
+            tot += dt
+            if tot > budget_s:
+                break
+        stages = {}
+        for name in list(_CPU_STAGES):
+            v = [p[name] for p in per if name in p]
+            if v:
+                stages[name] = {"median_ms": round(1e3 * float(np.median(v)), 3), "p90_ms": round(1e3 * float(np.percentile(v, 90)), 3)}
+        return ts, stages
+
+
+def cpu_info():
+    model = "unknown"
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("model name"):
+                    model = line.split(":", 1)[1].strip()
+                    break
+    except OSError:
+        pass
+    return model, os.cpu_count() or 1
 
 
 def run_reference(args):
     rank = env_int("RANK", 0)
     if rank != 0:
         return
-    from gencomm_b200 import synth
-    from oracle import ref_ops as R
-    cores = os.cpu_count() or 1
+    shape = args.shape
+    model, cores = cpu_info()
     torch.set_num_threads(cores)
-    pfn = synth.pfn_weights(0)
-    rng = synth.SQUARE_RANGE
-    for w in range(args.warmup):
-        cpu_frame(R, synth, rng, 10_000 + w, pfn)
-    total, done = 0.0, 0
-    for k in range(args.steps):
-        dt, _ = cpu_frame(R, synth, rng, 20_000 + k, pfn)
-        total += dt
-        done += 1
-        if total > 150.0:   # bounded sample: the whole run must end within a few minutes whatever K is
-            break
+    cpu = CpuFrame(shape)
+    ts, stages = cpu.timed_frames(max(args.warmup, 1), args.steps, 0, budget_s=120.0)
+    done, total = len(ts), float(np.sum(ts))
     fps = done / total
-    sample = (f"{done} frames timed (K = {args.steps} requested, 150 s cap), 1 frame per step (4 agents x 100k pts), "
-              f"torch CPU threads={torch.get_num_threads()}")
+    k1 = None
+    if args.cpu_protocol:   # BASELINE.md section 3: also k = 1 thread (bounded: a frame takes ~10x longer)
+        torch.set_num_threads(1)
+        t1, s1 = cpu.timed_frames(1, 3, 500, budget_s=120.0)
+        torch.set_num_threads(cores)
+        k1 = {"threads": 1, "frames": len(t1), "median_ms": 1e3 * float(np.median(t1)), "p90_ms": 1e3 * float(np.percentile(t1, 90)),
+              "frames_per_s": len(t1) / float(np.sum(t1)), "stages": s1}
+    cpu.close()
+    gpu_eager = None
+    if torch.cuda.is_available() and not args.no_gpu_eager:
+        # the like-for-like GPU bar (BASELINE.md section 3): the SAME reference op sequence, torch eager on the B200
+        # (cuDNN / ATen kernels, PyTorch defaults incl. TF32 convolutions); voxelization stays on the CPU as in the reference
+        try:
+            torch.cuda.set_device(env_int("LOCAL_RANK", 0))
+            g = CpuFrame(shape, device="cuda")
+            tg, sg = g.timed_frames(3, 20, 900, budget_s=60.0)
+            g.close()
+            gpu_eager = {"frames": len(tg), "median_ms": 1e3 * float(np.median(tg)), "p90_ms": 1e3 * float(np.percentile(tg, 90)),
+                         "frames_per_s": len(tg) / float(np.sum(tg)), "stages": sg,
+                         "note": "oracle op sequence (= the reference's torch ops) run eagerly on cuda:0, 1 frame per call, "
+                                 "CPU voxelizer + H2D of the voxels + host NMS included as in the reference's loop"}
+        except Exception as exc:
+            gpu_eager = {"error": repr(exc)}
+    sample = (f"{done} frames timed after {max(args.warmup, 1)} warm-up (K = {args.steps} requested, 120 s cap), 1 frame per "
+              f"step ({SHAPES[shape]['agents']} agents x 100k pts), torch CPU threads={cores}, {model}")
     print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
-        "steps": done, "warmup": args.warmup, "ms_per_step": 1e3 * total / done,
+        "impl": "reference", "metric": SHAPES[shape]["metric"], "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
+        "steps": done, "warmup": max(args.warmup, 1), "ms_per_step": 1e3 * total / done,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "frames_per_step": 1, "agents": N_AGENTS, "points_per_agent": POINTS,
-                   "fusion": FUSION},
-        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
+        "config": {"workload": SHAPES[shape]["workload"], "frames_per_step": 1, "agents": SHAPES[shape]["agents"],
+                   "points_per_agent": POINTS, "fusion": FUSION},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample,
+                         "cpu_model": model, "median_ms": 1e3 * float(np.median(ts)), "p90_ms": 1e3 * float(np.percentile(ts, 90)),
+                         "stages": stages, "k1": k1},
+        "gpu_eager_baseline": gpu_eager,
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0}))
 
 
 # ------------------------------------------------------------------------------------------------
-# secondary measurement (BASELINE.json configs[2] shape): GenComm 3-step conditional-diffusion sampler
+# secondary measurements
 # ------------------------------------------------------------------------------------------------
-def gencomm_sampler_extra(dev, frames=8, agents=4, C=128, H=64, W=128, iters=10):
-    """GenComm eval sampler (cond_diff.py:331-383) on F frames x 4 agents of OPV2V-H feature shape, device resident,
-    CUDA events.  Reported next to the headline; not part of `value`."""
+def _time_calls(fn, iters, warm=3):
+    for _ in range(warm):
+        fn()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def gencomm_sampler_extra(dev, frames=8, agents=4, C=128, H=64, W=128, iters=20):
+    """GenComm eval sampler (cond_diff.py:331-383) on F frames x N agents, device resident, pre-drawn noise, CUDA events."""
     import gencomm_b200 as G
     from gencomm_b200 import synth
     torch.manual_seed(0)
@@ -215,115 +397,81 @@ def gencomm_sampler_extra(dev, frames=8, agents=4, C=128, H=64, W=128, iters=10)
     n0, steps = synth.sampler_noise(40, A, C, H, W, T=3)
     noise = (n0.to(dev), torch.stack(steps).to(dev))
     rl = torch.full((frames,), agents, dtype=torch.int64)
-    out = {"workload": f"configs[2]-shaped: GenComm sampler, {frames} frames x {agents} agents, C={C}, {H}x{W}, T=3",
-           "launches_per_call": 1 + 3 * 28}
-    for name in ("tc", "bf16", "fp32"):
+    flop = 486.8e6 if C == 128 else 788.8e6
+    hbm = A * 3 * (4 * (C + 2) * H * W + 8 * C * H * W)
+    out = {"workload": f"GenComm sampler, {frames} frames x {agents} agents, C={C}, {H}x{W}, T=3", "mandatory_hbm_bytes": hbm}
+    for name in ("cluster", "tc", "fp32"):
         m.precision = name
-        for _ in range(3):
-            m(feat, cond, rl, noise=noise)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        torch.cuda.synchronize()
-        e0.record()
-        for _ in range(iters):
-            m(feat, cond, rl, noise=noise)
-        e1.record()
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / iters
-        out[name] = {"ms_per_call": ms, "frames_per_s": frames / (ms * 1e-3),
-                     "tflops": frames * agents * 3 * 486.8e6 / (ms * 1e-3) / 1e12}   # 486.8 MFLOP per agent-step
-    out["precision_note"] = ("tc: conv_in/conv_out as bf16 tcgen05 implicit GEMMs + full-resolution width-8 middle layers as tf32 "
-                             "tcgen05 implicit GEMMs (fp32 TMEM accumulation; GroupNorm statistics, half-resolution layers and "
-                             "posterior arithmetic fp32); bf16: conv_in/conv_out only; fp32: all CUDA-core fp32")
+        ms = _time_calls(lambda: m(feat, cond, rl, noise=noise), iters)
+        out[name] = {"ms_per_call": ms, "frames_per_s": frames / (ms * 1e-3), "tflops": A * 3 * flop / (ms * 1e-3) / 1e12,
+                     "hbm_frac_of_mandatory": hbm / (ms * 1e-3) / 1e9 / load_peaks()[0]}
+    out["launches_per_call"] = {"cluster": 1 + 3 * 3, "tc": 1 + 3 * 28}
+    out["precision_note"] = ("cluster (default): bf16 tcgen05 conv_in / conv_out + ONE cluster-resident launch for the 26 width-8 "
+                             "layers (tf32 tcgen05, activations in distributed shared memory); tc: the same arithmetic as one "
+                             "kernel per layer; fp32: all CUDA-core fp32")
     return out
 
 
-def message_extractor_extra(dev, frames=8, agents=4, C=128, H=64, W=128, iters=10):
-    """MessageExtractorv2 (message_extractor_v2.py:70-120) on the same feature shape, device
-    resident, CUDA events.  Reported next to the headline; not part of `value`."""
+def component_extras(dev, frames=8, agents=4, C=128, H=64, W=128, iters=10):
     import gencomm_b200 as G
     torch.manual_seed(0)
-    m = G.MessageExtractorv2(C, 2).to(dev).eval()
     A = frames * agents
     xs = [torch.randn(A, C, H, W, device=dev) for _ in range(3)]
-    for k in range(3):
-        m(xs[k])
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
-    e0.record()
-    for k in range(iters):
-        m(xs[k % 3])
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / iters
-    flops = 2.0 * A * H * W * (9 * C * (18 + 64) + 64 * 64 + 2 * 64)
-    return {"workload": f"MessageExtractorv2, {frames} frames x {agents} agents, C={C}, {H}x{W}", "launches_per_call": 5,
-            "ms_per_call": ms, "frames_per_s": frames / (ms * 1e-3), "tflops": flops / (ms * 1e-3) / 1e12,
-            "precision_note": "offset1 3x3: bf16x3 (value + residual operands, three tcgen05 MMAs, fp32 accumulation); "
-                              "deformable 3x3: bf16 operands, fp32 TMEM accumulation; pool / excite / 1x1 tail fp32"}
+    out = {}
+    me = G.MessageExtractorv2(C, 2).to(dev).eval()
+    k = [0]
+
+    def call(m):
+        k[0] += 1
+        return m(xs[k[0] % 3])
+    ms = _time_calls(lambda: call(me), iters)
+    out["message_extractor"] = {"ms_per_call": ms, "tflops": 2.0 * A * H * W * (9 * C * (18 + 64) + 64 * 64 + 2 * 64) / (ms * 1e-3) / 1e12}
+    en = G.Enhancer(C, [8, 8], 4).to(dev).eval()
+    ms = _time_calls(lambda: call(en), iters)
+    out["enhancer"] = {"ms_per_call": ms,
+                       "tflops": 2.0 * A * H * W * (9 * (C // 4) ** 2 + 4 * C * C + 2 * C * C + 2 * C * 9) / (ms * 1e-3) / 1e12}
+    out["workload"] = f"{frames} frames x {agents} agents, C={C}, {H}x{W}"
+    return out
 
 
-def detector_extra(dev, frames=8, agents=4, points=100_000, iters=5):
-    """The whole stage-1 GenComm detector (heter_model_baseline_w_gencomm_stage1.py:174-297, m1_att.yaml model args) from
-    raw points to decoded, NMS-filtered boxes (voxel_postprocessor.py:1084-1244): every stage on the B200 kernels,
-    device resident, CUDA events.  Reported next to the headline; not part of `value`."""
-    import gencomm_b200 as G
-    from gencomm_b200 import synth
-    m = G.HeterModelBaselineWGenComm(synth.gencomm_stage1_args("att"))
-    m.load_state_dict(synth.fill_state_dict(m.state_dict(), 11))
-    m = m.to(dev).eval()
-    clouds, pairwise = synth.heter_frames(7000, [agents] * frames, points)
-    off = np.concatenate([[0], np.cumsum([len(c) for c in clouds])]).astype(np.int32)
-    data = {"inputs_m1": {"points": torch.from_numpy(np.concatenate(clouds)).to(dev),
-                          "point_offsets": torch.from_numpy(off).to(dev), "max_agent_points": points},
-            "agent_modality_list": ["m1"] * (frames * agents), "pairwise_t_matrix": torch.from_numpy(pairwise).to(dev),
-            "record_len": torch.full((frames,), agents, dtype=torch.int64, device=dev)}
-    pp = G.VoxelPostprocessor(synth.postprocess_params(score_threshold=0.6), train=False)
-    anchors = torch.from_numpy(pp.generate_anchor_box()).float().to(dev)
-
-    def run():
-        out = m(dict(data))
-        return pp.post_process_batch(out["cls_preds"], out["reg_preds"], out["dir_preds"], anchors)
-
-    for _ in range(2):
-        det = run()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+def hbm_step_section(dev, rank, F, K, Wm, peak):
+    """BASELINE configs[1]: voxelize + PFN + scatter -> 256x256x64 canvas -> warp + AttFusion, device resident; the two
+    north-star HBM kernels with the WHOLE front-end unit timed (voxelizer kernels included)."""
+    from gencomm_b200 import pipeline, synth
+    rng, pfn = synth.SQUARE_RANGE, synth.pfn_weights(0)
+    pipe = pipeline.FramePipeline(F, 4, POINTS, rng, synth.VOXEL_SIZE, 70000, FUSION, 5, dev, pfn)
+    n_sets = 3
+    sets = []
+    for s in range(n_sets):
+        p, pw = pipeline.synthetic_step_inputs(1 + rank * n_sets + s, F, 4, POINTS, rng)
+        sets.append((torch.from_numpy(p).to(dev), torch.from_numpy(pw).to(dev)))
+    for w in range(Wm):
+        pipe.step(*sets[w % n_sets])
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(K)]
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
-    e0.record()
-    for _ in range(iters):
-        det = run()
-    e1.record()
+    t0.record()
+    for k in range(K):
+        ev[k][0].record()
+        pipe.step(*sets[k % n_sets], ev_canvas=ev[k][1:3], ev_fuse=ev[k][3:5])
+    t1.record()
     torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / iters
-    return {"workload": f"HeterModelBaselineWGenComm (m1_att) + decode/NMS, {frames} frames x {agents} agents x {points} points, "
-                        "OPV2V-H grid, C=128 at 64x128, T=3 sampler on tensor cores", "ms_per_call": ms,
-            "frames_per_s": frames / (ms * 1e-3), "detections_per_frame": det[2].tolist(),
-            "stages": "pillars, BaseBEVBackbone, shrink header, MessageExtractorv2, GenComm sampler, Enhancer, warp + AttFusion, "
-                      "heads, decode + rotated NMS (scripts/bench_detector.py prints the per-stage times)"}
-
-
-def enhancer_extra(dev, frames=8, agents=4, C=128, H=64, W=128, iters=10):
-    """Enhancer (enhancer.py:335-383) on the same feature shape, device resident, CUDA events."""
-    import gencomm_b200 as G
-    torch.manual_seed(0)
-    m = G.Enhancer(C, [8, 8], 4).to(dev).eval()
-    A = frames * agents
-    xs = [torch.randn(A, C, H, W, device=dev) for _ in range(3)]
-    for k in range(3):
-        m(xs[k])
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
-    e0.record()
-    for k in range(iters):
-        m(xs[k % 3])
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / iters
-    flops = 2.0 * A * H * W * (9 * (C // 4) ** 2 + 4 * C * C + 2 * C * C + 2 * C * 9)
-    return {"workload": f"Enhancer, {frames} frames x {agents} agents, C={C}, {H}x{W}",
-            "launches_per_call": 11 + C // 64 + C // 128, "ms_per_call": ms, "frames_per_s": frames / (ms * 1e-3),
-            "tflops": flops / (ms * 1e-3) / 1e12,
-            "precision_note": "partial_conv3 / linear1 / linear2: bf16x3 tcgen05 GEMMs (fp32-grade); LayerNorms, depth-wise "
-                              "conv + gate, pool / excite fp32"}
+    ms = t0.elapsed_time(t1) / K
+    front = float(np.mean([e[0].elapsed_time(e[2]) for e in ev]))      # voxelizer kernels + canvas writer
+    canvas = float(np.mean([e[1].elapsed_time(e[2]) for e in ev]))
+    fuse = float(np.mean([e[3].elapsed_time(e[4]) for e in ev]))
+    kern = {
+        "front end: k_cell_assign+k_pillar_count+k_pillar_assign+k_slot_insert+k_canvas_persist (voxelize+PFN+scatter)":
+            {"ms": front, "bytes": pipe.scatter_bytes()},
+        "k_canvas_persist alone (PFN+scatter writer)": {"ms": canvas, "bytes": pipe.scatter_bytes()},
+        "k_fuse_persist<ATT> (warp+regroup+AttFusion, 4x64x256x256)": {"ms": fuse, "bytes": pipe.fuse_bytes()},
+    }
+    for v in kern.values():
+        v["gbs"] = v["bytes"] / (v["ms"] * 1e-3) / 1e9
+        v["frac"] = v["gbs"] / peak
+    return {"workload": HBM_WORKLOAD, "frames_per_step": F, "ms_per_step": ms, "frames_per_s": F / (ms * 1e-3),
+            "l2": f"{n_sets} input sets cycled; {pipe.scatter_bytes() / 1e6:.0f} MB canvas traffic per step >> 126 MB L2",
+            "kernels": kern, "checksum": float(pipe.fused.double().sum().item())}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -333,79 +481,87 @@ def run_ours(args):
     import torch.distributed as dist
 
     import gencomm_b200  # noqa: F401  (raises if the CUDA library is missing)
-    from gencomm_b200 import pipeline, synth
+    from gencomm_b200 import pipeline, shard
 
     rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    affinity = bind_to_gpu_numa(local)      # before any pinned allocation
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    shape = args.shape
+    N = SHAPES[shape]["agents"]
     F, K, Wm = args.frames_per_step, args.steps, max(args.warmup, 3)
-    rng = synth.SQUARE_RANGE
-    pfn = synth.pfn_weights(0)
     peak, peak_src = load_peaks()
+    tpeak, tpeak_src = load_tensor_peak()
 
     # CPU baseline first (rank 0, N=1 only), bounded sample of the same workload
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        from oracle import ref_ops as R
-        cores = os.cpu_count() or 1
+        model, cores = cpu_info()
         torch.set_num_threads(cores)
-        cpu_frame(R, synth, rng, 10_000, pfn)
-        n, tot = 0, 0.0
-        while n < 3 or (tot < 10.0 and n < 12):
-            dt, _ = cpu_frame(R, synth, rng, 20_000 + n, pfn)
-            tot += dt
-            n += 1
-        cpu_baseline = {"value": n / tot, "unit": "frames/s", "cores": cores, "kind": "port",
-                        "sample": f"{n} frames (4 agents x 100k pts each) of the same workload after 1 warm-up, "
-                                  f"oracle restatement of the reference CPU path, torch threads={cores}"}
+        cpu = CpuFrame(shape)
+        ts, stages = cpu.timed_frames(1, 6, 0, budget_s=20.0)
+        cpu.close()
+        cpu_baseline = {"value": len(ts) / float(np.sum(ts)), "unit": "frames/s", "cores": cores, "kind": "port",
+                        "cpu_model": model, "median_ms": 1e3 * float(np.median(ts)), "stages": stages,
+                        "sample": f"{len(ts)} frames ({N} agents x 100k pts each) of the same workload after 1 warm-up "
+                                  f"(20 s cap), oracle restatement of the reference CPU path, torch threads={cores}"}
 
-    pipe = pipeline.FramePipeline(F, N_AGENTS, POINTS, rng, synth.VOXEL_SIZE, 70000, FUSION, 5, dev, pfn)
-    n_sets = 3   # distinct input sets cycled through; canvas traffic per step (>0.5 GB) far exceeds the 126 MB L2
+    pipe = pipeline.DetectorPipeline(F, N, POINTS, shape=shape, fusion=FUSION, device=dev)
+    n_sets = 3   # distinct input sets cycled; every stage streams >> 126 MB per step (canvas alone is 1.1 GB)
     host_pts, host_pw = [], []
     for s in range(n_sets):
-        p, pw = pipeline.synthetic_step_inputs(1 + rank * n_sets + s, F, N_AGENTS, POINTS, rng)
+        p, pw = pipeline.synthetic_detector_inputs(1 + rank * n_sets + s, F, N, POINTS, pipe.lidar_range)
         host_pts.append(torch.from_numpy(p).pin_memory())
         host_pw.append(torch.from_numpy(pw).pin_memory())
     dev_pts = [t.to(dev) for t in host_pts]
     dev_pw = [t.to(dev) for t in host_pw]
+    gathered_det = torch.empty((world * F, shard.DET_WIDTH), dtype=torch.float32, device=dev) if world > 1 else None
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def full_step(pts, pw):
+        boxes, scores, counts = pipe.step(pts, pw)
+        if world > 1:      # the path's one exchange step: every rank ends the step with every frame's detections
+            return shard.gather_detections_device(boxes, scores, counts, out=gathered_det)
+        return boxes, scores, counts
+
     # ---------------- device-resident timing ----------------
     sampler = ClockSampler(local) if rank == 0 else None   # covers both timed regions (device-resident and e2e)
+    pipe.enable_stage_timing()
     for w in range(Wm):
-        pipe.step(dev_pts[w % n_sets], dev_pw[w % n_sets])
-    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(K)]
+        full_step(dev_pts[w % n_sets], dev_pw[w % n_sets])
+    torch.cuda.synchronize()
+    pipe._marks.clear()
     t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     if sampler:
         sampler.mark()
     t_start.record()
     for k in range(K):
-        pipe.step(dev_pts[k % n_sets], dev_pw[k % n_sets], ev_canvas=ev[k][0:2], ev_fuse=ev[k][2:4])
+        res = full_step(dev_pts[k % n_sets], dev_pw[k % n_sets])
     t_end.record()
     barrier()
     elapsed_ms = t_start.elapsed_time(t_end)
-    canvas_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in ev]))
-    fuse_ms = float(np.mean([e[2].elapsed_time(e[3]) for e in ev]))
-    checksum = float(pipe.fused.double().sum().item())
+    stage_ms = pipe.stage_ms(K)
+    pipe._marks = None     # the e2e region below runs on side streams: no hook events there
+    det_counts = (res[:, 0] if world > 1 else res[2].float()).tolist()
+    checksum = float((res if world > 1 else shard.pack_detections(*res)).double().sum().item())
 
-    # ---------------- end-to-end timing: pinned host inputs -> device -> pinned host result ----------------
+    # ---------------- end-to-end timing: pinned host points -> device -> detections back in pinned host memory ----------------
     s_in, s_comp, s_out = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream()
     slots = 2
     d_pts = [torch.empty_like(dev_pts[0]) for _ in range(slots)]
     d_pw = [torch.empty_like(dev_pw[0]) for _ in range(slots)]
-    d_out = [torch.empty_like(pipe.fused) for _ in range(slots)]
-    h_out = [torch.empty(pipe.fused.shape, dtype=torch.float32).pin_memory() for _ in range(slots)]
+    d_out = [torch.empty((F, shard.DET_WIDTH), dtype=torch.float32, device=dev) for _ in range(slots)]
+    h_out = [torch.empty((F, shard.DET_WIDTH), dtype=torch.float32).pin_memory() for _ in range(slots)]
     ev_in = [torch.cuda.Event() for _ in range(slots)]
     ev_comp = [torch.cuda.Event() for _ in range(slots)]
     ev_out = [torch.cuda.Event() for _ in range(slots)]
-    own_fused = pipe.fused
 
     def e2e_step(k):
         s = k % slots
@@ -417,8 +573,7 @@ def run_ours(args):
         with torch.cuda.stream(s_comp):
             s_comp.wait_event(ev_in[s])
             s_comp.wait_event(ev_out[s])         # D2H of step k-2 has drained this slot's result
-            pipe.fused = d_out[s]
-            pipe.step(d_pts[s], d_pw[s])
+            d_out[s].copy_(shard.pack_detections(*pipe.step(d_pts[s], d_pw[s])))
             ev_comp[s].record()
         with torch.cuda.stream(s_out):
             s_out.wait_event(ev_comp[s])
@@ -438,100 +593,193 @@ def run_ours(args):
     barrier()
     e2e_ms = e_start.elapsed_time(e_end)
     clocks = sampler.stop() if sampler else None
-    pipe.fused = own_fused
     h2d = host_pts[0].numel() * 4 + host_pw[0].numel() * 8
     d2h = h_out[0].numel() * 4
     e2e_check = float(h_out[(K - 1) % slots].double().sum().item())
 
-    sampler_extra = None
-    me_extra = None
-    enh_extra = None
-    det_extra = None
+    # ---------------- secondary sections (rank 0, N = 1) ----------------
+    extras = {}
     if rank == 0 and world == 1 and not args.no_extras:
-        try:
-            sampler_extra = gencomm_sampler_extra(dev)
-        except Exception as exc:   # secondary measurement must never take the headline down
-            sampler_extra = {"error": repr(exc)}
-        try:
-            me_extra = message_extractor_extra(dev)
-        except Exception as exc:
-            me_extra = {"error": repr(exc)}
-        try:
-            enh_extra = enhancer_extra(dev)
-        except Exception as exc:
-            enh_extra = {"error": repr(exc)}
-        try:
-            det_extra = detector_extra(dev)
-        except Exception as exc:
-            det_extra = {"error": repr(exc)}
+        del d_pts, d_pw, d_out
+        for name, fn in (("hbm_step", lambda: hbm_step_section(dev, rank, 8, max(K, 50), 3, peak)),
+                         ("gencomm_sampler", lambda: gencomm_sampler_extra(dev)),
+                         ("components", lambda: component_extras(dev)),
+                         ("other_shape", lambda: other_shape_section(dev, "v2xreal" if shape == "opv2v_h" else "opv2v_h", F)),
+                         ("single_frame", lambda: single_frame_section(dev, shape))):
+            try:
+                extras[name] = fn()
+            except Exception as exc:   # a secondary measurement must never take the headline down
+                extras[name] = {"error": repr(exc)}
+            torch.cuda.empty_cache()
 
     # ---------------- max over ranks, gather of checksums + timings ----------------
     times = torch.tensor([elapsed_ms, e2e_ms], dtype=torch.float64, device=dev)
     gathered = None
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-        mine = torch.tensor([checksum, e2e_check, elapsed_ms, e2e_ms, canvas_ms, fuse_ms], dtype=torch.float64, device=dev)
+        mine = torch.tensor([checksum, e2e_check, elapsed_ms, e2e_ms] + [stage_ms.get(k, 0.0) for k in STAGE_ORDER],
+                            dtype=torch.float64, device=dev)
         gathered = [torch.empty_like(mine) for _ in range(world)]
         dist.all_gather(gathered, mine)
     elapsed_ms, e2e_ms = float(times[0]), float(times[1])
 
     if rank == 0:
         frames = world * F * K
-        kernels = {
-            "k_canvas_persist (PFN+scatter)": {"ms": canvas_ms, "bytes": pipe.scatter_bytes()},
-            "k_fuse_persist<ATT> (warp+regroup+AttFusion)": {"ms": fuse_ms, "bytes": pipe.fuse_bytes()},
-        }
-        for v in kernels.values():
-            v["gbs"] = v["bytes"] / (v["ms"] * 1e-3) / 1e9
-            v["frac"] = v["gbs"] / peak
-        dom = max(kernels, key=lambda n: kernels[n]["ms"])
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tpath):
-            with open(tpath) as f:
-                traffic = json.load(f).get(dom)
+        work = pipe.work()
+        kernels = {}
+        for st, w in work.items():
+            ms = stage_ms.get(st)
+            if not ms:
+                continue
+            e = {"ms": ms, "bound": w["bound"]}
+            if "bytes" in w:
+                e.update({"bytes": w["bytes"], "gbs": w["bytes"] / (ms * 1e-3) / 1e9})
+                e["hbm_frac"] = e["gbs"] / peak
+            if "flops" in w:
+                e.update({"flops": w["flops"], "tflops": w["flops"] / (ms * 1e-3) / 1e12})
+                e["tensor_frac"] = e["tflops"] / tpeak
+            kernels[STAGE_KERNELS.get(st, st)] = e
+        dom_stage = max(stage_ms, key=stage_ms.get)
+        dom = kernels.get(STAGE_KERNELS.get(dom_stage, dom_stage))
+        roofline = None
+        if dom is not None:
+            if dom["bound"] == "tensor":
+                roofline = {"bound": "tensor", "kernel": STAGE_KERNELS[dom_stage], "achieved": dom["tflops"], "peak": tpeak,
+                            "unit": "TFLOP/s", "frac": dom["tensor_frac"], "traffic": kernel_traffic("k_me_conv"),
+                            "peak_source": tpeak_src, "algorithmic_flops_per_step": dom["flops"], "ms_per_step": dom["ms"],
+                            "note": "dense fp32-grade convolution FLOPs; the kernel issues 3 bf16 MMAs per product (bf16x3), "
+                                    "so the tensor pipe executes 3x this figure"}
+            else:
+                roofline = {"bound": "hbm", "kernel": STAGE_KERNELS[dom_stage], "achieved": dom["gbs"], "peak": peak,
+                            "unit": "GB/s", "frac": dom["hbm_frac"], "traffic": None, "peak_source": peak_src,
+                            "algorithmic_bytes_per_step": dom["bytes"], "ms_per_step": dom["ms"]}
         line = {
-            "metric": METRIC, "value": frames / (elapsed_ms * 1e-3), "unit": "frames/s", "n_gpus": world,
+            "metric": SHAPES[shape]["metric"], "value": frames / (elapsed_ms * 1e-3), "unit": "frames/s", "n_gpus": world,
             "steps": K, "warmup": Wm, "ms_per_step": elapsed_ms / K, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "frames_per_step_per_gpu": F, "agents": N_AGENTS,
+            "vs_baseline": None, "dtype": "f32 (tensor-core operands bf16x3 / tf32 / bf16, fp32 accumulation)", "data": "synthetic",
+            "config": {"workload": SHAPES[shape]["workload"], "frames_per_step_per_gpu": F, "agents": N,
                        "points_per_agent": POINTS, "grid": [pipe.nx, pipe.ny], "fusion": FUSION,
-                       "l2": f"{n_sets} distinct input sets cycled; per-step canvas traffic "
-                             f"{pipe.scatter_bytes() / 1e6:.0f} MB >> 126 MB L2 (inputs larger than L2)",
-                       "not_in_step": "backbone/shrink/heads (SURVEY 8f rank 2; built, measured separately: scripts/bench_backbone.py, bench_det_tail.py)"},
+                       "sampler_precision": pipe.model.gencomm.precision, "weights": "seeded synthetic (synth.fill_state_dict)",
+                       "noise": "drawn on the device with torch.randn inside the step, like the reference",
+                       "l2": f"{n_sets} distinct input sets cycled; every stage streams more than the 126 MB L2 per step "
+                             f"(canvas {F * N * 64 * pipe.nx * pipe.ny * 4 / 1e6:.0f} MB)"},
             "clocks": clocks,
             "e2e": {"value": frames / (e2e_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / K,
-                    "note": "pinned host points+poses -> device -> fused BEV map copied back to pinned host memory, "
-                            "3-stream double-buffered"},
-            "gpu_launches": K * pipeline.KERNELS_PER_STEP,
-            "roofline": {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["gbs"], "peak": peak, "unit": "GB/s",
-                         "frac": kernels[dom]["frac"], "traffic": traffic, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": kernels[dom]["bytes"], "ms_per_launch": kernels[dom]["ms"]},
+                    "note": "pinned host points + poses -> device -> padded detections (count | scores | boxes per frame) "
+                            "copied back to pinned host memory, 3 streams, double buffered; ranks bound to their GPU's NUMA node"},
+            "cpu_affinity": affinity,
+            "collective": ({"op": "all_gather_into_tensor (NCCL)", "bytes_per_rank_per_step": F * shard.DET_WIDTH * 4,
+                            "in_timed_region": True, "payload": "padded gc_postprocess output of the rank's frames"}
+                           if world > 1 else None),
+            "gpu_launches": K * pipeline_launches(pipe, stage_ms),
+            "roofline": roofline,
             "kernels": kernels,
+            "stage_ms": {k: round(v, 4) for k, v in stage_ms.items()},
+            "detections_per_frame": det_counts[:F],
             "cpu_baseline": cpu_baseline,
-            "gencomm_sampler": sampler_extra,
-            "message_extractor": me_extra,
-            "enhancer": enh_extra,
-            "detector": det_extra,
             "checksum": checksum,
         }
+        line.update(extras)
         if gathered is not None:
-            line["per_rank"] = [[float(x) for x in g.tolist()] for g in gathered]
+            line["per_rank"] = {"columns": ["checksum", "e2e_checksum", "elapsed_ms", "e2e_ms"] + list(STAGE_ORDER),
+                                "rows": [[float(x) for x in g.tolist()] for g in gathered]}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
 
+STAGE_ORDER = ("pillars", "backbone", "shrink", "message_extractor", "sampler", "enhancer", "warp_fuse", "postprocess")
+STAGE_KERNELS = {
+    "pillars": "front end: k_cell_assign+k_pillar_count+k_pillar_assign+k_slot_insert+k_canvas (voxelize+PFN+scatter, 512x256 grid)",
+    "backbone": "k_me_conv (BaseBEVBackbone, 19 3x3 + 21 deblock-phase tcgen05 implicit GEMMs)",
+    "warp_fuse": "k_fuse_persist<ATT> (warp+regroup+AttFusion at the native shape)",
+    "sampler": "GenComm sampler (k_q_sample, 3 x [k_conv_in_tc, k_unet_middle_cluster, k_conv_out_tc] + torch.randn noise)",
+}
+
+
+def pipeline_launches(pipe, stage_ms):
+    """Kernels of this repo launched per detector step (counted from the launch sequence of each stage; the torch.randn /
+    elementwise launches of the wrappers are not counted)."""
+    n = 5                      # front end
+    n += 41                    # backbone: to_planes + 19 convs + 1 + 4 + 16 deblock phases
+    n += 3                     # shrink header: to_planes + 2 convs
+    n += 5                     # message extractor
+    cluster = pipe.model.gencomm.precision == "cluster"
+    n += 2 + 1 + 3 * (3 if cluster else 28)   # weight pack x2, q_sample, steps
+    n += 11 + pipe.C // 64 + pipe.C // 128    # enhancer
+    n += 2                     # normalize_pairwise_tfm + warp_fuse
+    n += 2                     # heads: to_planes + GEMM
+    n += 4                     # decode, select, iou, greedy
+    return n
+
+
+def other_shape_section(dev, shape, F):
+    """The other frame shape (configs[3] when the headline is configs[2]) at N = 1, device resident."""
+    from gencomm_b200 import pipeline
+    N = SHAPES[shape]["agents"]
+    pipe = pipeline.DetectorPipeline(F, N, POINTS, shape=shape, fusion=FUSION, device=dev)
+    sets = []
+    for s in range(2):
+        p, pw = pipeline.synthetic_detector_inputs(50 + s, F, N, POINTS, pipe.lidar_range)
+        sets.append((torch.from_numpy(p).to(dev), torch.from_numpy(pw).to(dev)))
+    pipe.enable_stage_timing()
+    k = [0]
+
+    def call():
+        k[0] += 1
+        return pipe.step(*sets[k[0] % 2])
+    for _ in range(2):
+        det = call()
+    torch.cuda.synchronize()
+    pipe._marks.clear()
+    iters = 6
+    ms = _time_calls(call, iters, warm=0)
+    stages = pipe.stage_ms(iters)
+    return {"workload": SHAPES[shape]["workload"], "frames_per_step": F, "ms_per_step": ms, "frames_per_s": F / (ms * 1e-3),
+            "stage_ms": {k2: round(v, 4) for k2, v in stages.items()}, "detections_per_frame": det[2].tolist()}
+
+
+def single_frame_section(dev, shape):
+    """The reference's actual operating point (tools/inference.py:114-120 runs batch 1): one frame per call, eager launches
+    and the same sequence replayed from a CUDA graph."""
+    from gencomm_b200 import pipeline
+    N = SHAPES[shape]["agents"]
+    pipe = pipeline.DetectorPipeline(1, N, POINTS, shape=shape, fusion=FUSION, device=dev)
+    p, pw = pipeline.synthetic_detector_inputs(77, 1, N, POINTS, pipe.lidar_range)
+    pts, pwd = torch.from_numpy(p).to(dev), torch.from_numpy(pw).to(dev)
+    eager = _time_calls(lambda: pipe.step(pts, pwd), 20)
+    out = {"workload": f"1 frame x {N} agents per call (batch-1 inference loop)", "eager_ms": eager}
+    try:
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                pipe.step(pts, pwd)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            det = pipe.step(pts, pwd)
+        ms = _time_calls(graph.replay, 50)
+        out.update({"cuda_graph_ms": ms, "frames_per_s_graph": 1e3 / ms, "detections": int(det[2][0].item())})
+    except Exception as exc:
+        out["cuda_graph_error"] = repr(exc)
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--shape", default="opv2v_h", choices=sorted(SHAPES))
     ap.add_argument("--frames-per-step", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-extras", action="store_true", help="skip the secondary GenComm sampler measurement")
+    ap.add_argument("--no-extras", action="store_true", help="skip the secondary sections (configs[1] HBM step, sampler, ...)")
+    ap.add_argument("--cpu-protocol", action="store_true", help="--impl reference: also time k = 1 thread (BASELINE.md section 3)")
+    ap.add_argument("--no-gpu-eager", action="store_true", help="--impl reference: skip the torch-eager-on-GPU bar")
     args = ap.parse_args()
     # The contract is ONE JSON line on stdout.  Libraries write to fd 1 behind Python's back (NCCL prints its version
     # banner there at communicator creation), so fd 1 is pointed at stderr for the whole run and the JSON line goes to a

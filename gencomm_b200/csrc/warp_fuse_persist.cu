@@ -331,8 +331,11 @@ __device__ __forceinline__ void fast_loop(Ctx &x, const float (&wt)[kTileMaxN][4
                         // tensor-memory park: 4 columns per channel = the (up to 4) parked agents of this pixel
                         if (x.park_mode) {
                             constexpr int o = IDENT0 ? 1 : 0;   // first parked agent
+                            // with at most 3 parked agents the fourth column carries the identity ego, so the output
+                            // pass below never goes back to global memory (r02: 16 dependent L2 round trips per tile)
+                            constexpr bool kEgoCol = IDENT0 && N <= 4;
                             tmem_st4(x.tmem_park + (uint32_t)((c0 + G * kc) * 4), v[o < N ? o : 0], v[o + 1 < N ? o + 1 : 0],
-                                     v[o + 2 < N ? o + 2 : 0], v[o + 3 < N ? o + 3 : 0]);
+                                     v[o + 2 < N ? o + 2 : 0], kEgoCol ? v[0] : v[o + 3 < N ? o + 3 : 0]);
                         }
                     } else if (x.park_mode) {
                         static_for<N>([&](auto j_) {
@@ -362,28 +365,50 @@ __device__ __forceinline__ void fast_loop(Ctx &x, const float (&wt)[kTileMaxN][4
 
     if constexpr (kTmemOK && MODE == GC_FUSE_ATT) {
         if (x.park_tmem && x.park_mode) {
-            // out = sum_j a_j w_j from the vectors parked in tensor memory: one 16-column load = 4 channels x 4 agents
+            // out = sum_j a_j w_j from the vectors parked in tensor memory: one 16-column load = 4 channels x 4 agents;
+            // two loads in flight per iteration (C % 8 == 0 takes the unrolled body)
             constexpr int o = IDENT0 ? 1 : 0;
+            constexpr bool kEgoCol = IDENT0 && N <= 4;
             tmem_wait_st();
             const float *sp = x.src_pix;
-            for (int c = 0; c < x.C; c += 4) {   // C % 4 == 0 in this mode
-                float pv[16], ego[4];
-                tmem_ld16(x.tmem_park + (uint32_t)(c * 4), pv);
-                if (IDENT0) {
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) ego[i] = x.active ? __ldg(sp + (size_t)i * x.plane) : 0.0f;
-                }
-                tmem_wait_ld();
+            auto emit = [&](const float (&pv)[16], const float (&ego)[4], float *d) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     float acc = 0.0f;
 #pragma unroll
                     for (int j = 0; j < N; ++j) {
-                        const float v = (j == 0 && IDENT0) ? ego[i] : pv[i * 4 + (j - o < 0 ? 0 : j - o)];
+                        const float v = (j == 0 && IDENT0) ? (kEgoCol ? pv[i * 4 + 3] : ego[i]) : pv[i * 4 + (j - o < 0 ? 0 : j - o)];
                         acc = __fmaf_rn(score[j], v, acc);
                     }
-                    if (x.active) dst[(size_t)i * x.plane] = acc;
+                    if (x.active) d[(size_t)i * x.plane] = acc;
                 }
+            };
+            int c = 0;
+            for (; c + 8 <= x.C; c += 8) {
+                float pa[16], pb[16], ea[4] = {0.f, 0.f, 0.f, 0.f}, eb[4] = {0.f, 0.f, 0.f, 0.f};
+                tmem_ld16(x.tmem_park + (uint32_t)(c * 4), pa);
+                tmem_ld16(x.tmem_park + (uint32_t)(c * 4 + 16), pb);
+                if (IDENT0 && !kEgoCol) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        ea[i] = x.active ? __ldg(sp + (size_t)i * x.plane) : 0.0f;
+                        eb[i] = x.active ? __ldg(sp + (size_t)(i + 4) * x.plane) : 0.0f;
+                    }
+                }
+                tmem_wait_ld();
+                emit(pa, ea, dst);
+                emit(pb, eb, dst + 4 * x.plane);
+                dst += 8 * x.plane; sp += 8 * x.plane;
+            }
+            for (; c < x.C; c += 4) {   // C % 4 == 0 in this mode
+                float pv[16], ego[4] = {0.f, 0.f, 0.f, 0.f};
+                tmem_ld16(x.tmem_park + (uint32_t)(c * 4), pv);
+                if (IDENT0 && !kEgoCol) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) ego[i] = x.active ? __ldg(sp + (size_t)i * x.plane) : 0.0f;
+                }
+                tmem_wait_ld();
+                emit(pv, ego, dst);
                 dst += 4 * x.plane; sp += 4 * x.plane;
             }
             return;
@@ -809,6 +834,7 @@ int warp_fuse_persist(const float *feat, const int32_t *agent_offsets, int n_fra
         case 2: return GC_LAUNCH(MODE, 16, 8, 2, 2);                                \
         case 4: return GC_LAUNCH(MODE, 16, 16, 1, 2);                               \
         case 5: return GC_LAUNCH(MODE, 16, 16, 1, 4);                               \
+        case 6: return GC_LAUNCH(MODE, 16, 8, 1, 4);                                \
         default: return GC_LAUNCH(MODE, 16, 16, 1, 2);                              \
     }
     // defaults from the B200 sweep profiles/r01g_bench_fuse_cfg*.txt: 16x16 tiles, one thread per pixel; 4 channels per
@@ -816,7 +842,10 @@ int warp_fuse_persist(const float *feat, const int32_t *agent_offsets, int n_fra
     const int dflt = nmax > 5 ? 4 : 5;
     if (mode == GC_FUSE_WARP_ONLY) { GC_VARIANTS(GC_FUSE_WARP_ONLY, (nmax > 5 ? 4 : 4)) }
     if (mode == GC_FUSE_MAX) { GC_VARIANTS(GC_FUSE_MAX, dflt) }
-    GC_VARIANTS(GC_FUSE_ATT, dflt)
+    // AttFusion: the one-pass TMEM park needs (P / 128) * 4C <= 512 columns: 16x16 tiles up to C = 64, 16x8 tiles up to
+    // C = 128 (the OPV2V-H feature shape); beyond that two passes through the ring
+    const int att = (nmax <= 5 && C % 4 == 0 && C > 64 && C <= 128) ? 6 : dflt;
+    GC_VARIANTS(GC_FUSE_ATT, att)
 #undef GC_VARIANTS
 #undef GC_LAUNCH
 }

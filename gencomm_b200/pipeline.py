@@ -101,3 +101,124 @@ def synthetic_step_inputs(step_seed, n_frames, n_agents, points_per_agent, lidar
             clouds.append(synth.lidar_points(frame, a, points_per_agent, lidar_range=lidar_range))
         pws.append(synth.pairwise_t_matrix(frame, n_agents, max_cav, spread=(half_w, half_h)))
     return np.concatenate(clouds), np.stack(pws)
+
+
+# ------------------------------------------------------------------------------------------------
+# The whole GenComm frame: raw points -> NMS-filtered boxes (BASELINE.json configs[2] / configs[3])
+# ------------------------------------------------------------------------------------------------
+DETECTOR_STAGES = {"encoder_m1": "pillars", "backbone_m1": "backbone", "shrinker_m1": "shrink",
+                   "message_extractor_m1": "message_extractor", "gencomm": "sampler", "enhancer": "enhancer",
+                   "fusion_net": "warp_fuse"}
+
+
+class DetectorPipeline:
+    """F collaborative frames per step through ``HeterModelBaselineWGenComm`` (the reference's model call,
+    tools/inference_utils.py:141-142) and ``VoxelPostprocessor`` (voxel_postprocessor.py:1084-1244):
+
+        points [F*N*P,4] + pairwise [F,L,L,4,4] f64 -> pillars -> BaseBEVBackbone -> shrink -> MessageExtractorv2 ->
+        GenComm sampler (T=3, noise drawn on the device like the reference) -> Enhancer -> warp + Att/Max fusion ->
+        heads -> decode + rotated NMS -> boxes [F,1000,8,3], scores [F,1000], counts [F]
+
+    ``shape``: "opv2v_h" (m1_att.yaml: C=128 at 64x128) or "v2xreal" (C=256, z +-15 m; synth.gencomm_v2xreal_args).
+    Everything is asynchronous on the current stream; weights are the seeded synthetic fill of synth.fill_state_dict."""
+
+    def __init__(self, n_frames, n_agents, points_per_agent, shape="opv2v_h", fusion="att", device="cuda", seed=11,
+                 score_threshold=0.6, precision=None):
+        from . import synth
+        from .heter_model_baseline_w_gencomm_stage1 import HeterModelBaselineWGenComm
+        from .postprocess import VoxelPostprocessor
+        self.F, self.N, self.P = int(n_frames), int(n_agents), int(points_per_agent)
+        self.device = torch.device(device)
+        self.shape = shape
+        self.args = synth.gencomm_v2xreal_args(fusion) if shape == "v2xreal" else synth.gencomm_stage1_args(fusion)
+        self.lidar_range = list(self.args["lidar_range"])
+        m = HeterModelBaselineWGenComm(self.args)
+        m.load_state_dict(synth.fill_state_dict(m.state_dict(), seed))
+        self.model = m.to(self.device).eval()
+        if precision is not None:
+            self.model.gencomm.precision = precision
+        pparams = synth.postprocess_params(score_threshold=score_threshold)
+        pparams["gt_range"] = list(self.lidar_range)
+        pparams["anchor_args"]["cav_lidar_range"] = list(self.lidar_range)
+        self.post = VoxelPostprocessor(pparams, train=False)
+        self.anchors = torch.from_numpy(self.post.generate_anchor_box()).float().to(self.device)
+        A = self.F * self.N
+        self.C = int(self.args["in_head"])
+        self.point_offsets = torch.arange(0, A * self.P + 1, self.P, dtype=torch.int32, device=self.device)
+        self.record_len = torch.full((self.F,), self.N, dtype=torch.int64, device=self.device)
+        self.modalities = ["m1"] * A
+        g = ops.grid_size(self.lidar_range, self.args["m1"]["encoder_args"]["voxel_size"])
+        self.nx, self.ny = int(g[0]), int(g[1])
+        self._marks = None
+
+    # ---- algorithmic work per step (SURVEY.md 8d), the denominators of the per-stage roofline figures ----
+    def work(self):
+        A, C, H, W = self.F * self.N, self.C, self.ny // 4, self.nx // 4
+        b = self.args["m1"]["backbone_args"]
+        flops, cin, h, w = 0.0, 64, self.ny, self.nx
+        for n, s, f in zip(b["layer_nums"], b["layer_strides"], b["num_filters"]):
+            h, w = h // s, w // s
+            flops += 2.0 * 9 * cin * f * h * w + n * 2.0 * 9 * f * f * h * w
+            cin = f
+        h, w = self.ny, self.nx
+        for s, f, u, nf in zip(b["layer_strides"], b["num_filters"], b["upsample_strides"], b["num_upsample_filter"]):
+            h, w = h // s, w // s
+            flops += 2.0 * f * nf * (h * u) * (w * u)
+        return {
+            "pillars": {"bound": "hbm", "bytes": A * (16 * self.P + 4 * 64 * self.ny * self.nx)},
+            "backbone": {"bound": "tensor", "flops": A * flops},
+            "warp_fuse": {"bound": "hbm", "bytes": self.F * (4 * self.N * C * H * W + 4 * C * H * W + 48 * self.N)},
+            "sampler": {"bound": "hbm", "bytes": A * 3 * (4 * (C + 2) * H * W + 8 * C * H * W),
+                        "flops": A * 3 * (486.8e6 if C == 128 else 788.8e6 if C == 256 else 0.0)},
+        }
+
+    def enable_stage_timing(self):
+        """Forward hooks that record CUDA events around every sub-module (current stream)."""
+        self._marks = []
+
+        def ev():
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            return e
+        for name, label in DETECTOR_STAGES.items():
+            mod = getattr(self.model, name)
+            mod.register_forward_pre_hook(lambda _m, _i, label=label: self._mark(label, 0))
+            mod.register_forward_hook(lambda _m, _i, _o, label=label: self._mark(label, 1))
+        self._ev = ev
+
+    def _mark(self, label, kind):
+        if self._marks is not None:      # set to None to stop recording (the hooks stay registered)
+            self._marks.append((label, kind, self._ev()))
+
+    def stage_ms(self, n_steps):
+        """Mean per-step milliseconds of each stage since the marks were last cleared (call after a synchronize)."""
+        per = {}
+        for (l0, k0, a), (l1, k1, b) in zip(self._marks[0::2], self._marks[1::2]):
+            assert l0 == l1 and k0 == 0 and k1 == 1
+            per[l0] = per.get(l0, 0.0) + a.elapsed_time(b) / n_steps
+        self._marks.clear()
+        return per
+
+    def step(self, points, pairwise, noise=None):
+        data = {"inputs_m1": {"points": points, "point_offsets": self.point_offsets, "max_agent_points": self.P},
+                "agent_modality_list": self.modalities, "pairwise_t_matrix": pairwise, "record_len": self.record_len}
+        if noise is not None:
+            data["gencomm_noise"] = noise
+        out = self.model(data)
+        self._mark("postprocess", 0)
+        det = self.post.post_process_batch(out["cls_preds"], out["reg_preds"], out["dir_preds"], self.anchors)
+        self._mark("postprocess", 1)
+        return det
+
+
+def synthetic_detector_inputs(step_seed, n_frames, n_agents, points_per_agent, lidar_range, max_cav=5):
+    """Host inputs of one detector step: points [F*N*P,4] f32, pairwise [F,L,L,4,4] f64 (agents within ~40 m of the ego so
+    that their canvases overlap after the warp, like synth.heter_frames)."""
+    from . import synth
+    clouds, pws = [], []
+    for f in range(n_frames):
+        frame = step_seed * 1000 + f
+        for a in range(n_agents):
+            clouds.append(synth.lidar_points(frame, a, points_per_agent, lidar_range=lidar_range))
+        pws.append(synth.pairwise_t_matrix(frame, n_agents, max_cav, spread=(40.0, 15.0)))
+    return np.concatenate(clouds), np.stack(pws)

@@ -124,3 +124,41 @@ def gather_detections(local, n_frames, device, k_max=1000):
     if missing:
         raise RuntimeError(f"frames {missing} were not processed by any rank")
     return out
+
+
+DET_WIDTH = 1 + 1000 + 24 * 1000     # count, scores [1000], boxes [1000,8,3] per frame
+
+
+def pack_detections(boxes, scores, counts):
+    """Device-side payload of the detection all-gather: [F, DET_WIDTH] f32 = count | scores | boxes, rows beyond the count
+    zeroed (``gc_postprocess`` leaves them unspecified).  No host sync."""
+    F, top = scores.shape
+    valid = (torch.arange(top, device=scores.device)[None, :] < counts[:, None]).to(scores.dtype)
+    return torch.cat([counts.to(scores.dtype)[:, None], scores * valid, (boxes.reshape(F, top, 24) * valid[:, :, None]).reshape(F, -1)],
+                     dim=1)
+
+
+def gather_detections_device(boxes, scores, counts, out=None):
+    """All-gather the padded ``gc_postprocess`` output of this rank's F frames over every rank (the one
+    exchange step of the path, NCCL on the GPU box).  boxes [F,1000,8,3], scores [F,1000], counts [F] (device) ->
+    payload [world*F, DET_WIDTH] on every rank, rank-major (rank r holds global frames r*F .. r*F+F-1 of the step).
+    Asynchronous (the collective is enqueued on the current stream by torch.distributed); unpack with
+    ``unpack_detections``."""
+    payload = pack_detections(boxes, scores, counts)
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    if world == 1:
+        return payload
+    if out is None:
+        out = torch.empty((world * payload.shape[0], payload.shape[1]), dtype=payload.dtype, device=payload.device)
+    dist.all_gather_into_tensor(out, payload)
+    return out
+
+
+def unpack_detections(payload, top=1000):
+    """payload [n, DET_WIDTH] -> list of (boxes [K,8,3], scores [K]) per frame (host sync: the result is ragged)."""
+    p = payload.cpu()
+    out = []
+    for row in p:
+        k = int(row[0])
+        out.append((row[1 + top:1 + top + 24 * k].reshape(k, 8, 3).clone(), row[1:1 + k].clone()))
+    return out

@@ -171,6 +171,28 @@ def gencomm_stage1_args(fusion="att"):
     }
 
 
+V2XREAL_RANGE = [-102.4, -51.2, -15.0, 102.4, 51.2, 15.0]
+
+
+def gencomm_v2xreal_args(fusion="att"):
+    """V2X-Real-SHAPED ``model.args`` (hypes_yaml/v2xreal/GenComm_yamls/gencomm/stage2/m1m2m3m4_att_infer.yaml:27,51,
+    196-326): z range +-15 m with one 30 m voxel, C = 256 at 64 x 128 (shrink header dim 256, enhancer / message extractor /
+    AttFusion / heads on 256 channels, denoiser in_channels 256).  All agents use the m1 LiDAR PointPillars branch
+    (m4's identity backbone would give a 256 x 512 map that the reference cannot stack) and the
+    single-class head of the OPV2V configs (the yaml's 3-class anchors / multi-class post-processor are outside SURVEY 8)."""
+    a = gencomm_stage1_args(fusion)
+    rng = list(V2XREAL_RANGE)
+    a["lidar_range"] = rng
+    a["m1"]["encoder_args"].update({"voxel_size": [0.4, 0.4, 30], "lidar_range": rng})
+    a["m1"]["shrink_header"]["dim"] = [256]
+    a["enhancer"] = {"in_ch": 256}
+    a["message_extractor"] = {"in_ch": 256, "out_ch": 2}
+    a["att"] = {"feat_dim": 256}
+    a["in_head"] = 256
+    a["gencomm"]["model"].update({"embed_dim": 258, "in_channels": 256, "out_ch": 256})
+    return a
+
+
 def heter_frames(seed, record_len, n_points=30_000, max_cav=5):
     """Host inputs of a batch of collaborative frames for the full detector: per-agent clouds (list of [P,4] f32) and
     ``pairwise_t_matrix`` [B,L,L,4,4] f64; agents stay within ~40 m so their canvases overlap after the warp."""

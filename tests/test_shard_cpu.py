@@ -106,3 +106,37 @@ def test_world2_gloo_detection_gather():
             if k:
                 assert torch.equal(got[f][0], boxes) and torch.equal(got[f][1], scores)
             assert torch.equal(got[f][0], single[f][0]) and torch.equal(got[f][1], single[f][1])
+
+
+def fake_padded(rank, F=3, top=1000):
+    """What gc_postprocess hands over for a rank's F frames: padded boxes / scores with garbage beyond the count."""
+    g = torch.Generator().manual_seed(7 + rank)
+    counts = torch.tensor([(5 * rank + 3 * f) % 7 for f in range(F)], dtype=torch.int32)   # includes empty frames
+    return torch.randn(F, top, 8, 3, generator=g), torch.rand(F, top, generator=g), counts
+
+
+def _padded_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        out[rank] = shard.gather_detections_device(*fake_padded(rank))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_world2_gloo_padded_detection_gather():
+    """The bench's exchange step: all_gather_into_tensor of the packed padded detections (count | scores | boxes)."""
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_padded_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    assert torch.equal(out[0], out[1]) and out[0].shape == (6, shard.DET_WIDTH)
+    dets = shard.unpack_detections(out[0])
+    for rank in (0, 1):
+        boxes, scores, counts = fake_padded(rank)
+        single = shard.gather_detections_device(boxes, scores, counts)          # world 1: just the packed payload
+        assert torch.equal(single, out[0][3 * rank:3 * rank + 3])
+        for f in range(3):
+            k = int(counts[f])
+            b, s = dets[3 * rank + f]
+            assert b.shape == (k, 8, 3) and torch.equal(b, boxes[f, :k]) and torch.equal(s, scores[f, :k])
+        assert float(single[:, 1:1001].sum()) == float(sum(scores[f, :int(counts[f])].sum() for f in range(3)))  # padding zeroed
