@@ -842,10 +842,11 @@ int warp_fuse_persist(const float *feat, const int32_t *agent_offsets, int n_fra
     const int dflt = nmax > 5 ? 4 : 5;
     if (mode == GC_FUSE_WARP_ONLY) { GC_VARIANTS(GC_FUSE_WARP_ONLY, (nmax > 5 ? 4 : 4)) }
     if (mode == GC_FUSE_MAX) { GC_VARIANTS(GC_FUSE_MAX, dflt) }
-    // AttFusion: the one-pass TMEM park needs (P / 128) * 4C <= 512 columns: 16x16 tiles up to C = 64, 16x8 tiles up to
-    // C = 128 (the OPV2V-H feature shape); beyond that two passes through the ring
-    const int att = (nmax <= 5 && C % 4 == 0 && C > 64 && C <= 128) ? 6 : dflt;
-    GC_VARIANTS(GC_FUSE_ATT, att)
+    // AttFusion: the one-pass TMEM park needs (P / 128) * 4C <= 512 columns: 16x16 tiles up to C = 64; beyond that two
+    // passes through the ring.  Variant 6 (16x8 tiles, one pass up to C = 128) measured the same as two passes on
+    // 16x16 tiles at 4x128x64x128 (0.094 vs 0.097 ms, profiles/r02e_bench_fuse.txt): that shape is wave-quantisation
+    // and latency bound (256 tiles on 148 SMs), not pass-count bound -- kept selectable, not the default.
+    GC_VARIANTS(GC_FUSE_ATT, dflt)
 #undef GC_VARIANTS
 #undef GC_LAUNCH
 }

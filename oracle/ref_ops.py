@@ -104,7 +104,7 @@ def pillar_vfe(voxel_features, voxel_num_points, coords, weight, bn_weight, bn_b
     f_center[:, :, 1] = vf[:, :, 1] - (coords[:, 2].to(vf.dtype).unsqueeze(1) * voxel_size[1] + yo)
     f_center[:, :, 2] = vf[:, :, 2] - (coords[:, 1].to(vf.dtype).unsqueeze(1) * voxel_size[2] + zo)
     feats = torch.cat([vf, f_cluster, f_center], dim=-1)                                       # :134-143
-    slot = torch.arange(feats.shape[1], dtype=torch.int).view(1, -1)
+    slot = torch.arange(feats.shape[1], dtype=torch.int, device=vf.device).view(1, -1)
     mask = (voxel_num_points.int().unsqueeze(1) > slot).unsqueeze(-1).type_as(vf)              # :145-149
     feats = feats * mask
     x = F.linear(feats, weight)                                                                # :39
@@ -143,6 +143,17 @@ def pillar_vfe_kernel_order(voxel_features, voxel_num_points, coords, weight, sc
 # a4  PointPillarScatter.forward (models/sub_modules/point_pillar_scatter.py:19-76)
 # --------------------------------------------------------------------------------------------
 def scatter(pillar_features, coords, nx, ny, n_batch=None):
+    if pillar_features.is_cuda:   # torch-eager form of the same statements (bench.py's GPU-eager bar); nz == 1
+        if n_batch is None:
+            n_batch = int(coords[:, 0].max().item()) + 1                                        # :45
+        out = []
+        for b in range(n_batch):                                                               # :47-66
+            canvas = torch.zeros(pillar_features.shape[1], nx * ny, dtype=pillar_features.dtype, device=pillar_features.device)
+            m = coords[:, 0] == b
+            idx = (coords[m, 1] + coords[m, 2] * nx + coords[m, 3]).long()
+            canvas[:, idx] = pillar_features[m].t()
+            out.append(canvas)
+        return torch.stack(out, 0).view(n_batch, -1, ny, nx)                                    # :68-73
     pf = np.ascontiguousarray(pillar_features.numpy(), np.float32)
     co = np.ascontiguousarray(coords.numpy(), np.int32)
     if n_batch is None:
@@ -237,7 +248,7 @@ def _gn(x, sd, name):                                                           
 def timestep_embedding(t, dim):                                                                # unet.py:10-28
     half = dim // 2
     e = math.log(10000) / (half - 1)
-    e = torch.exp(torch.arange(half, dtype=torch.float32) * -e)
+    e = torch.exp(torch.arange(half, dtype=torch.float32, device=t.device) * -e)
     e = t.float()[:, None] * e[None, :]
     e = torch.cat([torch.sin(e), torch.cos(e)], dim=1)
     if dim % 2 == 1:
@@ -319,7 +330,7 @@ def gencomm_sample(spatial_features, conditions, record_len, sd, noise0, step_no
     b = x_start.shape[0]
     x = sch["sqrt_alphas_cumprod"][T - 1] * x_start + sch["sqrt_one_minus_alphas_cumprod"][T - 1] * noise0  # :372
     for k, t in enumerate(reversed(range(T))):                                                 # :325
-        tt = torch.full((b,), t, dtype=torch.long)
+        tt = torch.full((b,), t, dtype=torch.long, device=x.device)
         x_recon = unet_forward(torch.cat([conditions, x], dim=1), tt.float(), sd)              # :317-319
         if t == 0:
             x = x_recon                                                                        # :292-294,:313
@@ -362,10 +373,14 @@ def deform_bilinear(img, h, w):
 def deform_conv2d_3x3(x, offset, weight, bias):
     """torchvision.ops.deform_conv2d(x, offset, weight, bias, stride 1, padding 1, dilation 1), 3x3, one offset group.
     x [N,C,H,W]; offset [N,18,H,W] with channel 2k = dy and 2k+1 = dx of tap k = ky*3+kx; weight [O,C,3,3]."""
+    if x.is_cuda:   # bench.py's GPU-eager bar: the reference's actual call (message_extractor_v2.py:86, torchvision's CUDA kernel)
+        import torchvision
+        return torchvision.ops.deform_conv2d(x, offset, weight, bias, stride=1, padding=1)
     N, C, H, W = x.shape
     O = weight.shape[0]
-    ys, xs = torch.meshgrid(torch.arange(H, dtype=x.dtype), torch.arange(W, dtype=x.dtype), indexing="ij")
-    out = torch.empty(N, O, H, W, dtype=x.dtype)
+    ys, xs = torch.meshgrid(torch.arange(H, dtype=x.dtype, device=x.device), torch.arange(W, dtype=x.dtype, device=x.device),
+                            indexing="ij")
+    out = torch.empty(N, O, H, W, dtype=x.dtype, device=x.device)
     for n in range(N):
         cols = []
         for k in range(9):
