@@ -192,17 +192,31 @@ def bind_to_gpu_numa(local_rank):
         bus = f"{prop.pci_domain_id:04x}:{prop.pci_bus_id:02x}:{prop.pci_device_id:02x}.0"
         with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
             node = int(f.read().strip())
-        if node < 0:
-            return {"numa_node": None, "note": "no NUMA affinity reported for the GPU"}
-        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
-            cpus = set()
-            for part in f.read().strip().split(","):
-                lo, _, hi = part.partition("-")
-                cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus = set()
+        if node >= 0:
+            with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+                for part in f.read().strip().split(","):
+                    lo, _, hi = part.partition("-")
+                    cpus.update(range(int(lo), int(hi or lo) + 1))
+        else:   # sysfs has no node for the device (virtualised PCI): ask NVML for the ideal CPU set (nvidia-smi topo -m)
+            import pynvml
+            pynvml.nvmlInit()
+            h = None
+            for i in range(pynvml.nvmlDeviceGetCount()):
+                hi = pynvml.nvmlDeviceGetHandleByIndex(i)
+                if pynvml.nvmlDeviceGetPciInfo(hi).bus == prop.pci_bus_id:
+                    h = hi
+            words = (os.cpu_count() + 63) // 64
+            mask = pynvml.nvmlDeviceGetCpuAffinity(h, words) if h is not None else []
+            for wi, word in enumerate(mask):
+                cpus.update(wi * 64 + b for b in range(64) if (int(word) >> b) & 1)
+            if not cpus:
+                return {"numa_node": None, "note": "no NUMA / CPU affinity reported for the GPU"}
         allowed = os.sched_getaffinity(0) & cpus
         if allowed:
             os.sched_setaffinity(0, allowed)
-        return {"numa_node": node, "cpus": len(allowed) if allowed else 0, "pci": bus}
+        return {"numa_node": node if node >= 0 else None, "cpus": len(allowed) if allowed else 0, "pci": bus,
+                "source": "sysfs numa_node" if node >= 0 else "nvmlDeviceGetCpuAffinity"}
     except Exception as exc:   # best effort
         return {"numa_node": None, "note": repr(exc)}
 

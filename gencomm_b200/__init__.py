@@ -8,7 +8,7 @@ Hand-written CUDA behind a C ABI (include/gencomm_b200.h, csrc/), loaded through
 classes in ``gencomm_b200.modules`` carry the reference's operator names and signatures.
 """
 from . import _lib, ops, synth  # noqa: F401
-from .modules import (AttFusion, MaxFusion, PFNLayer, PillarVFE, PointPillar, PointPillarScatter,  # noqa: F401
+from .modules import (AttFusion, BEVFeatureInput, MaxFusion, PFNLayer, PillarVFE, PointPillar, PointPillarScatter,  # noqa: F401
                       SpVoxelPreprocessor, normalize_pairwise_tfm, regroup, warp_affine_simple, warp_feature)
 
 from .gencomm import Config, DiffusionUNet, GenComm  # noqa: F401

@@ -87,6 +87,9 @@ SIGNATURES = {
     "gc_lss_pool_workspace_bytes": (c_size_t, [c_int, c_int, c_void_p]),
     "gc_lss_voxel_pooling": (c_int, [c_void_p, c_void_p, ctypes.c_longlong, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                      c_void_p, c_void_p]),
+    "gc_lss_pool_det_workspace_bytes": (c_size_t, [c_int, c_int, c_void_p]),
+    "gc_lss_voxel_pooling_det": (c_int, [c_void_p, c_void_p, ctypes.c_longlong, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                                         c_void_p, c_void_p]),
     "gc_postprocess_workspace_bytes": (c_size_t, [c_int, c_int]),
     "gc_postprocess": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                ctypes.POINTER(PostParams), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),

@@ -78,9 +78,84 @@ k_lss_to_nchw(const float *__restrict__ grid_cl, int C, int nz, int ny, int nxx,
     }
 }
 
+// Deterministic variant: the reference's sort + cumsum is deterministic, fp32 reductions in L2 are not (their order varies
+// run to run).  Here every addend is converted to 40.24 fixed point and accumulated with 64-bit integer reductions, which
+// commute exactly: bit-identical results on every run, each addend rounded to 2^-24 (the fp32 spacing at magnitude 1).
+constexpr float kFixScale = 16777216.0f;          // 2^24
+__global__ void __launch_bounds__(256)
+k_lss_splat_det(const float *__restrict__ geom, const float *__restrict__ x, long long n_points, long long per_batch, int C,
+                float3 lo, float3 dx, int3 nx, unsigned long long *__restrict__ grid_cl) {
+    const long long p = (long long)blockIdx.x * (blockDim.x >> 4) + (threadIdx.x >> 4);     // 16 lanes per point
+    const int l16 = threadIdx.x & 15;
+    if (p >= n_points) return;
+    const float gx = __ldg(geom + 3 * p), gy = __ldg(geom + 3 * p + 1), gz = __ldg(geom + 3 * p + 2);
+    const float fx = __fdiv_rn(__fsub_rn(gx, lo.x), dx.x), fy = __fdiv_rn(__fsub_rn(gy, lo.y), dx.y), fz = __fdiv_rn(__fsub_rn(gz, lo.z), dx.z);
+    if (!(fx > -1.0f && fx < (float)nx.x && fy > -1.0f && fy < (float)nx.y && fz > -1.0f && fz < (float)nx.z)) return;
+    const int ix = (int)fx, iy = (int)fy, iz = (int)fz;
+    if (ix < 0 || ix >= nx.x || iy < 0 || iy >= nx.y || iz < 0 || iz >= nx.z) return;
+    const long long b = p / per_batch;
+    const size_t cell = (((size_t)b * nx.z + iz) * nx.y + iy) * nx.x + ix;
+    unsigned long long *dst = grid_cl + cell * (size_t)C;
+    const float *src = x + (size_t)p * C;
+    for (int c = l16; c < C; c += 16) {
+        const long long q = __float2ll_rn(__fmul_rn(__ldg(src + c), kFixScale));   // power-of-two scale: exact
+        if (q != 0) atomicAdd(dst + c, (unsigned long long)q);      // two's complement: signed sums wrap correctly
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_lss_det_to_nchw(const long long *__restrict__ grid_cl, int C, int nz, int ny, int nxx, float *__restrict__ out) {
+    __shared__ float t[32][33];
+    const int r = blockIdx.z, x0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int k = ty; k < 32; k += 8) {
+        const int xx = x0 + k, c = c0 + tx;
+        t[k][tx] = (xx < nxx && c < C) ? (float)((double)grid_cl[((size_t)r * nxx + xx) * C + c] * (1.0 / (double)kFixScale)) : 0.0f;
+    }
+    __syncthreads();
+    const int y = r % ny, z = (r / ny) % nz, b = r / (ny * nz);
+    for (int k = ty; k < 32; k += 8) {
+        const int c = c0 + k, xx = x0 + tx;
+        if (c < C && xx < nxx) out[(((size_t)b * nz * C + (size_t)z * C + c) * ny + y) * nxx + xx] = t[tx][k];
+    }
+}
+
 }  // namespace gc
 
 using namespace gc;
+
+extern "C" size_t gc_lss_pool_det_workspace_bytes(int n_batch, int C, const int *nx) {
+    if (n_batch <= 0 || C <= 0 || !nx || nx[0] <= 0 || nx[1] <= 0 || nx[2] <= 0) return 0;
+    return (size_t)n_batch * nx[2] * nx[1] * nx[0] * C * sizeof(long long);
+}
+
+extern "C" int gc_lss_voxel_pooling_det(const float *geom, const float *x, long long n_points, int n_batch, int C, const float *dx,
+                                        const float *bx, const int *nx, void *workspace, float *out, void *stream) {
+    GC_REQUIRE(n_points >= 0 && n_batch > 0 && C > 0 && dx && bx && nx && out && workspace, GC_EINVAL,
+               "gc_lss_voxel_pooling_det: bad arguments");
+    GC_REQUIRE(n_points % n_batch == 0, GC_EINVAL, "gc_lss_voxel_pooling_det: points must split evenly over the batch");
+    GC_REQUIRE(nx[0] > 0 && nx[1] > 0 && nx[2] > 0 && (size_t)n_batch * nx[2] * nx[1] <= 65535, GC_EINVAL,
+               "gc_lss_voxel_pooling_det: bad grid");
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaMemsetAsync(workspace, 0, gc_lss_pool_det_workspace_bytes(n_batch, C, nx), st);
+    GC_REQUIRE(e == cudaSuccess, (int)e, "gc_lss_voxel_pooling_det: memset: %s", cudaGetErrorString(e));
+    float3 lo, d;
+    lo.x = bx[0] - dx[0] / 2.0f; lo.y = bx[1] - dx[1] / 2.0f; lo.z = bx[2] - dx[2] / 2.0f;
+    d.x = dx[0]; d.y = dx[1]; d.z = dx[2];
+    const int3 n3 = make_int3(nx[0], nx[1], nx[2]);
+    if (n_points > 0) {
+        GC_REQUIRE(geom && x, GC_EINVAL, "gc_lss_voxel_pooling_det: null pointer");
+        const long long blocks = (n_points + 15) / 16;
+        GC_REQUIRE(blocks < (1ll << 31), GC_EUNSUPPORTED, "gc_lss_voxel_pooling_det: too many points");
+        k_lss_splat_det<<<(unsigned)blocks, 256, 0, st>>>(geom, x, n_points, n_points / n_batch, C, lo, d, n3,
+                                                         (unsigned long long *)workspace);
+        GC_LAUNCH_CHECK("k_lss_splat_det");
+    }
+    k_lss_det_to_nchw<<<dim3((nx[0] + 31) / 32, (C + 31) / 32, n_batch * nx[2] * nx[1]), 256, 0, st>>>((const long long *)workspace, C,
+                                                                                                   nx[2], nx[1], nx[0], out);
+    GC_LAUNCH_CHECK("k_lss_det_to_nchw");
+    return GC_OK;
+}
 
 extern "C" size_t gc_lss_pool_workspace_bytes(int n_batch, int C, const int *nx) {
     if (n_batch <= 0 || C <= 0 || C % 4 != 0 || !nx || nx[0] <= 0 || nx[1] <= 0 || nx[2] <= 0) return 0;

@@ -15,8 +15,13 @@ and the module file / class name that ``train_utils.create_model`` resolves (``t
 scatter canvas (pillars.cu), BaseBEVBackbone + shrink header (tcgen05 implicit GEMMs), MessageExtractorv2, the GenComm
 3-step sampler, Enhancer, warp + Max/Att fusion, detection heads.  Inference only; no CPU path.
 
-Scope: LiDAR ``point_pillar`` modalities and ``fusion_method`` max / att.  Camera (LSS) encoders,
-the other fusion networks and the training-only compressor raise ``NotImplementedError`` at construction.
+Scope: LiDAR ``point_pillar`` modalities and ``fusion_method`` max / att.  Camera modalities
+(``lift_splat_shoot``) enter at the encoder boundary: the reference's LSS image encoder (EfficientNet + frustum,
+heter_encoders.py:53-300; its voxel pooling is ``gencomm_b200.lss.VoxelPooling``) hands over its BEV feature as
+``data_dict['inputs_m{k}']['bev_feature']`` (or is plugged in with ``set_encoder``), and everything behind it -- backbone,
+shrink header, message extractor, the CenterCrop zero-padding to the LiDAR extent (:199-213) and the per-agent
+re-assembly of the modalities (:215-228) -- runs here.  The other fusion networks and the training-only compressor raise
+``NotImplementedError`` at construction.
 
 Extensions (ignored by the reference): ``data_dict['inputs_m{k}']`` may carry raw ``points`` + ``point_offsets`` (see
 ``modules.PointPillar``); ``data_dict['gencomm_noise'] = (noise0, step_noises)`` injects pre-drawn sampler noise
@@ -32,9 +37,9 @@ from .det_tail import DetectionHeads, DownsampleConv
 from .enhancer import Enhancer
 from .gencomm import GenComm
 from .message_extractor import MessageExtractorv2
-from .modules import AttFusion, MaxFusion, PointPillar, normalize_pairwise_tfm
+from .modules import AttFusion, BEVFeatureInput, MaxFusion, PointPillar, center_crop, normalize_pairwise_tfm
 
-_ENCODERS = {"pointpillar": PointPillar}
+_ENCODERS = {("lidar", "pointpillar"): PointPillar, ("camera", "liftsplatshoot"): BEVFeatureInput}
 
 
 class _HeadsMixin:
@@ -57,6 +62,7 @@ class _HeadsMixin:
 class HeterModelBaselineWGenComm(_HeadsMixin, nn.Module):
     GENCOMM_KEY = "gencomm"            # stage 2 reads args['diffcomm'] (…_stage2.py:36)
     MISSING_KEEP = 0.4                 # mask = rand > 0.4 (…_stage1.py:233)
+    CROP_MESSAGE = False               # stage 2 pads the camera agents' messages too (…_stage2.py:236); stage 1 does not
 
     def __init__(self, args):
         super().__init__()
@@ -72,11 +78,15 @@ class HeterModelBaselineWGenComm(_HeadsMixin, nn.Module):
             setting = args[modality_name]
             self.sensor_type_dict[modality_name] = setting['sensor_type']
             target = setting['core_method'].replace('_', '').lower()
-            if setting['sensor_type'] != 'lidar' or target not in _ENCODERS:
+            if (setting['sensor_type'], target) not in _ENCODERS:
                 raise NotImplementedError(
-                    f"gencomm_b200: modality {modality_name} ({setting['sensor_type']}/{setting['core_method']}) -- only "
-                    "LiDAR point_pillar encoders are on the B200 hot path (camera LSS: SURVEY.md 8f rank 4)")
-            setattr(self, f"encoder_{modality_name}", _ENCODERS[target](setting['encoder_args']))
+                    f"gencomm_b200: modality {modality_name} ({setting['sensor_type']}/{setting['core_method']}) -- LiDAR "
+                    "point_pillar encoders and camera lift_splat_shoot BEV features are on the B200 hot path")
+            setattr(self, f"encoder_{modality_name}", _ENCODERS[(setting['sensor_type'], target)](setting['encoder_args']))
+            if setting['sensor_type'] == 'camera':      # …_stage1.py:88-92
+                grid = setting['camera_mask_args']['grid_conf']
+                setattr(self, f"crop_ratio_W_{modality_name}", self.cav_range[3] / grid['xbound'][1])
+                setattr(self, f"crop_ratio_H_{modality_name}", self.cav_range[4] / grid['ybound'][1])
             setattr(self, f"depth_supervision_{modality_name}", False)
             if setting['backbone_args'] == 'identity':
                 setattr(self, f"backbone_{modality_name}", nn.Identity())
@@ -129,6 +139,11 @@ class HeterModelBaselineWGenComm(_HeadsMixin, nn.Module):
     def _make_message_extractor(args):
         return MessageExtractorv2(args['message_extractor']['in_ch'], args['message_extractor']['out_ch'])
 
+    def set_encoder(self, modality_name, module):
+        """Plug in an encoder for a modality (e.g. the reference's own ``LiftSplatShoot`` instance): it is called as
+        ``module(data_dict, modality_name)`` like heter_encoders' classes and must return the BEV feature on the device."""
+        setattr(self, f"encoder_{modality_name}", module)
+
     # hooks the stage-2 class overrides
     def _before_gencomm(self, feature):
         return None
@@ -162,6 +177,15 @@ class HeterModelBaselineWGenComm(_HeadsMixin, nn.Module):
             feature = getattr(self, f"shrinker_{m}")(feature)
             features[m] = feature
             messages[m] = getattr(self, f"message_extractor_{m}")(feature)
+
+        # camera feature maps cover the camera grid only: zero-pad them to the LiDAR extent (…_stage1.py:199-213)
+        for m in features:
+            if self.sensor_type_dict[m] == "camera":
+                h, w = features[m].shape[-2:]
+                th, tw = int(h * getattr(self, f"crop_ratio_H_{m}")), int(w * getattr(self, f"crop_ratio_W_{m}"))
+                features[m] = center_crop(features[m], th, tw)
+                if self.CROP_MESSAGE:
+                    messages[m] = center_crop(messages[m], th, tw)
 
         # restore the per-agent order from the per-modality batches (…_stage1.py:215-228)
         if len(features) == 1 and all(a == agent_modality_list[0] for a in agent_modality_list):

@@ -15,8 +15,13 @@ from .message_extractor import MessageExtractorv2
 class HeterModelBaselineWDiffCommStage2(HeterModelBaselineWGenComm):
     GENCOMM_KEY = "diffcomm"
     MISSING_KEEP = 0.1
+    CROP_MESSAGE = True        # :236
 
     def __init__(self, args):
+        if 'diffcomm' not in args and 'gencomm' in args:
+            # every shipped stage-2 yaml provides ``gencomm:`` while the class reads ``diffcomm`` (KeyError as shipped,
+            # SURVEY.md App. B.1): accept both
+            args = dict(args, diffcomm=args['gencomm'])
         self.trick = args.get('trick', False)
         super().__init__(args)
 

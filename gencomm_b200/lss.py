@@ -21,16 +21,20 @@ def gen_dx_bx(xbound, ybound, zbound):
     return dx, bx, nx
 
 
-def voxel_pooling(geom_feats, x, dx, bx, nx):
-    """geom_feats [B,N,D,H,W,3], x [B,N,D,H,W,C] -> [B, nz*C, ny, nx] (the reference's return value)."""
-    return ops.lss_voxel_pooling(geom_feats.float().contiguous(), x.float().contiguous(), dx, bx, nx)
+def voxel_pooling(geom_feats, x, dx, bx, nx, deterministic=False):
+    """geom_feats [B,N,D,H,W,3], x [B,N,D,H,W,C] -> [B, nz*C, ny, nx] (the reference's return value).
+    ``deterministic=True``: fixed-point integer reductions, bit-identical run to run like the reference's sort + cumsum
+    (the default fp32 reductions differ by ~1e-7 relative between runs)."""
+    return ops.lss_voxel_pooling(geom_feats.float().contiguous(), x.float().contiguous(), dx, bx, nx,
+                                 deterministic=deterministic)
 
 
 class VoxelPooling(nn.Module):
     """``VoxelPooling(grid_conf)(geom_feats, x)``; grid_conf = {'xbound','ybound','zbound'} as in the LSS yaml blocks."""
 
-    def __init__(self, grid_conf):
+    def __init__(self, grid_conf, deterministic=False):
         super().__init__()
+        self.deterministic = deterministic
         dx, bx, nx = gen_dx_bx(grid_conf['xbound'], grid_conf['ybound'], grid_conf['zbound'])
         self.dx = nn.Parameter(dx, requires_grad=False)      # heter_encoders.py:99-101 keeps them as frozen parameters
         self.bx = nn.Parameter(bx, requires_grad=False)
@@ -39,4 +43,4 @@ class VoxelPooling(nn.Module):
 
     @torch.no_grad()
     def forward(self, geom_feats, x):
-        return voxel_pooling(geom_feats, x, *self._host)
+        return voxel_pooling(geom_feats, x, *self._host, deterministic=self.deterministic)

@@ -241,6 +241,39 @@ class PointPillar(nn.Module):
                                  (v.x_offset, v.y_offset, v.z_offset), out=out)
 
 
+class BEVFeatureInput(nn.Module):
+    """Encoder boundary of a camera modality: returns the BEV feature [n, C, Hc, Wc] the reference's ``LiftSplatShoot``
+    encoder produced for the n agents of this modality (``data_dict['inputs_<m>']['bev_feature']``, device f32)."""
+
+    def __init__(self, args=None):
+        super().__init__()
+        self.args = args
+
+    def forward(self, data_dict, modality_name):
+        inp = data_dict[f'inputs_{modality_name}']
+        if 'bev_feature' not in inp:
+            raise KeyError(f"gencomm_b200: camera modality {modality_name} needs data_dict['inputs_{modality_name}']"
+                           "['bev_feature'] (the LSS encoder output) or an encoder plugged in with set_encoder()")
+        return inp['bev_feature'].contiguous()
+
+
+def center_crop(x, out_h, out_w):
+    """torchvision.transforms.CenterCrop((out_h, out_w)) on a [..., H, W] tensor: a target larger than the input is
+    zero-PADDED (left/top get floor, right/bottom ceil of the difference), then the centre window is taken."""
+    h, w = x.shape[-2:]
+    if out_w > w or out_h > h:
+        pl = (out_w - w) // 2 if out_w > w else 0
+        pt = (out_h - h) // 2 if out_h > h else 0
+        pr = (out_w - w + 1) // 2 if out_w > w else 0
+        pb = (out_h - h + 1) // 2 if out_h > h else 0
+        x = torch.nn.functional.pad(x, (pl, pr, pt, pb))
+        h, w = x.shape[-2:]
+        if (h, w) == (out_h, out_w):
+            return x
+    top, left = int(round((h - out_h) / 2.0)), int(round((w - out_w) / 2.0))
+    return x[..., top:top + out_h, left:left + out_w]
+
+
 # ------------------------------------------------------------------------------------------------
 # pose normalisation, warp, regroup, fusion
 # ------------------------------------------------------------------------------------------------

@@ -568,7 +568,7 @@ def postprocess(cls_preds, reg_preds, dir_preds, anchors, params, tfm=None, work
 # --------------------------------------------------------------------------------------------
 # (8f rank 4) LSS voxel pooling
 # --------------------------------------------------------------------------------------------
-def lss_voxel_pooling(geom_feats, x, dx, bx, nx, vector=True):
+def lss_voxel_pooling(geom_feats, x, dx, bx, nx, vector=True, deterministic=False):
     """geom_feats [B,N,D,H,W,3] f32, x [B,N,D,H,W,C] f32 (cuda); dx / bx / nx: the three-element tensors of gen_dx_bx
     (host or device) -> [B, nz*C, ny, nx] f32."""
     lib = _lib.load()
@@ -583,6 +583,12 @@ def lss_voxel_pooling(geom_feats, x, dx, bx, nx, vector=True):
     out = torch.empty(B, int(nxh[2]) * C, int(nxh[1]), int(nxh[0]), dtype=torch.float32, device=x.device)
     n = x.numel() // C
     nxp = nxh.ctypes.data_as(ctypes.c_void_p)
+    if deterministic:   # fixed-point integer reductions: bit-identical run to run (gc_lss_voxel_pooling_det)
+        ws = torch.empty(lib.gc_lss_pool_det_workspace_bytes(B, C, nxp), dtype=torch.uint8, device=x.device)
+        _lib.check(lib.gc_lss_voxel_pooling_det(_ptr(geom_feats), _ptr(x), n, B, C, dxh.ctypes.data_as(ctypes.c_void_p),
+                                                bxh.ctypes.data_as(ctypes.c_void_p), nxp, _ptr(ws), _ptr(out), _stream()),
+                   "gc_lss_voxel_pooling_det")
+        return out
     ws_bytes = lib.gc_lss_pool_workspace_bytes(B, C, nxp) if vector else 0
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device) if ws_bytes else None
     _lib.check(lib.gc_lss_voxel_pooling(_ptr(geom_feats), _ptr(x), n, B, C, dxh.ctypes.data_as(ctypes.c_void_p),

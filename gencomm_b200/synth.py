@@ -193,6 +193,29 @@ def gencomm_v2xreal_args(fusion="att"):
     return a
 
 
+CAMERA_GRID_CONF = {"xbound": [-51.2, 51.2, 0.4], "ybound": [-51.2, 51.2, 0.4], "zbound": [-10, 10, 20.0],
+                    "ddiscr": [2, 50, 48], "mode": "LID"}   # grid_conf_m2 of the OPV2V-H camera yamls: 256 x 256 x 1
+
+
+def gencomm_stage2_hetero_args(fusion="att"):
+    """``model.args`` of hypes_yaml/opv2v/GenComm_yamls/gencomm/stage2/m1m2_att.yaml:150-262 -- LiDAR PointPillars (m1)
+    + camera Lift-Splat-Shoot (m2) agents.  m2: the LSS encoder emits a 128-channel BEV feature on the 256 x 256 camera
+    grid (+-51.2 m), one backbone level + shrink header take it to 128 x 64 x 64, and the model zero-pads it to the LiDAR
+    extent 64 x 128 (crop ratio W = 102.4 / 51.2).  The sampler block sits under ``diffcomm`` (what the class reads)."""
+    a = gencomm_stage1_args(fusion)
+    a["diffcomm"] = a.pop("gencomm")
+    a["m2"] = {"core_method": "lift_splat_shoot", "sensor_type": "camera",
+               "encoder_args": {"anchor_number": 2, "grid_conf": dict(CAMERA_GRID_CONF), "img_downsample": 8,
+                                "img_features": 128, "use_depth_gt": False, "depth_supervision": False,
+                                "camera_encoder": "EfficientNet"},
+               "camera_mask_args": {"cav_lidar_range": list(OPV2V_H_RANGE), "grid_conf": dict(CAMERA_GRID_CONF)},
+               "backbone_args": {"layer_nums": [3], "layer_strides": [2], "num_filters": [64], "upsample_strides": [1],
+                                 "num_upsample_filter": [128], "inplanes": 128},
+               "aligner_args": {"core_method": "identity"},
+               "shrink_header": {"kernal_size": [3], "stride": [2], "padding": [1], "dim": [128], "input_dim": 128}}
+    return a
+
+
 def heter_frames(seed, record_len, n_points=30_000, max_cav=5):
     """Host inputs of a batch of collaborative frames for the full detector: per-agent clouds (list of [P,4] f32) and
     ``pairwise_t_matrix`` [B,L,L,4,4] f64; agents stay within ~40 m so their canvases overlap after the warp."""

@@ -308,6 +308,14 @@ size_t gc_lss_pool_workspace_bytes(int n_batch, int C, const int *nx); /* 0 when
 int gc_lss_voxel_pooling(const float *geom, const float *x, long long n_points, int n_batch, int C, const float *dx,
                          const float *bx, const int *nx, void *workspace /* or NULL */, float *out, void *stream);
 
+/* Deterministic variant of gc_lss_voxel_pooling (the reference's sort + cumsum is deterministic; fp32 reductions in L2 are
+ * not): addends go through 40.24 fixed point and 64-bit integer reductions, which commute exactly -> bit-identical
+ * results on every run; each addend is rounded to 2^-24.  workspace: gc_lss_pool_det_workspace_bytes bytes (required). */
+size_t gc_lss_pool_det_workspace_bytes(int n_batch, int C, const int *nx);
+int gc_lss_voxel_pooling_det(const float *geom_feats, const float *x, long long n_points, int n_batch, int C,
+                             const float *dx /*[3] host*/, const float *bx /*[3] host*/, const int *nx /*[3] host*/,
+                             void *workspace, float *out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -278,6 +278,104 @@ def gen_heter_model(ns):
           "|pred| max", float(out["pred_feature"].abs().max()))
 
 
+HETER2_RECORD_LEN = [3, 2]
+HETER2_MODALITIES = ["m1", "m2", "m1", "m1", "m2"]     # per-agent order; the ego of each frame is LiDAR (ego_modality m1)
+HETER2_SEED, HETER2_WSEED = 4300, 17
+
+
+def heter2_inputs():
+    """Inputs of tests/golden/heter_model_stage2.npz, regenerated from seeds (also used by the tests): LiDAR voxels of the
+    three m1 agents, the synthetic LSS BEV feature [2,128,256,256] of the two m2 (camera) agents (75 % empty cells, like
+    a splatted frustum), poses, record_len, sampler noise."""
+    n = sum(HETER2_RECORD_LEN)
+    clouds_all, pairwise = synth.heter_frames(HETER2_SEED, HETER2_RECORD_LEN, HETER_POINTS)
+    lidar = [c for c, m in zip(clouds_all, HETER2_MODALITIES) if m == "m1"]
+    voxels = ref_ops.collate_voxels([ref_ops.voxelize(c, synth.OPV2V_H_RANGE, [0.4, 0.4, 4.0]) for c in lidar])
+    bev = synth.bev_features(HETER2_SEED, HETER2_MODALITIES.count("m2"), 128, 256, 256, sparsity=0.75)
+    noise0, steps = synth.sampler_noise(HETER2_SEED, n, 128, 64, 128, T=3)
+    return voxels, bev, torch.from_numpy(pairwise), torch.tensor(HETER2_RECORD_LEN, dtype=torch.int64), noise0, steps
+
+
+def gen_heter_model_stage2(ns):
+    """The UNMODIFIED HeterModelBaselineWDiffCommStage2 (m1m2_att.yaml model args: LiDAR m1 + camera m2) on two frames
+    (3 + 2 agents, modalities interleaved).  Only the third-party-dependent image encoder is replaced: heter_encoders'
+    LiftSplatShoot (EfficientNet) is swapped for a stub that returns the injected BEV feature, so the camera branch
+    (backbone with inplanes 128, shrink header, message extractor), the CenterCrop zero-padding of features AND messages
+    (:223-236), the per-agent re-assembly (:245-256), sampler, Enhancer, AttFusion and heads are all reference code."""
+    import torch.nn as nn
+    import opencood.models.gencomm_modules.cond_diff as cd
+    import opencood.models.heter_encoders as he
+    import opencood.models.heter_model_baseline_w_gencomm_stage2 as st2
+
+    class LiftSplatShoot(nn.Module):   # stand-in for the image encoder only
+        def __init__(self, args):
+            super().__init__()
+
+        def forward(self, data_dict, modality_name):
+            return data_dict[f"inputs_{modality_name}"]["bev_feature"]
+
+    orig = he.LiftSplatShoot
+    he.LiftSplatShoot = LiftSplatShoot
+    try:
+        model = st2.HeterModelBaselineWDiffCommStage2(synth.gencomm_stage2_hetero_args("att")).eval()
+    finally:
+        he.LiftSplatShoot = orig
+    model.load_state_dict(synth.fill_state_dict(model.state_dict(), HETER2_WSEED))
+    voxels, bev, pairwise, record_len, n0, steps = heter2_inputs()
+    data = {"inputs_m1": voxels, "inputs_m2": {"bev_feature": bev}, "agent_modality_list": list(HETER2_MODALITIES),
+            "pairwise_t_matrix": pairwise, "record_len": record_len}
+    C, H, W = 128, 64, 128
+    queue = [n0, torch.zeros(1, C, H, W), torch.zeros(1, C, H, W)]
+    step_queue = list(steps)
+    orig_randn_like, orig_noise_like = torch.randn_like, cd.noise_like
+    torch.randn_like = lambda t, *a, **k: queue.pop(0).to(t)
+    cd.noise_like = lambda shape, device, repeat=False: step_queue.pop(0)
+    try:
+        with torch.no_grad():
+            out = model(data)
+    finally:
+        torch.randn_like, cd.noise_like = orig_randn_like, orig_noise_like
+    assert not queue and not step_queue
+    keys = sorted(model.state_dict().keys())
+    np.savez_compressed(os.path.join(OUT, "heter_model_stage2.npz"), state_dict_keys=np.array(keys),
+                        cls_preds=out["cls_preds"].numpy(), reg_preds=out["reg_preds"].numpy(),
+                        dir_preds=out["dir_preds"].numpy(), message=out["message"].numpy(),
+                        gt_feature_c8=out["gt_feature"][:, ::8].numpy(), pred_feature_c8=out["pred_feature"][:, ::8].numpy())
+    print("heter_model_stage2.npz: cls", tuple(out["cls_preds"].shape), "gt", tuple(out["gt_feature"].shape),
+          "camera feature nonzero columns", int((out["gt_feature"][1].abs().sum((0, 1)) > 0).sum()),
+          "|cls| max", float(out["cls_preds"].abs().max()))
+
+
+def gen_collate(ns):
+    """The UNMODIFIED SpVoxelPreprocessor.collate_batch_dict / collate_batch_list (sp_voxel_preprocessor.py:87-174), called
+    unbound (the constructor needs spconv): pins the agent-index column and the concatenation order of the collated
+    voxel tensors that feed PillarVFE."""
+    import importlib
+    import types
+    import sys
+    for name in ("open3d", "pypcd"):    # pcd_utils.py:10-12 (point-cloud file IO; never called here)
+        ref_import._stub(name, pypcd=ref_import._Anything())
+    for name in ("spconv", "spconv.utils", "spconv.pytorch", "spconv.pytorch.utils", "cumm", "cumm.tensorview"):
+        ref_import._stub(name, VoxelGenerator=ref_import._Anything, VoxelGeneratorV2=ref_import._Anything,
+                         Point2VoxelCPU3d=ref_import._Anything, tv=ref_import._Anything())
+    mod = importlib.import_module("opencood.data_utils.pre_processor.sp_voxel_preprocessor")
+    cls = mod.SpVoxelPreprocessor
+    clouds = [synth.lidar_points(77, a, 6000 + 500 * a) for a in range(3)]
+    per_agent = [ref_ops.voxelize(c, synth.OPV2V_H_RANGE, [0.4, 0.4, 4.0]) for c in clouds]
+    as_np = [{k: np.asarray(v) for k, v in d.items()} for d in per_agent]
+    me = types.SimpleNamespace(collate_batch_list=cls.collate_batch_list, collate_batch_dict=cls.collate_batch_dict)
+    res_list = cls.collate_batch(me, as_np)                                   # list form (:87-110, :112-142)
+    batch = {k: [d[k] for d in as_np] for k in as_np[0]}
+    res_dict = cls.collate_batch(me, batch)                                   # dict form (:144-174)
+    for k in res_list:
+        assert torch.equal(res_list[k], res_dict[k]), k
+    np.savez_compressed(os.path.join(OUT, "collate.npz"), voxel_coords=res_dict["voxel_coords"].numpy(),
+                        voxel_num_points=res_dict["voxel_num_points"].numpy(),
+                        voxel_features_checksum=np.float64(res_dict["voxel_features"].double().sum()),
+                        dtypes=np.array([str(res_dict[k].dtype) for k in ("voxel_features", "voxel_coords", "voxel_num_points")]))
+    print("collate.npz:", {k: (tuple(v.shape), str(v.dtype)) for k, v in res_dict.items()})
+
+
 POSTPROCESS_CASES = {"mid": (1, -3.0, False), "cap": (2, -1.0, False), "few": (4, -4.5, True), "none": (3, -9.0, False)}
 
 
@@ -318,14 +416,20 @@ def gen_lss_pool(ns):
                            ("z2", dict(synth.LSS_GRID_CONF, zbound=[-10, 10, 10.0], xbound=[-20.0, 20.0, 0.8]), {"B": 1, "N": 3})):
         dx, bx, nx = ref_ops.gen_dx_bx(conf["xbound"], conf["ybound"], conf["zbound"])
         geom, x = synth.lss_frustum(31, grid_conf=conf, **kw)
-        for quick in (False, True):
+        both = {}
+        for quick in (False, True):   # cumsum_trick (camera_utils.py:209-217) and the QuickCumsum autograd function (:220-246)
             me = types.SimpleNamespace(dx=dx, bx=bx, nx=nx, use_quickcumsum=quick)
-            res = LiftSplatShoot.voxel_pooling(me, geom, x)
+            both[quick] = LiftSplatShoot.voxel_pooling(me, geom, x)
+        res = both[False]
         nz = torch.nonzero(res.abs().sum(1))          # occupied cells only: the grid is sparse
+        nzq = torch.nonzero(both[True].abs().sum(1))
+        assert torch.equal(nz, nzq), "the two cumsum variants disagree on the occupied cells"
         out[f"{name}/shape"] = np.array(res.shape)
         out[f"{name}/cells"] = nz.numpy().astype(np.int32)
         out[f"{name}/values"] = res[nz[:, 0], :, nz[:, 1], nz[:, 2]].numpy()
-        print("lss_pool", name, tuple(res.shape), "occupied cells", nz.shape[0])
+        out[f"{name}/values_quickcumsum"] = both[True][nz[:, 0], :, nz[:, 1], nz[:, 2]].numpy()
+        print("lss_pool", name, tuple(res.shape), "occupied cells", nz.shape[0], "max |cumsum_trick - QuickCumsum|",
+              float((both[False] - both[True]).abs().max()))
     np.savez_compressed(os.path.join(OUT, "lss_pool.npz"), **out)
 
 
@@ -340,6 +444,8 @@ def main():
     gen_det_tail(ns)
     gen_backbone(ns)
     gen_heter_model(ns)
+    gen_heter_model_stage2(ns)
+    gen_collate(ns)
     gen_postprocess(ns)
     gen_lss_pool(ns)
     for f in sorted(os.listdir(OUT)):

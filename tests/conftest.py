@@ -116,3 +116,15 @@ def lss_case(name):
     conf = dict(synth.LSS_GRID_CONF, **(over or {}))
     geom, x = synth.lss_frustum(31, grid_conf=conf, **kw)
     return geom, x, conf
+
+
+@pytest.fixture(scope="session")
+def golden_heter_model_stage2():
+    return load_golden("heter_model_stage2.npz")
+
+
+@pytest.fixture(scope="session")
+def heter2_inputs():
+    """(voxels, bev_feature, pairwise, record_len, noise0, step_noises) of tests/golden/heter_model_stage2.npz."""
+    from oracle import gen_golden
+    return gen_golden.heter2_inputs()

@@ -133,3 +133,76 @@ def test_detector_is_inference_only():
     m.train()
     with pytest.raises(RuntimeError, match="inference-only"):
         m({})
+
+
+def _data2(heter2_inputs):
+    voxels, bev, pairwise, record_len, n0, steps = heter2_inputs
+    return {"inputs_m1": {k: v.to(DEV) for k, v in voxels.items()}, "inputs_m2": {"bev_feature": bev.to(DEV)},
+            "agent_modality_list": list(gen_golden.HETER2_MODALITIES), "pairwise_t_matrix": pairwise.to(DEV),
+            "record_len": record_len.to(DEV), "gencomm_noise": (n0.to(DEV), torch.stack(list(steps)).to(DEV))}
+
+
+@pytest.mark.parametrize("precision,tmax,tmean", [("fp32", 2e-2, 1e-2), (None, 5e-2, 3e-2)])
+def test_stage2_lidar_camera_detector_matches_unmodified_reference(golden_heter_model_stage2, heter2_inputs, precision, tmax, tmean):
+    """HeterModelBaselineWDiffCommStage2 with LiDAR (m1) + camera (m2) agents, 3 + 2 agents with interleaved modalities,
+    against the UNMODIFIED reference class (only its EfficientNet image encoder stubbed to return the injected BEV
+    feature): camera backbone (inplanes 128) + shrink + message extractor, CenterCrop zero-padding of the camera
+    features and messages to 64 x 128, per-agent re-assembly, sampler, Enhancer, AttFusion, heads."""
+    m = _model(synth.gencomm_stage2_hetero_args("att"), G.HeterModelBaselineWDiffCommStage2, seed=gen_golden.HETER2_WSEED)
+    if precision is not None:
+        m.gencomm.precision = precision
+    out = m(_data2(heter2_inputs))
+    g = golden_heter_model_stage2
+    assert out["gt_feature"].shape == (5, 128, 64, 128) and out["message"].shape == (5, 2, 64, 128)
+    # the camera agents (1 and 4) carry exact zeros outside the central 64 columns, features and messages alike
+    for a in (1, 4):
+        assert float(out["gt_feature"][a][:, :, :32].abs().max()) == 0.0 and float(out["gt_feature"][a][:, :, 96:].abs().max()) == 0.0
+        assert float(out["message"][a][:, :, :32].abs().max()) == 0.0 and float(out["message"][a][:, :, 96:].abs().max()) == 0.0
+    _check(out, g, tmax, tmean)
+
+
+def _match_detections(boxes_a, scores_a, boxes_b, scores_b):
+    """Greedy one-to-one matching of two detection sets by bottom-face centre distance; returns (matched pairs,
+    max centre distance, max |score difference|) over the pairs closer than 0.5 m."""
+    ca, cb = boxes_a[:, :4, :2].mean(1), boxes_b[:, :4, :2].mean(1)
+    d = torch.cdist(ca, cb)
+    pairs, used = [], set()
+    for i in torch.argsort(scores_a, descending=True).tolist():
+        j = int(torch.argmin(d[i]))
+        if float(d[i, j]) < 0.5 and j not in used:
+            used.add(j)
+            pairs.append((i, j))
+    if not pairs:
+        return pairs, 0.0, 0.0
+    ia, ib = torch.tensor([p[0] for p in pairs]), torch.tensor([p[1] for p in pairs])
+    return pairs, float(d[ia, ib].max()), float((scores_a[ia] - scores_b[ib]).abs().max())
+
+
+def test_detections_from_default_precision_match_reference_fp32_heads(golden_heter_model, heter_inputs):
+    """Detection-level parity of the shipped (tensor-core) precision: the head maps of the UNMODIFIED fp32 reference model
+    (golden) and the GPU detector's own head maps go through the same post-processor at the shipped thresholds
+    (score 0.2, NMS 0.15).  Bound: every reference detection whose score clears the threshold by more than 0.05 has a
+    GPU detection within 0.25 m of its centre and 0.05 of its score, and vice versa; the kept counts differ by at most
+    3 % (candidates within the logit error of the threshold may flip)."""
+    g = golden_heter_model
+    out = _model()(_data(heter_inputs))
+    params = synth.postprocess_params(score_threshold=0.2)
+    pp = G.VoxelPostprocessor(params, train=False)
+    anchors = pp.generate_anchor_box()
+    ref = pp.post_process_batch(T(g["cls_preds"]).to(DEV), T(g["reg_preds"]).to(DEV), T(g["dir_preds"]).to(DEV), anchors)
+    got = pp.post_process_batch(out["cls_preds"], out["reg_preds"], out["dir_preds"], anchors)
+    for f in range(2):
+        kr, kg = int(ref[2][f]), int(got[2][f])
+        rb, rs = ref[0][f, :kr].cpu(), ref[1][f, :kr].cpu()
+        gb, gs = got[0][f, :kg].cpu(), got[1][f, :kg].cpu()
+        pairs, dmax, smax = _match_detections(rb, rs, gb, gs)
+        strong_r = int((rs > 0.25).sum())
+        matched_r = {i for i, _ in pairs}
+        missed = [i for i in range(kr) if float(rs[i]) > 0.25 and i not in matched_r]
+        matched_g = {j for _, j in pairs}
+        extra = [j for j in range(kg) if float(gs[j]) > 0.25 and j not in matched_g]
+        print(f"frame {f}: reference {kr} detections ({strong_r} above 0.25), gpu {kg}; matched {len(pairs)}, "
+              f"max centre distance {dmax:.3f} m, max score diff {smax:.3f}; unmatched strong: ref {len(missed)}, gpu {len(extra)}")
+        assert kr > 20 and abs(kr - kg) <= max(3, 0.03 * kr)
+        assert not missed and not extra
+        assert dmax <= 0.25 and smax <= 0.05

@@ -48,3 +48,22 @@ def test_voxel_pooling_function_form_and_empty_input():
     assert float((d3 - a[:, :3]).abs().max()) <= 1e-5
     far = torch.full_like(geom, 1.0e4)
     assert float(G.voxel_pooling(far.to(DEV), x.to(DEV), dx, bx, nx).abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("name", list(LSS_CASES))
+def test_deterministic_voxel_pooling(golden_lss_pool, name):
+    """deterministic=True: fixed-point 64-bit integer reductions -> bit-identical on every run (the reference's sort +
+    cumsum is deterministic too), same occupied cells, same accuracy bound as the fp32-reduction path."""
+    g = golden_lss_pool
+    geom, x, conf = lss_case(name)
+    pool = G.VoxelPooling(conf, deterministic=True).to(DEV)
+    a = pool(geom.to(DEV), x.to(DEV))
+    for _ in range(3):
+        assert torch.equal(pool(geom.to(DEV), x.to(DEV)), a)
+    out = a.cpu()
+    cells = T(g[f"{name}/cells"]).long()
+    assert torch.equal(torch.nonzero(out.abs().sum(1)), cells)
+    assert float((out[cells[:, 0], :, cells[:, 1], cells[:, 2]] - T(g[f"{name}/values"])).abs().max()) <= 2e-4
+    dx, bx, nx = R.gen_dx_bx(conf["xbound"], conf["ybound"], conf["zbound"])
+    exact = R.lss_voxel_pooling_exact(geom, x, dx, bx, nx)
+    assert float((out.double() - exact).abs().max()) <= 1e-5 * float(exact.abs().max())

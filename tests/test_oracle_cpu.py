@@ -193,10 +193,13 @@ def test_create_model_resolves_the_gencomm_detectors():
     assert set(m2.state_dict().keys()) == set(m1.state_dict().keys())
     with pytest.raises(NotImplementedError):
         G.create_model({"model": {"core_method": "point_pillar_v2vnet", "args": {}}})
-    cam = synth.gencomm_stage1_args("att")
-    cam["m2"] = dict(cam["m1"], sensor_type="camera", core_method="lift_splat_shoot")
+    # camera (lift_splat_shoot) modalities enter at the encoder boundary (BEV feature input); other encoders are refused
+    cam = G.HeterModelBaselineWDiffCommStage2(synth.gencomm_stage2_hetero_args("att"))
+    assert isinstance(cam.encoder_m2, G.BEVFeatureInput) and cam.crop_ratio_W_m2 == 2.0 and cam.crop_ratio_H_m2 == 1.0
+    sec = synth.gencomm_stage1_args("att")
+    sec["m3"] = dict(sec["m1"], core_method="second")
     with pytest.raises(NotImplementedError, match="LiDAR"):
-        G.HeterModelBaselineWGenComm(cam)
+        G.HeterModelBaselineWGenComm(sec)
     bad = synth.gencomm_stage1_args("att")
     bad["fusion_method"] = "v2xvit"
     with pytest.raises(NotImplementedError, match="fusion_method"):
@@ -286,3 +289,62 @@ def test_quad_iou_properties():
         assert abs(v - iou(p + 7.5, q + 7.5)) < 1e-5                          # translation
         assert abs(iou(p, p) - 1.0) < 1e-6
         assert abs(v - float(R.polygon_iou(p, q))) < 1e-6                     # C vs Python restatement
+
+
+def test_lss_both_cumsum_variants_are_pinned(golden_lss_pool):
+    """heter_encoders.py:202-207 picks cumsum_trick or the QuickCumsum autograd function by ``use_quickcumsum``: the
+    fixture holds BOTH results of the unmodified method; their forward arithmetic is the same, and the restatement
+    reproduces them bit for bit."""
+    from conftest import LSS_CASES, lss_case
+    g = golden_lss_pool
+    for name in LSS_CASES:
+        assert np.array_equal(g[f"{name}/values"], g[f"{name}/values_quickcumsum"]), name
+        geom, x, conf = lss_case(name)
+        dx, bx, nx = R.gen_dx_bx(conf["xbound"], conf["ybound"], conf["zbound"])
+        out = R.lss_voxel_pooling(geom, x, dx, bx, nx)
+        cells = T(g[f"{name}/cells"]).long()
+        assert torch.equal(out[cells[:, 0], :, cells[:, 1], cells[:, 2]], T(g[f"{name}/values_quickcumsum"])), name
+
+
+def test_collate_matches_reference():
+    """SpVoxelPreprocessor.collate_batch (list and dict form, sp_voxel_preprocessor.py:87-174), run unbound from the
+    unmodified class (tests/golden/collate.npz): the agent-index column, concatenation order and dtypes of the collated
+    voxel tensors -- for the oracle's collate_voxels and for the drop-in's host-side collate."""
+    import os
+    from gencomm_b200 import SpVoxelPreprocessor, synth
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "collate.npz"))
+    clouds = [synth.lidar_points(77, a, 6000 + 500 * a) for a in range(3)]
+    per_agent = [R.voxelize(c, synth.OPV2V_H_RANGE, [0.4, 0.4, 4.0]) for c in clouds]
+    ours = R.collate_voxels(per_agent)
+    as_np = [{k: np.asarray(v) for k, v in d.items()} for d in per_agent]
+    drop_list = SpVoxelPreprocessor.collate_batch_list(as_np)
+    drop_dict = SpVoxelPreprocessor.collate_batch_dict({k: [d[k] for d in as_np] for k in as_np[0]})
+    for res in (ours, drop_list, drop_dict):
+        assert np.array_equal(np.asarray(res["voxel_coords"]), g["voxel_coords"])
+        assert np.array_equal(np.asarray(res["voxel_num_points"]), g["voxel_num_points"])
+        assert float(torch.as_tensor(res["voxel_features"]).double().sum()) == float(g["voxel_features_checksum"])
+        assert [str(torch.as_tensor(res[k]).dtype) for k in ("voxel_features", "voxel_coords", "voxel_num_points")] == list(g["dtypes"])
+    assert g["voxel_coords"][:, 0].max() == 2 and g["voxel_coords"].dtype == np.int32
+
+
+def test_stage2_hetero_state_dict_keys_match_reference():
+    """The LiDAR + camera stage-2 drop-in exposes exactly the parameters of the unmodified reference model with its image
+    encoder stubbed out (tests/golden/heter_model_stage2.npz): a reference checkpoint loads with strict=False, the only
+    keys left over being the encoder_m2.* (EfficientNet / LSS) weights that stay with the reference."""
+    import os
+    from gencomm_b200 import HeterModelBaselineWDiffCommStage2, synth
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "heter_model_stage2.npz"))
+    m = HeterModelBaselineWDiffCommStage2(synth.gencomm_stage2_hetero_args("att"))
+    assert sorted(m.state_dict().keys()) == list(g["state_dict_keys"])
+    # the yaml spelling (``gencomm:`` instead of ``diffcomm:``) is accepted too
+    a = synth.gencomm_stage2_hetero_args("att")
+    a["gencomm"] = a.pop("diffcomm")
+    assert sorted(HeterModelBaselineWDiffCommStage2(a).state_dict().keys()) == list(g["state_dict_keys"])
+
+
+def test_center_crop_matches_torchvision():
+    import torchvision
+    from gencomm_b200.modules import center_crop
+    x = torch.randn(2, 3, 7, 10)
+    for th, tw in ((7, 20), (7, 10), (4, 6), (9, 5), (14, 21), (6, 11)):
+        assert torch.equal(center_crop(x, th, tw), torchvision.transforms.CenterCrop((th, tw))(x)), (th, tw)
