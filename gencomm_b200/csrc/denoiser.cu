@@ -21,6 +21,8 @@
 // 128-bit accesses.  conv_in ((C+2)->8) and conv_out (8->C) are implicit GEMMs over the NCHW
 // boundary tensors; the sampler arithmetic (q_posterior + noise) is fused into conv_out's
 // epilogue, q_sample is one elementwise kernel.  28 launches per step, 0 host syncs.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "denoiser_cluster.cuh"
 #include "denoiser_tc.cuh"
@@ -456,8 +458,13 @@ static int unet_eval(cudaStream_t st, int A, int C, int H, int W, const float *c
         unet_cluster_eligible(C, H, W) && conv_in_tc_eligible(C, H, W) && conv_out_tc_eligible(C, H, W)) {
         Bias8 bi;
         for (int i = 0; i < 8; ++i) bi.b[i] = tail.conv_in_bias[i];
-        p[0].tiles = conv_in_tc_tiles(H, W);
-        if (int rc = conv_in_tc(st, A, cond, ws.x, ws.tc_packed, bi, C, H, W, p[0].data, p[0].stats)) return rc;
+        if (conv_in_tc2_eligible(C, H, W) && !getenv("GC_CONV_IN_V1")) {
+            p[0].tiles = conv_in_tc2_tiles(H);
+            if (int rc = conv_in_tc2(st, A, cond, ws.x, ws.tc_packed, bi, C, H, W, p[0].data, p[0].stats)) return rc;
+        } else {
+            p[0].tiles = conv_in_tc_tiles(H, W);
+            if (int rc = conv_in_tc(st, A, cond, ws.x, ws.tc_packed, bi, C, H, W, p[0].data, p[0].stats)) return rc;
+        }
         if (int rc = unet_middle_cluster(st, A, p[0].data, rec_dev, p[11].data, p[11].stats)) return rc;
         p[11].tiles = kCl;
         Affine8 aff;
@@ -468,7 +475,10 @@ static int unet_eval(cudaStream_t st, int A, int C, int H, int W, const float *c
     Bias8 bi;
     for (int i = 0; i < 8; ++i) bi.b[i] = tail.conv_in_bias[i];
     const dim3 gridP((W + kTW - 1) / kTW, (H + kTH - 1) / kTH, A);
-    if ((precision & GC_PREC_TC_CONV_IN) && conv_in_tc_eligible(C, H, W)) {                        // hs[0], tcgen05
+    if ((precision & GC_PREC_TC_CONV_IN) && conv_in_tc2_eligible(C, H, W) && !getenv("GC_CONV_IN_V1")) {   // hs[0], tcgen05
+        p[0].tiles = conv_in_tc2_tiles(H);
+        if (int rc = conv_in_tc2(st, A, cond, ws.x, ws.tc_packed, bi, C, H, W, p[0].data, p[0].stats)) return rc;
+    } else if ((precision & GC_PREC_TC_CONV_IN) && conv_in_tc_eligible(C, H, W)) {
         p[0].tiles = conv_in_tc_tiles(H, W);
         if (int rc = conv_in_tc(st, A, cond, ws.x, ws.tc_packed, bi, C, H, W, p[0].data, p[0].stats)) return rc;
     } else {

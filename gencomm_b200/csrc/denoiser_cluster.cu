@@ -34,7 +34,8 @@ namespace cl {
 namespace cg = cooperative_groups;
 using namespace umma;
 
-constexpr int kThreads = 256;
+constexpr int kThreads = 512;                      // 16 warps: halves every per-thread latency chain (r02c: 19 % issue-active at 8 warps)
+constexpr int kWarps = kThreads / 32;
 constexpr int kRowPx = 130;                        // staged pixels per operand row: x = -1 .. 128
 constexpr int kFBytes = 8 * 2 * 128 * 16;          // one full-resolution raw tensor band: [8 rows][2 halves][128 px] float4
 constexpr int kQBytes = 4 * 2 * 64 * 16;           // half resolution: [4 rows][2 halves][64 px] float4
@@ -51,7 +52,7 @@ constexpr int kSmemBytes = kOffMisc + 1024;
 
 struct Misc {
     float ga[16], gb[16];
-    float part[8][8];
+    float part[kWarps][8];
     uint64_t mma_bar[2], done_bar[2], rec_bar[2];
     uint32_t tmem;
 };
@@ -205,8 +206,11 @@ struct Ctx {
     uint32_t tmem;
     uint32_t ph_mma[2], ph_done[2], ph_rec[2];   // mbarrier phase parities (uniform across the CTA)
     int tid, warp, lane;
+    long long *trace;     // GC_CL_DEBUG & 32: per-layer clock64 timeline of CTA 0 / thread 0: [layer][16]
+    int trace_row;
     int dbg;              // timing experiments (GC_CL_DEBUG): 1 skip MMAs, 2 skip staging, 4 skip epilogue math, 8 skip cluster barriers
 };
+#define GC_TRACE(c, k) do { if ((c).trace != nullptr && (c).tid == 0) (c).trace[(c).trace_row * 16 + (k)] = clock64(); } while (0)
 #define MISC_ADDR(c, member) ((c).smem + kOffMisc + (uint32_t)offsetof(Misc, member))
 
 // ------------------------------------------------------------------------------------------------
@@ -296,7 +300,7 @@ __device__ __forceinline__ void push_stats(const Ctx &c, float (&q8)[8], int out
         const int vi = c.tid & 7, peer = c.tid >> 3;
         float t = 0.0f;
 #pragma unroll
-        for (int w = 0; w < 8; ++w) t += lds1(MISC_ADDR(c, part) + (uint32_t)(w * 8 + vi) * 4u);
+        for (int w = 0; w < kWarps; ++w) t += lds1(MISC_ADDR(c, part) + (uint32_t)(w * 8 + vi) * 4u);
         st_cluster(mapa(c.smem + kOffStats + (uint32_t)(((out_buf * kCl) + (int)c.rank) * 8 + vi) * 4u, (uint32_t)peer), t);
         if (gstats != nullptr && peer == 0) gstats[c.rank * 8 + vi] = t;
     }
@@ -346,8 +350,8 @@ __device__ __forceinline__ void conv_layer(Ctx &c, const LayerCfg &L, uint32_t r
     constexpr uint32_t kPlane = PROWS * kRowPx * 16u;
     const int y0 = (int)c.rank * R;
 
-#pragma unroll
-    for (int g = 0; g < NG; ++g) {
+#pragma unroll 1
+    for (int g = 0; g < NG; ++g) {      // not unrolled: the kernel is instruction-cache bound (r02c: 14 % no-instruction stalls)
         const int i0 = CG == 1 ? (g == 0 ? 0 : NRA) : 2 * g, i1 = CG == 1 ? (g == 0 ? NRA : NR) : 2 * g + 2;
         if (CG == 2 && g >= 2) {   // the slots of group g were read by the MMAs of group g - 2
             mbar_wait(MISC_ADDR(c, mma_bar) + (uint32_t)(g & 1) * 8u, c.ph_mma[g & 1]);
@@ -361,9 +365,13 @@ __device__ __forceinline__ void conv_layer(Ctx &c, const LayerCfg &L, uint32_t r
                 stage_rows<CG, HALF, UP, GN, (2 * RW + kThreads - 1) / kThreads>(c, L, i0, i1);
             }
         }
+        if (g == 0) GC_TRACE(c, 4);
         fence_async_smem();
+        if (g == 0) GC_TRACE(c, 5);
         tc_fence_before();
         __syncthreads();
+        if (g == 0) GC_TRACE(c, 6);
+        if (g == NG - 1) GC_TRACE(c, 7);
         if (c.warp == 0) {         // warp-uniform branch; one elected lane issues
             tc_fence_after();
             constexpr uint32_t idesc = make_idesc_tf32(128, 32);
@@ -384,6 +392,7 @@ __device__ __forceinline__ void conv_layer(Ctx &c, const LayerCfg &L, uint32_t r
             if (CG == 2) commit_elect(MISC_ADDR(c, mma_bar) + (uint32_t)(g & 1) * 8u);
             if (g == GA) commit_elect(MISC_ADDR(c, done_bar));
             if (g == NG - 1) commit_elect(MISC_ADDR(c, done_bar) + 8u);
+            if (g == NG - 1) GC_TRACE(c, 8);
         }
     }
     if (CG == 2) {   // consume the two ring commits nobody waited for (keeps the phase bookkeeping in step)
@@ -395,8 +404,8 @@ __device__ __forceinline__ void conv_layer(Ctx &c, const LayerCfg &L, uint32_t r
     }
 
     // ---- epilogue, phase by phase: thread = pixel x of NROW consecutive output rows ----
-    constexpr int NROW = R / 4;                        // 2 (full) / 1 (half) rows per thread and phase
-    const int q = c.warp & 3, hsel = c.warp >> 2;
+    constexpr int NROW = 1;                            // one row per thread and phase: 4 (full) / 2 (half) row groups of 4 warps
+    const int q = c.warp & 3, hsel = c.warp >> 2;      // hsel 0..3
     const int px = q * 32 + c.lane;
     float q8[8];
 #pragma unroll
@@ -413,13 +422,12 @@ __device__ __forceinline__ void conv_layer(Ctx &c, const LayerCfg &L, uint32_t r
         mbar_wait(MISC_ADDR(c, done_bar) + (uint32_t)ph * 8u, c.ph_done[ph]);
         c.ph_done[ph] ^= 1u;
         tc_fence_after();
-        if (px >= PXW || (c.dbg & 4)) continue;        // warp-uniform (half resolution: lane quarters 2, 3 idle)
-        const int r0 = ph * (R / 2) + hsel * NROW;
+        GC_TRACE(c, 9 + 2 * ph);
+        if (px >= PXW || hsel >= R / 2 || (c.dbg & 4)) continue;   // warp-uniform (half resolution: 4 of the 16 warps work)
+        const int r0 = ph * (R / 2) + hsel;
         float acc[NROW * 8];
         const uint32_t ta = c.tmem + ((uint32_t)(q * 32) << 16) + 8u * (r0 + 2);
-        if (NROW == 2) {
-            tmem_ld16_nowait(ta, acc);
-        } else {
+        {
             uint32_t rr[8];
             asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                          : "=r"(rr[0]), "=r"(rr[1]), "=r"(rr[2]), "=r"(rr[3]), "=r"(rr[4]), "=r"(rr[5]), "=r"(rr[6]), "=r"(rr[7])
@@ -473,13 +481,16 @@ __device__ __forceinline__ void conv_layer(Ctx &c, const LayerCfg &L, uint32_t r
             }
         }
     }
+    GC_TRACE(c, 12);
     tc_fence_before();
     push_stats(c, q8, L.out, gstats);
+    GC_TRACE(c, 13);
 }
 
 // down.0.downsample (unet.py:59-78): pad (0,1,0,1) + 3x3 stride 2, no GroupNorm, on CUDA cores (thread = output pixel).
 __device__ __forceinline__ void down_layer(Ctx &c, const LayerCfg &L, uint32_t rec_saddr) {
-    const int r = c.tid >> 6, ox = c.tid & 63;
+    const bool act = c.tid < 256;                      // 4 rows x 64 output pixels; the other warps only join the reduction
+    const int r = (c.tid >> 6) & 3, ox = c.tid & 63;
     float acc[8];
     {
         const float4 b0 = lds4(rec_saddr + kClRecBias * 4u), b1 = lds4(rec_saddr + kClRecBias * 4u + 16u);
@@ -494,7 +505,7 @@ __device__ __forceinline__ void down_layer(Ctx &c, const LayerCfg &L, uint32_t r
 #pragma unroll
         for (int kx = 0; kx < 3; ++kx) {
             const int sx = 2 * ox + kx;
-            if (!row_ok || sx >= 128) continue;
+            if (!act || !row_ok || sx >= 128) continue;
             const uint32_t a = mapa(c.smem + kOffF + buf_off(L.in_a) + (uint32_t)((sy * 2) * 128 + sx) * 16u, srank);
             const float4 v0 = ld_cluster4(a), v1 = ld_cluster4(a + 128u * 16u);
             const float vv[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
@@ -510,13 +521,17 @@ __device__ __forceinline__ void down_layer(Ctx &c, const LayerCfg &L, uint32_t r
         }
     }
     const uint32_t poff = (uint32_t)((r * 2) * 64 + ox) * 16u, out_base = c.smem + kOffF + buf_off(L.out);
-    sts4(out_base + poff, make_float4(acc[0], acc[1], acc[2], acc[3]));
-    sts4(out_base + poff + 64u * 16u, make_float4(acc[4], acc[5], acc[6], acc[7]));
     float q8[8];
 #pragma unroll
-    for (int p = 0; p < 4; ++p) {
-        q8[2 * p] = acc[2 * p] + acc[2 * p + 1];
-        q8[2 * p + 1] = acc[2 * p] * acc[2 * p] + acc[2 * p + 1] * acc[2 * p + 1];
+    for (int p = 0; p < 8; ++p) q8[p] = 0.0f;
+    if (act) {
+        sts4(out_base + poff, make_float4(acc[0], acc[1], acc[2], acc[3]));
+        sts4(out_base + poff + 64u * 16u, make_float4(acc[4], acc[5], acc[6], acc[7]));
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            q8[2 * p] = acc[2 * p] + acc[2 * p + 1];
+            q8[2 * p + 1] = acc[2 * p] * acc[2 * p] + acc[2 * p + 1] * acc[2 * p + 1];
+        }
     }
     push_stats(c, q8, L.out, nullptr);
 }
@@ -530,6 +545,8 @@ __device__ __forceinline__ void middle_layers(Ctx &c, const float *rec_g, float 
     for (int l = 0; l < kClLayers; ++l) {
         const LayerCfg L = c_layers[l];
         const int rb = l & 1;
+        c.trace_row = l;
+        GC_TRACE(c, 0);
         // record of the next layer: its buffer was last read during layer l - 1, which this CTA has finished
         if (c.tid == 0 && l + 1 < kClLayers)
             bulk_load(c.smem + kOffRec + (uint32_t)((rb ^ 1) * kClRecBytes), rec_g + (size_t)(l + 1) * kClRecFloats, kClRecBytes,
@@ -541,16 +558,20 @@ __device__ __forceinline__ void middle_layers(Ctx &c, const float *rec_g, float 
             for (int j = 0; j < 13; ++j) tmem_zero8(ta + 8u * j);
             tmem_wait_st();
         }
+        GC_TRACE(c, 1);
         mbar_wait(MISC_ADDR(c, rec_bar) + (uint32_t)rb * 8u, c.ph_rec[rb]);
         c.ph_rec[rb] ^= 1u;
+        GC_TRACE(c, 2);
         // one cluster barrier per layer: the producer's raw rows + statistics are visible, and every CTA is done
         // reading what this layer is about to overwrite
         if (!(c.dbg & 8)) cluster_wait(); else __syncthreads();
+        GC_TRACE(c, 3);
         const uint32_t rec_saddr = c.smem + kOffRec + (uint32_t)(rb * kClRecBytes);
         if (L.gn) {
             gn_coeffs(c, L, rec_saddr);
             __syncthreads();
         }
+        GC_TRACE(c, 14);
         const bool last = l == kClLayers - 1;
         if (L.kind == kDownK) {
             down_layer(c, L, rec_saddr);
@@ -564,6 +585,7 @@ __device__ __forceinline__ void middle_layers(Ctx &c, const float *rec_g, float 
             else conv_layer<2, false, false, true>(c, L, rec_saddr, nullptr, nullptr);
         }
         if (!(c.dbg & 8)) cluster_arrive();
+        GC_TRACE(c, 15);
     }
 }
 
@@ -573,7 +595,7 @@ __device__ __forceinline__ void middle_layers(Ctx &c, const float *rec_g, float 
 // ------------------------------------------------------------------------------------------------
 __global__ void __cluster_dims__(kCl, 1, 1) __launch_bounds__(kThreads, 1)
 k_unet_middle_cluster(const float *__restrict__ h0, const float *__restrict__ rec_g, float *__restrict__ out,
-                      float *__restrict__ stats_out, int n_agents, int dbg) {
+                      float *__restrict__ stats_out, int n_agents, int dbg, long long *trace) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     Ctx c;
     c.smem = smem_u32(smem_raw);
@@ -582,6 +604,8 @@ k_unet_middle_cluster(const float *__restrict__ h0, const float *__restrict__ re
     c.lane = c.tid & 31;
     c.rank = blockIdx.x % kCl;
     c.dbg = dbg;
+    c.trace = (blockIdx.x == 0) ? trace : nullptr;
+    c.trace_row = 0;
     c.ph_mma[0] = c.ph_mma[1] = c.ph_done[0] = c.ph_done[1] = c.ph_rec[0] = c.ph_rec[1] = 0u;
     const int n_clusters = gridDim.x / kCl, cluster_id = blockIdx.x / kCl;
     Misc *misc = reinterpret_cast<Misc *>(smem_raw + kOffMisc);
@@ -604,19 +628,19 @@ k_unet_middle_cluster(const float *__restrict__ h0, const float *__restrict__ re
     for (int agent = cluster_id; agent < n_agents; agent += n_clusters) {
         // ---- load this CTA's band of h0 into F0 and publish its GroupNorm partial sums ----
         {
-            const int q = c.warp & 3, hsel = c.warp >> 2, px = q * 32 + c.lane, r0 = hsel * 4;
+            const int q = c.warp & 3, hsel = c.warp >> 2, px = q * 32 + c.lane, r0 = hsel * 2;
             float q8[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) q8[i] = 0.0f;
-            float4 v[4][2];
+            float4 v[2][2];
 #pragma unroll
-            for (int r = 0; r < 4; ++r) {
+            for (int r = 0; r < 2; ++r) {
                 const float4 *src = reinterpret_cast<const float4 *>(h0 + (((size_t)agent * 64 + c.rank * 8 + r0 + r) * 128 + px) * 8);
                 v[r][0] = __ldg(src);
                 v[r][1] = __ldg(src + 1);
             }
 #pragma unroll
-            for (int r = 0; r < 4; ++r) {
+            for (int r = 0; r < 2; ++r) {
                 const uint32_t poff = (uint32_t)(((r0 + r) * 2) * 128 + px) * 16u;
                 sts4(c.smem + kOffF + buf_off(F0) + poff, v[r][0]);
                 sts4(c.smem + kOffF + buf_off(F0) + poff + 128u * 16u, v[r][1]);
@@ -676,7 +700,22 @@ int unet_middle_cluster(cudaStream_t st, int A, const float *h0, const float *re
     if (int rc = cluster_grid((const void *)cl::k_unet_middle_cluster, cl::kSmemBytes, A, &n_clusters)) return rc;
     static int dbg = -1;
     if (dbg < 0) { const char *e = getenv("GC_CL_DEBUG"); dbg = e ? atoi(e) : 0; }
-    cl::k_unet_middle_cluster<<<n_clusters * kCl, cl::kThreads, cl::kSmemBytes, st>>>(h0, rec_dev, out, stats_out, A, dbg);
+    static long long *trace = nullptr;
+    if ((dbg & 32) && trace == nullptr) {
+        cudaMalloc(&trace, kClLayers * 16 * sizeof(long long));
+        cudaMemset(trace, 0, kClLayers * 16 * sizeof(long long));
+    }
+    cl::k_unet_middle_cluster<<<n_clusters * kCl, cl::kThreads, cl::kSmemBytes, st>>>(h0, rec_dev, out, stats_out, A, dbg, trace);
+    if (trace != nullptr) {   // debug only: dump the timeline of the last agent CTA 0 processed
+        cudaStreamSynchronize(st);
+        long long h[kClLayers * 16];
+        cudaMemcpy(h, trace, sizeof(h), cudaMemcpyDeviceToHost);
+        for (int l = 0; l < kClLayers; ++l) {
+            fprintf(stderr, "trace layer %2d:", l);
+            for (int k = 1; k < 16; ++k) fprintf(stderr, " %lld", h[l * 16 + k] ? h[l * 16 + k] - h[l * 16] : -1);
+            fprintf(stderr, "\n");
+        }
+    }
     GC_LAUNCH_CHECK("k_unet_middle_cluster");
     return GC_OK;
 }

@@ -351,6 +351,199 @@ k_conv_in_tc(const float *__restrict__ cond, const float *__restrict__ x, const 
 
 
 // ------------------------------------------------------------------------------------------------
+// conv_in, second version ("input-row stationary", the formulation of denoiser_cluster.cu): one CTA = 8 output rows x 128
+// pixels of one agent.  Per chunk of 16 input channels the 10 input rows are staged ONCE as bf16 pixel vectors
+// (thread = 4 pixels x 8 channels: eight coalesced 16-byte loads, an in-register transpose, four 16-byte stores) and
+// every staged row feeds the three output rows it contributes to with ONE MMA per tap kx:
+//   D[128 px of input row i, 32] += A_i[128, 16 ch] * B_kx[16 ch, 4 blocks x 8 cout]   (block j = tap row ky = 2 - j)
+// into TMEM columns 8 i .. 8 i + 31 (the accumulator of output row r lives at column 8 (r + 2)): 30 MMAs per chunk for 8
+// output rows instead of 72, input rows read 1.25x instead of 1.5x, and 256 CTAs for 32 agents = one wave at 2 CTAs/SM
+// (the first version ran 512 CTAs on 444 slots: r01 112 us for 139 MB).
+//   wp2: [chunk][kx 3][k group 2][block 4][cout 8][8 bf16] packed by k_pack_conv_in_w2
+// ------------------------------------------------------------------------------------------------
+constexpr int kIn2Rows = 8, kIn2Staged = kIn2Rows + 2, kIn2RowPx = 130, kIn2Threads = 256;
+constexpr int kIn2PlaneU4 = kIn2Staged * kIn2RowPx;                 // uint4 per channel-group plane
+constexpr int kIn2BufBytes = 2 * kIn2PlaneU4 * 16;                  // one chunk: two planes = 41600 B
+
+__global__ void k_pack_conv_in_w2(const float *__restrict__ w, int C, int chunks, uint4 *__restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= chunks * 3 * 2 * 4 * 8) return;
+    const int n = i & 7, j = (i >> 3) & 3, gsel = (i >> 5) & 1, kx = (i >> 6) % 3, q = (i >> 6) / 3;
+    const int g = 2 * q + gsel;
+    float f[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const int kc = 8 * g + c;                       // GEMM channel: x_0..x_{C-1}, cond_0, cond_1, zeros
+        const int cin = kc < C ? kc + 2 : kc - C;       // reference channel (cond first)
+        f[c] = (j < 3 && kc < C + 2) ? __ldg(w + ((size_t)cin * 9 + (2 - j) * 3 + kx) * 8 + n) : 0.0f;
+    }
+    out[i] = pack8(f);
+}
+
+__device__ __forceinline__ void mma_bf16_elect(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred pe, pa;\n\t"
+        "setp.eq.b32 pa, 0, 0;\n\t"
+        "elect.sync _|pe, 0xffffffff;\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, pa;\n\t"
+        "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc) : "memory");
+}
+__device__ __forceinline__ void commit_elect(uint32_t bar) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred pe;\n\t"
+        "elect.sync _|pe, 0xffffffff;\n\t"
+        "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
+        "}" ::"r"(bar) : "memory");
+}
+
+__global__ void __launch_bounds__(kIn2Threads)
+k_conv_in_tc2(const float *__restrict__ cond, const float *__restrict__ x, const uint4 *__restrict__ wp2, Bias8 bias, int C, int H,
+              int W, float *__restrict__ out, float *__restrict__ stats_out) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    // [A: 2 buffers][2 groups][10 rows][130 px][16 B]  |  [B: chunks][3 kx][2 groups][4 blocks][8 cout][16 B]
+    uint4 *a_s = reinterpret_cast<uint4 *>(smem);
+    uint4 *b_s = reinterpret_cast<uint4 *>(smem + 2 * kIn2BufBytes);
+    __shared__ __align__(8) uint64_t s_empty[2], s_done, s_wbar;
+    __shared__ uint32_t s_tmem;
+    __shared__ float s_part[kIn2Threads / 32][8];
+
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    const int agent = blockIdx.y, y0 = blockIdx.x * kIn2Rows;            // W == 128: one tile per row band
+    const int groups = C / 8 + 1, chunks = (groups + 1) / 2;
+    const size_t plane = (size_t)H * W;
+
+    if (warp == 0) tmem_alloc<128>(&s_tmem);
+    if (tid == 32) {
+        mbar_init(smem_u32(&s_empty[0]), 1); mbar_init(smem_u32(&s_empty[1]), 1); mbar_init(smem_u32(&s_done), 1);
+        mbar_init(smem_u32(&s_wbar), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // x halo columns (pixels -1 and 128) are outside the image for W == 128: zero once, staging never touches them
+    for (int i = tid; i < 2 * 2 * kIn2Staged * 2; i += kIn2Threads) {
+        const int side = i & 1, r = (i >> 1) % kIn2Staged, pl = (i >> 1) / kIn2Staged;
+        a_s[(pl * kIn2Staged + r) * kIn2RowPx + (side ? kIn2RowPx - 1 : 0)] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = __shfl_sync(0xffffffffu, s_tmem, 0);
+    if (tid == 0) bulk_load(smem_u32(b_s), wp2, (uint32_t)chunks * 3u * 1024u, smem_u32(&s_wbar));
+    if (warp < 4) {   // zero the 8 (10 + 3) accumulator columns
+        const uint32_t ta = tmem + ((uint32_t)(warp * 32) << 16);
+#pragma unroll
+        for (int j = 0; j < 13; ++j)
+            asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1};" ::"r"(ta + 8u * j), "r"(0u) : "memory");
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
+    const uint32_t a_base = smem_u32(a_s), b_base = smem_u32(b_s);
+    constexpr uint32_t idesc = make_idesc(128, 32);
+    constexpr uint32_t kPlaneBytes = kIn2PlaneU4 * 16u;
+
+    for (int q = 0; q < chunks; ++q) {
+        const int b = q & 1;
+        if (q >= 2) mbar_wait(smem_u32(&s_empty[b]), (uint32_t)((q >> 1) - 1) & 1u);   // MMAs of chunk q - 2 retired
+        uint4 *buf = a_s + b * 2 * kIn2PlaneU4;
+        // ---- stage chunk q: item = (group, row, 4-pixel quad); 2 x 10 x 32 = 640 items ----
+        for (int it = tid; it < 2 * kIn2Staged * 32; it += kIn2Threads) {
+            const int quad = it & 31, r = (it >> 5) % kIn2Staged, gsel = (it >> 5) / kIn2Staged;
+            const int g = 2 * q + gsel, gy = y0 - 1 + r;
+            if (gy < 0 || gy >= H) continue;                    // row outside the image: its MMAs are skipped
+            float4 v[8];
+            if (g < C / 8) {
+                const float *src = x + ((size_t)agent * C + 8 * g) * plane + (size_t)gy * W + quad * 4;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) v[c] = __ldg(reinterpret_cast<const float4 *>(src + (size_t)c * plane));
+            } else {
+#pragma unroll
+                for (int c = 0; c < 8; ++c) v[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (g == C / 8) {
+                    const float *src = cond + (size_t)agent * 2 * plane + (size_t)gy * W + quad * 4;
+                    v[0] = __ldg(reinterpret_cast<const float4 *>(src));
+                    v[1] = __ldg(reinterpret_cast<const float4 *>(src + plane));
+                }
+            }
+            uint4 *dst = buf + (gsel * kIn2Staged + r) * kIn2RowPx + 1 + quad * 4;
+            { const float f[8] = {v[0].x, v[1].x, v[2].x, v[3].x, v[4].x, v[5].x, v[6].x, v[7].x}; dst[0] = pack8(f); }
+            { const float f[8] = {v[0].y, v[1].y, v[2].y, v[3].y, v[4].y, v[5].y, v[6].y, v[7].y}; dst[1] = pack8(f); }
+            { const float f[8] = {v[0].z, v[1].z, v[2].z, v[3].z, v[4].z, v[5].z, v[6].z, v[7].z}; dst[2] = pack8(f); }
+            { const float f[8] = {v[0].w, v[1].w, v[2].w, v[3].w, v[4].w, v[5].w, v[6].w, v[7].w}; dst[3] = pack8(f); }
+        }
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();
+        if (warp == 0) {
+            tc_fence_after();
+            if (q == 0) mbar_wait(smem_u32(&s_wbar), 0u);       // weights landed (bulk copy)
+            const uint32_t a_buf = a_base + (uint32_t)b * (uint32_t)kIn2BufBytes;
+            for (int i = 0; i < kIn2Staged; ++i) {
+                const int gy = y0 - 1 + i;
+                if (gy < 0 || gy >= H) continue;
+                const uint64_t a0 = make_desc(a_buf + (uint32_t)(i * kIn2RowPx) * 16u, kPlaneBytes, 128u);
+                const uint64_t b0 = make_desc(b_base + (uint32_t)(q * 3) * 1024u, 512u, 128u);
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx) mma_bf16_elect(tmem + 8u * i, a0 + (uint64_t)kx, b0 + (uint64_t)(kx * 64), idesc);
+            }
+            commit_elect(smem_u32(&s_empty[b]));
+            if (q == chunks - 1) commit_elect(smem_u32(&s_done));
+        }
+    }
+    mbar_wait(smem_u32(&s_done), 0u);
+    tc_fence_after();
+
+    // ---- epilogue: thread = pixel x of 4 output rows; bias, NHWC8 store, GroupNorm partial sums of the band ----
+    const int qd = warp & 3, hsel = warp >> 2, px = qd * 32 + lane, r0 = hsel * 4;
+    float q8[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) q8[i] = 0.0f;
+    {
+        float acc[32];
+        const uint32_t ta = tmem + ((uint32_t)(qd * 32) << 16) + 8u * (r0 + 2);
+        {
+            float t0[16], t1[16];
+            tmem_ld16(ta, t0);
+            tmem_ld16(ta + 16u, t1);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) { acc[i] = t0[i]; acc[16 + i] = t1[i]; }
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            float *v = acc + 8 * r;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] += bias.b[i];
+            float4 *dst = reinterpret_cast<float4 *>(out + (((size_t)agent * H + y0 + r0 + r) * W + px) * 8);
+            dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+            dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+#pragma unroll
+            for (int p = 0; p < 4; ++p) {
+                q8[2 * p] += v[2 * p] + v[2 * p + 1];
+                q8[2 * p + 1] += v[2 * p] * v[2 * p] + v[2 * p + 1] * v[2 * p + 1];
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) q8[i] += __shfl_xor_sync(0xffffffffu, q8[i], m);
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s_part[warp][i] = q8[i];
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (tid < 8) {
+        float t = 0.0f;
+#pragma unroll
+        for (int w = 0; w < kIn2Threads / 32; ++w) t += s_part[w][tid];
+        stats_out[((size_t)agent * gridDim.x + blockIdx.x) * 8 + tid] = t;
+    }
+    if (warp == 0) tmem_free<128>(tmem);
+}
+
+// ------------------------------------------------------------------------------------------------
 // Width-8 middle layers on tensor cores: 3x3 conv, CIN (8 or 16) -> 8 channels on NHWC8 fp32 tensors, tf32 operands
 // (fp32 storage, no conversion pass), fp32 accumulation in TMEM.  unet.py:117-138 (ResnetBlock), :40-56 (Upsample).
 // grid = (W/128, ceil(H/4), A), 128 threads; H, W are the OUTPUT dims (kUp: the input is H/2 x W/2).
@@ -572,9 +765,14 @@ bool conv_in_tc_eligible(int C, int H, int W) {
 
 int conv_in_tc_tiles(int H, int W) { return (W / 128) * ((H + tc::kInRows - 1) / tc::kInRows); }
 
-size_t conv_tc_packed_bytes(int C) {   // conv_in B operand, then conv_out B operand
+static size_t conv_tc_packed_v1_bytes(int C) {   // conv_in B operand (v1 layout), then conv_out B operand
     const size_t chunks = (size_t)(C / 8 + 1 + 1) / 2;
-    return align_up(chunks * 9 * 2 * 8 * 16, 256) + (size_t)12 * C * 16;
+    return align_up(align_up(chunks * 9 * 2 * 8 * 16, 256) + (size_t)12 * C * 16, 256);
+}
+
+size_t conv_tc_packed_bytes(int C) {   // + conv_in B operand in the input-row-stationary layout (k_conv_in_tc2)
+    const size_t chunks = (size_t)(C / 8 + 1 + 1) / 2;
+    return conv_tc_packed_v1_bytes(C) + chunks * 3 * 1024;
 }
 
 int conv_tc_pack_weights(cudaStream_t st, const float *w_in, const float *w_out, int C, void *packed) {
@@ -583,6 +781,8 @@ int conv_tc_pack_weights(cudaStream_t st, const float *w_in, const float *w_out,
     uint4 *pout = reinterpret_cast<uint4 *>(reinterpret_cast<char *>(packed) + align_up((size_t)chunks * 9 * 2 * 8 * 16, 256));
     tc::k_pack_conv_in_w<<<(chunks * 9 * 2 * 8 + 127) / 128, 128, 0, st>>>(w_in, C, chunks, pin);
     tc::k_pack_conv_out_w<<<(12 * C + 127) / 128, 128, 0, st>>>(w_out, C, pout);
+    uint4 *pin2 = reinterpret_cast<uint4 *>(reinterpret_cast<char *>(packed) + conv_tc_packed_v1_bytes(C));
+    tc::k_pack_conv_in_w2<<<(chunks * 3 * 64 + 127) / 128, 128, 0, st>>>(w_in, C, chunks, pin2);
     GC_LAUNCH_CHECK("conv_tc_pack_weights");
     return GC_OK;
 }
@@ -609,6 +809,31 @@ static int pick_nt(int C) {
     if (C % 128 == 0) return 128;
     if (C % 64 == 0) return 64;
     return 0;
+}
+
+// conv_in v2: W == 128, H % 8 == 0, C % 8 == 0; shared memory: two operand buffers + the whole B operand
+bool conv_in_tc2_eligible(int C, int H, int W) {
+    if (W != 128 || H % tc::kIn2Rows != 0 || C % 8 != 0 || C < 8) return false;
+    const int chunks = (C / 8 + 1 + 1) / 2;
+    return (size_t)2 * tc::kIn2BufBytes + (size_t)chunks * 3 * 1024 <= 220 * 1024;
+}
+
+int conv_in_tc2_tiles(int H) { return H / tc::kIn2Rows; }
+
+int conv_in_tc2(cudaStream_t st, int A, const float *cond, const float *x, const void *packed, const Bias8 &bias, int C, int H,
+                int W, float *out, float *stats_out) {
+    const int chunks = (C / 8 + 1 + 1) / 2;
+    const uint4 *w = reinterpret_cast<const uint4 *>(reinterpret_cast<const char *>(packed) + conv_tc_packed_v1_bytes(C));
+    const size_t smem = (size_t)2 * tc::kIn2BufBytes + (size_t)chunks * 3 * 1024;
+    static size_t configured = 0;
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(tc::k_conv_in_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { (void)cudaGetLastError(); set_error("k_conv_in_tc2: cudaFuncSetAttribute failed (%d)", (int)e); return (int)e; }
+        configured = smem;
+    }
+    tc::k_conv_in_tc2<<<dim3(H / tc::kIn2Rows, A), tc::kIn2Threads, smem, st>>>(cond, x, w, bias, C, H, W, out, stats_out);
+    GC_LAUNCH_CHECK("k_conv_in_tc2");
+    return GC_OK;
 }
 
 bool conv_out_tc_eligible(int C, int H, int W) {

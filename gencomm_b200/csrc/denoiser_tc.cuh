@@ -29,6 +29,12 @@ int conv_in_tc_tiles(int H, int W);   // number of GroupNorm partial-sum tiles p
 int conv_in_tc(cudaStream_t st, int A, const float *cond, const float *x, const void *packed, const Bias8 &bias, int C, int H,
                int W, float *out, float *stats_out);
 
+// conv_in, input-row-stationary version (8 rows per CTA, 3 MMAs per staged row and chunk): W == 128, H % 8 == 0.
+bool conv_in_tc2_eligible(int C, int H, int W);
+int conv_in_tc2_tiles(int H);
+int conv_in_tc2(cudaStream_t st, int A, const float *cond, const float *x, const void *packed, const Bias8 &bias, int C, int H,
+                int W, float *out, float *stats_out);
+
 // norm_out + swish + conv_out (+ sampler update) on tensor cores (unet.py:341-343).  Eligible when
 // W % 128 == 0 and C % 64 == 0.
 bool conv_out_tc_eligible(int C, int H, int W);
