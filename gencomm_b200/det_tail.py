@@ -23,6 +23,15 @@ class DoubleConv(nn.Module):
         self.stride, self.out_channels = stride, out_channels
         self._key, self._blobs = None, None
 
+    def invalidate(self):
+        """Drop the packed-weight cache.  The cache key is (data_ptr, _version) of every parameter, which in-place writes
+        through ``p.data`` do not change: call this after such an update (``load_state_dict`` does it by itself)."""
+        self._key = None
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        self._key = None
+        return super()._load_from_state_dict(*args, **kwargs)
+
     @torch.no_grad()
     def forward(self, x):
         c0, c2 = self.double_conv[0], self.double_conv[2]
@@ -60,6 +69,15 @@ class DetectionHeads(nn.Module):
         self.reg_head = nn.Conv2d(in_head, 7 * anchor_number * num_class, kernel_size=1)
         self.dir_head = nn.Conv2d(in_head, dir_bins * anchor_number, kernel_size=1)
         self._key, self._blobs = None, None
+
+    def invalidate(self):
+        """Drop the packed-weight cache.  The cache key is (data_ptr, _version) of every parameter, which in-place writes
+        through ``p.data`` do not change: call this after such an update (``load_state_dict`` does it by itself)."""
+        self._key = None
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        self._key = None
+        return super()._load_from_state_dict(*args, **kwargs)
 
     @torch.no_grad()
     def forward(self, x):

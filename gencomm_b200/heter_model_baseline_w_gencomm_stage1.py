@@ -139,6 +139,23 @@ class HeterModelBaselineWGenComm(_HeadsMixin, nn.Module):
     def _make_message_extractor(args):
         return MessageExtractorv2(args['message_extractor']['in_ch'], args['message_extractor']['out_ch'])
 
+    def invalidate(self):
+        """Drop every packed-weight cache of the detector (after in-place parameter writes through ``p.data``)."""
+        for m in self.modules():
+            if m is not self and hasattr(m, "invalidate"):
+                m.invalidate()
+        for key in ("_heads", "_heads_single"):
+            h = getattr(self, key, None)
+            if h is not None:
+                h.invalidate()
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        for key in ("_heads", "_heads_single"):      # the fused-heads helper is not a registered sub-module
+            h = getattr(self, key, None)
+            if h is not None:
+                h.invalidate()
+        return super()._load_from_state_dict(*args, **kwargs)
+
     def set_encoder(self, modality_name, module):
         """Plug in an encoder for a modality (e.g. the reference's own ``LiftSplatShoot`` instance): it is called as
         ``module(data_dict, modality_name)`` like heter_encoders' classes and must return the BEV feature on the device."""

@@ -45,6 +45,15 @@ class BEVDeformableExtractor(nn.Module):
         self._packed = None
         self._params = None
 
+    def invalidate(self):
+        """Drop the packed-weight cache.  The cache key is (data_ptr, _version) of every parameter, which in-place writes
+        through ``p.data`` do not change: call this after such an update (``load_state_dict`` does it by itself)."""
+        self._key = None
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        self._key = None
+        return super()._load_from_state_dict(*args, **kwargs)
+
     def _blobs(self):
         ps = list(self.parameters())
         key = tuple((p.data_ptr(), p._version) for p in ps)

@@ -151,6 +151,14 @@ class PillarVFE(nn.Module):
     def get_output_feature_dim(self):
         return self.num_filters[-1]
 
+    def invalidate(self):
+        """Drop the packed PFN table (needed after in-place writes through ``p.data``, which the cache key cannot see)."""
+        self._pfn_cache = None
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        self._pfn_cache = None
+        return super()._load_from_state_dict(*args, **kwargs)
+
     def pfn_table(self, device):
         """Packed [64,16] PFN table on `device`, rebuilt whenever a parameter/buffer changes."""
         layer = self.pfn_layers[0]
