@@ -410,14 +410,29 @@ def gencomm_sampler_extra(dev, frames=8, agents=4, C=128, H=64, W=128, iters=20)
     cond = synth.bev_features(40, A, 2, H, W, salt=4).to(dev)
     n0, steps = synth.sampler_noise(40, A, C, H, W, T=3)
     noise = (n0.to(dev), torch.stack(steps).to(dev))
-    rl = torch.full((frames,), agents, dtype=torch.int64)
+    rl = torch.full((frames,), agents, dtype=torch.int64, device=dev)   # on the device: no H2D copy inside the CUDA graph
     flop = 486.8e6 if C == 128 else 788.8e6
     hbm = A * 3 * (4 * (C + 2) * H * W + 8 * C * H * W)
     out = {"workload": f"GenComm sampler, {frames} frames x {agents} agents, C={C}, {H}x{W}, T=3", "mandatory_hbm_bytes": hbm}
     for name in ("cluster", "tc", "fp32"):
         m.precision = name
         ms = _time_calls(lambda: m(feat, cond, rl, noise=noise), iters)
-        out[name] = {"ms_per_call": ms, "frames_per_s": frames / (ms * 1e-3), "tflops": A * 3 * flop / (ms * 1e-3) / 1e12,
+        try:   # device time of the same call replayed from a CUDA graph (the eager figure includes the host launch path)
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                m(feat, cond, rl, noise=noise)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                m(feat, cond, rl, noise=noise)
+            eager_ms, ms = ms, _time_calls(graph.replay, iters)
+        except Exception as exc:
+            eager_ms = ms
+            out.setdefault("graph_errors", {})[name] = repr(exc)
+        out[name] = {"ms_per_call": ms, "eager_ms_per_call": eager_ms, "frames_per_s": frames / (ms * 1e-3),
+                     "tflops": A * 3 * flop / (ms * 1e-3) / 1e12,
                      "hbm_frac_of_mandatory": hbm / (ms * 1e-3) / 1e9 / load_peaks()[0]}
     out["launches_per_call"] = {"cluster": 1 + 3 * 3, "tc": 1 + 3 * 28}
     out["precision_note"] = ("cluster (default): bf16 tcgen05 conv_in / conv_out + ONE cluster-resident launch for the 26 width-8 "

@@ -35,7 +35,7 @@ def main():
     cond = synth.bev_features(40, A, 2, H, W, salt=4).cuda()
     n0, steps = synth.sampler_noise(40, A, C, H, W, T=3)
     noise = (n0.cuda(), torch.stack(steps).cuda())
-    rl = torch.full((a.frames,), a.agents, dtype=torch.int64)
+    rl = torch.full((a.frames,), a.agents, dtype=torch.int64).cuda()
     for name in (("cluster", "tc", "bf16", "fp32") if a.precision == "both" else (a.precision,)):
         m.precision = name
         for _ in range(3):
@@ -48,8 +48,32 @@ def main():
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / a.iters
-        print(f"sampler {name}: {a.frames} frames x {a.agents} agents C={C} {H}x{W}: {ms:.3f} ms/call, "
-              f"{a.frames / ms * 1e3:.0f} frames/s, {A * 3 * 486.8e6 / (ms * 1e-3) / 1e12:.1f} TFLOP/s (C=128 flop count)", flush=True)
+        # the same call replayed from a CUDA graph: device time without the host-side launch path
+        gms = float("nan")
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                m(feat, cond, rl, noise=noise)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                m(feat, cond, rl, noise=noise)
+            for _ in range(3):
+                g.replay()
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(a.iters):
+                g.replay()
+            e1.record()
+            torch.cuda.synchronize()
+            gms = e0.elapsed_time(e1) / a.iters
+        except Exception as exc:
+            print("graph capture failed:", repr(exc))
+        flop = 486.8e6 if C == 128 else 788.8e6
+        print(f"sampler {name}: {a.frames} frames x {a.agents} agents C={C} {H}x{W}: {ms:.3f} ms/call eager, {gms:.3f} ms/call "
+              f"CUDA graph, {a.frames / gms * 1e3:.0f} frames/s, {A * 3 * flop / (gms * 1e-3) / 1e12:.1f} TFLOP/s", flush=True)
 
 
 if __name__ == "__main__":
