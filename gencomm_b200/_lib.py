@@ -74,6 +74,9 @@ SIGNATURES = {
     "gc_double_conv_pack": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "gc_double_conv": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                c_void_p, c_void_p]),
+    "gc_double_conv_planes_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
+    "gc_double_conv_planes": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                                      c_void_p, c_void_p]),
     "gc_det_heads_packed_bytes": (c_size_t, [c_int, c_int]),
     "gc_det_heads_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "gc_det_heads_pack": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),

@@ -54,6 +54,9 @@ class BaseBEVBackbone(nn.Module):
         self._strides = [int(s) for s in layer_strides]
         self._ups = [int(s) for s in upsample_strides]
         self._key, self._packed = None, None
+        # True: 'spatial_features_2d' is an ops.PlaneFeature (channel-last bf16 value + residual planes) for this package's
+        # DownsampleConv instead of an NCHW fp32 tensor -- the model sets it when the shrink header follows directly
+        self.emit_planes = False
 
     def invalidate(self):
         """Drop the packed-weight cache.  The cache key is (data_ptr, _version) of every parameter, which in-place writes
@@ -94,18 +97,29 @@ class BaseBEVBackbone(nn.Module):
         A, C, H, W = x.shape
         levels = self._pack()
         planes, h, w = ops.to_planes(x), H, W
-        out, ch_off = None, 0
+        out, ch_off, C_out = None, 0, self.num_bev_features
         for (convs, phases, up_bias, up_out, up_in), up in zip(levels, self._ups):
             c_in = None
             for packed, bias, n_out, c_in, stride in convs:
                 planes, h, w = ops.conv_planes(planes, A, c_in, h, w, packed, bias, n_out, 9, stride=stride)
             if out is None:
-                out = torch.empty(A, self.num_bev_features, h * up, w * up, dtype=torch.float32, device=x.device)
-            elif (h * up, w * up) != tuple(out.shape[2:]):
+                Hu, Wu = h * up, w * up
+                if self.emit_planes:
+                    oh = torch.empty(A * Hu * Wu * C_out * 2, dtype=torch.uint8, device=x.device)
+                    out = (oh, torch.empty_like(oh))
+                else:
+                    out = torch.empty(A, C_out, Hu, Wu, dtype=torch.float32, device=x.device)
+            elif (h * up, w * up) != (Hu, Wu):
                 raise ValueError("BaseBEVBackbone: the deblock outputs do not share one resolution")
             for dy, dx, packed in phases:
-                ops.conv_planes(planes, A, up_in, h, w, packed, up_bias, up_out, 1, out_nchw=out, out_ch_off=ch_off, up=up,
-                                up_dy=dy, up_dx=dx)
+                if self.emit_planes:
+                    ops.conv_planes(planes, A, up_in, h, w, packed, up_bias, up_out, 1, out_planes=out, out_ch_total=C_out,
+                                    out_ch_off=ch_off, up=up, up_dy=dy, up_dx=dx)
+                else:
+                    ops.conv_planes(planes, A, up_in, h, w, packed, up_bias, up_out, 1, out_nchw=out, out_ch_off=ch_off, up=up,
+                                    up_dy=dy, up_dx=dx)
             ch_off += up_out
+        if self.emit_planes:
+            out = ops.PlaneFeature(out[0], out[1], (A, C_out, Hu, Wu))
         data_dict['spatial_features_2d'] = out
         return data_dict

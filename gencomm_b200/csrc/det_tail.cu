@@ -11,6 +11,7 @@
 #include "common.cuh"
 #include <stdlib.h>
 
+#include "conv_rows.cuh"
 #include "implicit_gemm.cuh"
 
 namespace gc {
@@ -43,6 +44,8 @@ static int launch_n(int n, cudaStream_t st, dim3 grid, const uint4 *xh, const ui
     return launch<256, TAPS, EPI>(st, grid, xh, xl, wp, bias, C, H, W, n, out, H_in, W_in, stride);
 }
 static inline int pad_n(int n) { return n <= 32 ? 32 : n <= 64 ? 64 : n <= 128 ? 128 : 256; }
+static int double_conv_from_planes(cudaStream_t st, int A, const uint4 *xh, const uint4 *xl, int c_in, int H, int W, int stride,
+                                   int c_out, const void *packed, const float *bias, float *mid, float *out);
 static inline size_t packed_conv_bytes(int taps, int cin, int n) { return (size_t)taps * cin * pad_n(n) * 2 * 2; }
 
 struct Ws {
@@ -116,10 +119,27 @@ extern "C" int gc_double_conv(const float *x, int total_agents, int c_in, int H,
     const dim3 grid(Ho * Wo / me::kPix, A);
     me::k_me_to_nhwc<<<dim3((H * W + 63) / 64, c_in / 64, A), 256, 0, st>>>(x, c_in, H * W, ws.xh, ws.xl);
     GC_LAUNCH_CHECK("k_me_to_nhwc(x)");
-    if (int rc = dt::launch_n<9, 3>(c_out, st, grid, ws.xh, ws.xl, p1, bias, c_in, Ho, Wo, ws.mid, H, W, stride)) return rc;
-    me::k_me_to_nhwc<<<dim3((Ho * Wo + 63) / 64, c_out / 64, A), 256, 0, st>>>(ws.mid, c_out, Ho * Wo, ws.xh, ws.xl);
-    GC_LAUNCH_CHECK("k_me_to_nhwc(mid)");
-    return dt::launch_n<9, 3>(c_out, st, grid, ws.xh, ws.xl, p2, bias + c_out, c_out, Ho, Wo, out, Ho, Wo, 1);
+    return dt::double_conv_from_planes(st, A, ws.xh, ws.xl, c_in, H, W, stride, c_out, packed, bias, ws.mid, out);
+}
+extern "C" size_t gc_double_conv_planes_workspace_bytes(int total_agents, int H, int W, int stride, int c_out) {
+    if (total_agents <= 0 || c_out <= 0 || H <= 0 || W <= 0 || stride <= 0) return 0;
+    const int Ho = (H + 2 - 3) / stride + 1, Wo = (W + 2 - 3) / stride + 1;
+    return align_up((size_t)total_agents * c_out * Ho * Wo * 4, 256);
+}
+extern "C" int gc_double_conv_planes(const void *xh, const void *xl, int total_agents, int c_in, int H, int W, int stride, int c_out,
+                                     const void *packed, const float *bias /* [2][c_out] */, void *workspace, float *out,
+                                     void *stream) {
+    GC_REQUIRE(total_agents >= 0 && total_agents <= 65535, GC_EINVAL, "gc_double_conv_planes: bad agent count");
+    if (total_agents == 0) return GC_OK;
+    GC_REQUIRE(xh && xl && packed && bias && workspace && out, GC_EINVAL, "gc_double_conv_planes: null pointer");
+    GC_REQUIRE(c_in > 0 && c_in % 64 == 0 && c_out > 0 && c_out % 64 == 0 && c_out <= 256, GC_EUNSUPPORTED,
+               "gc_double_conv_planes: channels must be multiples of 64, c_out <= 256 (got %d -> %d)", c_in, c_out);
+    GC_REQUIRE(stride == 1 || stride == 2, GC_EUNSUPPORTED, "gc_double_conv_planes: stride must be 1 or 2 (got %d)", stride);
+    const int Ho = (H + 2 - 3) / stride + 1, Wo = (W + 2 - 3) / stride + 1;
+    GC_REQUIRE(H > 0 && W > 0 && (Ho * Wo) % me::kPix == 0, GC_EUNSUPPORTED,
+               "gc_double_conv_planes: output H*W must be a multiple of 128 (got %dx%d)", Ho, Wo);
+    return dt::double_conv_from_planes((cudaStream_t)stream, total_agents, (const uint4 *)xh, (const uint4 *)xl, c_in, H, W, stride,
+                                       c_out, packed, bias, (float *)workspace, out);
 }
 
 extern "C" size_t gc_det_heads_packed_bytes(int C, int n_out) { return C > 0 && n_out > 0 ? dt::packed_conv_bytes(1, C, n_out) : 0; }
@@ -202,6 +222,27 @@ static int launch_layer_n(int n, Args... args) {
     return launch_layer<256, TAPS, EPI>(args...);
 }
 
+// DoubleConv on channel-last planes: conv3x3(stride) + ReLU written as planes into `mid` (two planes of A*c_out*Ho*Wo*2 bytes
+// = the bytes of one fp32 tensor), conv3x3 + ReLU -> fp32 NCHW.  No fp32 intermediate, no second layout conversion.
+static int double_conv_from_planes(cudaStream_t st, int A, const uint4 *xh, const uint4 *xl, int c_in, int H, int W, int stride,
+                                   int c_out, const void *packed, const float *bias, float *mid, float *out) {
+    const int Ho = (H + 2 - 3) / stride + 1, Wo = (W + 2 - 3) / stride + 1;
+    const uint4 *p1 = (const uint4 *)packed;
+    const uint4 *p2 = (const uint4 *)((const char *)packed + align_up(packed_conv_bytes(9, c_in, c_out), 256));
+    const dim3 grid(Ho * Wo / me::kPix, A);
+    uint4 *mh = (uint4 *)mid, *ml = (uint4 *)((char *)mid + (size_t)A * c_out * Ho * Wo * 2);
+    if (stride == 1 && conv_rows_eligible(9, 1, c_in, c_out, Ho, Wo)) {
+        if (int rc = conv_rows(st, A, xh, xl, p1, bias, c_in, c_out, Ho, Wo, c_out, 0, nullptr, mh, ml)) return rc;
+    } else if (int rc = launch_layer_n<9, 5>(c_out, st, grid, xh, xl, p1, bias, c_in, Ho, Wo, c_out, c_out, 0, (float *)nullptr, mh, ml,
+                                             H, W, stride, 1, 0, 0)) {
+        return rc;
+    }
+    if (conv_rows_eligible(9, 1, c_out, c_out, Ho, Wo))
+        return conv_rows(st, A, mh, ml, p2, bias + c_out, c_out, c_out, Ho, Wo, c_out, 0, out, nullptr, nullptr);
+    return launch_layer_n<9, 3>(c_out, st, grid, (const uint4 *)mh, (const uint4 *)ml, p2, bias + c_out, c_out, Ho, Wo, c_out, c_out,
+                                0, out, (uint4 *)nullptr, (uint4 *)nullptr, Ho, Wo, 1, 1, 0, 0);
+}
+
 }  // namespace dt
 }  // namespace gc
 
@@ -244,14 +285,16 @@ extern "C" int gc_conv_planes(const void *xh, const void *xl, int total_agents, 
     cudaStream_t st = (cudaStream_t)stream;
     const dim3 grid(Ho * Wo / me::kPix, total_agents);
     const uint4 *a = (const uint4 *)xh, *b = (const uint4 *)xl, *wp = (const uint4 *)packed;
+    // wide stride-1 layers: the row-staged kernel (conv_rows.cu) reads every input row once per channel chunk instead of nine times
+    if (up == 1 && conv_rows_eligible(taps, stride, c_in, n_out, Ho, Wo))
+        return conv_rows(st, total_agents, xh, xl, packed, bias, c_in, n_out, Ho, Wo, out_ch_total, out_ch_off, out_nchw, oh, ol);
     if (oh) {
-        GC_REQUIRE(up == 1 && n_out % 16 == 0, GC_EUNSUPPORTED,
-                   "gc_conv_planes: plane outputs need n_out %% 16 == 0 and no up-sampling");
+        GC_REQUIRE(n_out % 16 == 0, GC_EUNSUPPORTED, "gc_conv_planes: plane outputs need n_out %% 16 == 0");
         if (taps == 9)
             return dt::launch_layer_n<9, 5>(n_out, st, grid, a, b, wp, bias, c_in, Ho, Wo, n_out, out_ch_total, out_ch_off,
-                                            (float *)nullptr, (uint4 *)oh, (uint4 *)ol, H_in, W_in, stride, 1, 0, 0);
+                                            (float *)nullptr, (uint4 *)oh, (uint4 *)ol, H_in, W_in, stride, up, up_dy, up_dx);
         return dt::launch_layer_n<1, 5>(n_out, st, grid, a, b, wp, bias, c_in, Ho, Wo, n_out, out_ch_total, out_ch_off,
-                                        (float *)nullptr, (uint4 *)oh, (uint4 *)ol, H_in, W_in, stride, 1, 0, 0);
+                                        (float *)nullptr, (uint4 *)oh, (uint4 *)ol, H_in, W_in, stride, up, up_dy, up_dx);
     }
     if (taps == 9)
         return dt::launch_layer_n<9, 3>(n_out, st, grid, a, b, wp, bias, c_in, Ho, Wo, n_out, out_ch_total, out_ch_off, out_nchw,

@@ -420,8 +420,8 @@ k_me_conv(const uint4 *__restrict__ xh, const uint4 *__restrict__ xl, const floa
         for (int c16 = 0; c16 < NOUT / 2; c16 += 16) {
             float v[16];
             tmem_ld16(taddr + (uint32_t)c16, v);
-            if (EPI == 5) {   // bias + ReLU -> channel-last bf16 value + residual planes [A][HW][out_ch_total]: the next
-                              // layer's A operand, no fp32 NCHW round trip and no layout conversion between layers
+            if (EPI == 5) {   // bias + ReLU -> channel-last bf16 value + residual planes [A][HW * up * up][out_ch_total]: the
+                              // next layer's A operand, no fp32 NCHW round trip and no layout conversion between layers
                 uint32_t h[8], l[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
@@ -431,7 +431,7 @@ k_me_conv(const uint4 *__restrict__ xh, const uint4 *__restrict__ xl, const floa
                     l[i] = pack_bf16(bf16_residual(a), bf16_residual(b));
                 }
                 if (ch0 + c16 < n_store) {
-                    const size_t o = ((size_t)agent * HW + p_out) * (out_ch_total >> 3) + ((out_ch_off + ch0 + c16) >> 3);
+                    const size_t o = ((size_t)agent * hw_store + p_store) * (out_ch_total >> 3) + ((out_ch_off + ch0 + c16) >> 3);
                     oh[o] = make_uint4(h[0], h[1], h[2], h[3]); oh[o + 1] = make_uint4(h[4], h[5], h[6], h[7]);
                     ol[o] = make_uint4(l[0], l[1], l[2], l[3]); ol[o + 1] = make_uint4(l[4], l[5], l[6], l[7]);
                 }

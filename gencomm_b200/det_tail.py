@@ -39,6 +39,8 @@ class DoubleConv(nn.Module):
         if key != self._key:
             self._blobs = ops.double_conv_pack(c0.weight, c0.bias, c2.weight, c2.bias)
             self._key = key
+        if isinstance(x, ops.PlaneFeature):      # handed over by this package's BaseBEVBackbone (emit_planes)
+            return ops.double_conv_planes(x, self._blobs[0], self._blobs[1], self.out_channels, self.stride)
         return ops.double_conv(x.contiguous(), self._blobs[0], self._blobs[1], self.out_channels, self.stride)
 
 

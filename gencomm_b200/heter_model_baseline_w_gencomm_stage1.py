@@ -188,10 +188,18 @@ class HeterModelBaselineWGenComm(_HeadsMixin, nn.Module):
                 data_dict = dict(data_dict)
                 data_dict[f'inputs_{m}'] = dict(inp, batch_size=counts[m])
             feature = getattr(self, f"encoder_{m}")(data_dict, m)
-            backbone = getattr(self, f"backbone_{m}")
+            backbone, shrinker = getattr(self, f"backbone_{m}"), getattr(self, f"shrinker_{m}")
             if not isinstance(backbone, nn.Identity):
-                feature = backbone({"spatial_features": feature})['spatial_features_2d']
-            feature = getattr(self, f"shrinker_{m}")(feature)
+                # the shrink header follows directly: the deblocks write its operand planes, no NCHW fp32 round trip
+                fused = isinstance(backbone, BaseBEVBackbone) and isinstance(shrinker, DownsampleConv)
+                try:
+                    if fused:
+                        backbone.emit_planes = True
+                    feature = backbone({"spatial_features": feature})['spatial_features_2d']
+                finally:
+                    if fused:
+                        backbone.emit_planes = False
+            feature = shrinker(feature)
             features[m] = feature
             messages[m] = getattr(self, f"message_extractor_{m}")(feature)
 

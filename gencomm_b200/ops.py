@@ -447,6 +447,32 @@ def double_conv(x, packed, bias, c_out, stride, workspace=None):
     return out
 
 
+class PlaneFeature:
+    """A feature map kept as channel-last bf16 value + residual planes (the tcgen05 convolutions' operand layout) instead of
+    NCHW fp32: what BaseBEVBackbone hands to DownsampleConv when both are this package's (``emit_planes``)."""
+
+    def __init__(self, xh, xl, shape):
+        self.xh, self.xl, self.shape = xh, xl, tuple(shape)      # shape = (A, C, H, W)
+
+    @property
+    def device(self):
+        return self.xh.device
+
+
+def double_conv_planes(feat, packed, bias, c_out, stride, workspace=None):
+    """DoubleConv over a PlaneFeature -> fp32 NCHW [A, c_out, Ho, Wo]."""
+    lib = _lib.load()
+    A, c_in, H, W = feat.shape
+    Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
+    if workspace is None:
+        workspace = torch.empty(max(lib.gc_double_conv_planes_workspace_bytes(A, H, W, stride, c_out), 1), dtype=torch.uint8,
+                                device=feat.device)
+    out = torch.empty(A, c_out, Ho, Wo, dtype=torch.float32, device=feat.device)
+    _lib.check(lib.gc_double_conv_planes(_ptr(feat.xh), _ptr(feat.xl), A, c_in, H, W, int(stride), int(c_out), _ptr(packed),
+                                         _ptr(bias), _ptr(workspace), _ptr(out), _stream()), "gc_double_conv_planes")
+    return out
+
+
 def det_heads_pack(weights, biases):
     """weights: 1x1 conv weights [n_i, C, 1, 1] (cls, reg, dir); returns (packed, bias, splits)."""
     lib = _lib.load()
@@ -502,12 +528,19 @@ def to_planes(x):
 
 
 def conv_planes(planes, A, c_in, H_in, W_in, packed, bias, n_out, taps, stride=1, out_nchw=None, out_ch_off=0, up=1,
-                up_dy=0, up_dx=0):
+                up_dy=0, up_dx=0, out_planes=None, out_ch_total=None):
     """ReLU(conv(planes) + bias).  Returns the output planes (xh, xl) when out_nchw is None, else writes into out_nchw
-    [A, C_total, Ho*up, Wo*up] at channel offset out_ch_off and phase (up_dy, up_dx)."""
+    [A, C_total, Ho*up, Wo*up] at channel offset out_ch_off and phase (up_dy, up_dx).  out_planes = (oh, ol) of
+    [A, Ho*up*Wo*up, out_ch_total] bf16 writes the planes into an existing buffer at the same offset / phase."""
     lib = _lib.load()
     xh, xl = planes
     Ho, Wo = ((H_in - 1) // stride + 1, (W_in - 1) // stride + 1) if taps == 9 else (H_in, W_in)
+    if out_planes is not None:
+        oh, ol = out_planes
+        _lib.check(lib.gc_conv_planes(_ptr(xh), _ptr(xl), A, c_in, H_in, W_in, stride, taps, n_out, _ptr(packed), _ptr(bias),
+                                      _ptr(oh), _ptr(ol), None, int(out_ch_total), out_ch_off, up, up_dy, up_dx, _stream()),
+                   "gc_conv_planes")
+        return out_planes, Ho, Wo
     if out_nchw is None:
         oh = torch.empty(max(A * Ho * Wo * n_out * 2, 1), dtype=torch.uint8, device=xh.device)
         ol = torch.empty_like(oh)

@@ -248,6 +248,11 @@ size_t gc_double_conv_workspace_bytes(int total_agents, int c_in, int H, int W, 
 int gc_double_conv_pack(const float *w1, const float *w2, int c_in, int c_out, void *packed, void *stream);
 int gc_double_conv(const float *x, int total_agents, int c_in, int H, int W, int stride, int c_out, const void *packed,
                    const float *bias, void *workspace, float *out, void *stream);
+/* the same layer over channel-last planes (gc_to_planes / gc_conv_planes outputs, [A][H*W][c_in]): what the shrink header
+ * runs when the backbone hands its deblock outputs over as planes instead of NCHW fp32 (no layout conversion in between) */
+size_t gc_double_conv_planes_workspace_bytes(int total_agents, int H, int W, int stride, int c_out);
+int gc_double_conv_planes(const void *xh, const void *xl, int total_agents, int c_in, int H, int W, int stride, int c_out,
+                          const void *packed, const float *bias, void *workspace, float *out, void *stream);
 size_t gc_det_heads_packed_bytes(int C, int n_out);
 size_t gc_det_heads_workspace_bytes(int n_frames, int C, int H, int W);
 int gc_det_heads_pack(const float *w, int C, int n_out, void *packed, void *stream);
@@ -259,9 +264,9 @@ int gc_det_heads(const float *x, int n_frames, int C, int H, int W, int n_out, c
  *   gc_to_planes   x [A][C][HW] f32 -> channel-last bf16 value + residual planes (2 x A*HW*C*2 bytes), C % 64 == 0
  *   gc_conv_pack   w [n_out][c_in][taps] f32 (taps = 9: 3x3, row-major ky,kx; taps = 1: 1x1; BatchNorm already folded)
  *   gc_conv_planes ReLU(conv(planes) + bias): 3x3 with padding 1 and stride 1|2, or 1x1; written as the next layer's
- *                  planes (oh, ol: [A][Ho*Wo][out_ch_total] bf16, channels out_ch_off..) or as NCHW fp32 out_nchw
- *                  [A][out_ch_total][Ho*up][Wo*up] at pixel (y*up + up_dy, x*up + up_dx) -- one phase of a
- *                  ConvTranspose2d whose kernel equals its stride `up` (up = 1: an ordinary NCHW store).
+ *                  planes (oh, ol: [A][Ho*up*Wo*up][out_ch_total] bf16, channels out_ch_off..) or as NCHW fp32 out_nchw
+ *                  [A][out_ch_total][Ho*up][Wo*up], in both cases at pixel (y*up + up_dy, x*up + up_dx) -- one phase of
+ *                  a ConvTranspose2d whose kernel equals its stride `up` (up = 1: an ordinary store).
  *   Output H*W must be a multiple of 128; n_out <= 256.  bf16x3 tcgen05 GEMMs (fp32-grade).
  * ------------------------------------------------------------------------------------------- */
 size_t gc_conv_packed_bytes(int taps, int c_in, int n_out);

@@ -58,3 +58,29 @@ def test_backbone_refuses_training_mode():
     m = BaseBEVBackbone(BACKBONE_CFG, 64).to(DEV).train()
     with pytest.raises(RuntimeError, match="inference-only"):
         m({"spatial_features": torch.zeros(1, 64, 64, 128, device=DEV)})
+
+
+def test_plane_handover_to_shrink_header_is_bit_identical():
+    """BaseBEVBackbone(emit_planes) -> DownsampleConv over the channel-last planes (deblock phases written pixel-shuffled into
+    the planes, DoubleConv without the NCHW fp32 round trip) returns exactly what the NCHW hand-over returns: the value /
+    residual split of an fp32 activation is the same function in the layout-conversion kernel and in the conv epilogue."""
+    from gencomm_b200 import DownsampleConv, ops
+    torch.manual_seed(9)
+    cfg = {"layer_nums": [3, 5, 8], "layer_strides": [2, 2, 2], "num_filters": [64, 128, 256],
+           "upsample_strides": [1, 2, 4], "num_upsample_filter": [128, 128, 128]}
+    bb = BaseBEVBackbone(cfg, 64).eval()
+    _randomise_bn(bb)
+    bb = bb.to(DEV)
+    x = synth.bev_features(78, 2, 64, 128, 256, sparsity=0.7).to(DEV)
+    for stride in (2, 1):
+        sh = DownsampleConv({"kernal_size": [3], "stride": [stride], "padding": [1], "dim": [128], "input_dim": 384}).to(DEV).eval()
+        nchw = bb({"spatial_features": x})["spatial_features_2d"]
+        want = sh(nchw)
+        bb.emit_planes = True
+        try:
+            feat = bb({"spatial_features": x})["spatial_features_2d"]
+        finally:
+            bb.emit_planes = False
+        assert isinstance(feat, ops.PlaneFeature) and feat.shape == tuple(nchw.shape)
+        got = sh(feat)
+        assert got.shape == want.shape and torch.equal(got, want), float((got - want).abs().max())
