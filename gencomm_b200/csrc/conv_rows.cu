@@ -45,11 +45,6 @@ __host__ __device__ constexpr int a_stage_bytes(int R) { return 2 * plane_bytes(
 __host__ __device__ constexpr int b_stage_bytes(int NOUT) { return 2 * kSc * NOUT * 2; }   // hi plane, lo plane (k_me_pack, split)
 __host__ __device__ constexpr int smem_bytes(int NOUT, int R, int NB) { return 2 * a_stage_bytes(R) + NB * b_stage_bytes(NOUT); }
 
-__device__ __forceinline__ bool elect_one() {
-    uint32_t p;
-    asm volatile("{\n\t.reg .pred pe;\n\telect.sync _|pe, 0xffffffff;\n\tselp.u32 %0, 1, 0, pe;\n\t}" : "=r"(p));
-    return p != 0;
-}
 // 16-byte asynchronous copy global -> shared; bytes == 0 writes zeros (the source address must still be valid)
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, uint32_t bytes) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");

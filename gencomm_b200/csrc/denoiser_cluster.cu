@@ -186,11 +186,6 @@ __device__ __forceinline__ void st_async4(uint32_t remote_addr, float4 v, uint32
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ bool elect_one() {
-    uint32_t p;
-    asm volatile("{\n\t.reg .pred pe;\n\telect.sync _|pe, 0xffffffff;\n\tselp.u32 %0, 1, 0, pe;\n\t}" : "=r"(p));
-    return p != 0;
-}
 // Issued inside an `if (elect_one())` branch of a converged warp with operands derived from kernel parameters, constants
 // and loop counters only: ptxas then keeps the descriptors in uniform registers (UIADD3 + UTCHMMA, 3 instructions per MMA).
 // Predicating every MMA on its own elect.sync, or branching on tid == 0, costs 5 R2UR per MMA (~100 cycles each measured).

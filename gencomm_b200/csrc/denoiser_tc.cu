@@ -158,7 +158,7 @@ k_conv_out_tc(const float *__restrict__ in, const float *__restrict__ st_in, int
     tc_fence_after();
     const uint32_t tmem = s_tmem;
 
-    if (tid == 0) {
+    if (leader_of_warp0()) {
         constexpr uint32_t idesc = make_idesc(128, NT);
 #pragma unroll
         for (int j = 0; j < 6; ++j) {   // K = 16 slices: row ky = j/2, taps kx = 2*(j%2), 2*(j%2)+1
@@ -287,7 +287,7 @@ k_conv_in_tc(const float *__restrict__ cond, const float *__restrict__ x, const 
         fence_async_smem();
         tc_fence_before();
         __syncthreads();
-        if (tid == 0) {
+        if (leader_of_warp0()) {
             tc_fence_after();
             const uint32_t a_buf = a_base + (uint32_t)b * kBufBytes;
 #pragma unroll 1
@@ -664,7 +664,7 @@ k_conv_c8_tc(const float *__restrict__ in_a, const float *__restrict__ in_b, con
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = s_tmem;
-    if (tid == 0) {
+    if (leader_of_warp0()) {
         constexpr uint32_t idesc = make_idesc_tf32(128, 16);
         constexpr uint32_t kPlaneBytes = kMidPlaneU4 * 16u;
         const uint32_t a_base = smem_u32(a_s), b_base = smem_u32(b_s);

@@ -157,7 +157,8 @@ k_me_conv(const uint4 *__restrict__ xh, const uint4 *__restrict__ xl, const floa
     __shared__ __align__(16) int4 s_o[kPix];      // pixel index (y*W + x) of the four bilinear corners of the tap
     __shared__ __align__(16) float4 s_w[kPix];    // their weights (0 for a corner outside the image)
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform for the role branches
     const int agent = blockIdx.y, tile = blockIdx.x;
     const int HW = H * W;
     const int chunks = c_in / SC, stages = TAPS * chunks;
@@ -186,8 +187,8 @@ k_me_conv(const uint4 *__restrict__ xh, const uint4 *__restrict__ xl, const floa
         static_assert(SC == 32, "the plain path stages 32 channels (4 groups) per stage");
         constexpr uint32_t kBPlane = SC * NOUT * 2;
         if (warp == kThreads / 32) {
-            // feeder warp (one lane): B(s+1) bulk copy as soon as its buffer is free, then the MMAs of stage s
-            if (lane == 0) {
+            // feeder warp (one elected lane): B(s+1) bulk copy as soon as its buffer is free, then the MMAs of stage s
+            if (elect_one()) {
                 bulk_load(smem_u32(b_s), wp, kBBytes, smem_u32(&s_full[0]));
                 for (int s = 0; s < stages; ++s) {
                     const int b = s & 1;
@@ -379,7 +380,7 @@ k_me_conv(const uint4 *__restrict__ xh, const uint4 *__restrict__ xl, const floa
         fence_async_smem();
         tc_fence_before();
         __syncthreads();
-        if (tid == 0) {
+        if (warp == 0 && elect_one()) {
             if (kBulkB) mbar_wait(smem_u32(&s_full[b]), (uint32_t)(s >> 1) & 1u);   // the stage's weights have landed
             tc_fence_after();
             const uint32_t a_buf = a_base + (uint32_t)b * kAStage, b_buf = b_base + (uint32_t)b * kBBytes;

@@ -122,7 +122,7 @@ k_me_offset_row3(const uint4 *__restrict__ xh, const uint4 *__restrict__ xl, con
         fence_async_smem();
         tc_fence_before();
         __syncthreads();
-        if (tid == 0) {
+        if (leader_of_warp0()) {
             tc_fence_after();
             const uint32_t a_addr = s_base + (uint32_t)b * kR3Stage, b_addr = a_addr + 2u * kR3Plane;
 #pragma unroll
@@ -320,7 +320,7 @@ k_me_tail_tc(const float *__restrict__ b1, const float *__restrict__ attn, const
     tc_fence_before();
     __syncthreads();
     const uint32_t tmem = s_tmem;
-    if (tid == 0) {
+    if (leader_of_warp0()) {
         tc_fence_after();
         constexpr uint32_t idesc = make_idesc(128, 64);
         const uint32_t ah = smem_u32(a_hi), al = smem_u32(a_lo), bh = smem_u32(b_hi), bl = smem_u32(b_lo);

@@ -33,6 +33,17 @@ __device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
         "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// One lane of a converged warp.  MMA issue code belongs inside `if (elect_one())` (or leader_of_warp0()): ptxas then keeps the
+// descriptors in uniform registers and emits back-to-back UTCHMMA.  `if (tid == 0)` / `if (lane == 0)` instead wraps every
+// tcgen05 instruction in an ELECT / BRA.U.ANY waterfall loop (~100 cycles per MMA, profiles/r02z_mma_issue.txt).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t p;
+    asm volatile("{\n\t.reg .pred pe;\n\telect.sync _|pe, 0xffffffff;\n\tselp.u32 %0, 1, 0, pe;\n\t}" : "=r"(p));
+    return p != 0;
+}
+__device__ __forceinline__ bool leader_of_warp0() {   // 1-D blocks; every lane of warp 0 must reach the call
+    return __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0) == 0 && elect_one();
+}
 __device__ __forceinline__ void mma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }

@@ -1,0 +1,5 @@
+#!/bin/bash
+timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -5
+timeout 300 python scripts/bench_backbone.py --agents 32 2>&1 | tail -1
+GC_CONV_MT2=1 timeout 300 python scripts/bench_backbone.py --agents 32 2>&1 | tail -1
+timeout 300 python scripts/probe/post_anomaly.py 2>&1 | tail -4

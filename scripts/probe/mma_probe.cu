@@ -6,11 +6,6 @@
 #include "../../gencomm_b200/csrc/umma.cuh"
 using namespace gc::umma;
 
-__device__ __forceinline__ bool elect_one() {
-    uint32_t p;
-    asm volatile("{\n\t.reg .pred pe;\n\telect.sync _|pe, 0xffffffff;\n\tselp.u32 %0, 1, 0, pe;\n\t}" : "=r"(p));
-    return p != 0;
-}
 __device__ __forceinline__ uint64_t desc(uint32_t saddr, uint32_t lbo, uint32_t sbo, uint32_t layout) {
     return make_desc(saddr, lbo, sbo) | ((uint64_t)layout << 61);
 }
