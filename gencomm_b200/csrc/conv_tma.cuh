@@ -56,13 +56,14 @@ __device__ __forceinline__ void bulk_copy(uint32_t dst, const void *src, uint32_
 // K-major SWIZZLE_64B operand: rows of 64 bytes, 8-row groups 512 bytes apart (LBO unused), layout type 4 in bits 61-63
 __device__ __forceinline__ uint64_t make_desc_sw64(uint32_t saddr) { return make_desc(saddr, 16u, 512u) | (4ull << 61); }
 
-// H x W: the map (stride 1: input grid = output grid); tiles of BH rows x BW pixels, BW = min(W, 128), BH = 128 / BW.
+// H x W: the output grid; tiles of BH rows x BW pixels, BW = min(W, 128), BH = 128 / BW.  stride 2: the tensor maps traverse the
+// input with element strides {1, 2, 2, 1} (box {32, 2 BW, 2 BH, 1} -> BW x BH pixels in shared memory), start (2 x0 + kx - 1, ..).
 // EPI as in k_me_conv: 0 bias, 1 bias + GELU, 3 bias + ReLU -> fp32 [A][out_ch_total][H*up][W*up] at (y*up + up_dy, x*up + up_dx);
 // 2 bias + GELU -> fp32 channel-last [A][HW][out_ch_total]; 5 bias + ReLU -> bf16 value + residual planes [A][HW*up*up][out_ch_total]
 template <int NOUT, int TAPS, int EPI>
 __global__ void __launch_bounds__(kThreads, 1)
 k_conv_tma(const __grid_constant__ CUtensorMap map_h, const __grid_constant__ CUtensorMap map_l, const uint4 *__restrict__ wp,
-           const float *__restrict__ bias, int n_tiles, int c_in, int H, int W, int BW, int n_store, int out_ch_total, int out_ch_off,
+           const float *__restrict__ bias, int n_tiles, int c_in, int H, int W, int BW, int stride, int n_store, int out_ch_total, int out_ch_off,
            float *__restrict__ out, uint4 *__restrict__ oh, uint4 *__restrict__ ol, int up, int up_dy, int up_dx) {
     constexpr int NS = ring_depth(NOUT);
     constexpr int kBStage = b_stage_bytes(NOUT), kBPlane = kSc * NOUT * 2;
@@ -135,8 +136,8 @@ k_conv_tma(const __grid_constant__ CUtensorMap map_h, const __grid_constant__ CU
                     const int ky = TAPS == 1 ? 1 : tap / 3, kx = TAPS == 1 ? 1 : tap - 3 * ky;
                     const uint32_t bar = smem_u32(&full[sb]), a_dst = a_base + (uint32_t)sb * kAStage;
                     mbar_expect_tx(bar, (uint32_t)(kAStage + kBStage));
-                    tma_load_4d(a_dst, &map_h, chunk * kSc, x0 + kx - 1, y0 + ky - 1, agent, bar);
-                    tma_load_4d(a_dst + kAPlane, &map_l, chunk * kSc, x0 + kx - 1, y0 + ky - 1, agent, bar);
+                    tma_load_4d(a_dst, &map_h, chunk * kSc, x0 * stride + kx - 1, y0 * stride + ky - 1, agent, bar);
+                    tma_load_4d(a_dst + kAPlane, &map_l, chunk * kSc, x0 * stride + kx - 1, y0 * stride + ky - 1, agent, bar);
                     bulk_copy(b_base + (uint32_t)sb * kBStage, wp + (size_t)s * (kBStage / 16), kBStage, bar);
                 }
             }
@@ -217,24 +218,25 @@ inline PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
     }
     return fn;
 }
-// planes [A][H][W][C] bf16 as the 4-D tensor (C, W, H, A); box = {32 channels, BW, BH, 1}, 64-byte swizzle, zero fill outside
-inline bool encode_plane_map(CUtensorMap *map, const void *plane, int A, int H, int W, int C, int BW, int BH) {
+// planes [A][H][W][C] bf16 as the 4-D tensor (C, W, H, A); box = {32 channels, BW, BH, 1} output pixels, 64-byte swizzle, zero fill
+// outside; H x W is the INPUT grid, every stride-th pixel is loaded
+inline bool encode_plane_map(CUtensorMap *map, const void *plane, int A, int H, int W, int C, int BW, int BH, int stride) {
     PFN_cuTensorMapEncodeTiled_v12000 encode = get_encode();
     if (!encode) return false;
     const cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)A};
     const cuuint64_t gstride[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
-    const cuuint32_t box[4] = {(cuuint32_t)kSc, (cuuint32_t)BW, (cuuint32_t)BH, 1};
-    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    const cuuint32_t box[4] = {(cuuint32_t)kSc, (cuuint32_t)(BW * stride), (cuuint32_t)(BH * stride), 1};
+    const cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
     return encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void *>(plane), gdim, gstride, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-// stride-1 layers whose map tiles into BH x BW = 128-pixel boxes; GC_CONV_TMA=0 disables (A/B against k_me_conv)
+// layers whose output map tiles into BH x BW = 128-pixel boxes; GC_CONV_TMA=0 disables, =1 restricts to stride 1 (A/B)
 inline bool conv_tma_eligible(int stride, int C, int c_in, int H, int W, int up) {
     static int on = -1;
-    if (on < 0) { const char *e = getenv("GC_CONV_TMA"); on = (e && e[0] == '0') ? 0 : 1; }
-    if (!on || stride != 1 || C % 8 != 0 || c_in % kSc != 0 || c_in > C) return false;
+    if (on < 0) { const char *e = getenv("GC_CONV_TMA"); on = e ? atoi(e) : 2; }
+    if (!on || (stride != 1 && !(stride == 2 && on >= 2)) || C % 8 != 0 || c_in % kSc != 0 || c_in > C) return false;
     const int BW = W < 128 ? W : 128;
     if (BW < 8 || (BW & (BW - 1)) != 0 || W % BW != 0) return false;
     return H % (128 / BW) == 0 && up >= 1;
@@ -242,8 +244,8 @@ inline bool conv_tma_eligible(int stride, int C, int c_in, int H, int W, int up)
 
 template <int NOUT, int TAPS, int EPI>
 static int launch_conv_tma(cudaStream_t st, int A, const uint4 *xh, const uint4 *xl, const uint4 *wp, const float *bias, int C, int c_in,
-                           int H, int W, int n_store, int out_ch_total, int out_ch_off, float *out, uint4 *oh, uint4 *ol, int up,
-                           int up_dy, int up_dx) {
+                           int H, int W, int H_in, int W_in, int stride, int n_store, int out_ch_total, int out_ch_off, float *out,
+                           uint4 *oh, uint4 *ol, int up, int up_dy, int up_dx) {
     constexpr int kSmem = smem_bytes(NOUT);
     static_assert(kSmem <= 227 * 1024, "k_conv_tma: shared memory");
     static int sms = 0;
@@ -261,12 +263,13 @@ static int launch_conv_tma(cudaStream_t st, int A, const uint4 *xh, const uint4 
     }
     const int BW = W < 128 ? W : 128, BH = 128 / BW;
     CUtensorMap mh, ml;
-    if (!encode_plane_map(&mh, xh, A, H, W, C, BW, BH) || !encode_plane_map(&ml, xl, A, H, W, C, BW, BH)) {
-        set_error("k_conv_tma: cuTensorMapEncodeTiled failed (A=%d H=%d W=%d C=%d)", A, H, W, C);
+    const int Hi = H_in > 0 ? H_in : H, Wi = W_in > 0 ? W_in : W;
+    if (!encode_plane_map(&mh, xh, A, Hi, Wi, C, BW, BH, stride) || !encode_plane_map(&ml, xl, A, Hi, Wi, C, BW, BH, stride)) {
+        set_error("k_conv_tma: cuTensorMapEncodeTiled failed (A=%d H=%d W=%d C=%d stride=%d)", A, Hi, Wi, C, stride);
         return (int)cudaErrorInvalidValue;
     }
     const int n_tiles = A * (H * W / me::kPix);
-    k_conv_tma<NOUT, TAPS, EPI><<<n_tiles < sms ? n_tiles : sms, kThreads, kSmem, st>>>(mh, ml, wp, bias, n_tiles, c_in, H, W, BW, n_store,
+    k_conv_tma<NOUT, TAPS, EPI><<<n_tiles < sms ? n_tiles : sms, kThreads, kSmem, st>>>(mh, ml, wp, bias, n_tiles, c_in, H, W, BW, stride, n_store,
                                                                                        out_ch_total, out_ch_off, out, oh, ol, up, up_dy, up_dx);
     GC_LAUNCH_CHECK("k_conv_tma");
     return GC_OK;

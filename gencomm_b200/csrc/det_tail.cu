@@ -25,8 +25,8 @@ template <int NOUT, int TAPS, int EPI>
 static int launch(cudaStream_t st, dim3 grid, const uint4 *xh, const uint4 *xl, const uint4 *wp, const float *bias, int C, int H,
                   int W, int n_store, float *out, int H_in, int W_in, int stride) {
     if (ct::conv_tma_eligible(stride, C, C, H, W, 1))
-        return ct::launch_conv_tma<NOUT, TAPS, EPI>(st, (int)grid.y, xh, xl, wp, bias, C, C, H, W, n_store, n_store, 0, out, nullptr,
-                                                    nullptr, 1, 0, 0);
+        return ct::launch_conv_tma<NOUT, TAPS, EPI>(st, (int)grid.y, xh, xl, wp, bias, C, C, H, W, H_in, W_in, stride, n_store, n_store, 0,
+                                                    out, nullptr, nullptr, 1, 0, 0);
     constexpr int kSmem = conv_smem_bytes(NOUT, true, kSc);
     static bool done = false;
     if (!done) {
@@ -193,8 +193,8 @@ static int launch_layer_mt(cudaStream_t st, dim3 grid, const uint4 *xh, const ui
                            int Ho, int Wo, int n_out, int out_total, int out_off, float *out, uint4 *oh, uint4 *ol, int H_in,
                            int W_in, int stride, int up, int up_dy, int up_dx) {
     if (MT == 1 && ct::conv_tma_eligible(stride, C, C, Ho, Wo, up))
-        return ct::launch_conv_tma<NOUT, TAPS, EPI>(st, (int)grid.y, xh, xl, wp, bias, C, C, Ho, Wo, n_out, out_total, out_off, out, oh, ol,
-                                                    up, up_dy, up_dx);
+        return ct::launch_conv_tma<NOUT, TAPS, EPI>(st, (int)grid.y, xh, xl, wp, bias, C, C, Ho, Wo, H_in, W_in, stride, n_out, out_total,
+                                                    out_off, out, oh, ol, up, up_dy, up_dx);
     constexpr int kSmem = conv_smem_bytes(NOUT, true, kSc, MT);
     static bool done = false;
     if (!done) {
