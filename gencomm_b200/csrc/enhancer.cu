@@ -22,6 +22,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "conv_tma.cuh"
 #include "implicit_gemm.cuh"
 
 namespace gc {
@@ -265,6 +266,9 @@ static inline size_t pk_total(int C) { return pk_lin2_off(C) + (size_t)(C / 128)
 template <int NOUT, int TAPS, int EPI>
 static int launch_conv(cudaStream_t st, dim3 grid, const uint4 *xh, const uint4 *xl, const uint4 *wp, const float *bias, int C,
                        int c_in, int H, int W, int n_store, int out_total, int out_off, float *out) {
+    if (ct::conv_tma_eligible(1, C, c_in, H, W, 1))      // TMA-fed persistent kernel (conv_tma.cuh), bit-identical results
+        return ct::launch_conv_tma<NOUT, TAPS, EPI>(st, (int)grid.y, xh, xl, wp, bias, C, c_in, H, W, H, W, 1, n_store, out_total, out_off,
+                                                    out, nullptr, nullptr, 1, 0, 0);
     constexpr int kSmem = conv_smem_bytes(NOUT, true, kSc);
     static bool done = false;
     if (!done) {
