@@ -1,0 +1,5 @@
+#!/bin/bash
+timeout 240 python -m pytest tests/test_backbone_gpu.py tests/test_det_tail_gpu.py -m gpu -x -q 2>&1 | tail -8
+timeout 120 python scripts/bench_backbone.py --agents 32 2>&1 | tail -1
+GC_CONV_MC=0 timeout 120 python scripts/bench_backbone.py --agents 32 2>&1 | tail -1
+timeout 200 bash scripts/gpu_r2ac.sh
