@@ -93,10 +93,15 @@ class BaseBEVBackbone(nn.Module):
     def forward(self, data_dict):
         if self.training:
             raise RuntimeError("gencomm_b200 BaseBEVBackbone is inference-only (BatchNorm is folded): call .eval()")
-        x = data_dict['spatial_features'].contiguous()
-        A, C, H, W = x.shape
+        x = data_dict['spatial_features']
         levels = self._pack()
-        planes, h, w = ops.to_planes(x), H, W
+        if isinstance(x, ops.PlaneFeature):      # handed over by this package's PointPillar (emit_planes)
+            (A, C, H, W), planes = x.shape, (x.xh, x.xl)
+        else:
+            x = x.contiguous()
+            A, C, H, W = x.shape
+            planes = ops.to_planes(x)
+        h, w = H, W
         out, ch_off, C_out = None, 0, self.num_bev_features
         for (convs, phases, up_bias, up_out, up_in), up in zip(levels, self._ups):
             c_in = None

@@ -30,11 +30,13 @@ constexpr int kThreads = kStagers + kEpi + 32;   // warp 12 feeds the tensor cor
 constexpr int kRowPx = 130;       // staged pixels per row: x0 - 1 .. x0 + 128
 constexpr int kSc = 32;           // channels per chunk (4 groups of 8 = two K = 16 MMAs per plane pair)
 
-#ifdef CR_TRACE                   // scripts/probe/conv_rows_trace.cu: clock64 timeline of CTA 8
-__device__ long long g_trace[64];
-#define CR_T(i) do { if (blockIdx.x == 8 && (i) < 64) g_trace[i] = clock64(); } while (0)
+#ifdef CR_TRACE                   // scripts/probe/conv_rows_trace.cu: where CTA 8's roles wait
+__device__ long long g_trace[16];
+#define CR_ACC(i, expr) do { const long long t__ = clock64(); expr; if (blockIdx.x == 8) g_trace[i] += clock64() - t__; } while (0)
+#define CR_SET(i, v) do { if (blockIdx.x == 8) g_trace[i] = (v); } while (0)
 #else
-#define CR_T(i) do { } while (0)
+#define CR_ACC(i, expr) do { expr; } while (0)
+#define CR_SET(i, v) do { } while (0)
 #endif
 
 // [plane hi|lo][group 4][row R+2][130 px][16 B]; the group stride is padded by 16 bytes so that the four groups of a pixel
@@ -92,7 +94,7 @@ k_conv_rows(const uint4 *__restrict__ xh, const uint4 *__restrict__ xl, const ui
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = s_tmem;
-    if (tid == 0) CR_T(0);
+    const long long t_begin = clock64();
 
     if (warp == (kStagers + kEpi) / 32) {
         // ---- feeder: one elected lane streams the weights and issues every MMA ----
@@ -109,18 +111,17 @@ k_conv_rows(const uint4 *__restrict__ xh, const uint4 *__restrict__ xl, const ui
             int s = 0, g = 0;
             for (int k = 0; k < my_tiles; ++k) {
                 const int set = k & 1;
-                if (k >= 2) { mbar_wait(smem_u32(&acc_empty[set]), (uint32_t)((k >> 1) - 1) & 1u); tc_fence_after(); }
+                if (k >= 2) { CR_ACC(1, mbar_wait(smem_u32(&acc_empty[set]), (uint32_t)((k >> 1) - 1) & 1u)); tc_fence_after(); }
                 const uint32_t acc0 = tmem + (uint32_t)(set * kSet);
                 for (int c = 0; c < chunks; ++c, ++g) {
                     const int ab = g & 1;
-                    mbar_wait(smem_u32(&a_full[ab]), (uint32_t)(g >> 1) & 1u);
+                    CR_ACC(0, mbar_wait(smem_u32(&a_full[ab]), (uint32_t)(g >> 1) & 1u));
                     tc_fence_after();
-                    CR_T(16 + 2 * g);
                     const uint64_t a_desc0 = make_desc(a_base + (uint32_t)ab * kAStage, (uint32_t)kGroup, 128u);
 #pragma unroll 1
                     for (int tap = 0; tap < 9; ++tap, ++s) {
                         const int ky = tap / 3, kx = tap - 3 * ky, nb = s % NB;
-                        mbar_wait(smem_u32(&b_full[nb]), (uint32_t)(s / NB) & 1u);
+                        CR_ACC(2, mbar_wait(smem_u32(&b_full[nb]), (uint32_t)(s / NB) & 1u));
                         const uint64_t b_desc0 = make_desc(b_base + (uint32_t)nb * kBStage, NOUT * 16u, 128u);
                         const uint64_t a_tap = a_desc0 + (uint64_t)(ky * kRowPx + kx);
                         const uint32_t first = (c > 0 || tap > 0) ? 1u : 0u;
@@ -143,12 +144,11 @@ k_conv_rows(const uint4 *__restrict__ xh, const uint4 *__restrict__ xl, const ui
                         // refill the buffer the PREVIOUS step used (its MMAs retire while this step's execute)
                         if (s >= 1 && s - 1 + NB < total) {
                             const int pb = (s - 1) % NB;
-                            mbar_wait(smem_u32(&b_empty[pb]), (uint32_t)((s - 1) / NB) & 1u);
+                            CR_ACC(3, mbar_wait(smem_u32(&b_empty[pb]), (uint32_t)((s - 1) / NB) & 1u));
                             load_b(s - 1 + NB);
                         }
                     }
                     mma_commit(smem_u32(&a_empty[ab]));
-                    CR_T(17 + 2 * g);
                 }
                 mma_commit(smem_u32(&acc_full[set]));
             }
@@ -166,7 +166,10 @@ k_conv_rows(const uint4 *__restrict__ xh, const uint4 *__restrict__ xl, const ui
             const uint4 *src_plane[2] = {xh + (size_t)agent * HW * C8, xl + (size_t)agent * HW * C8};
             for (int c = 0; c < chunks; ++c, ++g) {
                 const int ab = g & 1;
-                if (g >= 2) mbar_wait(smem_u32(&a_empty[ab]), (uint32_t)((g >> 1) - 1) & 1u);   // MMAs of chunk g - 2 retired
+                if (g >= 2) {   // MMAs of chunk g - 2 retired
+                    if (tid == 0) CR_ACC(4, mbar_wait(smem_u32(&a_empty[ab]), (uint32_t)((g >> 1) - 1) & 1u));
+                    else mbar_wait(smem_u32(&a_empty[ab]), (uint32_t)((g >> 1) - 1) & 1u);
+                }
                 const uint32_t dst = a_base + (uint32_t)ab * kAStage;
 #pragma unroll 5
                 for (int k = 0; k < kIters; ++k) {
@@ -183,7 +186,6 @@ k_conv_rows(const uint4 *__restrict__ xh, const uint4 *__restrict__ xl, const ui
                 cp_async_wait_all();
                 fence_async_smem();
                 mbar_arrive(smem_u32(&a_full[ab]));
-                if (tid == 0) CR_T(1 + g);
             }
         }
     } else {
@@ -196,7 +198,6 @@ k_conv_rows(const uint4 *__restrict__ xh, const uint4 *__restrict__ xl, const ui
             const int set = k & 1;
             mbar_wait(smem_u32(&acc_full[set]), (uint32_t)(k >> 1) & 1u);
             tc_fence_after();
-            if (tid == kStagers) CR_T(40 + 2 * k);
 #pragma unroll 1
             for (int r = 0; r < R; ++r) {
                 const size_t p_out = (size_t)(y0 + r) * W + x;
@@ -228,11 +229,11 @@ k_conv_rows(const uint4 *__restrict__ xh, const uint4 *__restrict__ xl, const ui
             }
             tc_fence_before();
             mbar_arrive(smem_u32(&acc_empty[set]));
-            if (tid == kStagers) CR_T(41 + 2 * k);
         }
     }
     tc_fence_before();
     __syncthreads();
+    if (tid == 0) CR_SET(5, clock64() - t_begin);
     if (warp == 0) tmem_free<512>(tmem);
 }
 

@@ -20,6 +20,8 @@
 //      pair, loop over the <=32 valid points only) and stores every canvas byte exactly once with
 //      128-bit coalesced stores.  No memset, no pillar_features round trip.
 // All of it is HBM-bound integer/byte work + ~1 kFLOP per pillar; no tensor cores.
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 #include <cuda.h>
@@ -502,6 +504,103 @@ k_canvas(Src src, int nx, int ny, int C, float *__restrict__ canvas) {
             }
         }
         __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// 4a'. the same canvas written as channel-last bf16 value + residual planes ([A][ny*nx][64] each): the operand layout of the
+// backbone's tensor-core convolutions.  When PointPillar feeds this package's BaseBEVBackbone the fp32 NCHW canvas (1.07 GB
+// for 32 agents at 512 x 256) is never written and never converted (k_me_to_nhwc: 1.07 GB read + 1.07 GB written).  Same
+// values: the planes are bf16(x) and bf16(x - bf16(x)) of the fp32 feature k_canvas would have stored.
+// The tile is kept pixel-major in shared memory; a pixel's 64 channels are 128 contiguous bytes per plane and the 128 pixels
+// of the tile are contiguous in global memory, so every store instruction writes 512 contiguous bytes.
+// ------------------------------------------------------------------------------------------------
+constexpr int kPlaneTileStride = GC_PFN_OUT + 4;   // floats per pixel row of the tile (16-byte aligned, bank-skewed)
+
+__global__ void __launch_bounds__(256, 4)
+k_canvas_planes(FusedSrc src, int nx, int ny, uint4 *__restrict__ xh, uint4 *__restrict__ xl) {
+    __shared__ __align__(16) float tile[kTileX * kPlaneTileStride];
+    __shared__ int s_code[kTileX];
+    __shared__ int s_list[kTileX];
+    __shared__ unsigned s_mask[4];
+    __shared__ float4 s_stage[8][32];   // per-warp point exchange of pfn_pillar
+
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int x0 = blockIdx.x * kTileX, y = blockIdx.y, b = blockIdx.z;
+    const int ncell = nx * ny;
+
+    if (t < kTileX) {
+        const int x = x0 + t;
+        const int code = (x < nx) ? src.code(b, y * nx + x, ncell) : -1;
+        const bool occ = (x < nx) && FusedSrc::occupied(code);
+        s_code[t] = code;
+        const unsigned bal = __ballot_sync(0xffffffffu, occ);
+        if (lane == 0) s_mask[warp] = bal;
+    }
+    {
+        float4 *t4 = reinterpret_cast<float4 *>(tile);
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = t; i < kTileX * kPlaneTileStride / 4; i += 256) t4[i] = z;
+    }
+    __syncthreads();
+    const unsigned m0 = s_mask[0], m1 = s_mask[1], m2 = s_mask[2], m3 = s_mask[3];
+    const int n_occ = __popc(m0) + __popc(m1) + __popc(m2) + __popc(m3);
+    if (t < kTileX) {
+        const unsigned mine = warp == 0 ? m0 : warp == 1 ? m1 : warp == 2 ? m2 : m3;
+        if ((mine >> lane) & 1u) {
+            int pos = __popc(mine & ((1u << lane) - 1u));
+            pos += (warp > 0 ? __popc(m0) : 0) + (warp > 1 ? __popc(m1) : 0) + (warp > 2 ? __popc(m2) : 0);
+            s_list[pos] = t;
+        }
+    }
+    __syncthreads();
+    if (warp < n_occ) {   // warp-uniform; one warp per occupied cell, the software pipeline of k_canvas<FusedSrc>
+        const FusedSrc &fs = src;
+        const PfnLane wa = load_pfn(fs.pfn, lane), wb = load_pfn(fs.pfn, lane + 32);
+        const int pbase = __ldg(fs.point_offsets + b);
+        const float cy = __fadd_rn(__fmul_rn((float)y, fs.vy), fs.oy);
+        auto slot_of = [&](int k) -> uint32_t {
+            const unsigned pid = (unsigned)s_code[s_list[k]] & ~kPillarBit;
+            return __ldg(fs.slots + ((size_t)b * fs.max_voxels + pid) * 32 + lane);
+        };
+        auto point_of = [&](uint32_t idx) -> float4 {
+            return idx != kEmpty ? __ldg(fs.points + pbase + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
+        };
+        uint32_t idx_cur = slot_of(warp);
+        uint32_t idx_nxt = (warp + 8 < n_occ) ? slot_of(warp + 8) : kEmpty;
+        float4 p_cur = point_of(idx_cur);
+        for (int k = warp; k < n_occ; k += 8) {
+            const float4 p_nxt = point_of(idx_nxt);
+            const uint32_t idx_nxt2 = (k + 16 < n_occ) ? slot_of(k + 16) : kEmpty;
+            const int xc = s_list[k];
+            const int n = __popc(__ballot_sync(0xffffffffu, idx_cur != kEmpty));   // slots fill from 0
+            const float cx = __fadd_rn(__fmul_rn((float)(x0 + xc), fs.vx), fs.ox);
+            const float2 r = pfn_pillar(wa, wb, p_cur, n, cx, cy, fs.cz, s_stage[warp]);
+            tile[xc * kPlaneTileStride + lane] = r.x;
+            tile[xc * kPlaneTileStride + lane + 32] = r.y;
+            idx_cur = idx_nxt; p_cur = p_nxt; idx_nxt = idx_nxt2;
+        }
+    }
+    __syncthreads();
+    // ---- store phase: item = (pixel, 8-channel group); eight lanes write one pixel's 128 bytes, a warp four pixels ----
+    const size_t row = ((size_t)b * ncell + (size_t)y * nx + x0) * (GC_PFN_OUT / 8);
+#pragma unroll
+    for (int it = 0; it < kTileX * (GC_PFN_OUT / 8) / 256; ++it) {
+        const int i = it * 256 + t, px = i / (GC_PFN_OUT / 8), g = i % (GC_PFN_OUT / 8);
+        if (x0 + px >= nx) continue;
+        const float4 a = *reinterpret_cast<const float4 *>(tile + px * kPlaneTileStride + g * 8);
+        const float4 c = *reinterpret_cast<const float4 *>(tile + px * kPlaneTileStride + g * 8 + 4);
+        const float v[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
+        uint32_t h[4], l[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const __nv_bfloat162 hh = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+            const __nv_bfloat162 ll = __floats2bfloat162_rn(v[2 * j] - __bfloat162float(hh.x), v[2 * j + 1] - __bfloat162float(hh.y));
+            h[j] = *reinterpret_cast<const uint32_t *>(&hh);
+            l[j] = *reinterpret_cast<const uint32_t *>(&ll);
+        }
+        xh[row + (size_t)i] = make_uint4(h[0], h[1], h[2], h[3]);
+        xl[row + (size_t)i] = make_uint4(l[0], l[1], l[2], l[3]);
     }
 }
 
@@ -1346,5 +1445,35 @@ extern "C" int gc_pillar_canvas(const float *points, const int32_t *point_offset
     k_canvas<FusedSrc><<<dim3((g.grid[0] + kTileX - 1) / kTileX, g.grid[1], n_agents), 256, 0,
                          (cudaStream_t)stream>>>(src, g.grid[0], g.grid[1], GC_PFN_OUT, canvas);
     GC_LAUNCH_CHECK("k_canvas<FusedSrc>");
+    return GC_OK;
+}
+
+// The fused front end with the canvas written as the backbone's operand planes (k_canvas_planes); same arguments as
+// gc_pillar_canvas, xh / xl: [n_agents][ny*nx][64] bf16 value / residual.
+extern "C" int gc_pillar_canvas_planes(const float *points, const int32_t *point_offsets, int n_agents, int total_points,
+                                       const gcVoxelGeom *geom, const void *workspace, const float *pfn,
+                                       const float centre_offset[3], void *xh, void *xl, void *stream) {
+    GeomDev g;
+    if (int rc = make_geom(geom, &g)) return rc;
+    GC_REQUIRE(g.grid[2] == 1, GC_EUNSUPPORTED, "PointPillarScatter requires nz == 1 (point_pillar_scatter.py:17)");
+    GC_REQUIRE(points && point_offsets && workspace && pfn && centre_offset && xh && xl, GC_EINVAL,
+               "gc_pillar_canvas_planes: null pointer");
+    GC_REQUIRE(n_agents > 0 && n_agents <= 65535 && g.grid[1] <= 65535, GC_EINVAL, "gc_pillar_canvas_planes: bad sizes");
+    const VoxelWorkspace w = carve_workspace(const_cast<void *>(workspace), *geom, n_agents, total_points);
+    FusedSrc src;
+    src.points = (const float4 *)points;
+    src.point_offsets = point_offsets;
+    src.cell_code = w.cell_code;
+    src.slots = w.slots;
+    src.pfn = pfn;
+    src.max_voxels = g.max_voxels;
+    src.vx = g.voxel[0];
+    src.vy = g.voxel[1];
+    src.ox = centre_offset[0];
+    src.oy = centre_offset[1];
+    src.cz = 0.0f * g.voxel[2] + centre_offset[2];
+    k_canvas_planes<<<dim3((g.grid[0] + kTileX - 1) / kTileX, g.grid[1], n_agents), 256, 0, (cudaStream_t)stream>>>(
+        src, g.grid[0], g.grid[1], (uint4 *)xh, (uint4 *)xl);
+    GC_LAUNCH_CHECK("k_canvas_planes");
     return GC_OK;
 }

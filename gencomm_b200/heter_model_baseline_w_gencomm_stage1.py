@@ -187,8 +187,17 @@ class HeterModelBaselineWGenComm(_HeadsMixin, nn.Module):
                 # the agent count is known on the host: spares PointPillarScatter's `.item()` sync (point_pillar_scatter.py:45)
                 data_dict = dict(data_dict)
                 data_dict[f'inputs_{m}'] = dict(inp, batch_size=counts[m])
-            feature = getattr(self, f"encoder_{m}")(data_dict, m)
-            backbone, shrinker = getattr(self, f"backbone_{m}"), getattr(self, f"shrinker_{m}")
+            encoder, backbone = getattr(self, f"encoder_{m}"), getattr(self, f"backbone_{m}")
+            shrinker = getattr(self, f"shrinker_{m}")
+            # raw points straight into this package's backbone: the canvas is written as its operand planes
+            planes_in = isinstance(encoder, PointPillar) and isinstance(backbone, BaseBEVBackbone) and 'points' in inp
+            try:
+                if planes_in:
+                    encoder.emit_planes = True
+                feature = encoder(data_dict, m)
+            finally:
+                if planes_in:
+                    encoder.emit_planes = False
             if not isinstance(backbone, nn.Identity):
                 # the shrink header follows directly: the deblocks write its operand planes, no NCHW fp32 round trip
                 fused = isinstance(backbone, BaseBEVBackbone) and isinstance(shrinker, DownsampleConv)

@@ -222,6 +222,9 @@ class PointPillar(nn.Module):
         self.lidar_range, self.voxel_size = args['lidar_range'], args['voxel_size']
         self.max_voxels = int(args.get('max_voxels', 70000))
         self._pre = None
+        # True: the raw-point path returns an ops.PlaneFeature (the backbone's operand planes) instead of the fp32 canvas --
+        # set by the model when this package's BaseBEVBackbone consumes the canvas directly
+        self.emit_planes = False
 
     def forward(self, data_dict, modality_name):
         inp = data_dict[f'inputs_{modality_name}']
@@ -245,6 +248,9 @@ class PointPillar(nn.Module):
             self._pre = SpVoxelPreprocessor(params, train=False, device=points.device)
         ws = self._pre.voxelize_device(points, point_offsets, max_agent_points)
         v = self.pillar_vfe
+        if self.emit_planes and out is None:
+            return ops.pillar_canvas_planes(points, point_offsets, ws, v.pfn_table(points.device),
+                                            (v.x_offset, v.y_offset, v.z_offset))
         return ops.pillar_canvas(points, point_offsets, ws, v.pfn_table(points.device),
                                  (v.x_offset, v.y_offset, v.z_offset), out=out)
 

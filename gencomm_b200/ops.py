@@ -179,6 +179,21 @@ def scatter_canvas(pillar_features, voxel_coords, nx, ny, n_batch, out=None, cel
     return out
 
 
+def pillar_canvas_planes(points, point_offsets, ws, pfn, centre_off):
+    """Voxelizer workspace -> BEV canvas as a PlaneFeature (channel-last bf16 value + residual planes, shape [A,64,ny,nx])."""
+    lib = _lib.load()
+    _chk(points, "points", torch.float32, 2)
+    _chk(point_offsets, "point_offsets", torch.int32, 1)
+    _chk(pfn, "pfn", torch.float32, 2)
+    g = ws.geom
+    xh = torch.empty(max(ws.n_agents * g.grid[1] * g.grid[0] * 64 * 2, 1), dtype=torch.uint8, device=points.device)
+    xl = torch.empty_like(xh)
+    _lib.check(lib.gc_pillar_canvas_planes(_ptr(points), _ptr(point_offsets), ws.n_agents, ws.total_points,
+                                           ctypes.byref(g), _ptr(ws.buf), _ptr(pfn), _lib.f3(centre_off), _ptr(xh), _ptr(xl),
+                                           _stream()), "gc_pillar_canvas_planes")
+    return PlaneFeature(xh, xl, (ws.n_agents, 64, g.grid[1], g.grid[0]))
+
+
 def pillar_canvas(points, point_offsets, ws, pfn, centre_off, out=None):
     """Voxelizer workspace -> BEV canvas [A,64,ny,nx] (PFN + scatter fused)."""
     lib = _lib.load()

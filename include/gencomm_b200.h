@@ -124,6 +124,11 @@ int gc_scatter_canvas(const float *pillar_features, const int32_t *coords, int n
 int gc_pillar_canvas(const float *points, const int32_t *point_offsets, int n_agents, int total_points,
                      const gcVoxelGeom *geom /*[host]*/, const void *workspace, const float *pfn,
                      const float centre_offset[3] /*[host]*/, float *canvas, void *stream);
+/* The same canvas as channel-last bf16 value + residual planes xh, xl [n_agents][ny*nx][64] (the operand layout of
+ * gc_conv_planes): what PointPillar hands to this package's BaseBEVBackbone -- no fp32 canvas, no gc_to_planes pass. */
+int gc_pillar_canvas_planes(const float *points, const int32_t *point_offsets, int n_agents, int total_points,
+                            const gcVoxelGeom *geom /*[host]*/, const void *workspace, const float *pfn,
+                            const float centre_offset[3] /*[host]*/, void *xh, void *xl, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
  * (a6)+(a7)+(a8)/(a9) regroup + warp_affine_simple + MaxFusion / AttFusion

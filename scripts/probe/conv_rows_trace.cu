@@ -1,4 +1,4 @@
-// clock64 timeline of one CTA of k_conv_rows at the backbone's level-1 / level-2 shapes (arbitrary operand contents).
+// where the roles of one CTA of k_conv_rows wait at the backbone's level-1 / level-2 shapes (arbitrary operand contents).
 #define CR_TRACE 1
 #include <cstdarg>
 #include <cstdio>
@@ -21,15 +21,12 @@ static void run(int A, int C, int NOUT, int H, int W) {
         if (rc || e != cudaSuccess) { printf("failed rc=%d %s\n", rc, cudaGetErrorString(e)); exit(1); }
     }
     float ms; cudaEventElapsedTime(&ms, e0, e1);
-    long long t[64];
+    long long t[16];
     cudaMemcpyFromSymbol(t, gc::cr::g_trace, sizeof(t));
-    printf("A=%d C=%d NOUT=%d %dx%d: %.1f us\n", A, C, NOUT, H, W, ms * 1e3f);
-    // 1 + g: chunk g staged; 16 + 2g / 17 + 2g: MMAs of chunk g start / issued; 40 + 2k / 41 + 2k: epilogue of tile k start / end
-    for (int g = 0; g < 12; ++g) if (t[1 + g]) printf("  chunk %2d staged   %8lld\n", g, t[1 + g] - t[0]);
-    for (int g = 0; g < 12; ++g) if (t[16 + 2 * g]) printf("  chunk %2d mma      %8lld .. %8lld\n", g, t[16 + 2 * g] - t[0], t[17 + 2 * g] - t[0]);
-    for (int k = 0; k < 12; ++k) if (t[40 + 2 * k]) printf("  tile  %2d epilogue %8lld .. %8lld\n", k, t[40 + 2 * k] - t[0], t[41 + 2 * k] - t[0]);
-    cudaMemset(nullptr, 0, 0);
-    { long long z[64] = {0}; cudaMemcpyToSymbol(gc::cr::g_trace, z, sizeof(z)); }
+    printf("A=%d C=%d NOUT=%d %dx%d: %.1f us | CTA 8 (last launch; counters accumulate over 3): %lld cycles; feeder waits: operand rows %lld, "
+           "accumulator %lld, weights %lld, weight slot %lld; stagers wait for a free operand buffer %lld\n", A, C, NOUT, H, W, ms * 1e3f, t[5],
+           t[0] / 3, t[1] / 3, t[2] / 3, t[3] / 3, t[4] / 3);
+    { long long z[16] = {0}; cudaMemcpyToSymbol(gc::cr::g_trace, z, sizeof(z)); }
     cudaFree(xh); cudaFree(xl); cudaFree(w); cudaFree(oh); cudaFree(ol); cudaFree(bias);
 }
 int main() {

@@ -161,6 +161,14 @@ def test_fused_front_end_full_size(rng, uniform, writer, monkeypatch):
     # size-independent property: occupied canvas cells == voxel coordinates
     occ = (canvas != 0).any(1).nonzero()
     assert occ.shape[0] <= batch["voxel_coords"].shape[0]
+    # the canvas written directly as the backbone's operand planes == the layout conversion of the fp32 canvas, bit for bit
+    if writer == "tile":
+        enc.emit_planes = True
+        feat = enc({"inputs_m1": {"points": pts, "point_offsets": off, "max_agent_points": max(sizes)}}, "m1")
+        enc.emit_planes = False
+        assert isinstance(feat, ops.PlaneFeature) and feat.shape == tuple(ref.shape)
+        xh, xl = ops.to_planes(ref.to(DEV))
+        assert torch.equal(feat.xh, xh) and torch.equal(feat.xl, xl)
 
 
 @pytest.mark.parametrize("writer", ["tile", "persist"])
