@@ -122,14 +122,21 @@ k_enh_dw_cl(const float *__restrict__ u, const float *__restrict__ prm, Prm L, i
 #pragma unroll
     for (int k = 0; k < 9; ++k) w[k] = *reinterpret_cast<const float4 *>(&s_dw[k][4 * q]);
     const float4 bias = *reinterpret_cast<const float4 *>(&s_dw[9][4 * q]);
-    float4 top[3], mid[3], bot[3];
+    // software pipeline: the three pixels of row r + 2 and the gate of row r + 1 are in flight while row r is computed (the
+    // first version issued the row loads at the top of the iteration and the gate load right before its use: two exposed
+    // memory latencies per row at 16 warps per SM -- FMUL / FFMA on just-loaded data took 57 % of the stall samples, 361 us)
+    auto gate = [&](int r) { return r < H ? __ldg(ub + (size_t)(r * W + x) * C + (C2 >> 2)) : z; };
+    float4 top[3], mid[3], bot[3], nxt[3];
     row3(r0 - 1, top);
     row3(r0, mid);
+    row3(r0 + 1, bot);
+    float4 g = gate(r0);
 #pragma unroll 1
     for (int i = 0; i < kDwRows; ++i) {
         const int r = r0 + i;
         if (r >= H) break;
-        row3(r + 1, bot);
+        row3(r + 2, nxt);
+        const float4 g_nxt = gate(r + 1);
         float4 acc = bias;   // tap order ky*3+kx like the reference weight layout
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
@@ -147,14 +154,14 @@ k_enh_dw_cl(const float *__restrict__ u, const float *__restrict__ prm, Prm L, i
             acc.z = fmaf(w[6 + k].z, bot[k].z, acc.z); acc.w = fmaf(w[6 + k].w, bot[k].w, acc.w);
         }
         const size_t pa = (size_t)a * HW + (size_t)r * W + x;
-        const float4 g = __ldg(ub + (size_t)(r * W + x) * C + (C2 >> 2));
         const float r0v = gelu_erf(acc.x) * g.x, r1v = gelu_erf(acc.y) * g.y, r2v = gelu_erf(acc.z) * g.z,
                     r3v = gelu_erf(acc.w) * g.w;
         const size_t o = pa * (C2 >> 2) + (c0 >> 2) + q;
         vh[o] = make_uint2(pack_bf16(r0v, r1v), pack_bf16(r2v, r3v));
         vl[o] = make_uint2(pack_bf16(bf16_residual(r0v), bf16_residual(r1v)), pack_bf16(bf16_residual(r2v), bf16_residual(r3v)));
 #pragma unroll
-        for (int k = 0; k < 3; ++k) { top[k] = mid[k]; mid[k] = bot[k]; }
+        for (int k = 0; k < 3; ++k) { top[k] = mid[k]; mid[k] = bot[k]; bot[k] = nxt[k]; }
+        g = g_nxt;
     }
 }
 

@@ -537,11 +537,8 @@ k_canvas_planes(FusedSrc src, int nx, int ny, uint4 *__restrict__ xh, uint4 *__r
         const unsigned bal = __ballot_sync(0xffffffffu, occ);
         if (lane == 0) s_mask[warp] = bal;
     }
-    {
-        float4 *t4 = reinterpret_cast<float4 *>(tile);
-        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int i = t; i < kTileX * kPlaneTileStride / 4; i += 256) t4[i] = z;
-    }
+    // (no zero fill of the tile: an occupied cell's 64 channels are all written by its warp, empty cells are stored as zeros
+    // straight from registers -- 84 % of the cells at 100 k points per 512 x 256 grid)
     __syncthreads();
     const unsigned m0 = s_mask[0], m1 = s_mask[1], m2 = s_mask[2], m3 = s_mask[3];
     const int n_occ = __popc(m0) + __popc(m1) + __popc(m2) + __popc(m3);
@@ -588,6 +585,11 @@ k_canvas_planes(FusedSrc src, int nx, int ny, uint4 *__restrict__ xh, uint4 *__r
     for (int it = 0; it < kTileX * (GC_PFN_OUT / 8) / 256; ++it) {
         const int i = it * 256 + t, px = i / (GC_PFN_OUT / 8), g = i % (GC_PFN_OUT / 8);
         if (x0 + px >= nx) continue;
+        if (!FusedSrc::occupied(s_code[px])) {
+            xh[row + (size_t)i] = make_uint4(0u, 0u, 0u, 0u);
+            xl[row + (size_t)i] = make_uint4(0u, 0u, 0u, 0u);
+            continue;
+        }
         const float4 a = *reinterpret_cast<const float4 *>(tile + px * kPlaneTileStride + g * 8);
         const float4 c = *reinterpret_cast<const float4 *>(tile + px * kPlaneTileStride + g * 8 + 4);
         const float v[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
