@@ -4,7 +4,7 @@
 
 namespace gc {
 
-// taps == 9, stride 1, W % 128 == 0, c_in % 32 == 0 and n_out in {64 (H % 4 == 0), 128 (H % 2 == 0)}; GC_CONV_ROWS=0 disables
+// taps == 9, stride 1, W % 128 == 0, c_in % 32 == 0 and n_out in {64 (H % 4 == 0), 128 (H % 2 == 0)}; GC_CONV_ROWS=1 enables (k_conv_tma is the default for these layers)
 bool conv_rows_eligible(int taps, int stride, int c_in, int n_out, int H, int W);
 
 // ReLU(conv3x3(planes) + bias): output as channel-last bf16 value + residual planes (oh, ol != NULL) or fp32 NCHW

@@ -38,9 +38,12 @@ def test_backbone_matches_golden(golden_backbone):
     _close(out[:, ::4], T(g["ref_out_c4"]), "backbone")
 
 
-def test_backbone_shipped_config_matches_oracle():
+@pytest.mark.parametrize("rows", [False, True])
+def test_backbone_shipped_config_matches_oracle(rows, monkeypatch):
     """The GenComm m1 backbone (layer_nums [3,5,8], filters [64,128,256], up-sampling [1,2,4] -> 384 channels) on one
-    256 x 512 canvas."""
+    256 x 512 canvas; ``rows``: the 64- / 128-channel stride-1 layers through the row-staged kernel (conv_rows.cu, opt-in)
+    instead of the TMA-fed one."""
+    monkeypatch.setenv("GC_CONV_ROWS", "1" if rows else "0")
     torch.manual_seed(5)
     cfg = {"layer_nums": [3, 5, 8], "layer_strides": [2, 2, 2], "num_filters": [64, 128, 256],
            "upsample_strides": [1, 2, 4], "num_upsample_filter": [128, 128, 128]}
