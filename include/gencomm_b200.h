@@ -144,6 +144,9 @@ int gc_pillar_canvas_planes(const float *points, const int32_t *point_offsets, i
  *   affine_grid is evaluated in float64 and only the grid is rounded to float32, exactly like
  *   F.affine_grid(theta_f64).to(src); sampling follows ATen's grid_sampler_2d (bilinear, zeros
  *   padding, align_corners=False).
+ *   max_agents_per_frame is a HOST-side promise used to pick a kernel specialisation (no device -> host sync to read
+ *   record_len): it must be >= every record_len entry.  A smaller value is a contract violation -- the tiled kernels then
+ *   fuse only the first max_agents_per_frame agents of a frame and ignore the rest; pass <= 0 when unknown (L is used).
  * ------------------------------------------------------------------------------------------- */
 int gc_warp_fuse(const float *feat, const int32_t *agent_offsets, int n_frames, int total_agents,
                  int max_agents_per_frame /* host-side upper bound on any record_len entry; <= 0: unknown (L is used) */,
