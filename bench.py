@@ -808,7 +808,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--shape", default="opv2v_h", choices=sorted(SHAPES))
-    ap.add_argument("--frames-per-step", type=int, default=8)
+    ap.add_argument("--frames-per-step", type=int, default=15,
+                    help="collaborative frames per step and GPU.  15 frames x 4 agents = 60 agents = four full rounds of the 15 "
+                         "co-resident sampler clusters (8 frames: 32 agents = 2.13 rounds); measured 8 -> 876, 12 -> 882, 15 -> 925, "
+                         "16 -> 921, 24 -> 925 frames/s (profiles/r02ax_frames_per_step.txt)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the secondary sections (configs[1] HBM step, sampler, ...)")
     ap.add_argument("--cpu-protocol", action="store_true", help="--impl reference: also time k = 1 thread (BASELINE.md section 3)")
