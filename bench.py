@@ -677,7 +677,7 @@ def run_ours(args):
                             "unit": "TFLOP/s", "frac": dom["tensor_frac"], "traffic": kernel_traffic("k_conv_tma"),
                             "issued_tflops": 3.0 * dom["tflops"], "issued_frac": 3.0 * dom["tensor_frac"],
                             "peak_source": tpeak_src, "algorithmic_flops_per_step": dom["flops"], "ms_per_step": dom["ms"],
-                            "note": "achieved / frac count the dense fp32-grade convolution FLOPs of the 40 launches of the stage; the "
+                            "note": "achieved / frac count the dense fp32-grade convolution FLOPs of the 22 launches of the stage; the "
                                     "kernel issues 3 bf16 MMAs per product (bf16x3), so the tensor pipe executes issued_tflops = 3x "
                                     "that figure (issued_frac of the measured bf16 peak); traffic = ncu DRAM bytes of one 256-channel "
                                     "3x3 launch (profiles/traffic.json)"}
@@ -725,7 +725,7 @@ STAGE_ORDER = ("pillars", "backbone", "shrink", "message_extractor", "sampler", 
 STAGE_KERNELS = {
     "pillars": "front end: k_cell_assign+k_pillar_count+k_pillar_assign+k_slot_insert+k_canvas_planes (voxelize+PFN+scatter into the "
                "backbone's bf16 operand planes, 512x256 grid)",
-    "backbone": "k_conv_tma (BaseBEVBackbone, 19 3x3 + 21 deblock-phase TMA-fed tcgen05 implicit GEMMs, bf16x3)",
+    "backbone": "k_conv_tma (BaseBEVBackbone, 19 3x3 + 3 phase-fused deblock TMA-fed tcgen05 implicit GEMMs, bf16x3)",
     "warp_fuse": "k_fuse_persist<ATT> (warp+regroup+AttFusion at the native shape)",
     "sampler": "GenComm sampler (k_q_sample, 3 x [k_conv_in_tc, k_unet_middle_cluster, k_conv_out_tc] + torch.randn noise)",
 }
@@ -735,7 +735,7 @@ def pipeline_launches(pipe, stage_ms):
     """Kernels of this repo launched per detector step (counted from the launch sequence of each stage; the torch.randn /
     elementwise launches of the wrappers are not counted)."""
     n = 5                      # front end (the canvas is written as the backbone's operand planes: no to_planes)
-    n += 40                    # backbone: 19 convs + 1 + 4 + 16 deblock phases (written as the shrink header's planes)
+    n += 22                    # backbone: 19 convs + 3 deblocks (all phases of a ConvTranspose2d in one launch; shrink header's planes)
     n += 2                     # shrink header: 2 convs
     n += 5                     # message extractor
     cluster = pipe.model.gencomm.precision == "cluster"

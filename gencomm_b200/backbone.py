@@ -80,12 +80,12 @@ class BaseBEVBackbone(nn.Module):
                     w, b = _fold(m.weight.detach(), mods[i + 1])
                     convs.append((ops.conv_pack(w), b.float().contiguous(), m.out_channels, m.in_channels, m.stride[0]))
             wt, bt = _fold(deb[0].weight.detach(), deb[1], transposed=True)      # [c_in, c_out, up, up]
-            phases = []
+            phases = []      # phase (dy, dx) = a 1x1 GEMM; packed back to back in phase order dy * up + dx (gc_conv_planes, up_dy = -1)
             for dy in range(up):
                 for dx in range(up):
                     w1 = wt[:, :, dy, dx].t().contiguous().view(wt.shape[1], wt.shape[0], 1, 1)   # -> [c_out, c_in, 1, 1]
-                    phases.append((dy, dx, ops.conv_pack(w1)))
-            levels.append((convs, phases, bt.float().contiguous(), wt.shape[1], wt.shape[0]))
+                    phases.append(ops.conv_pack(w1))
+            levels.append((convs, torch.cat(phases), bt.float().contiguous(), wt.shape[1], wt.shape[0]))
         self._key, self._packed = key, levels
         return levels
 
@@ -116,13 +116,13 @@ class BaseBEVBackbone(nn.Module):
                     out = torch.empty(A, C_out, Hu, Wu, dtype=torch.float32, device=x.device)
             elif (h * up, w * up) != (Hu, Wu):
                 raise ValueError("BaseBEVBackbone: the deblock outputs do not share one resolution")
-            for dy, dx, packed in phases:
-                if self.emit_planes:
-                    ops.conv_planes(planes, A, up_in, h, w, packed, up_bias, up_out, 1, out_planes=out, out_ch_total=C_out,
-                                    out_ch_off=ch_off, up=up, up_dy=dy, up_dx=dx)
-                else:
-                    ops.conv_planes(planes, A, up_in, h, w, packed, up_bias, up_out, 1, out_nchw=out, out_ch_off=ch_off, up=up,
-                                    up_dy=dy, up_dx=dx)
+            # all up * up phases of the ConvTranspose2d in one call (one launch when the TMA kernel applies)
+            if self.emit_planes:
+                ops.conv_planes(planes, A, up_in, h, w, phases, up_bias, up_out, 1, out_planes=out, out_ch_total=C_out,
+                                out_ch_off=ch_off, up=up, up_dy=-1)
+            else:
+                ops.conv_planes(planes, A, up_in, h, w, phases, up_bias, up_out, 1, out_nchw=out, out_ch_off=ch_off, up=up,
+                                up_dy=-1)
             ch_off += up_out
         if self.emit_planes:
             out = ops.PlaneFeature(out[0], out[1], (A, C_out, Hu, Wu))

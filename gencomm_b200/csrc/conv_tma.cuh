@@ -98,6 +98,9 @@ __device__ __forceinline__ uint64_t make_desc_sw64(uint32_t saddr) { return make
 
 // H x W: the output grid; tiles of BH rows x BW pixels, BW = min(W, 128), BH = 128 / BW.  stride 2: the tensor maps traverse the
 // input with element strides {1, 2, 2, 1} (box {32, 2 BW, 2 BH, 1} -> BW x BH pixels in shared memory), start (2 x0 + kx - 1, ..).
+// up_dy < 0: ALL up * up phases of a ConvTranspose2d (kernel == stride == up) in one launch -- n_tiles counts (tile, phase) pairs,
+// phase = t % (up * up) writes pixel (y*up + phase / up, x*up + phase % up) with the weights at wp + phase * stages * stage bytes
+// (phases of one tile run on neighbouring CTAs at the same time: its operand comes from L2 once).
 // EPI as in k_me_conv: 0 bias, 1 bias + GELU, 3 bias + ReLU -> fp32 [A][out_ch_total][H*up][W*up] at (y*up + up_dy, x*up + up_dx);
 // 2 bias + GELU -> fp32 channel-last [A][HW][out_ch_total]; 5 bias + ReLU -> bf16 value + residual planes [A][HW*up*up][out_ch_total]
 // MC: CTA pairs (cluster of 2) walk tile pairs in lock step; each CTA fetches half of every weight stage and multicasts it to both
@@ -121,6 +124,7 @@ k_conv_tma(const __grid_constant__ CUtensorMap map_h, const __grid_constant__ CU
     const uint32_t b_base = a_base + NS * kAStage;
     const int BH = me::kPix / BW, tiles_x = W / BW, tiles_agent = tiles_x * (H / BH);
     const int chunks = c_in / kSc, stages = TAPS * chunks, HW = H * W;
+    const int n_phase = up_dy < 0 ? up * up : 1;
 
     if (warp == 0) tmem_alloc<2 * NOUT>(&s_tmem);
     if (tid == 32) {
@@ -175,8 +179,10 @@ k_conv_tma(const __grid_constant__ CUtensorMap map_h, const __grid_constant__ CU
         if (elect_one()) {
             int g = 0;
             for (int t = t0; t < n_tiles; t += t_step) {
-                const int agent = t / tiles_agent, rem = t - agent * tiles_agent;
+                const int ph = t % n_phase, tt = t / n_phase;
+                const int agent = tt / tiles_agent, rem = tt - agent * tiles_agent;
                 const int x0 = (rem % tiles_x) * BW, y0 = (rem / tiles_x) * BH;
+                const uint4 *wph = wp + (size_t)ph * stages * (kBStage / 16);
                 for (int s = 0; s < stages; ++s, ++g) {
                     const int sb = g % NS;
                     if (g >= NS) CT_ACC(2, mbar_wait(smem_u32(&empty[sb]), (uint32_t)((g / NS) - 1) & 1u));   // MMAs of stage g - NS retired
@@ -188,9 +194,9 @@ k_conv_tma(const __grid_constant__ CUtensorMap map_h, const __grid_constant__ CU
                     tma_load_4d(a_dst + kAPlane, &map_l, chunk * kSc, x0 * stride + kx - 1, y0 * stride + ky - 1, agent, bar);
                     if (MC)
                         bulk_copy_multicast(b_base + (uint32_t)sb * kBStage + (uint32_t)rank * (kBStage / 2),
-                                            wp + (size_t)s * (kBStage / 16) + (size_t)rank * (kBStage / 32), kBStage / 2, bar, (uint16_t)3);
+                                            wph + (size_t)s * (kBStage / 16) + (size_t)rank * (kBStage / 32), kBStage / 2, bar, (uint16_t)3);
                     else
-                        bulk_copy(b_base + (uint32_t)sb * kBStage, wp + (size_t)s * (kBStage / 16), kBStage, bar);
+                        bulk_copy(b_base + (uint32_t)sb * kBStage, wph + (size_t)s * (kBStage / 16), kBStage, bar);
                 }
             }
         }
@@ -201,10 +207,12 @@ k_conv_tma(const __grid_constant__ CUtensorMap map_h, const __grid_constant__ CU
         const int q4 = warp & 3, m = q4 * 32 + lane, col0 = (warp >> 2) * (NOUT / 2);
         int k = 0;
         for (int t = t0; t < n_tiles; t += t_step, ++k) {
-            const int agent = t / tiles_agent, rem = t - agent * tiles_agent;
+            const int ph = t % n_phase, tt = t / n_phase;
+            const int dy = up_dy < 0 ? ph / up : up_dy, dx = up_dy < 0 ? ph % up : up_dx;
+            const int agent = tt / tiles_agent, rem = tt - agent * tiles_agent;
             const int pyo = (rem / tiles_x) * BH + m / BW, pxo = (rem % tiles_x) * BW + m % BW;
             const int p_out = pyo * W + pxo;
-            const size_t p_store = (size_t)(pyo * up + up_dy) * (W * up) + pxo * up + up_dx;
+            const size_t p_store = (size_t)(pyo * up + dy) * (W * up) + pxo * up + dx;
             const int set = k & 1;
             if (tid == 0) CT_ACC(3, mbar_wait(smem_u32(&acc_full[set]), (uint32_t)(k >> 1) & 1u));
             else mbar_wait(smem_u32(&acc_full[set]), (uint32_t)(k >> 1) & 1u);
@@ -378,7 +386,7 @@ static int launch_conv_tma_mc(cudaStream_t st, int A, const uint4 *xh, const uin
         set_error("k_conv_tma: cuTensorMapEncodeTiled failed (A=%d H=%d W=%d C=%d stride=%d)", A, Hi, Wi, C, stride);
         return (int)cudaErrorInvalidValue;
     }
-    const int n_tiles = A * (H * W / me::kPix);
+    const int n_tiles = A * (H * W / me::kPix) * (up_dy < 0 ? up * up : 1);
     int grid = n_tiles < ctas ? n_tiles : ctas;
     if (MC) grid &= ~1;
     cudaLaunchConfig_t cfg = {};
@@ -405,7 +413,7 @@ static int launch_conv_tma(cudaStream_t st, int A, const uint4 *xh, const uint4 
     // short-K plane layers are bound by their epilogue: staged (coalesced) stores; deep-K layers by the operand ring: deeper ring
     const bool stg = stage_planes(NOUT, EPI) && TAPS * (c_in / kSc) <= 36;
     if constexpr (NOUT >= 128) {
-        if (mc_on && n_tiles % 2 == 0 && n_tiles >= 4) {
+        if (mc_on && up_dy >= 0 && n_tiles % 2 == 0 && n_tiles >= 4) {      // (fused phases: the CTAs of a pair would need different weights)
             if (stg)
                 return launch_conv_tma_mc<NOUT, TAPS, EPI, true, stage_planes(NOUT, EPI)>(st, A, xh, xl, wp, bias, C, c_in, H, W, H_in, W_in, stride,
                                                                                           n_store, out_ch_total, out_ch_off, out, oh, ol, up,

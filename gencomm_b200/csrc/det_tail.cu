@@ -281,9 +281,18 @@ extern "C" int gc_conv_planes(const void *xh, const void *xl, int total_agents, 
     GC_REQUIRE(xh && xl && packed && ((oh && ol) || out_nchw), GC_EINVAL, "gc_conv_planes: null pointer");
     GC_REQUIRE((taps == 1 || taps == 9) && c_in > 0 && c_in % 32 == 0 && n_out >= 8 && n_out <= 256 && n_out % 8 == 0,
                GC_EUNSUPPORTED, "gc_conv_planes: taps in {1,9}, c_in %% 32 == 0, n_out %% 8 == 0, n_out <= 256");
-    GC_REQUIRE((stride == 1 || stride == 2) && (taps == 9 || stride == 1) && up >= 1 && up_dy >= 0 && up_dy < up && up_dx >= 0 &&
-                   up_dx < up,
+    GC_REQUIRE((stride == 1 || stride == 2) && (taps == 9 || stride == 1) && up >= 1 &&
+                   ((up_dy >= 0 && up_dy < up && up_dx >= 0 && up_dx < up) || (up_dy == -1 && taps == 1)),
                GC_EUNSUPPORTED, "gc_conv_planes: bad stride / up-sampling phase");
+    if (up_dy == -1 && !(ct::conv_tma_eligible(stride, c_in, c_in, H_in, W_in, up) && n_out % 16 == 0 && n_out >= 64)) {
+        // all phases requested but the fused launch does not apply: one launch per phase
+        const size_t phase_bytes = gc_conv_packed_bytes(1, c_in, n_out);
+        for (int ph = 0; ph < up * up; ++ph)
+            if (int rc = gc_conv_planes(xh, xl, total_agents, c_in, H_in, W_in, stride, taps, n_out, (const char *)packed + ph * phase_bytes,
+                                        bias, oh, ol, out_nchw, out_ch_total, out_ch_off, up, ph / up, ph % up, stream))
+                return rc;
+        return GC_OK;
+    }
     const int Ho = taps == 9 ? (H_in - 1) / stride + 1 : H_in, Wo = taps == 9 ? (W_in - 1) / stride + 1 : W_in;
     GC_REQUIRE(Ho > 0 && Wo > 0 && (Ho * Wo) % me::kPix == 0, GC_EUNSUPPORTED,
                "gc_conv_planes: output H*W must be a multiple of 128 (got %dx%d)", Ho, Wo);

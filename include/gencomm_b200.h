@@ -274,7 +274,9 @@ int gc_det_heads(const float *x, int n_frames, int C, int H, int W, int n_out, c
  *   gc_conv_planes ReLU(conv(planes) + bias): 3x3 with padding 1 and stride 1|2, or 1x1; written as the next layer's
  *                  planes (oh, ol: [A][Ho*up*Wo*up][out_ch_total] bf16, channels out_ch_off..) or as NCHW fp32 out_nchw
  *                  [A][out_ch_total][Ho*up][Wo*up], in both cases at pixel (y*up + up_dy, x*up + up_dx) -- one phase of
- *                  a ConvTranspose2d whose kernel equals its stride `up` (up = 1: an ordinary store).
+ *                  a ConvTranspose2d whose kernel equals its stride `up` (up = 1: an ordinary store).  up_dy = -1 (1x1 only):
+ *                  ALL up * up phases in one call, `packed` = the phases' gc_conv_pack outputs back to back in the order
+ *                  dy * up + dx (gc_conv_packed_bytes(1, c_in, n_out) bytes each).
  *   Output H*W must be a multiple of 128; n_out <= 256.  bf16x3 tcgen05 GEMMs (fp32-grade).
  * ------------------------------------------------------------------------------------------- */
 size_t gc_conv_packed_bytes(int taps, int c_in, int n_out);
