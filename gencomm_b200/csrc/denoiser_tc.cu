@@ -100,6 +100,7 @@ __global__ void k_pack_conv_in_w(const float *__restrict__ w, int C, int chunks,
 //   mode 0: pred = x0;  mode 1: x <- (c1*x0 + c2*x) + sigma*noise   (NCHW f32)
 // ------------------------------------------------------------------------------------------------
 constexpr int kOutRowPx = 132;   // staged pixels per row: x0-1 .. x0+130 (taps kx = 0..3 of pixel 127 reach 130)
+constexpr int kOutRows = 4;      // image rows per CTA
 
 template <int NT>
 __global__ void __launch_bounds__(128)
@@ -118,7 +119,9 @@ k_conv_out_tc(const float *__restrict__ in, const float *__restrict__ st_in, int
     const int tid = threadIdx.x, warp = tid >> 5;
     const int splits = C / NT;
     const int agent = blockIdx.z / splits, co0 = (blockIdx.z % splits) * NT;
-    const int x0 = blockIdx.x * 128, y = blockIdx.y;
+    // kOutRows image rows per CTA: the weights (24 KB at NT = 128), bias and GroupNorm coefficients are loaded once per CTA instead of
+    // once per row (round 2; one row per CTA spent most of its time in that set-up: 16 warps per SM, long-scoreboard bound)
+    const int x0 = blockIdx.x * 128, y_first = blockIdx.y * kOutRows;
 
     if (warp == 0) tmem_alloc<NT>(&s_tmem);
     if (tid == 32) { mbar_init(smem_u32(&s_bar), 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
@@ -133,6 +136,19 @@ k_conv_out_tc(const float *__restrict__ in, const float *__restrict__ st_in, int
         b_s[i] = __ldg(wp + (size_t)kc * C + co0 + n);
     }
     __syncthreads();
+    const size_t plane = (size_t)H * W;
+    const uint32_t tmem_base = s_tmem;
+#pragma unroll 1
+    for (int yr = 0; yr < kOutRows; ++yr) {
+    const int y = y_first + yr;
+    if (y >= H) break;
+    // epilogue operands of this row's first 16 channels: in flight while the row is staged and multiplied
+    size_t idx = ((size_t)agent * C + co0) * plane + (size_t)y * W + x0 + tid;
+    float xv[16], nz[16];
+    if (mode != 0) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { xv[i] = x[idx + (size_t)i * plane]; nz[i] = __ldg(noise + idx + (size_t)i * plane); }
+    }
     // ---- A rows: GroupNorm + swish -> bf16; zero outside the image (padding applies AFTER the activation) ----
     for (int i = tid; i < 3 * kOutRowPx; i += 128) {
         const int r = i / kOutRowPx, px = i % kOutRowPx;
@@ -156,7 +172,7 @@ k_conv_out_tc(const float *__restrict__ in, const float *__restrict__ st_in, int
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem = s_tmem;
+    const uint32_t tmem = tmem_base;
 
     if (leader_of_warp0()) {
         constexpr uint32_t idesc = make_idesc(128, NT);
@@ -170,12 +186,11 @@ k_conv_out_tc(const float *__restrict__ in, const float *__restrict__ st_in, int
         }
         mma_commit(smem_u32(&s_bar));
     }
-    mbar_wait(smem_u32(&s_bar), 0u);
+    mbar_wait(smem_u32(&s_bar), (uint32_t)yr & 1u);
     tc_fence_after();
 
-    // ---- epilogue: lane = pixel; 16 channels per TMEM load; per-channel stores are 128 B per warp ----
-    const size_t plane = (size_t)H * W;
-    size_t idx = ((size_t)agent * C + co0) * plane + (size_t)y * W + x0 + tid;
+    // ---- epilogue: lane = pixel; 16 channels per TMEM load; per-channel stores are 128 B per warp; the x / noise values of the
+    // next 16 channels are loaded before the current 16 are combined and stored ----
     const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
 #pragma unroll 1
     for (int c0 = 0; c0 < NT; c0 += 16) {
@@ -185,20 +200,34 @@ k_conv_out_tc(const float *__restrict__ in, const float *__restrict__ st_in, int
 #pragma unroll
             for (int i = 0; i < 16; ++i) pred[idx + (size_t)i * plane] = v[i] + s_bias[c0 + i];
         } else {
-            float xv[16], nz[16];
+            float xn[16], nn[16];
+            if (c0 + 16 < NT) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) { xv[i] = x[idx + (size_t)i * plane]; nz[i] = __ldg(noise + idx + (size_t)i * plane); }
+                for (int i = 0; i < 16; ++i) {
+                    xn[i] = x[idx + (size_t)(16 + i) * plane];
+                    nn[i] = __ldg(noise + idx + (size_t)(16 + i) * plane);
+                }
+            }
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
                 const float mean = __fadd_rn(__fmul_rn(c1, v[i] + s_bias[c0 + i]), __fmul_rn(c2, xv[i]));
                 x[idx + (size_t)i * plane] = __fadd_rn(mean, __fmul_rn(sigma, nz[i]));
             }
+            if (c0 + 16 < NT) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) { xv[i] = xn[i]; nz[i] = nn[i]; }
+            }
         }
         idx += 16 * plane;
     }
+    // the next row overwrites the staged rows and the accumulator: every thread is past its TMEM reads
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) tmem_free<NT>(tmem);
+    tc_fence_after();
+    }   // rows
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_free<NT>(tmem_base);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -852,7 +881,7 @@ static int launch_out(cudaStream_t st, int A, const float *in, const float *st_i
         if (e != cudaSuccess) { (void)cudaGetLastError(); set_error("k_conv_out_tc: cudaFuncSetAttribute failed (%d)", (int)e); return (int)e; }
         configured = true;
     }
-    const dim3 grid(W / 128, H, A * (C / NT));
+    const dim3 grid(W / 128, (H + tc::kOutRows - 1) / tc::kOutRows, A * (C / NT));
     tc::k_conv_out_tc<NT><<<grid, 128, smem, st>>>(in, st_in, tiles_in, w, bias, aff, C, H, W, mode, c1, c2, sigma, noise, x,
                                                    pred, materialize);
     GC_LAUNCH_CHECK("k_conv_out_tc");
