@@ -41,7 +41,7 @@ struct VoxelWorkspace {
     int32_t *point_cell;    // [total_points] cell id or -1
     uint32_t *slots;        // [A][max_voxels][32] ascending point indices (kEmpty = free)
     int32_t *pillar_cell;   // [A][max_voxels] cell id of each pillar
-    int32_t *block_counts;  // [A][blocks_per_agent] first-point flags per 1024-point block
+    int32_t *block_counts;  // [A][blocks_per_agent] first-point counts per block (look-back flags of k_pillar_build)
     size_t bytes;
 };
 
@@ -59,8 +59,8 @@ inline VoxelWorkspace carve_workspace(void *base, const gcVoxelGeom &g, int n_ag
     w.point_cell = (int32_t *)take((size_t)(total_points > 0 ? total_points : 1) * 4);
     w.slots = (uint32_t *)take((size_t)n_agents * g.max_voxels * 32 * 4);
     w.pillar_cell = (int32_t *)take((size_t)n_agents * g.max_voxels * 4);
-    // one count per 1024-point block; any agent has at most total_points points
-    const size_t blocks = (size_t)(total_points + 1023) / 1024 + 1;
+    // one count / look-back flag per block of >= 128 points; any agent has at most total_points points
+    const size_t blocks = (size_t)(total_points + 127) / 128 + 2;
     w.block_counts = (int32_t *)take((size_t)n_agents * blocks * 4);
     w.bytes = off;
     return w;

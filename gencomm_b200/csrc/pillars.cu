@@ -228,6 +228,260 @@ k_slot_insert(const int32_t *__restrict__ point_offsets, const int32_t *__restri
 }
 
 // ------------------------------------------------------------------------------------------------
+// 2+3 fused (the default voxelizer since round 2): pillar ranking and slot insertion in ONE pass over the
+// points, k_pillar_build.  grid = (blocks_per_agent, n_agents), 256 threads x 4 items, item-major order like
+// k_pillar_assign.  Every dependency of a block points at a block with a lower linear index of the same agent
+// (the hardware dispatches blocks in linear order, the assumption every decoupled look-back scan makes):
+//   a. first-point flags (cell_code[cell] == i after k_cell_assign2), block total published at once with
+//      st.release into block_flags (kEmpty = not yet; cleared by k_cell_assign2) -- no dependency;
+//   b. warp 0 sums the totals of all preceding blocks of the agent (ld.acquire spin) = first pillar id;
+//   c. first points: pillar id (creation order), pillar_cell, slot row = {i, empty x 31} -- the first point of
+//      a cell is its smallest index, i.e. slot 0 for good -- then st.release of kPillarBit|pid into cell_code;
+//   d. every other point spins (ld.acquire) until its cell carries the pillar bit -- published by this block or
+//      an earlier one, after step b of that block -- and runs the conserving atomicMin chain of k_slot_insert.
+//      The four chains of a thread are interleaved so that their L2 round trips overlap.
+// Same final workspace as k_pillar_count + k_pillar_assign + k_slot_insert, bit for bit (the chain's final
+// state does not depend on the interleaving).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_u32(uint32_t *p, uint32_t v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// 1'. k_cell_assign with two points per thread (two independent load -> divide -> atomic chains) that also
+//     clears the look-back flags of k_pillar_build.
+__global__ void __launch_bounds__(256)
+k_cell_assign2(const float4 *__restrict__ points, const int32_t *__restrict__ point_offsets, int n_agents,
+               int total_points, GeomDev g, uint32_t *__restrict__ cell_code, int32_t *__restrict__ point_cell,
+               uint32_t *__restrict__ block_flags, int n_flags) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n_flags) block_flags[t] = kEmpty;
+    const int valid_points = __ldg(point_offsets + n_agents);
+    float4 p[2];
+    int gi[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+        gi[u] = blockIdx.x * 512 + u * 256 + threadIdx.x;
+        if (gi[u] < total_points && gi[u] < valid_points) p[u] = __ldg(points + gi[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+        if (gi[u] >= total_points) continue;
+        if (gi[u] >= valid_points) { point_cell[gi[u]] = -1; continue; }
+        const int a = find_segment(point_offsets, n_agents, gi[u]);
+        const float pv[3] = {p[u].x, p[u].y, p[u].z};
+        int c[3];
+        bool ok = true;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const float f = floorf(__fdiv_rn(__fsub_rn(pv[j], g.rmin[j]), g.voxel[j]));
+            ok = ok && (f >= 0.0f) && (f < (float)g.grid[j]);   // false for NaN
+            c[j] = (int)f;
+        }
+        int cell = -1;
+        if (ok) {
+            cell = (c[2] * g.grid[1] + c[1]) * g.grid[0] + c[0];
+            atomicMin(cell_code + (size_t)a * g.ncell + cell, (uint32_t)(gi[u] - __ldg(point_offsets + a)));
+        }
+        point_cell[gi[u]] = cell;
+    }
+}
+
+__device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_u32(uint32_t *p, uint32_t v) {
+    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// grid = (n_agents, chunks): blockIdx.x (dispatched fastest) is the agent, blockIdx.y the chunk of 256*IT points, so
+// the machine sweeps every agent's points in index order (late points of a crowded cell find 32 smaller indices in
+// place and leave without an atomic) and every block a block waits for -- same agent, lower chunk -- has a lower
+// linear index.  IT = points per thread: more independent chains per thread, but a wider in-flight index window.
+template <int IT, int NT>
+__global__ void __launch_bounds__(NT)
+k_pillar_build(const int32_t *__restrict__ point_offsets, const int32_t *__restrict__ point_cell,
+               uint32_t *__restrict__ cell_code, int ncell, int max_voxels, int blocks_per_agent,
+               uint32_t *__restrict__ block_flags, uint32_t *__restrict__ slots, int32_t *__restrict__ pillar_cell,
+               int32_t *__restrict__ n_pillars) {
+    constexpr int NW = NT / 32;
+    __shared__ int s_warp[IT][NW];
+    __shared__ int s_base;
+    const int a = blockIdx.x;
+    const int chunk = blockIdx.y;
+    const int base = __ldg(point_offsets + a);
+    const int n = __ldg(point_offsets + a + 1) - base;
+    const int i0 = chunk * (NT * IT);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t *codes = cell_code + (size_t)a * ncell;
+    uint32_t *bf = block_flags + (size_t)a * blocks_per_agent;
+
+    // a. flags
+    int cellv[IT];
+    uint32_t cv[IT];
+    bool flag[IT];
+    unsigned bal[IT];
+#pragma unroll
+    for (int it = 0; it < IT; ++it) {
+        const int i = i0 + it * NT + threadIdx.x;
+        cellv[it] = i < n ? __ldg(point_cell + base + i) : -1;
+    }
+#pragma unroll
+    for (int it = 0; it < IT; ++it) cv[it] = cellv[it] >= 0 ? __ldcg(codes + cellv[it]) : kEmpty;
+#pragma unroll
+    for (int it = 0; it < IT; ++it) {
+        flag[it] = cellv[it] >= 0 && cv[it] == (uint32_t)(i0 + it * NT + threadIdx.x);
+        bal[it] = __ballot_sync(0xffffffffu, flag[it]);
+        if (lane == 0) s_warp[it][warp] = __popc(bal[it]);
+    }
+    __syncthreads();
+    // b. publish the block total, then look back
+    if (warp == 0) {
+        int total = lane < IT * NW ? (&s_warp[0][0])[lane] : 0;
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) total += __shfl_xor_sync(0xffffffffu, total, m);
+        if (lane == 0) st_release_u32(bf + chunk, (uint32_t)total);
+        int t = 0;
+        for (int k0 = 0; k0 < chunk; k0 += 128) {   // four polls in flight per lane
+            uint32_t v[4];
+            bool again = true;
+            while (again) {
+                again = false;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int k = k0 + u * 32 + lane;
+                    v[u] = k < chunk ? ld_relaxed_u32(bf + k) : 0u;
+                    again = again || v[u] == kEmpty;
+                }
+            }
+            t += (int)(v[0] + v[1] + v[2] + v[3]);
+        }
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) t += __shfl_xor_sync(0xffffffffu, t, m);
+        if (lane == 0) {
+            s_base = t;
+            if (chunk == blocks_per_agent - 1) n_pillars[a] = t + total < max_voxels ? t + total : max_voxels;
+        }
+    }
+    __syncthreads();
+    // c. first points open their pillars: rows first, one fence, then the codes
+    int running = s_base;
+    uint32_t newcode[IT];
+    bool opened = false;
+#pragma unroll
+    for (int it = 0; it < IT; ++it) {
+        int before = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) {
+            const int v = s_warp[it][w];
+            before += (w < warp) ? v : 0;
+            total += v;
+        }
+        if (flag[it]) {
+            const int pid = running + before + __popc(bal[it] & ((1u << lane) - 1u));
+            if (pid < max_voxels) {
+                const size_t gp = (size_t)a * max_voxels + pid;
+                pillar_cell[gp] = cellv[it];
+                uint4 *s = reinterpret_cast<uint4 *>(slots + gp * 32);
+                const uint4 e = make_uint4(kEmpty, kEmpty, kEmpty, kEmpty);
+                __stcg(s, make_uint4((uint32_t)(i0 + it * NT + threadIdx.x), kEmpty, kEmpty, kEmpty));
+#pragma unroll
+                for (int k = 1; k < 8; ++k) __stcg(s + k, e);
+                newcode[it] = kPillarBit | (uint32_t)pid;
+            } else {
+                newcode[it] = kDropped;
+            }
+            opened = true;
+        }
+        running += total;
+    }
+    if (opened) {
+        __threadfence();   // rows visible device-wide before any code that points at them
+#pragma unroll
+        for (int it = 0; it < IT; ++it)
+            if (flag[it]) st_relaxed_u32(codes + cellv[it], newcode[it]);
+    }
+    // d. the other points: wait for the pillar of their cell, then insert
+    bool act[IT];
+    bool waiting = false;
+#pragma unroll
+    for (int it = 0; it < IT; ++it) {
+        act[it] = cellv[it] >= 0 && !flag[it];
+        waiting = waiting || (act[it] && !(cv[it] & kPillarBit));
+    }
+    while (waiting) {
+        waiting = false;
+#pragma unroll
+        for (int it = 0; it < IT; ++it)
+            if (act[it] && !(cv[it] & kPillarBit)) cv[it] = ld_relaxed_u32(codes + cellv[it]);
+#pragma unroll
+        for (int it = 0; it < IT; ++it) waiting = waiting || (act[it] && !(cv[it] & kPillarBit));
+    }
+    __threadfence();       // acquire side: the rows are read after the codes
+    uint32_t *srow[IT];
+    uint32_t v[IT];
+    int k[IT];
+    uint4 q0[IT];
+    uint32_t last[IT];
+#pragma unroll
+    for (int it = 0; it < IT; ++it) {
+        act[it] = act[it] && cv[it] < kDropped;
+        srow[it] = slots + ((size_t)a * max_voxels + (cv[it] & ~kPillarBit)) * 32;
+        v[it] = (uint32_t)(i0 + it * NT + threadIdx.x);
+        if (act[it]) {
+            q0[it] = __ldcg(reinterpret_cast<const uint4 *>(srow[it]));
+            last[it] = __ldcg(srow[it] + 31);
+        }
+    }
+    // The row is ascending at every instant and its values only decrease: a slot seen below v stays below v
+    // (see k_slot_insert), so the chain may start at the number of slots seen below v.  Two round trips at most:
+    // {first quad, last slot} -- a full row of smaller indices (late point of a crowded cell) or a free slot among
+    // the first four (most pillars hold a handful of points) ends the search -- then the other seven quads at once.
+#pragma unroll
+    for (int it = 0; it < IT; ++it) {
+        k[it] = 0;
+        if (!act[it]) continue;
+        if (last[it] < v[it]) { act[it] = false; continue; }   // 32 smaller indices in place
+        const uint4 u = q0[it];
+        k[it] = (u.x < v[it]) + (u.y < v[it]) + (u.z < v[it]) + (u.w < v[it]);
+        if (k[it] == 4) {
+            uint4 r[7];
+#pragma unroll
+            for (int q = 0; q < 7; ++q) r[q] = __ldcg(reinterpret_cast<const uint4 *>(srow[it]) + 1 + q);
+#pragma unroll
+            for (int q = 0; q < 7; ++q)
+                k[it] += (r[q].x < v[it]) + (r[q].y < v[it]) + (r[q].z < v[it]) + (r[q].w < v[it]);
+            if (k[it] >= 32) act[it] = false;
+        }
+    }
+    bool any = false;
+#pragma unroll
+    for (int it = 0; it < IT; ++it) any = any || act[it];
+    while (any) {
+        uint32_t old[IT];
+#pragma unroll
+        for (int it = 0; it < IT; ++it)
+            if (act[it]) old[it] = atomicMin(srow[it] + k[it], v[it]);
+        any = false;
+#pragma unroll
+        for (int it = 0; it < IT; ++it) {
+            if (!act[it]) continue;
+            if (old[it] == kEmpty) { act[it] = false; continue; }
+            v[it] = old[it] > v[it] ? old[it] : v[it];
+            if (++k[it] == 32) { act[it] = false; continue; }
+            if ((k[it] & 3) == 0 && __ldcg(srow[it] + 31) < v[it]) { act[it] = false; continue; }
+            any = true;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // PFN evaluation for one pillar by one warp ("kernel order", mirrored by oracle/pillar_ref.c).
 // Lane l owns output channels l and l+32; lane s also holds point s of the pillar.
 // ------------------------------------------------------------------------------------------------
@@ -1317,6 +1571,33 @@ extern "C" int gc_voxelize(const float *points, const int32_t *point_offsets, in
     const VoxelWorkspace w = carve_workspace(workspace, *geom, n_agents, total_points);
     const int bpa = blocks_per_agent(max_agent_points);
     cudaMemsetAsync(w.cell_code, 0xFF, (size_t)n_agents * g.ncell * 4, st);
+    // GC_VOXELIZE_IMPL=legacy keeps the round-1 four-kernel voxelizer (A/B and parity: tests run both)
+    const char *impl = getenv("GC_VOXELIZE_IMPL");
+    if (!(impl && strcmp(impl, "legacy") == 0)) {
+        const int n_flags = n_agents * (max_agent_points / 128 + 2);
+        const int work = total_points > 2 * n_flags ? total_points : 2 * n_flags;
+        k_cell_assign2<<<(work + 511) / 512, 256, 0, st>>>((const float4 *)points, point_offsets, n_agents, total_points,
+                                                          g, w.cell_code, w.point_cell, (uint32_t *)w.block_counts,
+                                                          n_flags);
+        GC_LAUNCH_CHECK("k_cell_assign2");
+        static int items = 0;
+        if (items == 0) {
+            const char *e = getenv("GC_VOXELIZE_ITEMS");   // A/B of the points per thread (1, 2, 4); CTAs of 128 threads
+            items = e ? atoi(e) : 2;                       // measured the same as 256 (profiles/r02bd_voxelizer_ab.txt)
+            if (items != 1 && items != 4) items = 2;
+        }
+        const int chunks = (max_agent_points + 256 * items - 1) / (256 * items) + 1;
+        GC_REQUIRE(chunks <= 65535, GC_EUNSUPPORTED, "gc_voxelize: too many points per agent");
+        uint32_t *flags = (uint32_t *)w.block_counts;
+#define GC_BUILD(IT_)                                                                                          \
+    k_pillar_build<IT_, 256><<<dim3(n_agents, chunks), 256, 0, st>>>(point_offsets, w.point_cell, w.cell_code, \
+                                                                     g.ncell, g.max_voxels, chunks, flags,     \
+                                                                     w.slots, w.pillar_cell, n_pillars)
+        if (items == 1) GC_BUILD(1); else if (items == 4) GC_BUILD(4); else GC_BUILD(2);
+#undef GC_BUILD
+        GC_LAUNCH_CHECK("k_pillar_build");
+        return GC_OK;
+    }
     if (total_points > 0) {
         k_cell_assign<<<(total_points + 255) / 256, 256, 0, st>>>((const float4 *)points, point_offsets, n_agents,
                                                                  total_points, g, w.cell_code, w.point_cell);

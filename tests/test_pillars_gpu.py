@@ -32,7 +32,14 @@ def _check_voxels(dev, ref):
     assert torch.equal(dev["voxel_features"].cpu(), ref["voxel_features"])
 
 
-def test_voxelize_matches_golden(golden_pillars):
+@pytest.fixture(params=["fused", "legacy"])
+def voxelizer(request, monkeypatch):
+    """Both voxelizers of gc_voxelize: k_cell_assign2 + k_pillar_build (default) and the round-1 four-kernel chain."""
+    monkeypatch.setenv("GC_VOXELIZE_IMPL", request.param)
+    return request.param
+
+
+def test_voxelize_matches_golden(golden_pillars, voxelizer):
     g = golden_pillars
     rng, vs, cap = g["lidar_range"].tolist(), g["voxel_size"].tolist(), int(g["max_voxels"])
     pre = SpVoxelPreprocessor(_params(rng, vs, cap), train=False)
@@ -45,8 +52,24 @@ def test_voxelize_matches_golden(golden_pillars):
         assert isinstance(single[k], np.ndarray) and np.array_equal(single[k], ref1[k]), k
 
 
+@pytest.mark.parametrize("cap", [200, 57])
+def test_voxelize_crowded_cells_across_blocks(cap, voxelizer):
+    """~250 points per cell spread over ~49 look-back blocks per agent: every pillar overflows its 32 slots, first points
+    and their followers sit in different blocks (the cross-block wait of k_pillar_build), run repeatedly on one workspace."""
+    rng, vs = [-4.0, -2.0, -3.0, 4.0, 2.0, 1.0], [0.4, 0.4, 4.0]
+    g = np.random.default_rng(7)
+    clouds = []
+    for n in (50_000, 1025, 30_000):
+        clouds.append(np.c_[g.uniform(-4.2, 4.2, n), g.uniform(-2.1, 2.1, n), g.uniform(-3, 1, n),
+                            g.random(n)].astype(np.float32))
+    pre = SpVoxelPreprocessor(_params(rng, vs, cap), train=False)
+    ref = _oracle_batch(clouds, rng, vs, cap)
+    for _ in range(3):
+        _check_voxels(pre.preprocess_batch(clouds), ref)
+
+
 @pytest.mark.parametrize("uniform,cap", [(False, 70000), (True, 70000), (True, 20000)])
-def test_voxelize_full_size_matches_oracle(uniform, cap):
+def test_voxelize_full_size_matches_oracle(uniform, cap, voxelizer):
     clouds = [synth.lidar_points(1, a, 100_000, uniform=uniform) for a in range(4)]
     pre = SpVoxelPreprocessor(_params(synth.OPV2V_H_RANGE, synth.VOXEL_SIZE, cap), train=False)
     d = pre.preprocess_batch(clouds)
@@ -56,7 +79,7 @@ def test_voxelize_full_size_matches_oracle(uniform, cap):
         assert d["voxel_features"].shape[0] == 4 * cap   # every agent hit the cap
 
 
-def test_voxelize_edge_cases():
+def test_voxelize_edge_cases(voxelizer):
     rng, vs = [-4.0, -2.0, -3.0, 4.0, 2.0, 1.0], [0.4, 0.4, 4.0]   # 20 x 10 grid (nx % 4 == 0, < one tile)
     g = np.random.default_rng(0)
     inside = np.c_[g.uniform(-4, 4, 500), g.uniform(-2, 2, 500), g.uniform(-3, 1, 500), g.random(500)].astype(np.float32)
