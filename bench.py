@@ -490,7 +490,7 @@ def hbm_step_section(dev, rank, F, K, Wm, peak):
     canvas = float(np.mean([e[1].elapsed_time(e[2]) for e in ev]))
     fuse = float(np.mean([e[3].elapsed_time(e[4]) for e in ev]))
     kern = {
-        "front end: k_cell_assign+k_pillar_count+k_pillar_assign+k_slot_insert+k_canvas_persist (voxelize+PFN+scatter)":
+        "front end: k_cell_assign2+k_pillar_build+k_canvas_persist (voxelize+PFN+scatter)":
             {"ms": front, "bytes": pipe.scatter_bytes()},
         "k_canvas_persist alone (PFN+scatter writer)": {"ms": canvas, "bytes": pipe.scatter_bytes()},
         "k_fuse_persist<ATT> (warp+regroup+AttFusion, 4x64x256x256)": {"ms": fuse, "bytes": pipe.fuse_bytes()},
@@ -723,7 +723,7 @@ def run_ours(args):
 
 STAGE_ORDER = ("pillars", "backbone", "shrink", "message_extractor", "sampler", "enhancer", "warp_fuse", "postprocess")
 STAGE_KERNELS = {
-    "pillars": "front end: k_cell_assign+k_pillar_count+k_pillar_assign+k_slot_insert+k_canvas_planes (voxelize+PFN+scatter into the "
+    "pillars": "front end: k_cell_assign2+k_pillar_build+k_canvas_planes (voxelize+PFN+scatter into the "
                "backbone's bf16 operand planes, 512x256 grid)",
     "backbone": "k_conv_tma (BaseBEVBackbone, 19 3x3 + 3 phase-fused deblock TMA-fed tcgen05 implicit GEMMs, bf16x3)",
     "warp_fuse": "k_fuse_persist<ATT> (warp+regroup+AttFusion at the native shape)",
@@ -734,7 +734,7 @@ STAGE_KERNELS = {
 def pipeline_launches(pipe, stage_ms):
     """Kernels of this repo launched per detector step (counted from the launch sequence of each stage; the torch.randn /
     elementwise launches of the wrappers are not counted)."""
-    n = 5                      # front end (the canvas is written as the backbone's operand planes: no to_planes)
+    n = 3                      # front end: k_cell_assign2, k_pillar_build, k_canvas_planes (no to_planes)
     n += 22                    # backbone: 19 convs + 3 deblocks (all phases of a ConvTranspose2d in one launch; shrink header's planes)
     n += 2                     # shrink header: 2 convs
     n += 5                     # message extractor

@@ -173,6 +173,7 @@ class HeterModelBaselineWGenComm(_HeadsMixin, nn.Module):
         if self.training:
             raise RuntimeError("gencomm_b200 HeterModelBaselineWGenComm is inference-only: call .eval()")
         output_dict = {}
+        predraw = 'gencomm_noise' not in data_dict and not self.missing_message
         agent_modality_list = data_dict['agent_modality_list']
         affine_matrix = normalize_pairwise_tfm(data_dict['pairwise_t_matrix'], self.H, self.W, self.fake_voxel_size)
         record_len = data_dict['record_len']
@@ -198,6 +199,10 @@ class HeterModelBaselineWGenComm(_HeadsMixin, nn.Module):
             finally:
                 if planes_in:
                     encoder.emit_planes = False
+            if predraw:
+                # sampler noise of this frame on a side stream: its generator kernels (HBM writes + ALU) run under the
+                # tensor-bound backbone instead of in front of the sampler (after the HBM-bound front end, not beside it)
+                self.gencomm.predraw()
             if not isinstance(backbone, nn.Identity):
                 # the shrink header follows directly: the deblocks write its operand planes, no NCHW fp32 round trip
                 fused = isinstance(backbone, BaseBEVBackbone) and isinstance(shrinker, DownsampleConv)

@@ -157,6 +157,51 @@ def test_default_noise_path_and_api():
     assert torch.equal(a, b)
 
 
+def test_noise_predraw_reproduces_inline_draws():
+    """predraw() (noise of the next evaluation drawn on a side stream, used by the detector) consumes the generator exactly
+    like the in-line draws: a seeded sequence of same-shape evaluations gives bit-identical outputs either way, a shape
+    change falls back to in-line draws (the pre-drawn set is dropped), and the injected-noise path leaves a pre-drawn set
+    untouched for the next call."""
+    m, _ = random_model(16, seed=2)
+    rl = torch.tensor([2, 1], device=DEV)
+    feat = synth.bev_features(33, 3, 16, 16, 24).to(DEV)
+    cond = synth.bev_features(33, 3, 2, 16, 24, salt=4).to(DEV)
+    feat_b = synth.bev_features(34, 2, 16, 16, 24).to(DEV)
+    cond_b = synth.bev_features(34, 2, 2, 16, 24, salt=4).to(DEV)
+
+    def run(predraw):
+        m.predraw_enabled = predraw
+        m._noise_shape = m._noise_ready = None
+        torch.manual_seed(1234)
+        outs = []
+        for k in range(4):
+            if predraw:
+                m.predraw()          # no-op before the first evaluation
+                assert (m._noise_ready is not None) == (k > 0)
+            o = m(feat, cond, rl)
+            outs.append((o["pred_feature"].clone(), o["t1"].clone(), o["t2"].clone()))
+        torch.cuda.synchronize()
+        return outs
+
+    inline, ahead = run(False), run(True)
+    for a, b in zip(inline, ahead):
+        for x, y in zip(a, b):
+            assert torch.equal(x, y)
+    # shape change: the pre-drawn set does not fit, in-line draws
+    m.predraw()
+    o = m(feat_b, cond_b, torch.tensor([2], device=DEV))
+    assert o["pred_feature"].shape == feat_b.shape and torch.isfinite(o["pred_feature"]).all() and m._noise_ready is None
+    m(feat, cond, rl)
+    # pre-drawn set survives an injected-noise call
+    m.predraw()
+    assert m._noise_ready is not None
+    n0, steps = synth.sampler_noise(33, 3, 16, 16, 24)
+    m(feat, cond, rl, noise=(n0.to(DEV), torch.stack(steps).to(DEV)))
+    assert m._noise_ready is not None
+    m(feat, cond, rl)
+    assert m._noise_ready is None
+
+
 @pytest.mark.parametrize("C,record_len", [(128, [4]), (256, [5]), (64, [3, 1, 2]), (64, [20])])
 def test_sampler_cluster_resident_path(C, record_len):
     """'cluster' (the module default): the 26 width-8 layers of an evaluation in one launch of 8-CTA clusters, one per
