@@ -48,6 +48,9 @@ SIGNATURES = {
                                  c_void_p]),
     "gc_pillar_canvas_planes": (c_int, [c_void_p, c_void_p, c_int, c_int, _GEOM_P, c_void_p, c_void_p, _F3, c_void_p,
                                         c_void_p, c_void_p]),
+    "gc_pillar_canvas_planes_sparse": (c_int, [c_void_p, c_void_p, c_int, c_int, _GEOM_P, c_void_p, c_void_p, _F3, c_void_p,
+                                               c_void_p, c_void_p]),
+    "gc_planes_clear_occupied": (c_int, [_GEOM_P, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "gc_warp_fuse": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int,
                              c_void_p, c_void_p]),
     "gc_normalize_pairwise_tfm": (c_int, [c_void_p, c_int, c_double, c_double, c_double, c_double, c_void_p,

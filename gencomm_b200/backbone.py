@@ -107,6 +107,8 @@ class BaseBEVBackbone(nn.Module):
             c_in = None
             for packed, bias, n_out, c_in, stride in convs:
                 planes, h, w = ops.conv_planes(planes, A, c_in, h, w, packed, bias, n_out, 9, stride=stride)
+                if isinstance(x, ops.PlaneFeature):
+                    x.consumed()     # the input planes have been read for the last time (PointPillar's sparse planes)
             if out is None:
                 Hu, Wu = h * up, w * up
                 if self.emit_planes:
@@ -124,6 +126,8 @@ class BaseBEVBackbone(nn.Module):
                 ops.conv_planes(planes, A, up_in, h, w, phases, up_bias, up_out, 1, out_nchw=out, out_ch_off=ch_off, up=up,
                                 up_dy=-1)
             ch_off += up_out
+        if isinstance(x, ops.PlaneFeature):
+            x.consumed()
         if self.emit_planes:
             out = ops.PlaneFeature(out[0], out[1], (A, C_out, Hu, Wu))
         data_dict['spatial_features_2d'] = out

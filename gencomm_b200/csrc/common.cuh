@@ -42,6 +42,7 @@ struct VoxelWorkspace {
     uint32_t *slots;        // [A][max_voxels][32] ascending point indices (kEmpty = free)
     int32_t *pillar_cell;   // [A][max_voxels] cell id of each pillar
     int32_t *block_counts;  // [A][blocks_per_agent] first-point counts per block (look-back flags of k_pillar_build)
+    int32_t *n_pillars;     // [A] copy of gc_voxelize's n_pillars output (read by the pillar-centric planes writer)
     size_t bytes;
 };
 
@@ -62,6 +63,7 @@ inline VoxelWorkspace carve_workspace(void *base, const gcVoxelGeom &g, int n_ag
     // one count / look-back flag per block of >= 128 points; any agent has at most total_points points
     const size_t blocks = (size_t)(total_points + 127) / 128 + 2;
     w.block_counts = (int32_t *)take((size_t)n_agents * blocks * 4);
+    w.n_pillars = (int32_t *)take((size_t)n_agents * 4);
     w.bytes = off;
     return w;
 }

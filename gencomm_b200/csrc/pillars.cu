@@ -771,6 +771,10 @@ k_canvas(Src src, int nx, int ny, int C, float *__restrict__ canvas) {
 // ------------------------------------------------------------------------------------------------
 constexpr int kPlaneTileStride = GC_PFN_OUT + 4;   // floats per pixel row of the tile (16-byte aligned, bank-skewed)
 
+// SPARSE: the planes are all-zero on entry (the caller keeps them so: gc_pillar_canvas_planes_sparse + gc_planes_clear_occupied),
+// only the occupied cells are written -- 16 % of the cells of a 100 k-point cloud on the 512 x 256 grid -- and a tile without
+// a pillar ends after its code load.
+template <bool SPARSE>
 __global__ void __launch_bounds__(256, 4)
 k_canvas_planes(FusedSrc src, int nx, int ny, uint4 *__restrict__ xh, uint4 *__restrict__ xl) {
     __shared__ __align__(16) float tile[kTileX * kPlaneTileStride];
@@ -796,6 +800,7 @@ k_canvas_planes(FusedSrc src, int nx, int ny, uint4 *__restrict__ xh, uint4 *__r
     __syncthreads();
     const unsigned m0 = s_mask[0], m1 = s_mask[1], m2 = s_mask[2], m3 = s_mask[3];
     const int n_occ = __popc(m0) + __popc(m1) + __popc(m2) + __popc(m3);
+    if (SPARSE && n_occ == 0) return;   // block-uniform
     if (t < kTileX) {
         const unsigned mine = warp == 0 ? m0 : warp == 1 ? m1 : warp == 2 ? m2 : m3;
         if ((mine >> lane) & 1u) {
@@ -840,8 +845,10 @@ k_canvas_planes(FusedSrc src, int nx, int ny, uint4 *__restrict__ xh, uint4 *__r
         const int i = it * 256 + t, px = i / (GC_PFN_OUT / 8), g = i % (GC_PFN_OUT / 8);
         if (x0 + px >= nx) continue;
         if (!FusedSrc::occupied(s_code[px])) {
-            xh[row + (size_t)i] = make_uint4(0u, 0u, 0u, 0u);
-            xl[row + (size_t)i] = make_uint4(0u, 0u, 0u, 0u);
+            if (!SPARSE) {
+                xh[row + (size_t)i] = make_uint4(0u, 0u, 0u, 0u);
+                xl[row + (size_t)i] = make_uint4(0u, 0u, 0u, 0u);
+            }
             continue;
         }
         const float4 a = *reinterpret_cast<const float4 *>(tile + px * kPlaneTileStride + g * 8);
@@ -858,6 +865,70 @@ k_canvas_planes(FusedSrc src, int nx, int ny, uint4 *__restrict__ xh, uint4 *__r
         xh[row + (size_t)i] = make_uint4(h[0], h[1], h[2], h[3]);
         xl[row + (size_t)i] = make_uint4(l[0], l[1], l[2], l[3]);
     }
+}
+
+// Pillar-centric writer of the sparse planes: no tiles, no block barriers.  With the empty cells already zero the canvas
+// geometry is irrelevant: warp w of agent a walks the pillars w, w + stride, ... of the agent (creation order = the order of
+// their slot rows), software-pipelined like the tile writers (slot row and cell two pillars ahead, points one ahead), and
+// stores a pillar's 64 channels as one 128-byte line per plane.  (k_canvas_planes<true> was bound by its per-tile chain
+// code load -> barrier -> slot row -> points -> PFN -> barrier -> store at four CTAs per SM: skipping 84 % of the stores
+// took only 0.75 -> 0.64 ms off it, profiles/r02bi_step_ab.txt.)
+// grid = (blocks per agent, n_agents), 256 threads.
+__global__ void __launch_bounds__(256)
+k_pillar_planes_sparse(FusedSrc src, const int32_t *__restrict__ pillar_cell, const int32_t *__restrict__ n_pillars, int nx,
+                       int ncell, uint32_t *__restrict__ xh, uint32_t *__restrict__ xl) {
+    __shared__ float4 s_stage[8][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, a = blockIdx.y;
+    const int np = __ldg(n_pillars + a);
+    const int stride = gridDim.x * 8;
+    int pid = blockIdx.x * 8 + warp;
+    if (pid >= np) return;   // warp-uniform
+    const PfnLane wa = load_pfn(src.pfn, lane), wb = load_pfn(src.pfn, lane + 32);
+    const int pbase = __ldg(src.point_offsets + a);
+    const size_t prow = (size_t)a * src.max_voxels;
+    auto slot_of = [&](int q) -> uint32_t { return q < np ? __ldg(src.slots + (prow + q) * 32 + lane) : kEmpty; };
+    auto cell_of = [&](int q) -> int { return q < np ? __ldg(pillar_cell + prow + q) : 0; };
+    auto point_of = [&](uint32_t idx) -> float4 {
+        return idx != kEmpty ? __ldg(src.points + pbase + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+    uint32_t idx_cur = slot_of(pid), idx_nxt = slot_of(pid + stride);
+    int cell_cur = cell_of(pid), cell_nxt = cell_of(pid + stride);
+    float4 p_cur = point_of(idx_cur);
+    const int src_lane = 2 * (lane & 15);
+    for (; pid < np; pid += stride) {
+        const float4 p_nxt = point_of(idx_nxt);
+        const uint32_t idx_nxt2 = slot_of(pid + 2 * stride);
+        const int cell_nxt2 = cell_of(pid + 2 * stride);
+        const int n = __popc(__ballot_sync(0xffffffffu, idx_cur != kEmpty));   // slots fill from 0
+        const int y = cell_cur / nx, x = cell_cur - y * nx;
+        const float cx = __fadd_rn(__fmul_rn((float)x, src.vx), src.ox);
+        const float cy = __fadd_rn(__fmul_rn((float)y, src.vy), src.oy);
+        const float2 r = pfn_pillar(wa, wb, p_cur, n, cx, cy, src.cz, s_stage[warp]);
+        // lane l holds channels l and l + 32; word j of the pixel's 128-byte line = channels 2j, 2j + 1
+        const float a0 = __shfl_sync(0xffffffffu, r.x, src_lane), a1 = __shfl_sync(0xffffffffu, r.x, src_lane + 1);
+        const float b0 = __shfl_sync(0xffffffffu, r.y, src_lane), b1 = __shfl_sync(0xffffffffu, r.y, src_lane + 1);
+        const float v0 = lane < 16 ? a0 : b0, v1 = lane < 16 ? a1 : b1;
+        const __nv_bfloat162 hh = __floats2bfloat162_rn(v0, v1);
+        const __nv_bfloat162 ll = __floats2bfloat162_rn(v0 - __bfloat162float(hh.x), v1 - __bfloat162float(hh.y));
+        const size_t o = ((size_t)a * ncell + cell_cur) * (GC_PFN_OUT / 2) + lane;
+        xh[o] = *reinterpret_cast<const uint32_t *>(&hh);
+        xl[o] = *reinterpret_cast<const uint32_t *>(&ll);
+        idx_cur = idx_nxt; p_cur = p_nxt; idx_nxt = idx_nxt2;
+        cell_cur = cell_nxt; cell_nxt = cell_nxt2;
+    }
+}
+
+// Zeroes the cells gc_pillar_canvas_planes_sparse wrote (the workspace still holds the pillar list): eight threads per
+// pillar, one 16-byte vector per plane each.  grid = (ceil(max_voxels * 8 / 256), n_agents).
+__global__ void __launch_bounds__(256)
+k_planes_clear(const int32_t *__restrict__ pillar_cell, const int32_t *__restrict__ n_pillars, int max_voxels, int ncell,
+               uint4 *__restrict__ xh, uint4 *__restrict__ xl) {
+    const int a = blockIdx.y, t = blockIdx.x * 256 + threadIdx.x, pid = t >> 3;
+    if (pid >= __ldg(n_pillars + a)) return;
+    const int cell = __ldg(pillar_cell + (size_t)a * max_voxels + pid);
+    const size_t o = ((size_t)a * ncell + cell) * (GC_PFN_OUT / 8) + (t & 7);
+    xh[o] = make_uint4(0u, 0u, 0u, 0u);
+    xl[o] = make_uint4(0u, 0u, 0u, 0u);
 }
 
 __device__ __forceinline__ float2 dup2(float v) { return make_float2(v, v); }
@@ -1559,7 +1630,7 @@ extern "C" size_t gc_voxelize_workspace_bytes(const gcVoxelGeom *geom, int n_age
     return carve_workspace(nullptr, *geom, n_agents, total_points).bytes;
 }
 
-extern "C" int gc_voxelize(const float *points, const int32_t *point_offsets, int n_agents, int total_points,
+static int voxelize_impl(const float *points, const int32_t *point_offsets, int n_agents, int total_points,
                            int max_agent_points, const gcVoxelGeom *geom, void *workspace, int32_t *n_pillars,
                            void *stream) {
     GeomDev g;
@@ -1617,6 +1688,16 @@ extern "C" int gc_voxelize(const float *points, const int32_t *point_offsets, in
                                                             g.max_voxels, w.slots);
         GC_LAUNCH_CHECK("k_slot_insert");
     }
+    return GC_OK;
+}
+
+extern "C" int gc_voxelize(const float *points, const int32_t *point_offsets, int n_agents, int total_points,
+                           int max_agent_points, const gcVoxelGeom *geom, void *workspace, int32_t *n_pillars,
+                           void *stream) {
+    if (int rc = voxelize_impl(points, point_offsets, n_agents, total_points, max_agent_points, geom, workspace, n_pillars, stream))
+        return rc;
+    const VoxelWorkspace w = carve_workspace(workspace, *geom, n_agents, total_points);
+    cudaMemcpyAsync(w.n_pillars, n_pillars, (size_t)n_agents * 4, cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
     return GC_OK;
 }
 
@@ -1733,9 +1814,9 @@ extern "C" int gc_pillar_canvas(const float *points, const int32_t *point_offset
 
 // The fused front end with the canvas written as the backbone's operand planes (k_canvas_planes); same arguments as
 // gc_pillar_canvas, xh / xl: [n_agents][ny*nx][64] bf16 value / residual.
-extern "C" int gc_pillar_canvas_planes(const float *points, const int32_t *point_offsets, int n_agents, int total_points,
-                                       const gcVoxelGeom *geom, const void *workspace, const float *pfn,
-                                       const float centre_offset[3], void *xh, void *xl, void *stream) {
+static int pillar_canvas_planes(bool sparse, const float *points, const int32_t *point_offsets, int n_agents, int total_points,
+                                const gcVoxelGeom *geom, const void *workspace, const float *pfn,
+                                const float centre_offset[3], void *xh, void *xl, void *stream) {
     GeomDev g;
     if (int rc = make_geom(geom, &g)) return rc;
     GC_REQUIRE(g.grid[2] == 1, GC_EUNSUPPORTED, "PointPillarScatter requires nz == 1 (point_pillar_scatter.py:17)");
@@ -1755,8 +1836,58 @@ extern "C" int gc_pillar_canvas_planes(const float *points, const int32_t *point
     src.ox = centre_offset[0];
     src.oy = centre_offset[1];
     src.cz = 0.0f * g.voxel[2] + centre_offset[2];
-    k_canvas_planes<<<dim3((g.grid[0] + kTileX - 1) / kTileX, g.grid[1], n_agents), 256, 0, (cudaStream_t)stream>>>(
-        src, g.grid[0], g.grid[1], (uint4 *)xh, (uint4 *)xl);
+    const dim3 grid((g.grid[0] + kTileX - 1) / kTileX, g.grid[1], n_agents);
+    if (sparse) {
+        static int sms = 0;
+        if (sms == 0) {
+            int dev = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        }
+        const char *e = getenv("GC_SPARSE_WRITER");   // A/B and tests: "tile" = k_canvas_planes<true>
+        if (e && strcmp(e, "tile") == 0) {
+            k_canvas_planes<true><<<grid, 256, 0, (cudaStream_t)stream>>>(src, g.grid[0], g.grid[1], (uint4 *)xh, (uint4 *)xl);
+        } else {
+            // four CTAs of eight warps per SM over all agents; a warp walks its pillars with stride = warps per agent
+            int bpa = (4 * sms + n_agents - 1) / n_agents;
+            const int cap = (g.max_voxels + 7) / 8;
+            bpa = bpa < 1 ? 1 : (bpa > cap ? cap : bpa);
+            k_pillar_planes_sparse<<<dim3(bpa, n_agents), 256, 0, (cudaStream_t)stream>>>(
+                src, w.pillar_cell, w.n_pillars, g.grid[0], g.ncell, (uint32_t *)xh, (uint32_t *)xl);
+        }
+    } else
+        k_canvas_planes<false><<<grid, 256, 0, (cudaStream_t)stream>>>(src, g.grid[0], g.grid[1], (uint4 *)xh, (uint4 *)xl);
     GC_LAUNCH_CHECK("k_canvas_planes");
+    return GC_OK;
+}
+
+extern "C" int gc_pillar_canvas_planes(const float *points, const int32_t *point_offsets, int n_agents, int total_points,
+                                       const gcVoxelGeom *geom, const void *workspace, const float *pfn,
+                                       const float centre_offset[3], void *xh, void *xl, void *stream) {
+    return pillar_canvas_planes(false, points, point_offsets, n_agents, total_points, geom, workspace, pfn, centre_offset, xh, xl,
+                                stream);
+}
+
+// Sparse maintenance of the planes: xh / xl are all-zero on entry, only the occupied cells are written; the caller calls
+// gc_planes_clear_occupied (same workspace, before the next gc_voxelize) once the planes have been consumed, which zeroes
+// exactly those cells again.  330 MB written + 330 MB cleared instead of 2.0 GB written per 60 agents at 512 x 256.
+extern "C" int gc_pillar_canvas_planes_sparse(const float *points, const int32_t *point_offsets, int n_agents, int total_points,
+                                              const gcVoxelGeom *geom, const void *workspace, const float *pfn,
+                                              const float centre_offset[3], void *xh, void *xl, void *stream) {
+    return pillar_canvas_planes(true, points, point_offsets, n_agents, total_points, geom, workspace, pfn, centre_offset, xh, xl,
+                                stream);
+}
+
+extern "C" int gc_planes_clear_occupied(const gcVoxelGeom *geom, int n_agents, int total_points, const void *workspace, void *xh,
+                                        void *xl, void *stream) {
+    GeomDev g;
+    if (int rc = make_geom(geom, &g)) return rc;
+    GC_REQUIRE(workspace && xh && xl, GC_EINVAL, "gc_planes_clear_occupied: null pointer");
+    GC_REQUIRE(n_agents > 0 && g.grid[2] == 1, GC_EINVAL, "gc_planes_clear_occupied: bad sizes");
+    const VoxelWorkspace w = carve_workspace(const_cast<void *>(workspace), *geom, n_agents, total_points);
+    GC_REQUIRE(n_agents <= 65535, GC_EUNSUPPORTED, "gc_planes_clear_occupied: too many agents");
+    k_planes_clear<<<dim3((g.max_voxels * 8 + 255) / 256, n_agents), 256, 0, (cudaStream_t)stream>>>(
+        w.pillar_cell, w.n_pillars, g.max_voxels, g.ncell, (uint4 *)xh, (uint4 *)xl);
+    GC_LAUNCH_CHECK("k_planes_clear");
     return GC_OK;
 }

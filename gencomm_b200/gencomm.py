@@ -13,6 +13,8 @@ import ctypes
 import math
 
 import numpy as np
+import os
+
 import torch
 import torch.nn as nn
 
@@ -276,7 +278,7 @@ class GenComm(nn.Module):
             self.register_buffer(k, v)
         self._ws = None
         # noise drawn ahead of its use, on a side stream (predraw()): the draws depend on nothing but the shape
-        self.predraw_enabled = True
+        self.predraw_enabled = os.environ.get("GC_NOISE_PREDRAW", "1") != "0"    # A/B switch
         self._noise_shape = None     # (A, C, H, W, device, dtype) of the last evaluation
         self._noise_bufs = None      # persistent n0 / t1n / t2n / steps
         self._noise_ready = None     # event recorded on the side stream after the draws; None = nothing drawn

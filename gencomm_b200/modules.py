@@ -20,6 +20,8 @@ must be CUDA tensors and the CUDA library must be built.
 import sys
 
 import numpy as np
+import os
+
 import torch
 import torch.nn as nn
 
@@ -225,6 +227,26 @@ class PointPillar(nn.Module):
         # True: the raw-point path returns an ops.PlaneFeature (the backbone's operand planes) instead of the fp32 canvas --
         # set by the model when this package's BaseBEVBackbone consumes the canvas directly
         self.emit_planes = False
+        # the planes live in a persistent buffer that is all-zero between frames: a frame writes its occupied cells only
+        # (16 % of the 512 x 256 grid at 100 k points) and zeroes them again once the backbone's first convolution has
+        # been enqueued (ops.PlaneFeature.consumed) -- 0.66 GB of stores per 60 agents instead of 2.0 GB
+        self.sparse_planes = os.environ.get("GC_SPARSE_PLANES", "1") != "0"     # A/B switch
+        self._planes = None
+        self._planes_dirty = False
+
+    def _planes_out(self, ws, device):
+        n = ops.plane_bytes(ws)
+        if self._planes is None or self._planes[0].numel() != n or self._planes[0].device != device:
+            self._planes = (torch.zeros(n, dtype=torch.uint8, device=device), torch.zeros(n, dtype=torch.uint8, device=device))
+        elif self._planes_dirty:     # the previous frame's planes were never released by a consumer
+            self._planes[0].zero_()
+            self._planes[1].zero_()
+        self._planes_dirty = True
+        return self._planes
+
+    def _planes_release(self, ws):
+        ops.planes_clear_occupied(ws, *self._planes)
+        self._planes_dirty = False
 
     def forward(self, data_dict, modality_name):
         inp = data_dict[f'inputs_{modality_name}']
@@ -249,8 +271,14 @@ class PointPillar(nn.Module):
         ws = self._pre.voxelize_device(points, point_offsets, max_agent_points)
         v = self.pillar_vfe
         if self.emit_planes and out is None:
-            return ops.pillar_canvas_planes(points, point_offsets, ws, v.pfn_table(points.device),
-                                            (v.x_offset, v.y_offset, v.z_offset))
+            if not self.sparse_planes:
+                return ops.pillar_canvas_planes(points, point_offsets, ws, v.pfn_table(points.device),
+                                                (v.x_offset, v.y_offset, v.z_offset))
+            feat = ops.pillar_canvas_planes(points, point_offsets, ws, v.pfn_table(points.device),
+                                            (v.x_offset, v.y_offset, v.z_offset), out=self._planes_out(ws, points.device),
+                                            sparse=True)
+            feat.on_consumed = lambda: self._planes_release(ws)
+            return feat
         return ops.pillar_canvas(points, point_offsets, ws, v.pfn_table(points.device),
                                  (v.x_offset, v.y_offset, v.z_offset), out=out)
 

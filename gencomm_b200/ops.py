@@ -179,19 +179,41 @@ def scatter_canvas(pillar_features, voxel_coords, nx, ny, n_batch, out=None, cel
     return out
 
 
-def pillar_canvas_planes(points, point_offsets, ws, pfn, centre_off):
-    """Voxelizer workspace -> BEV canvas as a PlaneFeature (channel-last bf16 value + residual planes, shape [A,64,ny,nx])."""
+def plane_bytes(ws):
+    """Bytes of one bf16 plane (value or residual) of the canvas of a voxelizer workspace."""
+    g = ws.geom
+    return max(ws.n_agents * g.grid[1] * g.grid[0] * 64 * 2, 1)
+
+
+def pillar_canvas_planes(points, point_offsets, ws, pfn, centre_off, out=None, sparse=False):
+    """Voxelizer workspace -> BEV canvas as a PlaneFeature (channel-last bf16 value + residual planes, shape [A,64,ny,nx]).
+    out = (xh, xl) uint8 buffers of plane_bytes(ws); sparse: the buffers are all-zero, only the occupied cells are written
+    (the caller zeroes them again with planes_clear_occupied once the planes have been consumed)."""
     lib = _lib.load()
     _chk(points, "points", torch.float32, 2)
     _chk(point_offsets, "point_offsets", torch.int32, 1)
     _chk(pfn, "pfn", torch.float32, 2)
     g = ws.geom
-    xh = torch.empty(max(ws.n_agents * g.grid[1] * g.grid[0] * 64 * 2, 1), dtype=torch.uint8, device=points.device)
-    xl = torch.empty_like(xh)
-    _lib.check(lib.gc_pillar_canvas_planes(_ptr(points), _ptr(point_offsets), ws.n_agents, ws.total_points,
-                                           ctypes.byref(g), _ptr(ws.buf), _ptr(pfn), _lib.f3(centre_off), _ptr(xh), _ptr(xl),
-                                           _stream()), "gc_pillar_canvas_planes")
+    if out is None:
+        if sparse:
+            raise ValueError("pillar_canvas_planes: sparse=True needs the caller's zeroed buffers (out=)")
+        xh = torch.empty(plane_bytes(ws), dtype=torch.uint8, device=points.device)
+        xl = torch.empty_like(xh)
+    else:
+        xh, xl = out
+        for t in (xh, xl):
+            if t.dtype != torch.uint8 or t.numel() != plane_bytes(ws) or t.device != points.device or not t.is_contiguous():
+                raise ValueError("pillar_canvas_planes: out must be two contiguous uint8 buffers of plane_bytes(ws)")
+    fn = lib.gc_pillar_canvas_planes_sparse if sparse else lib.gc_pillar_canvas_planes
+    _lib.check(fn(_ptr(points), _ptr(point_offsets), ws.n_agents, ws.total_points, ctypes.byref(g), _ptr(ws.buf), _ptr(pfn),
+                  _lib.f3(centre_off), _ptr(xh), _ptr(xl), _stream()), "gc_pillar_canvas_planes")
     return PlaneFeature(xh, xl, (ws.n_agents, 64, g.grid[1], g.grid[0]))
+
+
+def planes_clear_occupied(ws, xh, xl):
+    """Zeroes the cells pillar_canvas_planes(sparse=True) wrote from this workspace (before its next voxelize)."""
+    _lib.check(_lib.load().gc_planes_clear_occupied(ctypes.byref(ws.geom), ws.n_agents, ws.total_points, _ptr(ws.buf), _ptr(xh),
+                                                    _ptr(xl), _stream()), "gc_planes_clear_occupied")
 
 
 def pillar_canvas(points, point_offsets, ws, pfn, centre_off, out=None):
@@ -468,6 +490,12 @@ class PlaneFeature:
 
     def __init__(self, xh, xl, shape):
         self.xh, self.xl, self.shape = xh, xl, tuple(shape)      # shape = (A, C, H, W)
+        self.on_consumed = None    # called once by the consumer after its last read of the planes has been enqueued
+
+    def consumed(self):
+        cb, self.on_consumed = self.on_consumed, None
+        if cb is not None:
+            cb()
 
     @property
     def device(self):

@@ -129,6 +129,15 @@ int gc_pillar_canvas(const float *points, const int32_t *point_offsets, int n_ag
 int gc_pillar_canvas_planes(const float *points, const int32_t *point_offsets, int n_agents, int total_points,
                             const gcVoxelGeom *geom /*[host]*/, const void *workspace, const float *pfn,
                             const float centre_offset[3] /*[host]*/, void *xh, void *xl, void *stream);
+/* Sparse maintenance of the same planes (a persistent buffer of the caller that is all-zero between frames): only the
+ * occupied cells are written -- 16 % of a 512 x 256 grid at 100 k points -- and gc_planes_clear_occupied, called with the
+ * same workspace once the planes have been consumed (before the next gc_voxelize on that workspace), zeroes exactly those
+ * cells again.  Same plane contents as gc_pillar_canvas_planes, bit for bit. */
+int gc_pillar_canvas_planes_sparse(const float *points, const int32_t *point_offsets, int n_agents, int total_points,
+                                   const gcVoxelGeom *geom /*[host]*/, const void *workspace, const float *pfn,
+                                   const float centre_offset[3] /*[host]*/, void *xh, void *xl, void *stream);
+int gc_planes_clear_occupied(const gcVoxelGeom *geom /*[host]*/, int n_agents, int total_points, const void *workspace,
+                             void *xh, void *xl, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
  * (a6)+(a7)+(a8)/(a9) regroup + warp_affine_simple + MaxFusion / AttFusion

@@ -192,6 +192,34 @@ def test_fused_front_end_full_size(rng, uniform, writer, monkeypatch):
         assert isinstance(feat, ops.PlaneFeature) and feat.shape == tuple(ref.shape)
         xh, xl = ops.to_planes(ref.to(DEV))
         assert torch.equal(feat.xh, xh) and torch.equal(feat.xl, xl)
+        # that was the sparse path (persistent all-zero planes, occupied cells written, cleared on release); frames in a row,
+        # a frame that is never released (full re-zero on the next one), and the dense writer give the same planes
+        assert enc.sparse_planes and feat.on_consumed is not None and enc._planes_dirty
+        inp = {"inputs_m1": {"points": pts, "point_offsets": off, "max_agent_points": max(sizes)}}
+        enc.emit_planes = True
+        try:
+            monkeypatch.setenv("GC_SPARSE_WRITER", "tile")   # the tile writer's sparse form (default: pillar-centric kernel)
+            feat2 = enc(inp, "m1")                      # previous frame not released -> buffers re-zeroed
+            monkeypatch.delenv("GC_SPARSE_WRITER")
+            assert torch.equal(feat2.xh, xh) and torch.equal(feat2.xl, xl)
+            feat2.consumed()
+            assert not enc._planes_dirty and feat2.on_consumed is None
+            assert int(feat2.xh.count_nonzero()) == 0 and int(feat2.xl.count_nonzero()) == 0
+            half = pts[: sizes[0]]                       # a different frame (first agent only, the others empty)
+            off2 = torch.tensor([0] + [sizes[0]] * len(sizes), dtype=torch.int32, device=DEV)
+            inp2 = {"inputs_m1": {"points": half, "point_offsets": off2, "max_agent_points": sizes[0]}}
+            f3 = enc(inp2, "m1")
+            a3, b3 = f3.xh.clone(), f3.xl.clone()
+            f3.consumed()
+            f4 = enc(inp, "m1")
+            assert torch.equal(f4.xh, xh) and torch.equal(f4.xl, xl)
+            f4.consumed()
+            enc.sparse_planes = False
+            d3 = enc(inp2, "m1")
+            assert d3.on_consumed is None and torch.equal(d3.xh, a3) and torch.equal(d3.xl, b3)
+        finally:
+            enc.emit_planes = False
+            enc.sparse_planes = True
 
 
 @pytest.mark.parametrize("writer", ["tile", "persist"])
