@@ -538,6 +538,11 @@ def run_ours(args):
                                   f"(20 s cap), oracle restatement of the reference CPU path, torch threads={cores}"}
 
     pipe = pipeline.DetectorPipeline(F, N, POINTS, shape=shape, fusion=FUSION, device=dev)
+    # steps in flight: consecutive steps alternate between independent pipeline instances (own weights, workspaces, planes)
+    # on their own CUDA streams, so that the thin tails of one step -- NMS (15 - 128 CTAs), the sampler's 120-CTA cluster
+    # launches, the last wave of every persistent kernel -- are filled by the other step's kernels
+    n_fly = max(1, args.steps_in_flight)
+    pipes = [pipe] + [pipeline.DetectorPipeline(F, N, POINTS, shape=shape, fusion=FUSION, device=dev) for _ in range(n_fly - 1)]
     n_sets = 3   # distinct input sets cycled; every stage streams >> 126 MB per step (canvas alone is 1.1 GB)
     host_pts, host_pw = [], []
     for s in range(n_sets):
@@ -546,17 +551,18 @@ def run_ours(args):
         host_pw.append(torch.from_numpy(pw).pin_memory())
     dev_pts = [t.to(dev) for t in host_pts]
     dev_pw = [t.to(dev) for t in host_pw]
-    gathered_det = torch.empty((world * F, shard.DET_WIDTH), dtype=torch.float32, device=dev) if world > 1 else None
+    gathered_det = [torch.empty((world * F, shard.DET_WIDTH), dtype=torch.float32, device=dev) if world > 1 else None
+                    for _ in range(n_fly)]
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def full_step(pts, pw):
-        boxes, scores, counts = pipe.step(pts, pw)
+    def full_step(pts, pw, i=0):
+        boxes, scores, counts = pipes[i].step(pts, pw)
         if world > 1:      # the path's one exchange step: every rank ends the step with every frame's detections
-            return shard.gather_detections_device(boxes, scores, counts, out=gathered_det)
+            return shard.gather_detections_device(boxes, scores, counts, out=gathered_det[i])
         return boxes, scores, counts
 
     # ---------------- device-resident timing ----------------
@@ -575,15 +581,41 @@ def run_ours(args):
         res = full_step(dev_pts[k % n_sets], dev_pw[k % n_sets])
     t_end.record()
     barrier()
-    elapsed_ms = t_start.elapsed_time(t_end)
+    elapsed_ms = serial_ms = t_start.elapsed_time(t_end)
     stage_ms = pipe.stage_ms(K)
-    pipe._marks = None     # the e2e region below runs on side streams: no hook events there
+    pipe._marks = None     # the regions below run on side streams: no hook events there
+    if n_fly > 1:
+        # the headline region: the same K steps, n_fly in flight.  (The region above, one step in flight with the per-stage
+        # events, is what stage_ms / kernels / roofline are computed from and is reported as `one_in_flight`.)
+        fly = [torch.cuda.Stream() for _ in range(n_fly)]
+        cur = torch.cuda.current_stream()
+
+        def fly_steps(n):
+            out = None
+            for st in fly:
+                st.wait_stream(cur)
+            for k in range(n):
+                with torch.cuda.stream(fly[k % n_fly]):
+                    out = full_step(dev_pts[k % n_sets], dev_pw[k % n_sets], k % n_fly)
+            for st in fly:
+                cur.wait_stream(st)
+            return out
+
+        fly_steps(max(Wm, 2 * n_fly))
+        barrier()
+        t_start.record()
+        res = fly_steps(K)
+        t_end.record()
+        barrier()
+        elapsed_ms = t_start.elapsed_time(t_end)
     det_counts = (res[:, 0] if world > 1 else res[2].float()).tolist()
     checksum = float((res if world > 1 else shard.pack_detections(*res)).double().sum().item())
 
     # ---------------- end-to-end timing: pinned host points -> device -> detections back in pinned host memory ----------------
-    s_in, s_comp, s_out = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream()
-    slots = 2
+    s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+    slots = 2 * n_fly    # every step in flight is double buffered: the inputs of its successor on the same stream are
+                         # copied in while it computes
+    s_comps = [torch.cuda.Stream() for _ in range(n_fly)]   # slot s computes on pipeline / stream s % n_fly
     d_pts = [torch.empty_like(dev_pts[0]) for _ in range(slots)]
     d_pw = [torch.empty_like(dev_pw[0]) for _ in range(slots)]
     d_out = [torch.empty((F, shard.DET_WIDTH), dtype=torch.float32, device=dev) for _ in range(slots)]
@@ -595,28 +627,30 @@ def run_ours(args):
     def e2e_step(k):
         s = k % slots
         with torch.cuda.stream(s_in):
-            s_in.wait_event(ev_comp[s])          # compute of step k-2 has consumed this slot's inputs
+            s_in.wait_event(ev_comp[s])          # compute of step k - slots has consumed this slot's inputs
             d_pts[s].copy_(host_pts[k % n_sets], non_blocking=True)
             d_pw[s].copy_(host_pw[k % n_sets], non_blocking=True)
             ev_in[s].record()
+        s_comp = s_comps[s % len(s_comps)]
         with torch.cuda.stream(s_comp):
             s_comp.wait_event(ev_in[s])
-            s_comp.wait_event(ev_out[s])         # D2H of step k-2 has drained this slot's result
-            d_out[s].copy_(shard.pack_detections(*pipe.step(d_pts[s], d_pw[s])))
+            s_comp.wait_event(ev_out[s])         # D2H of step k - slots has drained this slot's result
+            d_out[s].copy_(shard.pack_detections(*pipes[s % len(s_comps)].step(d_pts[s], d_pw[s])))
             ev_comp[s].record()
         with torch.cuda.stream(s_out):
             s_out.wait_event(ev_comp[s])
             h_out[s].copy_(d_out[s], non_blocking=True)
             ev_out[s].record()
 
-    for w in range(Wm):
+    for w in range(max(Wm, slots)):
         e2e_step(w)
     barrier()
     e_start, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e_start.record(s_in)
     for k in range(K):
         e2e_step(k)
-    s_out.wait_stream(s_comp)
+    for s_comp in s_comps:
+        s_out.wait_stream(s_comp)
     s_out.wait_stream(s_in)
     e_end.record(s_out)
     barrier()
@@ -642,7 +676,7 @@ def run_ours(args):
             torch.cuda.empty_cache()
 
     # ---------------- max over ranks, gather of checksums + timings ----------------
-    times = torch.tensor([elapsed_ms, e2e_ms], dtype=torch.float64, device=dev)
+    times = torch.tensor([elapsed_ms, e2e_ms, serial_ms], dtype=torch.float64, device=dev)
     gathered = None
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
@@ -650,7 +684,7 @@ def run_ours(args):
                             dtype=torch.float64, device=dev)
         gathered = [torch.empty_like(mine) for _ in range(world)]
         dist.all_gather(gathered, mine)
-    elapsed_ms, e2e_ms = float(times[0]), float(times[1])
+    elapsed_ms, e2e_ms, serial_ms = float(times[0]), float(times[1]), float(times[2])
 
     if rank == 0:
         frames = world * F * K
@@ -692,19 +726,25 @@ def run_ours(args):
             "config": {"workload": SHAPES[shape]["workload"], "frames_per_step_per_gpu": F, "agents": N,
                        "points_per_agent": POINTS, "grid": [pipe.nx, pipe.ny], "fusion": FUSION,
                        "sampler_precision": pipe.model.gencomm.precision, "weights": "seeded synthetic (synth.fill_state_dict)",
-                       "noise": "drawn on the device with torch.randn inside the step, like the reference",
+                       "noise": "drawn on the device with torch.randn inside the step, like the reference (GenComm.predraw: on a "
+                                "side stream under the backbone)",
+                       "steps_in_flight": n_fly,
                        "l2": f"{n_sets} distinct input sets cycled; every stage streams more than the 126 MB L2 per step "
                              f"(canvas {F * N * 64 * pipe.nx * pipe.ny * 4 / 1e6:.0f} MB)"},
             "clocks": clocks,
             "e2e": {"value": frames / (e2e_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / K,
                     "note": "pinned host points + poses -> device -> padded detections (count | scores | boxes per frame) "
-                            "copied back to pinned host memory, 3 streams, double buffered; ranks bound to their GPU's NUMA node"},
+                            "copied back to pinned host memory; copy-in, copy-out and one compute stream per step in flight, "
+                            "double buffered; ranks bound to their GPU's NUMA node"},
             "cpu_affinity": affinity,
             "collective": ({"op": "all_gather_into_tensor (NCCL)", "bytes_per_rank_per_step": F * shard.DET_WIDTH * 4,
                             "in_timed_region": True, "payload": "padded gc_postprocess output of the rank's frames"}
                            if world > 1 else None),
             "gpu_launches": K * pipeline_launches(pipe, stage_ms),
+            "one_in_flight": {"ms_per_step": serial_ms / K, "frames_per_s": frames / (serial_ms * 1e-3),
+                              "note": "the same K steps, one after the other on one stream, with the per-stage CUDA events: "
+                                      "stage_ms, kernels and roofline are measured in this region"},
             "roofline": roofline,
             "kernels": kernels,
             "stage_ms": {k: round(v, 4) for k, v in stage_ms.items()},
@@ -812,6 +852,8 @@ def main():
                     help="collaborative frames per step and GPU.  15 frames x 4 agents = 60 agents = four full rounds of the 15 "
                          "co-resident sampler clusters (8 frames: 32 agents = 2.13 rounds); measured 8 -> 876, 12 -> 882, 15 -> 925, "
                          "16 -> 921, 24 -> 925 frames/s (profiles/r02ax_frames_per_step.txt)")
+    ap.add_argument("--steps-in-flight", type=int, default=2, choices=[1, 2, 3],
+                    help="independent pipeline instances / CUDA streams the consecutive steps alternate between")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the secondary sections (configs[1] HBM step, sampler, ...)")
     ap.add_argument("--cpu-protocol", action="store_true", help="--impl reference: also time k = 1 thread (BASELINE.md section 3)")
