@@ -701,6 +701,13 @@ def run_ours(args):
             if "flops" in w:
                 e.update({"flops": w["flops"], "tflops": w["flops"] / (ms * 1e-3) / 1e12})
                 e["tensor_frac"] = e["tflops"] / tpeak
+            if st == "pillars" and getattr(pipe.model.encoder_m1, "sparse_planes", False):
+                e["note"] = ("bytes = SURVEY 8(d)'s dense figure (16 B per point + every canvas byte once), kept so that rounds "
+                             "compare; the planes are maintained sparsely since r02bj -- a frame stores its occupied cells only "
+                             "(k_pillar_planes_sparse) and zeroes them again after the backbone's first convolution "
+                             "(k_planes_clear, ~0.08 ms per step, inside the backbone stage's time) -- so the DRAM traffic of the "
+                             "stage is ~1.1 GB per step (+ 0.28 GB for the clear), not 2.1 GB: ncu per kernel in "
+                             "profiles/r02bp_front_end_ncu.txt; hbm_frac is NOT a fraction of moved bytes for this stage")
             kernels[STAGE_KERNELS.get(st, st)] = e
         dom_stage = max(stage_ms, key=stage_ms.get)
         dom = kernels.get(STAGE_KERNELS.get(dom_stage, dom_stage))
@@ -763,19 +770,21 @@ def run_ours(args):
 
 STAGE_ORDER = ("pillars", "backbone", "shrink", "message_extractor", "sampler", "enhancer", "warp_fuse", "postprocess")
 STAGE_KERNELS = {
-    "pillars": "front end: k_cell_assign2+k_pillar_build+k_canvas_planes (voxelize+PFN+scatter into the "
+    "pillars": "front end: k_cell_assign2+k_pillar_build+k_pillar_planes_sparse (voxelize+PFN+scatter into the "
                "backbone's bf16 operand planes, 512x256 grid)",
     "backbone": "k_conv_tma (BaseBEVBackbone, 19 3x3 + 3 phase-fused deblock TMA-fed tcgen05 implicit GEMMs, bf16x3)",
     "warp_fuse": "k_fuse_persist<ATT> (warp+regroup+AttFusion at the native shape)",
-    "sampler": "GenComm sampler (k_q_sample, 3 x [k_conv_in_tc, k_unet_middle_cluster, k_conv_out_tc] + torch.randn noise)",
+    "sampler": "GenComm sampler (k_q_sample, 3 x [k_conv_in_tc, k_unet_middle_cluster, k_conv_out_tc]; the torch.randn noise "
+               "is drawn ahead on a side stream, under the backbone)",
 }
 
 
 def pipeline_launches(pipe, stage_ms):
     """Kernels of this repo launched per detector step (counted from the launch sequence of each stage; the torch.randn /
     elementwise launches of the wrappers are not counted)."""
-    n = 3                      # front end: k_cell_assign2, k_pillar_build, k_canvas_planes (no to_planes)
-    n += 22                    # backbone: 19 convs + 3 deblocks (all phases of a ConvTranspose2d in one launch; shrink header's planes)
+    n = 3                      # front end: k_cell_assign2, k_pillar_build, k_pillar_planes_sparse (no to_planes)
+    n += 22 + 1                # backbone: 19 convs + 3 deblocks (all phases of a ConvTranspose2d in one launch; shrink header's
+                               # planes) + k_planes_clear after the first conv
     n += 2                     # shrink header: 2 convs
     n += 5                     # message extractor
     cluster = pipe.model.gencomm.precision == "cluster"

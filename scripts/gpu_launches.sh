@@ -2,7 +2,7 @@
 # launch list of one detector step (ncu serialises launches: shares, not absolutes)
 OUT=gpurun_out; mkdir -p $OUT; TAG=${1:-r02z}
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $OUT/launches_step_$TAG.csv \
-    python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-extras --frames-per-step ${FRAMES:-15} > /dev/null 2>&1
+    python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-extras --steps-in-flight 1 --frames-per-step ${FRAMES:-15} > /dev/null 2>&1
 python - $OUT/launches_step_$TAG.csv <<'PY'
 import csv,sys
 rows=[r for r in csv.reader(open(sys.argv[1])) if len(r)>5]
