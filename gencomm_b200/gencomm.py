@@ -296,17 +296,23 @@ class GenComm(nn.Module):
                      'cluster': ops.PREC_CLUSTER_ALL}[value]
         self.denoiser.precision = int(value)
 
-    def _draw(self, shape):
-        """The four draws of an evaluation, in the reference's order, into persistent buffers."""
+    def _bufs(self, shape):
+        """Persistent n0 / t1n / t2n / steps buffers for a shape (allocated on the CURRENT stream: predraw() calls this
+        before it switches to its side stream, so the caching allocator never files them under the side stream)."""
         A, C, H, W, dev, dtype = shape
         if self._noise_bufs is None or self._noise_bufs[0].shape != (A, C, H, W) or self._noise_bufs[0].device != dev \
                 or self._noise_bufs[0].dtype != dtype:
             self._noise_bufs = (torch.empty(A, C, H, W, device=dev, dtype=dtype),
                                 torch.empty(1, C, H, W, device=dev), torch.empty(1, C, H, W, device=dev),
                                 torch.empty(self.num_timesteps, A, C, H, W, device=dev))
-        for b in self._noise_bufs:   # == torch.randn(shape): empty + normal_ on the default CUDA generator
-            b.normal_()
         return self._noise_bufs
+
+    def _draw(self, shape):
+        """The four draws of an evaluation, in the reference's order, into the persistent buffers."""
+        bufs = self._bufs(shape)
+        for b in bufs:   # == torch.randn(shape): empty + normal_ on the default CUDA generator
+            b.normal_()
+        return bufs
 
     def predraw(self):
         """Draws the Gaussian noise of the NEXT evaluation now, on a side stream, so that the generator kernels (HBM
@@ -322,6 +328,7 @@ class GenComm(nn.Module):
         if self._noise_stream is None:
             self._noise_stream = torch.cuda.Stream(device=shape[4])
         side = self._noise_stream
+        self._bufs(shape)            # (allocation, if any, on the caller's stream)
         side.wait_stream(main)       # the previous evaluation's kernels are done with the buffers
         with torch.cuda.stream(side):
             self._draw(shape)
