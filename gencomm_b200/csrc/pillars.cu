@@ -229,25 +229,22 @@ k_slot_insert(const int32_t *__restrict__ point_offsets, const int32_t *__restri
 
 // ------------------------------------------------------------------------------------------------
 // 2+3 fused (the default voxelizer since round 2): pillar ranking and slot insertion in ONE pass over the
-// points, k_pillar_build.  grid = (blocks_per_agent, n_agents), 256 threads x 4 items, item-major order like
-// k_pillar_assign.  Every dependency of a block points at a block with a lower linear index of the same agent
-// (the hardware dispatches blocks in linear order, the assumption every decoupled look-back scan makes):
+// points, k_pillar_build.  grid = (n_agents, chunks) with the agent fastest, 256 threads x IT points, item-major
+// order like k_pillar_assign.  Every dependency of a block points at a block with a lower linear index of the same
+// agent (the hardware dispatches blocks in linear order, the assumption every decoupled look-back scan makes):
 //   a. first-point flags (cell_code[cell] == i after k_cell_assign2), block total published at once with
 //      st.release into block_flags (kEmpty = not yet; cleared by k_cell_assign2) -- no dependency;
-//   b. warp 0 sums the totals of all preceding blocks of the agent (ld.acquire spin) = first pillar id;
+//   b. warp 0 sums the totals of all preceding blocks of the agent (ld.relaxed polls, four in flight per lane)
+//      = first pillar id of the block;
 //   c. first points: pillar id (creation order), pillar_cell, slot row = {i, empty x 31} -- the first point of
-//      a cell is its smallest index, i.e. slot 0 for good -- then st.release of kPillarBit|pid into cell_code;
-//   d. every other point spins (ld.acquire) until its cell carries the pillar bit -- published by this block or
-//      an earlier one, after step b of that block -- and runs the conserving atomicMin chain of k_slot_insert.
-//      The four chains of a thread are interleaved so that their L2 round trips overlap.
+//      a cell is its smallest index, i.e. slot 0 for good -- one __threadfence, then kPillarBit|pid into cell_code;
+//   d. every other point polls (ld.relaxed, then one __threadfence as the acquire) until its cell carries the pillar
+//      bit -- published by this block or an earlier one, after step b of that block -- and runs the conserving
+//      atomicMin chain of k_slot_insert.  The chains of a thread are interleaved so that their L2 round trips overlap.
 // Same final workspace as k_pillar_count + k_pillar_assign + k_slot_insert, bit for bit (the chain's final
-// state does not depend on the interleaving).
+// state does not depend on the interleaving; tests/test_voxelizer_model_cpu.py walks random interleavings of the
+// protocol on the CPU).
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t *p) {
-    uint32_t v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
 __device__ __forceinline__ void st_release_u32(uint32_t *p, uint32_t v) {
     asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
